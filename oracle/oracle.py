@@ -1,0 +1,210 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes loaders for the two CPU checkers:
+
+  * ``Restatement``  -> oracle/libfixca_oracle.so  (our plain-C restatement,
+    oracle/fixca_oracle.c; built anywhere by oracle/Makefile)
+  * ``Reference``    -> oracle/_ref/libfixca_ref.so (the reference's own fix-ca.c
+    compiled unmodified behind shim headers; built only where /root/reference
+    exists, travels prebuilt to the GPU box)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs import this module.  The product package
+(gimp-fix-ca_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+RESTATEMENT_SO = os.path.join(HERE, "libfixca_oracle.so")
+REFERENCE_SO = os.path.join(HERE, "_ref", "libfixca_ref.so")
+
+_c_int = ctypes.c_int
+_c_dp = ctypes.POINTER(ctypes.c_double)
+_c_vp = ctypes.c_void_p
+
+
+@dataclass
+class Params:
+    """FixCaParams (fix-ca.c:70-82) without the unused update_preview field."""
+
+    blue: float = 0.0
+    red: float = 0.0
+    lens_x: float = -1.0
+    lens_y: float = -1.0
+    interpolation: int = 1
+    saturation: float = 0.0
+    x_blue: float = 0.0
+    x_red: float = 0.0
+    y_blue: float = 0.0
+    y_red: float = 0.0
+
+    def as_array(self):
+        return (ctypes.c_double * 10)(
+            self.blue, self.red, self.lens_x, self.lens_y, float(self.interpolation),
+            self.saturation, self.x_blue, self.x_red, self.y_blue, self.y_red)
+
+
+def build(force: bool = False) -> None:
+    """Run oracle/Makefile (restatement always; _ref only where the reference is mounted)."""
+    if force or not os.path.exists(RESTATEMENT_SO) or (
+            os.path.exists("/root/reference/fix-ca.c") and not os.path.exists(REFERENCE_SO)):
+        subprocess.run(["make", "-C", HERE, "-s"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+def _img_args(src: np.ndarray):
+    assert src.ndim == 3 and src.flags["C_CONTIGUOUS"]
+    h, w, ch = src.shape
+    b = src.dtype.itemsize
+    if src.dtype.kind == "f":
+        bpc = -b
+    else:
+        bpc = b
+    return h, w, ch * b, bpc
+
+
+class Restatement:
+    def __init__(self):
+        build()
+        self.lib = ctypes.CDLL(RESTATEMENT_SO)
+        self.lib.fixca_oracle_region.argtypes = [_c_vp, _c_vp] + [_c_int] * 4 + [_c_dp] + [_c_int] * 4
+        self.lib.fixca_oracle_region.restype = _c_int
+        self.lib.fixca_oracle_region_mt.argtypes = [_c_vp, _c_vp] + [_c_int] * 4 + [_c_dp] + [_c_int] * 3
+        self.lib.fixca_oracle_region_mt.restype = _c_int
+        self.lib.fixca_oracle_axis.argtypes = [_c_int, _c_int, _c_dp, _c_int, _c_int, _c_vp, _c_vp]
+        self.lib.fixca_oracle_axis.restype = _c_int
+        self.lib.fixca_oracle_resolve_lens.argtypes = [_c_int, _c_int, _c_dp, _c_dp]
+
+    kind = "port"
+
+    def region(self, src: np.ndarray, p: Params, y1=None, y2=None, dst=None, threads: int = 1):
+        h, w, bytes_, bpc = _img_args(src)
+        y1 = 0 if y1 is None else y1
+        y2 = h if y2 is None else y2
+        if dst is None:
+            dst = np.zeros_like(src)
+        if threads > 1:
+            rc = self.lib.fixca_oracle_region_mt(src.ctypes.data, dst.ctypes.data, w, h, bytes_, bpc,
+                                                 p.as_array(), y1, y2, threads)
+        else:
+            rc = self.lib.fixca_oracle_region(src.ctypes.data, dst.ctypes.data, w, h, bytes_, bpc,
+                                              p.as_array(), 0, w, y1, y2)
+        if rc:
+            raise ValueError("fixca_oracle_region rc=%d" % rc)
+        return dst
+
+    def axis(self, w: int, h: int, p: Params, channel: int, axis: int):
+        n = h if axis else w
+        idx = np.zeros(n, dtype=np.int32)
+        frac = np.zeros(n, dtype=np.float64)
+        rc = self.lib.fixca_oracle_axis(w, h, p.as_array(), channel, axis, idx.ctypes.data, frac.ctypes.data)
+        if rc:
+            raise ValueError("fixca_oracle_axis rc=%d" % rc)
+        return idx, frac
+
+    def resolve_lens(self, w: int, h: int, lx: float, ly: float):
+        a, b = ctypes.c_double(lx), ctypes.c_double(ly)
+        self.lib.fixca_oracle_resolve_lens(w, h, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+
+class Reference:
+    """The reference's own code.  ``available()`` is False where it was never built."""
+
+    kind = "reference"
+
+    @staticmethod
+    def available() -> bool:
+        build()
+        return os.path.exists(REFERENCE_SO)
+
+    def __init__(self):
+        build()
+        self.lib = ctypes.CDLL(REFERENCE_SO)
+        L = self.lib
+        L.ref_fix_ca_region.argtypes = [_c_vp, _c_vp] + [_c_int] * 4 + [_c_dp] + [_c_int] * 5
+        L.ref_fix_ca_region.restype = None
+        L.ref_fix_ca_region_mt.argtypes = [_c_vp, _c_vp] + [_c_int] * 4 + [_c_dp] + [_c_int] * 3
+        L.ref_fix_ca_region_mt.restype = None
+        L.ref_sizeof_params.restype = _c_int
+        L.ref_color_size.argtypes = [ctypes.c_char_p, _c_int]
+        L.ref_color_size.restype = _c_int
+        L.ref_fake_set_drawable.argtypes = [_c_int] * 3 + [ctypes.c_char_p, _c_vp]
+        L.ref_fake_set_selection.argtypes = [_c_int] * 4
+        L.ref_fake_set_dialog_response.argtypes = [_c_int]
+        L.ref_fake_set_saved_params.argtypes = [_c_dp]
+        L.ref_fake_get_saved_params.argtypes = [_c_dp]
+        L.ref_fake_get_saved_params.restype = _c_int
+        L.ref_fake_last_message.restype = ctypes.c_char_p
+        L.ref_fake_counter.argtypes = [_c_int]
+        L.ref_fake_counter.restype = _c_int
+        L.ref_run.argtypes = [ctypes.c_char_p, _c_int, _c_int, _c_dp, _c_int]
+        L.ref_run.restype = _c_int
+        L.ref_dialog_lens.argtypes = [_c_int, _c_int, _c_dp, _c_dp]
+
+    def region(self, src: np.ndarray, p: Params, y1=None, y2=None, dst=None, threads: int = 1):
+        h, w, bytes_, bpc = _img_args(src)
+        y1 = 0 if y1 is None else y1
+        y2 = h if y2 is None else y2
+        if dst is None:
+            dst = np.zeros_like(src)
+        if threads > 1:
+            self.lib.ref_fix_ca_region_mt(src.ctypes.data, dst.ctypes.data, w, h, bytes_, bpc,
+                                          p.as_array(), y1, y2, threads)
+        else:
+            self.lib.ref_fix_ca_region(src.ctypes.data, dst.ctypes.data, w, h, bytes_, bpc,
+                                       p.as_array(), 0, w, y1, y2, 1)
+        return dst
+
+    def color_size(self, name: str, bpp: int) -> int:
+        return self.lib.ref_color_size(name.encode(), bpp)
+
+    def run(self, pixels: np.ndarray, fmt: str, run_mode: int, nparams: int, blue=0.0, red=0.0,
+            lens_x=-1.0, lens_y=-1.0, interpolation=0, x_blue=0.0, x_red=0.0, y_blue=0.0, y_red=0.0,
+            proc_name="Test-Fix-CA", selection=None, saved=None, dialog_ok=True):
+        """Drive the reference's real run() on an in-memory drawable (modified in place)."""
+        h, w, ch = pixels.shape
+        self.lib.ref_fake_set_drawable(w, h, ch * pixels.dtype.itemsize, fmt.encode(), pixels.ctypes.data)
+        if selection is not None:
+            self.lib.ref_fake_set_selection(*selection)
+        if saved is not None:
+            self.lib.ref_fake_set_saved_params(saved.as_array())
+        self.lib.ref_fake_set_dialog_response(1 if dialog_ok else 0)
+        f = (ctypes.c_double * 8)(blue, red, lens_x, lens_y, x_blue, x_red, y_blue, y_red)
+        return self.lib.ref_run(proc_name.encode(), run_mode, nparams, f, interpolation)
+
+    def last_message(self) -> str:
+        return self.lib.ref_fake_last_message().decode()
+
+    def counter(self, which: int) -> int:
+        return self.lib.ref_fake_counter(which)
+
+    def dialog_lens(self, w: int, h: int, lx: float, ly: float):
+        a, b = ctypes.c_double(lx), ctypes.c_double(ly)
+        self.lib.ref_dialog_lens(w, h, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+
+def best_checker():
+    """The strongest CPU checker present: the reference's own code, else the restatement."""
+    return Reference() if Reference.available() else Restatement()
+
+
+def synth_image(h: int, w: int, ch: int, dtype: str, seed: int, wide: bool = False) -> np.ndarray:
+    """Seeded synthetic image (PCG64), uniform noise: worst case for caches.
+    ``wide`` draws floats from [-0.5, 1.5) to exercise clip_d (fix-ca.c:873-880)."""
+    rng = np.random.default_rng(seed)
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        a = rng.random((h, w, ch), dtype=np.float64)
+        if wide:
+            a = a * 2.0 - 0.5
+        return np.ascontiguousarray(a.astype(dt))
+    return rng.integers(0, np.iinfo(dt).max, size=(h, w, ch), dtype=dt, endpoint=True)
