@@ -1,0 +1,850 @@
+// fixca_api.cu -- the C ABI of include/fixca_cuda.h: argument checking, the
+// geometry prologue of fix_ca_region (fix-ca.c:1033-1045), kernel selection and
+// tile planning, and the host region driver that replaces the middle of
+// fix_ca() (fix-ca.c:366-377): pinned staging, H2D / kernel / D2H pipelined by
+// row chunks on CUDA streams, one worker per GPU for row-banded multi-GPU runs.
+//
+// No CPU compute path exists here: without a usable GPU every compute entry
+// point returns FIXCA_ERR_NO_DEVICE / FIXCA_ERR_CUDA.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/fixca_cuda.h"
+#include "fixca_internal.h"
+
+using namespace fixca;
+
+// ---------------------------------------------------------------------------
+// errors, bookkeeping
+// ---------------------------------------------------------------------------
+static thread_local char tl_error[512] = "";
+static thread_local char tl_kernel[96] = "";
+static std::atomic<long> g_launches{0};
+
+static int fail(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(tl_error, sizeof tl_error, fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+	do {                                                                                    \
+		cudaError_t e_ = (expr);                                                        \
+		if (e_ != cudaSuccess)                                                          \
+			return fail(e_ == cudaErrorMemoryAllocation ? FIXCA_ERR_NOMEM : FIXCA_ERR_CUDA, \
+				    "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+static fixca_progress_fn g_progress = nullptr;
+static void *g_progress_user = nullptr;
+
+// ---------------------------------------------------------------------------
+// format and geometry
+// ---------------------------------------------------------------------------
+struct Format {
+	SampleKind kind;
+	int sample_bytes, nch, bpp;
+};
+
+static int parse_format(int bytes, int bpc, Format &f)
+{
+	switch (bpc) {
+	case 1:  f.kind = SK_U8;  f.sample_bytes = 1; break;
+	case 2:  f.kind = SK_U16; f.sample_bytes = 2; break;
+	case 4:  f.kind = SK_U32; f.sample_bytes = 4; break;
+	case 8:  f.kind = SK_U64; f.sample_bytes = 8; break;
+	case -4: f.kind = SK_F32; f.sample_bytes = 4; break;
+	case -8: f.kind = SK_F64; f.sample_bytes = 8; break;
+	default:
+		return fail(FIXCA_ERR_FORMAT, "unsupported bpc %d (the reference handles 1,2,4,8,-4,-8; fix-ca.c:688-707)", bpc);
+	}
+	if (bytes == 3 * f.sample_bytes)
+		f.nch = 3;
+	else if (bytes == 4 * f.sample_bytes)
+		f.nch = 4;
+	else
+		return fail(FIXCA_ERR_FORMAT, "bytes per pixel %d is neither RGB nor RGBA of %d-byte samples", bytes, f.sample_bytes);
+	f.bpp = bytes;
+	return FIXCA_OK;
+}
+
+// fix-ca.c:1033-1045
+static int make_geometry(int width, int height, const fixca_params *p, Geometry &g)
+{
+	if (p->interpolation < 0 || p->interpolation > 2)
+		return fail(FIXCA_ERR_INTERP, "interpolation %d outside 0..2", p->interpolation);
+	const int xc = (int)p->lens_x, yc = (int)p->lens_y;
+	int m = xc >= yc ? xc : yc;
+	if (width - xc > m) m = width - xc;
+	if (height - yc > m) m = height - yc;
+	const double den_blue = (double)m + p->blue, den_red = (double)m + p->red;
+	if (den_blue == 0.0 || den_red == 0.0 || den_blue != den_blue || den_red != den_red)
+		return fail(FIXCA_ERR_DEGENERATE,
+			    "max_dim + amount == 0 (max_dim %d, blue %g, red %g): the scale is infinite and the reference indexes out of bounds",
+			    m, p->blue, p->red);
+	const double s_blue = (double)m / den_blue, s_red = (double)m / den_red;
+	g.width = width;
+	g.height = height;
+	g.interp = p->interpolation;
+	g.x[CH_RED]  = Axis{xc, width, s_red, p->x_red};
+	g.x[CH_BLUE] = Axis{xc, width, s_blue, p->x_blue};
+	g.y[CH_RED]  = Axis{yc, height, s_red, p->y_red};
+	g.y[CH_BLUE] = Axis{yc, height, s_blue, p->y_blue};
+	auto ok = [](double s) { return s > 0.0 && s <= 1.0e300; };
+	auto fin = [](double v) { return v == v && v > -1.0e300 && v < 1.0e300; };
+	g.monotone = ok(s_blue) && ok(s_red) && fin(p->x_red) && fin(p->x_blue) && fin(p->y_red) && fin(p->y_blue);
+	return FIXCA_OK;
+}
+
+// Inclusive source-row range read by output rows [y1, y2).
+static void source_rows(const Geometry &g, int y1, int y2, int &lo, int &hi)
+{
+	if (g.monotone) {
+		span_needed(g.y[CH_RED], g.y[CH_BLUE], g.interp, y1, y2 - 1, lo, hi);
+		return;
+	}
+	lo = y1;
+	hi = y2 - 1;
+	for (int y = y1; y < y2; ++y)
+		for (int c = 0; c < 2; ++c) {
+			int l, h;
+			tap_range(g.y[c], g.interp, y, l, h);
+			lo = std::min(lo, l);
+			hi = std::max(hi, h);
+		}
+}
+
+// ---------------------------------------------------------------------------
+// planning
+// ---------------------------------------------------------------------------
+struct Plan {
+	const KernelEntry *k = nullptr;
+	KernelArgs args;
+	dim3 grid, block;
+	size_t smem = 0;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static const KernelEntry *pick_kernel(const Format &f, int interp, unsigned flags, bool tiled)
+{
+	if (interp == 0)
+		return lookup_none(f.sample_bytes, f.nch, tiled);
+	const bool fast = (flags & FIXCA_PRECISION_MASK) == FIXCA_PRECISION_FAST &&
+			  (f.kind == SK_U8 || f.kind == SK_U16 || f.kind == SK_F32);
+	return fast ? lookup_fast(f.kind, f.nch, interp, tiled) : lookup_exact(f.kind, f.nch, interp, tiled);
+}
+
+static int g_smem_optin[64];	// per device, 0 = not queried
+
+static int smem_limit(int dev)
+{
+	if (dev < 0 || dev >= 64)
+		return 48 * 1024;
+	if (!g_smem_optin[dev]) {
+		int v = 0;
+		if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0)
+			v = 48 * 1024;
+		g_smem_optin[dev] = v;
+	}
+	return g_smem_optin[dev];
+}
+
+// Largest source window (bytes per row, rows) any tile of a th-row grid needs.
+static void window_extent(const Geometry &g, int bpp, int y1, int y2, int tw, int th, int &max_wbytes, int &max_rows)
+{
+	max_wbytes = 0;
+	max_rows = 0;
+	for (int x0 = 0; x0 < g.width; x0 += tw) {
+		const int xl = std::min(x0 + tw, g.width) - 1;
+		int lo, hi;
+		span_needed(g.x[CH_RED], g.x[CH_BLUE], g.interp, x0, xl, lo, hi);
+		const int b0 = (lo * bpp) & ~15, b1 = ((hi + 1) * bpp + 15) & ~15;
+		max_wbytes = std::max(max_wbytes, b1 - b0);
+	}
+	for (int y0 = y1; y0 < y2; y0 += th) {
+		const int yl = std::min(y0 + th, y2) - 1;
+		int lo, hi;
+		span_needed(g.y[CH_RED], g.y[CH_BLUE], g.interp, y0, yl, lo, hi);
+		max_rows = std::max(max_rows, hi - lo + 1);
+	}
+}
+
+static int env_int(const char *name, int dflt)
+{
+	const char *s = getenv(name);
+	return (s && *s) ? atoi(s) : dflt;
+}
+
+static int make_plan(const Format &f, const Geometry &g, const void *d_src, size_t src_pitch, int src_row0,
+		     void *d_dst, size_t dst_pitch, int dst_row0, int y1, int y2, unsigned flags, int dev, Plan &pl)
+{
+	pl = Plan();
+	KernelArgs &a = pl.args;
+	memset(&a, 0, sizeof a);
+	a.src = (const unsigned char *)d_src;
+	a.dst = (unsigned char *)d_dst;
+	a.src_pitch = (long long)src_pitch;
+	a.dst_pitch = (long long)dst_pitch;
+	a.src_row0 = src_row0;
+	a.dst_row0 = dst_row0;
+	a.y1 = y1;
+	a.y2 = y2;
+	a.g = g;
+
+	const bool tma_ok = g.monotone && (src_pitch % 16 == 0) && (dst_pitch % 16 == 0) &&
+			    ((uintptr_t)d_src % 16 == 0) && ((uintptr_t)d_dst % 16 == 0);
+	bool want_tiled = tma_ok && !(flags & FIXCA_FORCE_DIRECT);
+
+	if (want_tiled) {
+		const KernelEntry *k = pick_kernel(f, g.interp, flags, true);
+		if (!k)
+			return fail(FIXCA_ERR_FORMAT, "no tiled kernel for this format");
+		const int limit = smem_limit(dev);
+		// Prefer the tallest tile that still leaves room for `want` CTAs per SM.
+		const int target_ctas = env_int("FIXCA_TILE_CTAS", 3);
+		const int forced_th = env_int("FIXCA_TILE_H", 0);
+		static const int th_choices[] = {64, 48, 32, 24, 16, 12, 8, 4};
+		const size_t sm_total = 227 * 1024;
+		int best_th = 0;
+		size_t best_smem = 0;
+		int best_wb = 0, best_rows = 0, best_off[3] = {0, 0, 0};
+		for (int pass = 0; pass < 2 && !best_th; ++pass) {
+			for (int th : th_choices) {
+				if (forced_th && th != forced_th)
+					continue;
+				if (th > 8 && th >= 2 * (y2 - y1) && !forced_th)
+					continue;	// tile much taller than the band
+				int wb, rows;
+				window_extent(g, f.bpp, y1, y2, k->tw, th, wb, rows);
+				const size_t off_ytab = align_up(sizeof(TileHeader), 16);
+				const size_t off_win = align_up(off_ytab + (size_t)2 * th * k->ycoef_bytes, 128);
+				const size_t off_out = align_up(off_win + (size_t)wb * rows, 128);
+				const size_t total = off_out + (size_t)th * k->tw * f.bpp;
+				const size_t budget = pass == 0 ? (sm_total / target_ctas - 1024) : (size_t)limit;
+				if (total <= budget && total <= (size_t)limit) {
+					best_th = th; best_smem = total; best_wb = wb; best_rows = rows;
+					best_off[0] = (int)off_ytab; best_off[1] = (int)off_win; best_off[2] = (int)off_out;
+					break;
+				}
+			}
+		}
+		if (best_th) {
+			pl.k = k;
+			a.th = best_th;
+			a.win_pitch = best_wb;
+			a.win_rows = best_rows;
+			a.off_ytab = best_off[0];
+			a.off_win = best_off[1];
+			a.off_out = best_off[2];
+			pl.smem = best_smem;
+			pl.block = dim3(2 * k->tw);
+			pl.grid = dim3((g.width + k->tw - 1) / k->tw, (y2 - y1 + best_th - 1) / best_th);
+			if (pl.grid.y > 65535)
+				want_tiled = false;
+			else
+				return FIXCA_OK;
+		} else {
+			want_tiled = false;
+		}
+	}
+	if (flags & FIXCA_FORCE_TILED)
+		return fail(FIXCA_ERR_ARG, "FIXCA_FORCE_TILED: the tiled kernel cannot take this call (%s)",
+			    tma_ok ? "source window exceeds shared memory" : "non-monotone map, or pitch/pointer not 16-byte aligned");
+
+	pl.k = pick_kernel(f, g.interp, flags, false);
+	if (!pl.k)
+		return fail(FIXCA_ERR_FORMAT, "no kernel for this format");
+	pl.block = dim3(64, 4);
+	pl.grid = dim3((g.width + 63) / 64, (y2 - y1 + 3) / 4);
+	pl.smem = 0;
+	if (pl.grid.y > 65535)
+		return fail(FIXCA_ERR_ARG, "band of %d rows is too tall for one launch", y2 - y1);
+	return FIXCA_OK;
+}
+
+static int launch_plan(const Plan &pl, cudaStream_t stream)
+{
+	if (pl.smem > 48 * 1024) {
+		// Opt in once per kernel function (per device context the attribute sticks).
+		CUDA_TRY(cudaFuncSetAttribute((const void *)pl.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+	}
+	KernelArgs a = pl.args;
+	void *params[] = {&a};
+	CUDA_TRY(cudaLaunchKernel((const void *)pl.k->fn, pl.grid, pl.block, params, pl.smem, stream));
+	g_launches.fetch_add(1);
+	snprintf(tl_kernel, sizeof tl_kernel, "%s", pl.k->name);
+	return FIXCA_OK;
+}
+
+static int check_common(const void *src, const void *dst, int width, int height, const fixca_params *p, int y1, int y2)
+{
+	if (!src || !dst || !p)
+		return fail(FIXCA_ERR_ARG, "NULL pointer argument");
+	if (width <= 0 || height <= 0)
+		return fail(FIXCA_ERR_ARG, "non-positive image size %dx%d", width, height);
+	if (y1 < 0 || y2 > height || y1 > y2)
+		return fail(FIXCA_ERR_ARG, "rows [%d,%d) outside 0..%d", y1, y2, height);
+	return FIXCA_OK;
+}
+
+static int current_device_or(int device, int &out)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) {
+		cudaGetLastError();
+		return fail(FIXCA_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "count 0");
+	}
+	if (device < 0) {
+		CUDA_TRY(cudaGetDevice(&out));
+	} else {
+		if (device >= n)
+			return fail(FIXCA_ERR_NO_DEVICE, "device %d requested, %d present", device, n);
+		out = device;
+	}
+	return FIXCA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// device-resident entry
+// ---------------------------------------------------------------------------
+extern "C" int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int src_row0, int src_rows,
+				     void *d_dst, size_t dst_pitch, int dst_row0,
+				     int width, int height, int bytes, int bpc,
+				     const fixca_params *params, int y1, int y2, unsigned flags, void *stream)
+{
+	int rc = check_common(d_src, d_dst, width, height, params, y1, y2);
+	if (rc) return rc;
+	Format f;
+	if ((rc = parse_format(bytes, bpc, f))) return rc;
+	if (f.kind == SK_U64 && params->interpolation != 0)
+		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples with Linear/Cubic need 80-bit long double arithmetic (fix-ca.c:728-733)");
+	Geometry g;
+	if ((rc = make_geometry(width, height, params, g))) return rc;
+	if (src_pitch < (size_t)width * bytes || dst_pitch < (size_t)width * bytes)
+		return fail(FIXCA_ERR_ARG, "pitch smaller than a row (%zu / %zu < %zu)", src_pitch, dst_pitch, (size_t)width * bytes);
+	if (y1 == y2)
+		return FIXCA_OK;
+	int lo, hi;
+	source_rows(g, y1, y2, lo, hi);
+	if (src_row0 < 0 || lo < src_row0 || hi >= src_row0 + src_rows || src_row0 + src_rows > height)
+		return fail(FIXCA_ERR_ARG, "source rows [%d,%d) do not cover the rows [%d,%d] that output rows [%d,%d) read",
+			    src_row0, src_row0 + src_rows, lo, hi, y1, y2);
+	if (dst_row0 < 0 || dst_row0 > y1)
+		return fail(FIXCA_ERR_ARG, "dst_row0 %d is past the first output row %d", dst_row0, y1);
+	int dev;
+	if ((rc = current_device_or(-1, dev))) return rc;
+	Plan pl;
+	if ((rc = make_plan(f, g, d_src, src_pitch, src_row0, d_dst, dst_pitch, dst_row0, y1, y2, flags, dev, pl))) return rc;
+	return launch_plan(pl, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// host region driver
+// ---------------------------------------------------------------------------
+namespace {
+
+struct DeviceCtx {
+	std::mutex mu;
+	int dev = -1;
+	bool ready = false;
+	cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
+	unsigned char *d_src = nullptr, *d_dst = nullptr;
+	size_t d_src_cap = 0, d_dst_cap = 0;
+	unsigned char *h_in = nullptr, *h_out = nullptr;	// pinned staging rings
+	size_t h_in_cap = 0, h_out_cap = 0;
+	std::vector<cudaEvent_t> events;
+
+	int init(int device)
+	{
+		if (ready) return FIXCA_OK;
+		dev = device;
+		CUDA_TRY(cudaSetDevice(dev));
+		CUDA_TRY(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
+		CUDA_TRY(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
+		CUDA_TRY(cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking));
+		ready = true;
+		return FIXCA_OK;
+	}
+	int reserve_dev(unsigned char *&p, size_t &cap, size_t need)
+	{
+		if (need <= cap) return FIXCA_OK;
+		if (p) { cudaFree(p); p = nullptr; cap = 0; }
+		CUDA_TRY(cudaMalloc(&p, need));
+		cap = need;
+		return FIXCA_OK;
+	}
+	int reserve_pinned(unsigned char *&p, size_t &cap, size_t need)
+	{
+		if (need <= cap) return FIXCA_OK;
+		if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+		CUDA_TRY(cudaHostAlloc(&p, need, cudaHostAllocDefault));
+		cap = need;
+		return FIXCA_OK;
+	}
+	int event(size_t i, cudaEvent_t &e)
+	{
+		while (events.size() <= i) {
+			cudaEvent_t ne;
+			CUDA_TRY(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming));
+			events.push_back(ne);
+		}
+		e = events[i];
+		return FIXCA_OK;
+	}
+	void release()
+	{
+		if (!ready) return;
+		cudaSetDevice(dev);
+		for (cudaEvent_t e : events) cudaEventDestroy(e);
+		events.clear();
+		if (d_src) cudaFree(d_src);
+		if (d_dst) cudaFree(d_dst);
+		if (h_in) cudaFreeHost(h_in);
+		if (h_out) cudaFreeHost(h_out);
+		d_src = d_dst = h_in = h_out = nullptr;
+		d_src_cap = d_dst_cap = h_in_cap = h_out_cap = 0;
+		cudaStreamDestroy(s_up); cudaStreamDestroy(s_run); cudaStreamDestroy(s_down);
+		ready = false;
+	}
+};
+
+DeviceCtx g_ctx[16];
+
+bool is_pinned(const void *p)
+{
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return at.type == cudaMemoryTypeHost;
+}
+
+} // namespace
+
+// One band [y1,y2) of a host image on one device: upload the source rows the
+// band reads, run, download.  Rows move in chunks so that H2D of chunk i+1,
+// the kernel of chunk i and D2H of chunk i-1 overlap (PCIe is full duplex).
+static int region_host_band(int dev, const unsigned char *src, unsigned char *dst, int width, int height,
+			    const Format &f, const fixca_params *params, const Geometry &g,
+			    int y1, int y2, unsigned flags, bool progress)
+{
+	if (dev < 0 || dev >= 16)
+		return fail(FIXCA_ERR_NO_DEVICE, "device ordinal %d out of range", dev);
+	DeviceCtx &cx = g_ctx[dev];
+	std::lock_guard<std::mutex> lock(cx.mu);
+	int rc;
+	if ((rc = cx.init(dev))) return rc;
+	CUDA_TRY(cudaSetDevice(dev));
+
+	const size_t row_bytes = (size_t)width * f.bpp;
+	const size_t pitch = align_up(row_bytes, 128);
+	int band_lo, band_hi;
+	source_rows(g, y1, y2, band_lo, band_hi);
+	const int src_rows = band_hi - band_lo + 1;
+	if ((rc = cx.reserve_dev(cx.d_src, cx.d_src_cap, pitch * src_rows))) return rc;
+	if ((rc = cx.reserve_dev(cx.d_dst, cx.d_dst_cap, pitch * (size_t)(y2 - y1)))) return rc;
+
+	// Chunking: ~32 MB of rows per chunk, at least 64 rows, at most 64 chunks.
+	int chunk_rows = (int)std::max<size_t>(64, (32u << 20) / std::max<size_t>(row_bytes, 1));
+	chunk_rows = std::max(chunk_rows, (y2 - y1 + 63) / 64);
+	chunk_rows = std::min(chunk_rows, y2 - y1);
+	const int nchunks = (y2 - y1 + chunk_rows - 1) / chunk_rows;
+
+	const bool src_pinned = is_pinned(src), dst_pinned = is_pinned(dst);
+	// Pageable callers go through pinned rings (2 slots per direction).
+	const int ring = 2;
+	size_t in_slot = 0, out_slot = 0;
+	if (!src_pinned) {
+		// a chunk uploads at most its own rows plus the whole halo on the first chunk
+		int worst = 0, prev = band_lo - 1;
+		for (int i = 0; i < nchunks; ++i) {
+			const int c1 = y1 + i * chunk_rows, c2 = std::min(c1 + chunk_rows, y2);
+			int lo, hi;
+			source_rows(g, c1, c2, lo, hi);
+			if (!g.monotone) { lo = band_lo; hi = band_hi; }
+			worst = std::max(worst, hi - prev);
+			prev = std::max(prev, hi);
+		}
+		in_slot = (size_t)std::max(worst, 1) * row_bytes;
+		if ((rc = cx.reserve_pinned(cx.h_in, cx.h_in_cap, in_slot * ring))) return rc;
+	}
+	if (!dst_pinned) {
+		out_slot = (size_t)chunk_rows * row_bytes;
+		if ((rc = cx.reserve_pinned(cx.h_out, cx.h_out_cap, out_slot * ring))) return rc;
+	}
+
+	if (progress && g_progress)
+		g_progress(0, 0.0, g_progress_user);
+
+	int uploaded_hi = band_lo - 1;	// highest source row already sent
+	std::vector<int> chunk_y1(nchunks), chunk_y2(nchunks);
+	// events: [3*i] upload done, [3*i+1] kernel done, [3*i+2] download done
+	auto retire = [&](int i) -> int {
+		cudaEvent_t e_down = nullptr;
+		int r = cx.event(3 * i + 2, e_down);
+		if (r) return r;
+		CUDA_TRY(cudaEventSynchronize(e_down));
+		if (!dst_pinned) {
+			const unsigned char *slot = cx.h_out + (size_t)(i % ring) * out_slot;
+			memcpy(dst + (size_t)chunk_y1[i] * row_bytes, slot, (size_t)(chunk_y2[i] - chunk_y1[i]) * row_bytes);
+		}
+		if (progress && g_progress)
+			for (int y = chunk_y1[i]; y < chunk_y2[i]; ++y)
+				if ((y - y1) % 8 == 0)
+					g_progress(1, (double)(y - y1) / (double)(y2 - y1), g_progress_user);
+		return FIXCA_OK;
+	};
+
+	for (int i = 0; i < nchunks; ++i) {
+		const int c1 = y1 + i * chunk_rows, c2 = std::min(c1 + chunk_rows, y2);
+		chunk_y1[i] = c1;
+		chunk_y2[i] = c2;
+		int lo, hi;
+		source_rows(g, c1, c2, lo, hi);
+		if (!g.monotone) { lo = band_lo; hi = band_hi; }
+		cudaEvent_t e_up = nullptr, e_run = nullptr, e_down = nullptr;
+		if ((rc = cx.event(3 * i, e_up)) || (rc = cx.event(3 * i + 1, e_run)) || (rc = cx.event(3 * i + 2, e_down))) return rc;
+
+		// the ring slot this chunk reuses must have been drained
+		if (i >= ring && (rc = retire(i - ring))) return rc;
+
+		if (hi > uploaded_hi) {
+			const int r0 = uploaded_hi + 1, nr = hi - uploaded_hi;
+			const unsigned char *from = src + (size_t)r0 * row_bytes;
+			if (!src_pinned) {
+				unsigned char *slot = cx.h_in + (size_t)(i % ring) * in_slot;
+				memcpy(slot, from, (size_t)nr * row_bytes);
+				from = slot;
+			}
+			CUDA_TRY(cudaMemcpy2DAsync(cx.d_src + (size_t)(r0 - band_lo) * pitch, pitch, from, row_bytes,
+						   row_bytes, nr, cudaMemcpyHostToDevice, cx.s_up));
+			uploaded_hi = hi;
+		}
+		CUDA_TRY(cudaEventRecord(e_up, cx.s_up));
+		CUDA_TRY(cudaStreamWaitEvent(cx.s_run, e_up, 0));
+		Plan pl;
+		if ((rc = make_plan(f, g, cx.d_src, pitch, band_lo, cx.d_dst, pitch, y1, c1, c2, flags, dev, pl))) return rc;
+		if ((rc = launch_plan(pl, cx.s_run))) return rc;
+		CUDA_TRY(cudaEventRecord(e_run, cx.s_run));
+		CUDA_TRY(cudaStreamWaitEvent(cx.s_down, e_run, 0));
+		unsigned char *to = dst_pinned ? dst + (size_t)c1 * row_bytes : cx.h_out + (size_t)(i % ring) * out_slot;
+		CUDA_TRY(cudaMemcpy2DAsync(to, row_bytes, cx.d_dst + (size_t)(c1 - y1) * pitch, pitch,
+					   row_bytes, c2 - c1, cudaMemcpyDeviceToHost, cx.s_down));
+		CUDA_TRY(cudaEventRecord(e_down, cx.s_down));
+	}
+	for (int i = std::max(0, nchunks - ring); i < nchunks; ++i)
+		if ((rc = retire(i))) return rc;
+	CUDA_TRY(cudaStreamSynchronize(cx.s_down));
+	if (progress && g_progress)
+		g_progress(1, 0.0, g_progress_user);
+	(void)height;
+	(void)params;
+	return FIXCA_OK;
+}
+
+static int host_prologue(const unsigned char *src, unsigned char *dst, int width, int height, int bytes, int bpc,
+			 const fixca_params *params, int x1, int x2, int y1, int y2, Format &f, Geometry &g)
+{
+	int rc = check_common(src, dst, width, height, params, y1, y2);
+	if (rc) return rc;
+	if ((rc = parse_format(bytes, bpc, f))) return rc;
+	if (x1 != 0 || x2 != width)
+		return fail(FIXCA_ERR_REGION, "columns [%d,%d) of %d: only full-width row bands are defined (the reference's own x1 != 0 path is broken)", x1, x2, width);
+	if (f.kind == SK_U64 && params->interpolation != 0)
+		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples with Linear/Cubic need 80-bit long double arithmetic (fix-ca.c:728-733)");
+	return make_geometry(width, height, params, g);
+}
+
+extern "C" int fixca_cuda_region_ex(const unsigned char *src, unsigned char *dst, int width, int height,
+				    int bytes, int bpc, const fixca_params *params,
+				    int x1, int x2, int y1, int y2, int show_progress, unsigned flags, int device)
+{
+	Format f;
+	Geometry g;
+	int rc = host_prologue(src, dst, width, height, bytes, bpc, params, x1, x2, y1, y2, f, g);
+	if (rc) return rc;
+	int dev;
+	if ((rc = current_device_or(device, dev))) return rc;
+	if (y1 == y2)
+		return FIXCA_OK;
+	int prev = -1;
+	cudaGetDevice(&prev);
+	rc = region_host_band(dev, src, dst, width, height, f, params, g, y1, y2, flags, show_progress != 0);
+	if (prev >= 0)
+		cudaSetDevice(prev);
+	return rc;
+}
+
+extern "C" int fixca_cuda_region(const unsigned char *src, unsigned char *dst, int width, int height,
+				 int bytes, int bpc, const fixca_params *params,
+				 int x1, int x2, int y1, int y2, int show_progress)
+{
+	unsigned flags = FIXCA_PRECISION_EXACT;
+	const char *e = getenv("FIXCA_PRECISION");
+	if (e && (e[0] == 'f' || e[0] == 'F'))
+		flags = FIXCA_PRECISION_FAST;
+	return fixca_cuda_region_ex(src, dst, width, height, bytes, bpc, params, x1, x2, y1, y2, show_progress, flags, -1);
+}
+
+extern "C" int fixca_split_bands(int y1, int y2, int nbands, int *band_y1, int *band_y2)
+{
+	if (nbands <= 0 || y1 > y2 || !band_y1 || !band_y2)
+		return fail(FIXCA_ERR_ARG, "bad band split request");
+	for (int i = 0; i < nbands; ++i) {
+		band_y1[i] = y1 + (int)((long long)(y2 - y1) * i / nbands);
+		band_y2[i] = y1 + (int)((long long)(y2 - y1) * (i + 1) / nbands);
+	}
+	return FIXCA_OK;
+}
+
+extern "C" int fixca_cuda_region_multi(const unsigned char *src, unsigned char *dst, int width, int height,
+				       int bytes, int bpc, const fixca_params *params, int y1, int y2,
+				       unsigned flags, const int *devices, int ndev)
+{
+	Format f;
+	Geometry g;
+	int rc = host_prologue(src, dst, width, height, bytes, bpc, params, 0, width, y1, y2, f, g);
+	if (rc) return rc;
+	int have = 0;
+	if (cudaGetDeviceCount(&have) != cudaSuccess || have <= 0) {
+		cudaGetLastError();
+		return fail(FIXCA_ERR_NO_DEVICE, "no CUDA device; this library has no CPU path");
+	}
+	if (ndev <= 0 || ndev > 16)
+		return fail(FIXCA_ERR_ARG, "ndev %d outside 1..16", ndev);
+	std::vector<int> dv(ndev), b1(ndev), b2(ndev), rcs(ndev, 0);
+	std::vector<std::string> errs(ndev);
+	for (int i = 0; i < ndev; ++i) {
+		dv[i] = devices ? devices[i] : i;
+		if (dv[i] < 0 || dv[i] >= have)
+			return fail(FIXCA_ERR_NO_DEVICE, "device %d requested, %d present", dv[i], have);
+	}
+	fixca_split_bands(y1, y2, ndev, b1.data(), b2.data());
+	std::vector<std::thread> workers;
+	for (int i = 0; i < ndev; ++i) {
+		if (b1[i] == b2[i])
+			continue;
+		workers.emplace_back([&, i]() {
+			rcs[i] = region_host_band(dv[i], src, dst, width, height, f, params, g, b1[i], b2[i], flags, false);
+			if (rcs[i])
+				errs[i] = tl_error;
+		});
+	}
+	for (std::thread &t : workers)
+		t.join();
+	for (int i = 0; i < ndev; ++i)
+		if (rcs[i])
+			return fail(rcs[i], "band %d on device %d: %s", i, dv[i], errs[i].c_str());
+	snprintf(tl_kernel, sizeof tl_kernel, "multi x%d", ndev);
+	return FIXCA_OK;
+}
+
+extern "C" int fixca_cuda_frames(const unsigned char *const *src_frames, unsigned char *const *dst_frames, int nframes,
+				 int width, int height, int bytes, int bpc, const fixca_params *params,
+				 unsigned flags, int device)
+{
+	if (nframes < 0 || (nframes > 0 && (!src_frames || !dst_frames)))
+		return fail(FIXCA_ERR_ARG, "bad frame list");
+	if (nframes == 0)
+		return FIXCA_OK;
+	Format f;
+	Geometry g;
+	int rc = host_prologue(src_frames[0], dst_frames[0], width, height, bytes, bpc, params, 0, width, 0, height, f, g);
+	if (rc) return rc;
+	int dev;
+	if ((rc = current_device_or(device, dev))) return rc;
+	int prev = -1;
+	cudaGetDevice(&prev);
+	CUDA_TRY(cudaSetDevice(dev));
+
+	// A ring of 3 slots, each with its own stream, device frame pair and pinned pair.
+	const int ring = std::min(3, nframes);
+	const size_t row_bytes = (size_t)width * bytes, pitch = align_up(row_bytes, 128);
+	const size_t frame_bytes = row_bytes * height, dev_bytes = pitch * height;
+	struct Slot { cudaStream_t s; unsigned char *d_src, *d_dst, *h_in, *h_out; int frame; };
+	std::vector<Slot> slots(ring);
+	auto cleanup = [&]() {
+		for (Slot &s : slots) {
+			if (s.s) { cudaStreamSynchronize(s.s); cudaStreamDestroy(s.s); }
+			if (s.d_src) cudaFree(s.d_src);
+			if (s.d_dst) cudaFree(s.d_dst);
+			if (s.h_in) cudaFreeHost(s.h_in);
+			if (s.h_out) cudaFreeHost(s.h_out);
+		}
+		if (prev >= 0) cudaSetDevice(prev);
+	};
+	for (Slot &s : slots) { s.s = nullptr; s.d_src = s.d_dst = s.h_in = s.h_out = nullptr; s.frame = -1; }
+	auto body = [&]() -> int {
+		for (Slot &s : slots) {
+			CUDA_TRY(cudaStreamCreateWithFlags(&s.s, cudaStreamNonBlocking));
+			CUDA_TRY(cudaMalloc(&s.d_src, dev_bytes));
+			CUDA_TRY(cudaMalloc(&s.d_dst, dev_bytes));
+			CUDA_TRY(cudaHostAlloc(&s.h_in, frame_bytes, cudaHostAllocDefault));
+			CUDA_TRY(cudaHostAlloc(&s.h_out, frame_bytes, cudaHostAllocDefault));
+		}
+		auto retire = [&](Slot &s) -> int {
+			if (s.frame < 0) return FIXCA_OK;
+			CUDA_TRY(cudaStreamSynchronize(s.s));
+			if (!is_pinned(dst_frames[s.frame]))
+				memcpy(dst_frames[s.frame], s.h_out, frame_bytes);
+			s.frame = -1;
+			return FIXCA_OK;
+		};
+		for (int i = 0; i < nframes; ++i) {
+			Slot &s = slots[i % ring];
+			int r = retire(s);
+			if (r) return r;
+			if (!src_frames[i] || !dst_frames[i])
+				return fail(FIXCA_ERR_ARG, "frame %d is NULL", i);
+			const unsigned char *from = src_frames[i];
+			if (!is_pinned(from)) {
+				memcpy(s.h_in, from, frame_bytes);
+				from = s.h_in;
+			}
+			unsigned char *to = is_pinned(dst_frames[i]) ? dst_frames[i] : s.h_out;
+			CUDA_TRY(cudaMemcpy2DAsync(s.d_src, pitch, from, row_bytes, row_bytes, height, cudaMemcpyHostToDevice, s.s));
+			Plan pl;
+			if ((r = make_plan(f, g, s.d_src, pitch, 0, s.d_dst, pitch, 0, 0, height, flags, dev, pl))) return r;
+			if ((r = launch_plan(pl, s.s))) return r;
+			CUDA_TRY(cudaMemcpy2DAsync(to, row_bytes, s.d_dst, pitch, row_bytes, height, cudaMemcpyDeviceToHost, s.s));
+			s.frame = i;
+		}
+		for (Slot &s : slots) {
+			int r = retire(s);
+			if (r) return r;
+		}
+		return FIXCA_OK;
+	};
+	rc = body();
+	cleanup();
+	return rc;
+}
+
+// ---------------------------------------------------------------------------
+// host-side logic
+// ---------------------------------------------------------------------------
+extern "C" int fixca_band_source_rows(int width, int height, const fixca_params *params, int y1, int y2,
+				      int *src_lo, int *src_hi)
+{
+	if (!params || !src_lo || !src_hi || width <= 0 || height <= 0 || y1 < 0 || y2 > height || y1 >= y2)
+		return fail(FIXCA_ERR_ARG, "bad arguments to fixca_band_source_rows");
+	Geometry g;
+	int rc = make_geometry(width, height, params, g);
+	if (rc) return rc;
+	source_rows(g, y1, y2, *src_lo, *src_hi);
+	return FIXCA_OK;
+}
+
+extern "C" void fixca_resolve_lens(int width, int height, double *lens_x, double *lens_y)
+{
+	// fix-ca.c:427-428: round (xImg/2) with integer division
+	if (lens_x && (*lens_x <= 0 || *lens_x >= width))
+		*lens_x = (double)(width / 2);
+	if (lens_y && (*lens_y <= 0 || *lens_y >= height))
+		*lens_y = (double)(height / 2);
+}
+
+extern "C" int fixca_check_params(const fixca_params *p)
+{
+	if (!p)
+		return fail(FIXCA_ERR_ARG, "NULL params");
+	// fix-ca.c:279-292
+	const double v[6] = {p->blue, p->red, p->x_blue, p->x_red, p->y_blue, p->y_red};
+	for (double d : v)
+		if (d < -FIXCA_INPUT_MAX || d > FIXCA_INPUT_MAX)
+			return fail(FIXCA_ERR_RANGE, "Parameter out of range!");
+	if (p->interpolation < 0 || p->interpolation > 2)
+		return fail(FIXCA_ERR_INTERP, "Parameter out of range!");
+	return FIXCA_OK;
+}
+
+extern "C" int fixca_color_size(const char *name, int bpp)
+{
+	// fix-ca.c:681-711
+	if (!name)
+		return FIXCA_BPC_UNSUPPORTED;
+	if (strstr(name, "double")) return -8;
+	if (strstr(name, "float")) return -4;
+	if (strstr(name, "u15")) return FIXCA_BPC_UNSUPPORTED;
+	if (!strstr(name, " u")) return FIXCA_BPC_UNSUPPORTED;
+	if (bpp > 32) return FIXCA_BPC_UNSUPPORTED;
+	if (bpp >= 24) return 8;
+	if (bpp >= 12) return 4;
+	if (bpp >= 6) return 2;
+	if (bpp >= 3) return 1;
+	return FIXCA_BPC_UNSUPPORTED;
+}
+
+extern "C" void fixca_params_default(fixca_params *p)
+{
+	if (!p) return;
+	// fix-ca.c:85-97
+	memset(p, 0, sizeof *p);
+	p->lens_x = -1.0;
+	p->lens_y = -1.0;
+	p->update_preview = 1;
+	p->interpolation = FIXCA_INTERP_LINEAR;
+}
+
+extern "C" void fixca_cuda_set_progress(fixca_progress_fn fn, void *user)
+{
+	g_progress = fn;
+	g_progress_user = user;
+}
+
+extern "C" const char *fixca_cuda_last_error(void) { return tl_error; }
+extern "C" const char *fixca_cuda_last_kernel(void) { return tl_kernel; }
+extern "C" long fixca_cuda_launch_count(void) { return g_launches.load(); }
+
+extern "C" const char *fixca_strerror(int code)
+{
+	switch (code) {
+	case FIXCA_OK: return "success";
+	case FIXCA_ERR_ARG: return "invalid argument";
+	case FIXCA_ERR_FORMAT: return "unsupported sample format";
+	case FIXCA_ERR_INTERP: return "interpolation outside 0..2";
+	case FIXCA_ERR_REGION: return "only full-width row bands are defined";
+	case FIXCA_ERR_DEGENERATE: return "max_dim + amount == 0";
+	case FIXCA_ERR_RANGE: return "parameter out of range";
+	case FIXCA_ERR_NO_DEVICE: return "no CUDA device";
+	case FIXCA_ERR_CUDA: return "CUDA error";
+	case FIXCA_ERR_UNSUPPORTED: return "u64 samples with Linear/Cubic are not supported";
+	case FIXCA_ERR_NOMEM: return "out of device or pinned memory";
+	default: return "unknown error";
+	}
+}
+
+extern "C" int fixca_cuda_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+extern "C" void fixca_cuda_release(void)
+{
+	for (DeviceCtx &c : g_ctx) {
+		std::lock_guard<std::mutex> lock(c.mu);
+		c.release();
+	}
+}
+
+extern "C" const char *fixca_version(void) { return "fixca-b200 0.1 (sm_100a)"; }

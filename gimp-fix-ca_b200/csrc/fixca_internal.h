@@ -1,0 +1,33 @@
+// fixca_internal.h -- glue between the host driver (fixca_api.cu) and the
+// kernel translation units (kernels_*.cu).
+#pragma once
+
+#include <cstddef>
+#include "fixca_kernels.cuh"
+
+namespace fixca {
+
+enum SampleKind { SK_U8 = 0, SK_U16, SK_U32, SK_U64, SK_F32, SK_F64, SK_COUNT };
+enum ArithKind  { AR_COPY = 0, AR_EXACT = 1, AR_FAST = 2 };
+
+// Every kernel has the signature  __global__ void k(const KernelArgs).
+typedef void (*kernel_fn)(const KernelArgs);
+
+struct KernelEntry {
+	kernel_fn   fn;
+	const char *name;	// "tiled/cubic/f32/u16x3"
+	int         tw;		// tile width (0 for direct kernels)
+	int         ycoef_bytes;// per-row table entry size (tiled)
+	int         sample_bytes;
+};
+
+constexpr int TILE_W = 128;
+
+// sample_bytes in {1,2,4,8}; nch in {3,4}
+const KernelEntry *lookup_none(int sample_bytes, int nch, bool tiled);
+// kind in {SK_U8,SK_U16,SK_U32,SK_F32,SK_F64}; interp in {1,2}
+const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled);
+// kind in {SK_U8,SK_U16,SK_F32}; interp in {1,2}
+const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled);
+
+} // namespace fixca

@@ -1,0 +1,240 @@
+"""fixca -- thin ctypes binding over the C ABI of include/fixca_cuda.h.
+
+Mirrors the reference plug-in's interface for the correction pass:
+
+* ``FixCaParams``            <- ``FixCaParams`` (fix-ca.c:70-82), same field names
+* ``fix_ca_region(...)``     <- ``fix_ca_region()`` (fix-ca.c:998-1001), same
+                                argument order and meaning, host (numpy) buffers
+* ``fix_ca_region_dev(...)`` device-resident variant (raw CUDA pointers)
+* ``resolve_lens``, ``check_params``, ``color_size``, ``band_source_rows`` ...
+
+This module does no computing of its own: every call goes through
+``lib/libfixca_cuda.so`` (hand-written sm_100a kernels).  If the library is
+missing, importing fails; if no GPU is usable the compute calls raise
+``FixCaError`` -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfixca_cuda.so")
+
+INTERP_NONE, INTERP_LINEAR, INTERP_CUBIC = 0, 1, 2
+PRECISION_EXACT, PRECISION_FAST = 0x0, 0x1
+FORCE_DIRECT, FORCE_TILED = 0x10, 0x20
+INPUT_MAX = 30.0
+
+OK = 0
+ERR_ARG, ERR_FORMAT, ERR_INTERP, ERR_REGION, ERR_DEGENERATE = -1, -2, -3, -4, -5
+ERR_RANGE, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -6, -7, -8, -9, -10
+
+# Every symbol include/fixca_cuda.h declares.
+EXPORTS = (
+    "fixca_cuda_region", "fixca_cuda_region_ex", "fixca_cuda_region_multi", "fixca_cuda_region_dev",
+    "fixca_cuda_frames", "fixca_band_source_rows", "fixca_split_bands", "fixca_resolve_lens",
+    "fixca_check_params", "fixca_color_size", "fixca_params_default", "fixca_cuda_set_progress",
+    "fixca_cuda_last_error", "fixca_strerror", "fixca_cuda_device_count", "fixca_cuda_last_kernel",
+    "fixca_cuda_launch_count", "fixca_cuda_release", "fixca_version",
+)
+
+
+class FixCaParams(ctypes.Structure):
+    """Layout-identical to the reference's FixCaParams (fix-ca.c:70-82), 80 bytes."""
+
+    _fields_ = [
+        ("blue", ctypes.c_double),
+        ("red", ctypes.c_double),
+        ("lens_x", ctypes.c_double),
+        ("lens_y", ctypes.c_double),
+        ("update_preview", ctypes.c_int),
+        ("interpolation", ctypes.c_int),
+        ("saturation", ctypes.c_double),
+        ("x_blue", ctypes.c_double),
+        ("x_red", ctypes.c_double),
+        ("y_blue", ctypes.c_double),
+        ("y_red", ctypes.c_double),
+    ]
+
+    def __init__(self, blue=0.0, red=0.0, lens_x=-1.0, lens_y=-1.0, interpolation=INTERP_LINEAR,
+                 saturation=0.0, x_blue=0.0, x_red=0.0, y_blue=0.0, y_red=0.0, update_preview=1):
+        # defaults of fix_ca_params_default (fix-ca.c:85-97)
+        super().__init__(blue, red, lens_x, lens_y, update_preview, interpolation, saturation,
+                         x_blue, x_red, y_blue, y_red)
+
+
+class FixCaError(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__("fixca error %d: %s" % (code, text))
+        self.code = code
+
+
+PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_double, ctypes.c_void_p)
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load lib/libfixca_cuda.so (raises OSError when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OSError("%s not found: build it with `make -C gimp-fix-ca_b200` "
+                      "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    i, vp, pp = ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(FixCaParams)
+    L.fixca_cuda_region.argtypes = [vp, vp, i, i, i, i, pp, i, i, i, i, i]
+    L.fixca_cuda_region_ex.argtypes = [vp, vp, i, i, i, i, pp, i, i, i, i, i, ctypes.c_uint, i]
+    L.fixca_cuda_region_multi.argtypes = [vp, vp, i, i, i, i, pp, i, i, ctypes.c_uint, ctypes.POINTER(i), i]
+    L.fixca_cuda_region_dev.argtypes = [vp, ctypes.c_size_t, i, i, vp, ctypes.c_size_t, i, i, i, i, i, pp, i, i,
+                                        ctypes.c_uint, vp]
+    L.fixca_cuda_frames.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), i, i, i, i, i, pp, ctypes.c_uint, i]
+    L.fixca_band_source_rows.argtypes = [i, i, pp, i, i, ctypes.POINTER(i), ctypes.POINTER(i)]
+    L.fixca_split_bands.argtypes = [i, i, i, ctypes.POINTER(i), ctypes.POINTER(i)]
+    L.fixca_resolve_lens.argtypes = [i, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    L.fixca_resolve_lens.restype = None
+    L.fixca_check_params.argtypes = [pp]
+    L.fixca_color_size.argtypes = [ctypes.c_char_p, i]
+    L.fixca_params_default.argtypes = [pp]
+    L.fixca_params_default.restype = None
+    L.fixca_cuda_set_progress.argtypes = [PROGRESS_FN, vp]
+    L.fixca_cuda_set_progress.restype = None
+    L.fixca_cuda_last_error.restype = ctypes.c_char_p
+    L.fixca_strerror.argtypes = [i]
+    L.fixca_strerror.restype = ctypes.c_char_p
+    L.fixca_cuda_last_kernel.restype = ctypes.c_char_p
+    L.fixca_cuda_launch_count.restype = ctypes.c_long
+    L.fixca_cuda_release.restype = None
+    L.fixca_version.restype = ctypes.c_char_p
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != OK:
+        raise FixCaError(rc, load().fixca_cuda_last_error().decode() or load().fixca_strerror(rc).decode())
+
+
+def bpc_of(dtype) -> int:
+    """The reference's bpc code (fix-ca.c:688-707) for a numpy dtype."""
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        return -dt.itemsize
+    if dt.kind == "u":
+        return dt.itemsize
+    raise ValueError("unsupported dtype %s" % dt)
+
+
+def fix_ca_region(src, dst, orig_width, orig_height, bytes, bpc, params, x1, x2, y1, y2, show_progress=True,
+                  flags=None, device=-1):
+    """fix_ca_region() of the reference (fix-ca.c:998-1001) on the GPU.
+
+    ``src`` / ``dst`` are host buffers (numpy arrays or integer addresses) of
+    ``orig_width * orig_height * bytes`` bytes; rows ``[y1, y2)`` of dst are written.
+    ``flags`` None means the library default (exact FP64 arithmetic)."""
+    L = load()
+    s = src.ctypes.data if isinstance(src, np.ndarray) else int(src)
+    d = dst.ctypes.data if isinstance(dst, np.ndarray) else int(dst)
+    if flags is None:
+        rc = L.fixca_cuda_region(s, d, orig_width, orig_height, bytes, bpc, ctypes.byref(params),
+                                 x1, x2, y1, y2, 1 if show_progress else 0)
+    else:
+        rc = L.fixca_cuda_region_ex(s, d, orig_width, orig_height, bytes, bpc, ctypes.byref(params),
+                                    x1, x2, y1, y2, 1 if show_progress else 0, flags, device)
+    _check(rc)
+
+
+def correct(image: np.ndarray, params: FixCaParams, y1=None, y2=None, out=None, flags=PRECISION_EXACT,
+            device=-1, devices=None) -> np.ndarray:
+    """Array-level convenience: (H, W, C) uint8/16/32/64/float32/float64 image in, corrected image out."""
+    assert image.ndim == 3 and image.flags["C_CONTIGUOUS"]
+    h, w, ch = image.shape
+    y1 = 0 if y1 is None else y1
+    y2 = h if y2 is None else y2
+    if out is None:
+        out = np.zeros_like(image)
+    bytes_ = ch * image.dtype.itemsize
+    if devices is not None:
+        arr = (ctypes.c_int * len(devices))(*devices)
+        _check(load().fixca_cuda_region_multi(image.ctypes.data, out.ctypes.data, w, h, bytes_, bpc_of(image.dtype),
+                                              ctypes.byref(params), y1, y2, flags, arr, len(devices)))
+    else:
+        fix_ca_region(image, out, w, h, bytes_, bpc_of(image.dtype), params, 0, w, y1, y2, True, flags, device)
+    return out
+
+
+def fix_ca_region_dev(d_src: int, src_pitch: int, src_row0: int, src_rows: int, d_dst: int, dst_pitch: int,
+                      dst_row0: int, width: int, height: int, bytes: int, bpc: int, params: FixCaParams,
+                      y1: int, y2: int, flags: int = PRECISION_EXACT, stream: int = 0) -> None:
+    """Device-resident pass (raw CUDA pointers, asynchronous on ``stream``)."""
+    _check(load().fixca_cuda_region_dev(d_src, src_pitch, src_row0, src_rows, d_dst, dst_pitch, dst_row0,
+                                        width, height, bytes, bpc, ctypes.byref(params), y1, y2, flags, stream))
+
+
+def correct_frames(frames, params: FixCaParams, flags=PRECISION_EXACT, device=-1):
+    """A stream of equal-shaped host frames through the pinned H2D / kernel / D2H ring."""
+    if not frames:
+        return []
+    h, w, ch = frames[0].shape
+    outs = [np.zeros_like(f) for f in frames]
+    n = len(frames)
+    src = (ctypes.c_void_p * n)(*[f.ctypes.data for f in frames])
+    dst = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+    _check(load().fixca_cuda_frames(src, dst, n, w, h, ch * frames[0].dtype.itemsize, bpc_of(frames[0].dtype),
+                                    ctypes.byref(params), flags, device))
+    return outs
+
+
+def band_source_rows(width: int, height: int, params: FixCaParams, y1: int, y2: int):
+    lo, hi = ctypes.c_int(), ctypes.c_int()
+    _check(load().fixca_band_source_rows(width, height, ctypes.byref(params), y1, y2, ctypes.byref(lo), ctypes.byref(hi)))
+    return lo.value, hi.value
+
+
+def split_bands(y1: int, y2: int, nbands: int):
+    a, b = (ctypes.c_int * nbands)(), (ctypes.c_int * nbands)()
+    _check(load().fixca_split_bands(y1, y2, nbands, a, b))
+    return list(zip(list(a), list(b)))
+
+
+def resolve_lens(width: int, height: int, lens_x: float, lens_y: float):
+    a, b = ctypes.c_double(lens_x), ctypes.c_double(lens_y)
+    load().fixca_resolve_lens(width, height, ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
+
+
+def check_params(params: FixCaParams) -> int:
+    return load().fixca_check_params(ctypes.byref(params))
+
+
+def color_size(format_name: str, bytes_per_pixel: int) -> int:
+    return load().fixca_color_size(format_name.encode(), bytes_per_pixel)
+
+
+def device_count() -> int:
+    return load().fixca_cuda_device_count()
+
+
+def last_kernel() -> str:
+    return load().fixca_cuda_last_kernel().decode()
+
+
+def launch_count() -> int:
+    return load().fixca_cuda_launch_count()
+
+
+_progress_keepalive = None
+
+
+def set_progress(fn) -> None:
+    """Install fn(kind, fraction) as the progress callback (None removes it)."""
+    global _progress_keepalive
+    if fn is None:
+        _progress_keepalive = ctypes.cast(None, PROGRESS_FN)
+    else:
+        _progress_keepalive = PROGRESS_FN(lambda kind, frac, user: fn(kind, frac))
+    load().fixca_cuda_set_progress(_progress_keepalive, None)

@@ -1,0 +1,225 @@
+/*
+ * fixca_cuda.h -- C ABI of the B200 (sm_100a) implementation of Fix-CA's
+ * per-pixel correction pass.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes.  Each entry
+ * point names the piece of the reference plug-in (JoesCat/gimp-fix-ca,
+ * fix-ca.c) it replaces or restates.  INTEGRATION.md shows the ~15-line patch
+ * that makes fix-ca.c call fixca_cuda_region() instead of its CPU row loop.
+ *
+ * There is no CPU fallback: every compute entry point fails with
+ * FIXCA_ERR_CUDA / FIXCA_ERR_NO_DEVICE when no usable GPU is present.
+ */
+#ifndef FIXCA_CUDA_H
+#define FIXCA_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define FIXCA_API __declspec(dllexport)
+#else
+#define FIXCA_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* Parameter block                                                            */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * Layout-identical to the reference's FixCaParams (fix-ca.c:70-82; 80 bytes on
+ * x86-64), so the plug-in can pass its own struct through a cast.  Values are
+ * the post-marshalling ones: lens_x / lens_y are truncated with (int) inside
+ * the pass (fix-ca.c:1033-1034); there is no -1,-1 reset here, that lives in
+ * the dialog only (fix-ca.c:427-428) -- see fixca_resolve_lens().
+ */
+typedef struct fixca_params {
+	double blue;		/* lateral amount, blue  (fix-ca.c:71) */
+	double red;		/* lateral amount, red   (fix-ca.c:72) */
+	double lens_x;		/* lens centre           (fix-ca.c:73) */
+	double lens_y;		/*                       (fix-ca.c:74) */
+	int    update_preview;	/* unused, as in the reference (fix-ca.c:75,223) */
+	int    interpolation;	/* 0 None, 1 Linear, 2 Cubic  (fix-ca.c:76,156) */
+	double saturation;	/* preview only (fix-ca.c:77); ignored by the pass */
+	double x_blue;		/* directional shifts (fix-ca.c:78-81) */
+	double x_red;
+	double y_blue;
+	double y_red;
+} fixca_params;
+
+#define FIXCA_INTERP_NONE   0
+#define FIXCA_INTERP_LINEAR 1
+#define FIXCA_INTERP_CUBIC  2
+
+/* Largest |amount| run() accepts: INPUT_MAX = SOURCE_ROWS/4 (fix-ca.c:64-65,279-292). */
+#define FIXCA_INPUT_MAX 30.0
+
+/* `bpc` codes, as produced by color_size() (fix-ca.c:681-711):
+ *   1, 2, 4, 8  unsigned integer samples of that many bytes
+ *   -4, -8      float, double
+ *   -99         unsupported (half, u15, ...)                                  */
+#define FIXCA_BPC_UNSUPPORTED (-99)
+
+/* ------------------------------------------------------------------------- */
+/* Status codes (0 = success; the reference's region returns void, its driver */
+/* maps any failure to GIMP_PDB_CALLING_ERROR, fix-ca.c:315-316)               */
+/* ------------------------------------------------------------------------- */
+#define FIXCA_OK               0
+#define FIXCA_ERR_ARG         (-1)	/* NULL pointer, non-positive size, bad rows   */
+#define FIXCA_ERR_FORMAT      (-2)	/* bpc / bytes-per-pixel not one the reference handles */
+#define FIXCA_ERR_INTERP      (-3)	/* interpolation outside 0..2                  */
+#define FIXCA_ERR_REGION      (-4)	/* x1 != 0 or x2 != width: the reference's own
+					   column-selection path is broken (SURVEY.md
+					   App. D #3); only full-width row bands are defined */
+#define FIXCA_ERR_DEGENERATE  (-5)	/* max_dim + amount == 0: scale is infinite and the
+					   reference itself indexes out of bounds        */
+#define FIXCA_ERR_RANGE       (-6)	/* fixca_check_params(): outside +-FIXCA_INPUT_MAX */
+#define FIXCA_ERR_NO_DEVICE   (-7)
+#define FIXCA_ERR_CUDA        (-8)	/* see fixca_cuda_last_error()                 */
+#define FIXCA_ERR_UNSUPPORTED (-9)	/* u64 samples with Linear/Cubic (the reference
+					   computes those in 80-bit long double,
+					   fix-ca.c:728-733,759-761)                     */
+#define FIXCA_ERR_NOMEM       (-10)
+
+/* ------------------------------------------------------------------------- */
+/* Flags                                                                      */
+/* ------------------------------------------------------------------------- */
+/* Arithmetic of Linear/Cubic (None is always a byte-exact gather):
+ *   EXACT  FP64 in the reference's operation order, no FMA contraction:
+ *          bit-identical to the reference for every format.  Default.
+ *   FAST   FP32 separable weights on raw sample values: within +-1 LSB of the
+ *          reference for u8/u16 (2 ulp for float); u32/f64 still run EXACT.   */
+#define FIXCA_PRECISION_EXACT  0x0u
+#define FIXCA_PRECISION_FAST   0x1u
+#define FIXCA_PRECISION_MASK   0x3u
+/* Kernel selection, for tests and profiling (default: tiled when it fits). */
+#define FIXCA_FORCE_DIRECT     0x10u	/* per-pixel global-memory gather kernel */
+#define FIXCA_FORCE_TILED      0x20u	/* fail instead of falling back to direct */
+
+/* ------------------------------------------------------------------------- */
+/* The pass, host buffers: replaces fix_ca_region()                           */
+/* ------------------------------------------------------------------------- */
+/*
+ * Same arguments and meaning as
+ *   static void fix_ca_region (guchar *srcPTR, guchar *dstPTR, gint orig_width,
+ *       gint orig_height, gint bytes, gint bpc, FixCaParams *params,
+ *       gint x1, gint x2, gint y1, gint y2, gboolean show_progress)
+ * (fix-ca.c:998-1001; call sites :373-374 and :656-657).  src and dst are
+ * caller-owned host arrays of width*height*bytes, tight rows.  Reads src only;
+ * writes exactly rows [y1,y2) of dst.  Synchronous.  Internally: pinned
+ * staging, H2D of the source rows the band needs, sm_100a kernels, D2H.
+ *
+ * show_progress != 0 issues the reference's progress sequence through the
+ * callback installed with fixca_cuda_set_progress().  show_progress == 0 is
+ * the preview call: the reference then also draws its saturation boost and
+ * centre-line overlay (fix-ca.c:1322-1327); those are NOT applied here (they
+ * never reach the final image) -- the corrected rows are returned as is.
+ */
+FIXCA_API int fixca_cuda_region(const unsigned char *src, unsigned char *dst,
+				int width, int height, int bytes, int bpc,
+				const fixca_params *params,
+				int x1, int x2, int y1, int y2, int show_progress);
+
+/* As above with FIXCA_* flags and an explicit CUDA device ordinal (-1 = current). */
+FIXCA_API int fixca_cuda_region_ex(const unsigned char *src, unsigned char *dst,
+				   int width, int height, int bytes, int bpc,
+				   const fixca_params *params,
+				   int x1, int x2, int y1, int y2, int show_progress,
+				   unsigned flags, int device);
+
+/*
+ * Row-banded across several GPUs of one box from one process (the multi-GPU
+ * form of fix_ca()'s middle, fix-ca.c:366-377): rows [y1,y2) are split into
+ * `ndev` contiguous full-width bands; each device receives its band plus the
+ * halo rows fixca_band_source_rows() reports, and writes its rows straight
+ * into the caller's dst.  Bands are independent (fix-ca.c:1091-1329), so there
+ * is no exchange between devices.  devices == NULL means 0..ndev-1.
+ */
+FIXCA_API int fixca_cuda_region_multi(const unsigned char *src, unsigned char *dst,
+				      int width, int height, int bytes, int bpc,
+				      const fixca_params *params, int y1, int y2,
+				      unsigned flags, const int *devices, int ndev);
+
+/* ------------------------------------------------------------------------- */
+/* The pass, device-resident (benchmarks, pipelines, per-rank bands)          */
+/* ------------------------------------------------------------------------- */
+/*
+ * d_src holds source rows [src_row0, src_row0 + src_rows) of a width x height
+ * image, row pitch src_pitch bytes; d_dst receives output rows [y1,y2) at
+ * d_dst + (y - dst_row0) * dst_pitch.  For a whole resident image pass
+ * src_row0 = dst_row0 = 0, src_rows = height.  The source rows present must
+ * cover fixca_band_source_rows(y1,y2) or FIXCA_ERR_ARG is returned.
+ * Asynchronous on `stream` (a cudaStream_t, NULL = default stream).  The tiled
+ * kernels need both pitches to be multiples of 16 bytes and both pointers
+ * 16-byte aligned; they may write the padding bytes [width*bytes, pitch) of
+ * the destination rows.  Otherwise the direct kernel is used.
+ */
+FIXCA_API int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int src_row0, int src_rows,
+				    void *d_dst, size_t dst_pitch, int dst_row0,
+				    int width, int height, int bytes, int bpc,
+				    const fixca_params *params, int y1, int y2,
+				    unsigned flags, void *stream);
+
+/*
+ * A stream of `nframes` equal-sized host frames (tight rows), same parameters:
+ * frames are pipelined H2D / kernel / D2H over a ring of pinned staging
+ * buffers on `device`.  src_frames[i] / dst_frames[i] are host pointers.
+ */
+FIXCA_API int fixca_cuda_frames(const unsigned char *const *src_frames, unsigned char *const *dst_frames,
+				int nframes, int width, int height, int bytes, int bpc,
+				const fixca_params *params, unsigned flags, int device);
+
+/* ------------------------------------------------------------------------- */
+/* Host-side logic (no GPU needed)                                            */
+/* ------------------------------------------------------------------------- */
+/* Inclusive range of source rows that output rows [y1,y2) read: row y itself
+ * (green/alpha copy, fix-ca.c:1094-1098) plus the red/blue taps reachable
+ * through the affine map (fix-ca.c:1105-1106, 1135-1158, 1204-1256). */
+FIXCA_API int fixca_band_source_rows(int width, int height, const fixca_params *params,
+				     int y1, int y2, int *src_lo, int *src_hi);
+
+/* Contiguous split of rows [y1,y2) into nbands bands; band i is
+ * [band_y1[i], band_y2[i]).  Arrays hold nbands entries. */
+FIXCA_API int fixca_split_bands(int y1, int y2, int nbands, int *band_y1, int *band_y2);
+
+/* The dialog's lens reset (fix-ca.c:427-428): a coordinate <= 0 or >= size
+ * becomes round(size / 2) (integer division).  The README's "-1,-1 resets to
+ * the image centre" behaviour, for callers that want it. */
+FIXCA_API void fixca_resolve_lens(int width, int height, double *lens_x, double *lens_y);
+
+/* run()'s non-interactive range check (fix-ca.c:279-295): FIXCA_OK or FIXCA_ERR_RANGE
+ * / FIXCA_ERR_INTERP. */
+FIXCA_API int fixca_check_params(const fixca_params *params);
+
+/* color_size() (fix-ca.c:681-711): babl format name + bytes per pixel -> bpc code. */
+FIXCA_API int fixca_color_size(const char *babl_format_name, int bytes_per_pixel);
+
+/* Defaults of fix_ca_params_default (fix-ca.c:85-97). */
+FIXCA_API void fixca_params_default(fixca_params *params);
+
+/* ------------------------------------------------------------------------- */
+/* Progress, errors, introspection                                            */
+/* ------------------------------------------------------------------------- */
+/* The reference's progress protocol (fix-ca.c:1022-1023, 1331-1332, 1335-1336):
+ * init once, update((y-y1)/(y2-y1)) for every row with (y-y1) % 8 == 0, then
+ * update(0.0).  kind: 0 = init, 1 = update. */
+typedef void (*fixca_progress_fn)(int kind, double fraction, void *user);
+FIXCA_API void fixca_cuda_set_progress(fixca_progress_fn fn, void *user);
+
+FIXCA_API const char *fixca_cuda_last_error(void);	/* thread-local text of the last failure */
+FIXCA_API const char *fixca_strerror(int code);
+FIXCA_API int  fixca_cuda_device_count(void);		/* 0 when no driver / no GPU */
+/* Name of the kernel variant the last fixca_cuda_region*() call on this thread launched
+ * ("tiled/cubic/f32/u16x3", "direct/...", "none/..."), and how many kernels it launched. */
+FIXCA_API const char *fixca_cuda_last_kernel(void);
+FIXCA_API long fixca_cuda_launch_count(void);		/* kernels launched by this library so far */
+FIXCA_API void fixca_cuda_release(void);		/* free cached device / pinned buffers */
+FIXCA_API const char *fixca_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIXCA_CUDA_H */

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Developer timing probe (not the contract bench): device-resident kernel time for a few
+workloads and tile-height settings, CUDA events on the launching stream."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gimp-fix-ca_b200"))
+import torch  # noqa: E402
+
+import fixca  # noqa: E402
+
+KW = dict(blue=3.0, red=-2.0, x_blue=0.7, x_red=-0.4, y_blue=0.3, y_red=-0.9)
+PEAK = 6458.7
+
+
+def run(name, h, w, ch, tdtype, bpc, interp, flags, reps=10, lens=None):
+    es = torch.empty((), dtype=tdtype).element_size()
+    bpp = ch * es
+    pitch = (w * bpp + 127) // 128 * 128
+    src = torch.randint(0, 255, (h, pitch), dtype=torch.uint8, device="cuda")
+    dst = torch.empty_like(src)
+    lx, ly = lens if lens else (w // 2, h // 2)
+    p = fixca.FixCaParams(interpolation=interp, lens_x=lx, lens_y=ly, **KW)
+    st = torch.cuda.current_stream().cuda_stream
+    call = lambda: fixca.fix_ca_region_dev(src.data_ptr(), pitch, 0, h, dst.data_ptr(), pitch, 0, w, h, bpp, bpc, p, 0, h, flags, st)
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); call(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    best, med = ts[0], ts[len(ts) // 2]
+    mp = h * w / 1e6
+    gbs = mp * 1e6 * 2 * bpp / (med * 1e-3) / 1e9
+    print("%-34s %-28s th=%-3s best %.3f ms  med %.3f ms  %9.0f MP/s  %7.0f GB/s  %.1f%% of %.0f"
+          % (name, fixca.last_kernel(), os.environ.get("FIXCA_TILE_H", "auto"), best, med, mp / (med * 1e-3), gbs, 100 * gbs / PEAK, PEAK), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    F, E = fixca.PRECISION_FAST, fixca.PRECISION_EXACT
+    if which in ("all", "target"):
+        run("100MP rgb16 cubic fast", 8192, 12288, 3, torch.int16, 2, 2, F)
+        run("100MP rgb16 cubic exact", 8192, 12288, 3, torch.int16, 2, 2, E, reps=5)
+        run("100MP rgb16 linear fast", 8192, 12288, 3, torch.int16, 2, 1, F)
+        run("100MP rgb16 none", 8192, 12288, 3, torch.int16, 2, 0, E)
+        run("100MP rgb16 cubic fast direct", 8192, 12288, 3, torch.int16, 2, 2, F | fixca.FORCE_DIRECT, reps=5)
+    if which in ("all", "cfgs"):
+        run("24MP rgb8 linear fast", 4000, 6000, 3, torch.uint8, 1, 1, F)
+        run("24MP rgb8 linear exact", 4000, 6000, 3, torch.uint8, 1, 1, E)
+        run("24MP rgb8 cubic fast", 4000, 6000, 3, torch.uint8, 1, 2, F)
+        run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
+        run("8K rgba16 cubic exact", 4320, 7680, 4, torch.int16, 2, 2, E, lens=(658, 1280))
+        run("50MP rgb f32 cubic fast", 6144, 8192, 3, torch.float32, -4, 2, F)
+        run("50MP rgb f32 cubic exact", 6144, 8192, 3, torch.float32, -4, 2, E)
+        run("4K rgb8 cubic fast", 2160, 3840, 3, torch.uint8, 1, 2, F)
+    if which == "sweep":
+        for th in (8, 16, 24, 32, 48, 64):
+            os.environ["FIXCA_TILE_H"] = str(th)
+            try:
+                run("100MP rgb16 cubic fast", 8192, 12288, 3, torch.int16, 2, 2, F)
+                run("100MP rgb16 cubic exact", 8192, 12288, 3, torch.int16, 2, 2, E, reps=3)
+                run("24MP rgb8 cubic fast", 4000, 6000, 3, torch.uint8, 1, 2, F)
+            except fixca.FixCaError as e:
+                print("th", th, e)

@@ -1,0 +1,46 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "gimp-fix-ca_b200"), os.path.join(ROOT, "oracle"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def restatement():
+    import oracle
+
+    return oracle.Restatement()
+
+
+@pytest.fixture(scope="session")
+def reference():
+    import oracle
+
+    if not oracle.Reference.available():
+        pytest.skip("oracle/_ref/libfixca_ref.so not built (needs /root/reference at build time)")
+    return oracle.Reference()
+
+
+@pytest.fixture(scope="session")
+def checker():
+    """Strongest CPU checker present: the reference's own code, else our restatement."""
+    import oracle
+
+    return oracle.best_checker()
+
+
+@pytest.fixture(scope="session")
+def fx():
+    """The product binding; the library must exist (there is no fallback)."""
+    import fixca
+
+    fixca.load()
+    return fixca

@@ -1,0 +1,64 @@
+"""Shared helpers for the parity tests."""
+import hashlib
+import json
+import os
+
+import numpy as np
+
+import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden", "golden.json")
+FIXTURE_RAW = os.path.join(ROOT, "oracle", "_ref", "full-branches.rgb")
+
+_golden = None
+
+
+def golden():
+    global _golden
+    if _golden is None:
+        with open(GOLDEN) as f:
+            _golden = json.load(f)
+    return _golden
+
+
+PKEYS = ("blue", "red", "lens_x", "lens_y", "interpolation", "x_blue", "x_red", "y_blue", "y_red")
+
+
+def oracle_params(c) -> orc.Params:
+    return orc.Params(**{k: c[k] for k in PKEYS if k in c})
+
+
+def fx_params(fx, c):
+    return fx.FixCaParams(**{k: c[k] for k in PKEYS if k in c})
+
+
+def case_image(c) -> np.ndarray:
+    return orc.synth_image(c["h"], c["w"], c["ch"], c["dtype"], c["seed"], c.get("wide", False))
+
+
+def md5(a: np.ndarray) -> str:
+    return hashlib.md5(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def fixture_image():
+    """The reference's test photo, decoded as GIMP decodes it (see tests/golden/make_golden.py)."""
+    if not os.path.exists(FIXTURE_RAW):
+        return None
+    h, w, c = golden()["fixture"]["shape"]
+    return np.fromfile(FIXTURE_RAW, dtype=np.uint8).reshape(h, w, c)
+
+
+def max_dim(w, h, lx, ly):
+    xc, yc = int(lx), int(ly)
+    return max(xc, yc, w - xc, h - yc)
+
+
+def lsb_diff(a: np.ndarray, b: np.ndarray):
+    """max |a-b| in LSB (ints) or absolute (floats), and the mismatching fraction."""
+    if a.dtype.kind == "f":
+        d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+        d = np.where(np.isnan(a) & np.isnan(b), 0.0, d)
+    else:
+        d = np.abs(a.astype(np.int64) - b.astype(np.int64))
+    return d.max() if d.size else 0, float((d != 0).mean()) if d.size else 0.0

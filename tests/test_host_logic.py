@@ -1,0 +1,140 @@
+"""CPU: the C-ABI library loads, exports what include/fixca_cuda.h declares, and its host-side
+logic (band halos, band split, lens reset, range check, format probe, argument errors) agrees
+with the oracle.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from helpers import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fixca_cuda.h")).read()
+    return sorted(set(re.findall(r"FIXCA_API[^;(]*?\b(fixca_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(fx):
+    lib = fx.load()
+    names = declared_symbols()
+    assert len(names) >= 19 and set(names) == set(fx.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_params_layout_matches_reference(fx):
+    # FixCaParams is 80 bytes on x86-64 (fix-ca.c:70-82); the plug-in passes its struct through a cast
+    assert ctypes.sizeof(fx.FixCaParams) == 80
+    assert fx.FixCaParams.interpolation.offset == 36 and fx.FixCaParams.saturation.offset == 40
+    assert fx.FixCaParams.y_red.offset == 72
+    p = fx.FixCaParams()
+    fx.load().fixca_params_default(ctypes.byref(p))
+    assert (p.blue, p.red, p.lens_x, p.lens_y, p.interpolation, p.saturation) == (0, 0, -1, -1, 1, 0)
+
+
+def test_no_gpu_fails_loudly(fx):
+    if fx.device_count() > 0:
+        pytest.skip("a GPU is present; the loud-failure path is for CPU-only hosts")
+    img = np.zeros((8, 8, 3), np.uint8)
+    with pytest.raises(fx.FixCaError) as e:
+        fx.correct(img, fx.FixCaParams())
+    assert e.value.code == fx.ERR_NO_DEVICE and "no CPU path" in str(e.value)
+
+
+def test_argument_errors_before_any_gpu_work(fx):
+    img = np.zeros((8, 8, 3), np.uint8)
+    out = np.zeros_like(img)
+    P = fx.FixCaParams
+
+    def rc(*a, **k):
+        with pytest.raises(fx.FixCaError) as e:
+            fx.fix_ca_region(*a, **k)
+        return e.value.code
+
+    assert rc(img, out, 8, 8, 3, 1, P(), 1, 8, 0, 8) == fx.ERR_REGION           # x1 != 0
+    assert rc(img, out, 8, 8, 3, 1, P(), 0, 7, 0, 8) == fx.ERR_REGION
+    assert rc(img, out, 8, 8, 3, -2, P(), 0, 8, 0, 8) == fx.ERR_FORMAT          # half
+    assert rc(img, out, 8, 8, 3, -99, P(), 0, 8, 0, 8) == fx.ERR_FORMAT
+    assert rc(img, out, 8, 8, 5, 1, P(), 0, 8, 0, 8) == fx.ERR_FORMAT
+    assert rc(img, out, 8, 8, 3, 1, P(interpolation=3), 0, 8, 0, 8) == fx.ERR_INTERP
+    assert rc(img, out, 8, 8, 3, 1, P(), 0, 8, 0, 9) == fx.ERR_ARG
+    assert rc(img, out, 0, 8, 3, 1, P(), 0, 0, 0, 8) == fx.ERR_ARG
+    assert rc(0, out, 8, 8, 3, 1, P(), 0, 8, 0, 8) == fx.ERR_ARG
+    # max_dim + amount == 0: the reference itself indexes out of bounds (scale = inf)
+    assert rc(img, out, 8, 8, 3, 1, P(lens_x=4, lens_y=4, red=-4.0), 0, 8, 0, 8) == fx.ERR_DEGENERATE
+    big = np.zeros((8, 8, 3), np.uint64)
+    assert rc(big, np.zeros_like(big), 8, 8, 24, 8, P(interpolation=2), 0, 8, 0, 8) == fx.ERR_UNSUPPORTED
+
+
+def test_band_source_rows_match_oracle_tables(fx, restatement):
+    rng = np.random.default_rng(5)
+    for n in range(200):
+        w, h = int(rng.integers(1, 400)), int(rng.integers(2, 400))
+        interp = n % 3
+        kw = dict(blue=float(rng.uniform(-30, 30)), red=float(rng.uniform(-30, 30)),
+                  lens_x=float(rng.integers(-3, w + 3)), lens_y=float(rng.integers(-3, h + 3)),
+                  x_blue=float(rng.uniform(-30, 30)), x_red=float(rng.uniform(-30, 30)),
+                  y_blue=float(rng.uniform(-30, 30)), y_red=float(rng.uniform(-30, 30)), interpolation=interp)
+        m = max(int(kw["lens_x"]), int(kw["lens_y"]), w - int(kw["lens_x"]), h - int(kw["lens_y"]))
+        if m + kw["blue"] == 0 or m + kw["red"] == 0:
+            continue
+        y1 = int(rng.integers(0, h - 1))
+        y2 = int(rng.integers(y1 + 1, h + 1))
+        lo, hi = fx.band_source_rows(w, h, fx.FixCaParams(**kw), y1, y2)
+        want_lo, want_hi = y1, y2 - 1
+        for ch in (0, 1):
+            idx, _ = restatement.axis(w, h, orc.Params(**kw), ch, 1)
+            seg = idx[y1:y2]
+            if interp == 0:
+                a, b = seg.min(), seg.max()
+            elif interp == 1:
+                a, b = seg.min(), min(seg.max() + 1, h - 1)
+            else:
+                a, b = max(seg.min() - 1, 0), min(seg.max() + 2, h - 1)
+            want_lo, want_hi = min(want_lo, a), max(want_hi, b)
+        assert (lo, hi) == (want_lo, want_hi), (n, w, h, kw, y1, y2)
+
+
+def test_halo_bound_from_survey(fx):
+    # 6000x4000 centre lens, a = +-30, shift = +-30 -> ~50 rows of displacement
+    p = fx.FixCaParams(blue=30, red=-30, y_blue=30, y_red=-30, lens_x=3000, lens_y=2000, interpolation=2)
+    lo, hi = fx.band_source_rows(6000, 4000, p, 0, 500)
+    assert lo == 0 and 499 + 10 <= hi <= 499 + 64
+    p = fx.FixCaParams(blue=6, red=-2.4, y_blue=1, lens_x=6144, lens_y=4096, interpolation=2)
+    lo, hi = fx.band_source_rows(12288, 8192, p, 4096, 6144)
+    assert 4096 - 4 <= lo <= 4096 and 6143 <= hi <= 6143 + 8
+
+
+def test_split_bands(fx):
+    for y1, y2, n in [(0, 8192, 8), (3, 1000, 7), (0, 5, 8), (10, 10, 3)]:
+        b = fx.split_bands(y1, y2, n)
+        assert b[0][0] == y1 and b[-1][1] == y2
+        assert all(b[i][1] == b[i + 1][0] for i in range(n - 1))
+        sizes = [e - s for s, e in b]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_resolve_lens_check_params_color_size(fx, restatement):
+    for (w, h, lx, ly) in [(1441, 2561, -1, -1), (100, 50, 0, 0), (100, 50, 100, 50), (100, 50, 30.5, 20.25), (7, 9, 7.5, -3)]:
+        assert fx.resolve_lens(w, h, lx, ly) == restatement.resolve_lens(w, h, lx, ly)
+    P = fx.FixCaParams
+    assert fx.check_params(P(blue=30, red=-30, x_blue=30, y_red=-30)) == fx.OK
+    for k in ("blue", "red", "x_blue", "x_red", "y_blue", "y_red"):
+        assert fx.check_params(P(**{k: 30.01})) == fx.ERR_RANGE
+        assert fx.check_params(P(**{k: -30.01})) == fx.ERR_RANGE
+    assert fx.check_params(P(interpolation=3)) == fx.ERR_INTERP
+    assert fx.check_params(P(lens_x=1e9)) == fx.OK           # lens is not range-checked (fix-ca.c:279-292)
+    for name, bpp, want in [("R'G'B' u8", 3, 1), ("R'G'B'A u8", 4, 1), ("RGB u16", 6, 2), ("RGBA u16", 8, 2),
+                            ("RGB u32", 12, 4), ("RGBA u32", 16, 4), ("RGBA u64", 32, 8), ("RGB float", 12, -4),
+                            ("RGBA double", 32, -8), ("RGB half", 6, -99), ("RGB u15", 6, -99), ("Y u8", 1, -99),
+                            ("RGBA u64x", 40, -99)]:
+        assert fx.color_size(name, bpp) == want
+
+
+def test_color_size_matches_reference(fx, reference):
+    for name in ("R'G'B' u8", "RGBA u16", "RGB u32", "RGB float", "RGBA double", "RGB half", "RGB u15", "CMYK u8", "RGB u8 double"):
+        for bpp in (1, 2, 3, 4, 6, 8, 11, 12, 16, 23, 24, 32, 33):
+            assert fx.color_size(name, bpp) == reference.color_size(name, bpp), (name, bpp)

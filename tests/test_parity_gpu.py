@@ -1,0 +1,290 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle.
+
+Bars (BASELINE.json north_star): interpolation None and the EXACT arithmetic are bit-exact for
+every format; FAST (FP32) Linear/Cubic is within +-1 LSB per channel for u8/u16 and within
+FLOAT_ABS_TOL for float32 images (tolerances written here)."""
+import ctypes
+import hashlib
+import itertools
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from fixture_io import encode_gimp_bmp24
+from helpers import case_image, fixture_image, fx_params, golden, lsb_diff, md5, oracle_params
+
+pytestmark = pytest.mark.gpu
+
+FAST_LSB_TOL = 1            # u8 / u16, FIXCA_PRECISION_FAST
+FLOAT_ABS_TOL = 1.0e-6      # float32 images, FIXCA_PRECISION_FAST (outputs are clipped to [0,1])
+
+KW = dict(blue=3.0, red=-2.0, x_blue=0.7, x_red=-0.4, y_blue=0.3, y_red=-0.9)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(fx):
+    assert fx.device_count() > 0, "these tests need a CUDA device; the product has no CPU path"
+
+
+# ---------------------------------------------------------------------------------------------
+# golden digests (produced by the reference's own code, tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("force", ["auto", "direct"])
+def test_golden_suite_bit_exact(fx, force):
+    flags = fx.PRECISION_EXACT | (fx.FORCE_DIRECT if force == "direct" else 0)
+    bad, kernels = [], set()
+    for c in golden()["suite"]:
+        got = fx.correct(case_image(c), fx_params(fx, c), flags=flags)
+        kernels.add(fx.last_kernel().split("/")[0])
+        if md5(got) != c["md5"]:
+            bad.append(c["name"])
+    assert not bad, "%d of %d golden cases differ (%s), first: %s" % (len(bad), len(golden()["suite"]), force, bad[:8])
+    assert ("tiled" in kernels) if force == "auto" else (kernels == {"direct"})
+
+
+def test_golden_suite_fast_within_tolerance(fx, checker):
+    worst = {"u1": 0, "u2": 0, "f4": 0.0}
+    for c in golden()["suite"]:
+        if c["dtype"] not in worst or c["interpolation"] == 0:
+            continue
+        img = case_image(c)
+        want = checker.region(img, oracle_params(c))
+        got = fx.correct(img, fx_params(fx, c), flags=fx.PRECISION_FAST)
+        d, _ = lsb_diff(got, want)
+        worst[c["dtype"]] = max(worst[c["dtype"]], d)
+        tol = FLOAT_ABS_TOL if c["dtype"] == "f4" else FAST_LSB_TOL
+        assert d <= tol, (c["name"], d, fx.last_kernel())
+    print("fast-mode worst |diff|:", worst)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's known-answer test (tests/test1.md5) and its variants
+# ---------------------------------------------------------------------------------------------
+def test_known_answer_test1_md5(fx):
+    img = fixture_image()
+    if img is None:
+        pytest.skip("oracle/_ref/full-branches.rgb missing (generated where /root/reference is mounted)")
+    g = golden()["fixture"]
+    out = fx.correct(img, fx.FixCaParams(blue=6.0, red=-2.4, lens_x=0, lens_y=0, interpolation=1))
+    assert "tiled/linear/f64" in fx.last_kernel()
+    assert md5(out) == g["test1_raw_md5"]
+    assert hashlib.md5(encode_gimp_bmp24(out)).hexdigest() == "c472550cda23c8cb717853ac0dd93e2b"
+
+
+def test_fixture_variants_bit_exact_and_fast(fx, checker):
+    img = fixture_image()
+    if img is None:
+        pytest.skip("fixture missing")
+    for interp, lens in itertools.product((0, 1, 2), ((0, 0), (658, 1280))):
+        p = fx.FixCaParams(blue=6.0, red=-2.4, lens_x=lens[0], lens_y=lens[1], interpolation=interp)
+        key = "i%d-lens%d,%d" % (interp, *lens)
+        out = fx.correct(img, p)
+        assert md5(out) == golden()["fixture"]["outputs"][key], key
+        if interp:
+            fast = fx.correct(img, p, flags=fx.PRECISION_FAST)
+            d, frac = lsb_diff(fast, out)
+            assert d <= FAST_LSB_TOL and frac < 1e-3, (key, d, frac)
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded matrix against the checker: formats x interpolation x kernels, awkward shapes
+# ---------------------------------------------------------------------------------------------
+SHAPES = [(1, 1), (2, 3), (7, 129), (129, 7), (64, 128), (65, 257), (301, 517), (97, 1000)]
+
+
+@pytest.mark.parametrize("dtype,ch", [("u1", 3), ("u1", 4), ("u2", 3), ("u2", 4), ("u4", 3), ("u4", 4),
+                                      ("f4", 3), ("f4", 4), ("f8", 3), ("f8", 4)])
+def test_matrix_exact(fx, checker, dtype, ch):
+    n = 0
+    for (h, w), interp, lens in itertools.product(SHAPES, (0, 1, 2), ("c", (0, 0), (-1, -1))):
+        n += 1
+        lx, ly = (w // 2, h // 2) if lens == "c" else lens
+        kw = dict(KW, lens_x=lx, lens_y=ly, interpolation=interp)
+        img = orc.synth_image(h, w, ch, dtype, seed=1000 + n, wide=bool(n % 2))
+        want = checker.region(img, orc.Params(**kw))
+        for flags in (fx.PRECISION_EXACT, fx.PRECISION_EXACT | fx.FORCE_DIRECT):
+            got = fx.correct(img, fx.FixCaParams(**kw), flags=flags)
+            assert got.tobytes() == want.tobytes(), (h, w, dtype, ch, interp, lens, fx.last_kernel())
+
+
+def test_none_is_bit_exact_for_every_sample_size_including_nan_payloads(fx, checker):
+    rng = np.random.default_rng(3)
+    for dt, ch in itertools.product(("u1", "u2", "u4", "u8"), (3, 4)):
+        img = rng.integers(0, np.iinfo(dt).max, size=(131, 259, ch), dtype=dt, endpoint=True)
+        kw = dict(KW, lens_x=100, lens_y=60, interpolation=0)
+        want = checker.region(img, orc.Params(**kw))
+        assert fx.correct(img, fx.FixCaParams(**kw)).tobytes() == want.tobytes()
+        # the same bits viewed as floats (NaN payloads, infinities) must pass through untouched
+        if dt in ("u4", "u8"):
+            fimg = img.view("f4" if dt == "u4" else "f8")
+            got = fx.correct(fimg, fx.FixCaParams(**kw))
+            assert got.tobytes() == want.tobytes()
+
+
+def test_large_shifts_and_fallback_kernel(fx, checker):
+    """+-30 lateral and +-30 opposite directional shifts: the union source window of a tile grows by
+    ~120 px; whichever kernel the planner picks must stay exact."""
+    img = orc.synth_image(400, 600, 3, "u2", 77)
+    kw = dict(blue=30.0, red=-30.0, x_blue=30.0, x_red=-30.0, y_blue=-30.0, y_red=30.0, lens_x=300, lens_y=200)
+    for interp in (0, 1, 2):
+        want = checker.region(img, orc.Params(interpolation=interp, **kw))
+        got = fx.correct(img, fx.FixCaParams(interpolation=interp, **kw))
+        assert got.tobytes() == want.tobytes(), (interp, fx.last_kernel())
+
+
+def test_negative_scale_uses_direct_kernel(fx, checker):
+    # max_dim + amount < 0: scale negative, the map decreases; the reference still produces output
+    img = orc.synth_image(20, 24, 3, "u1", 5)
+    kw = dict(blue=-30.0, red=-29.0, lens_x=12, lens_y=10)
+    for interp in (0, 1, 2):
+        want = checker.region(img, orc.Params(interpolation=interp, **kw))
+        got = fx.correct(img, fx.FixCaParams(interpolation=interp, **kw))
+        assert got.tobytes() == want.tobytes() and fx.last_kernel().startswith("direct")
+
+
+def test_clip_of_float_images(fx, checker):
+    # clip_d clamps float/double images to [0,1] in Linear/Cubic but not in None (fix-ca.c:873-880)
+    for dt in ("f4", "f8"):
+        img = orc.synth_image(90, 140, 3, dt, 9, wide=True)
+        for interp in (0, 1, 2):
+            kw = dict(KW, lens_x=70, lens_y=45, interpolation=interp)
+            want = checker.region(img, orc.Params(**kw))
+            got = fx.correct(img, fx.FixCaParams(**kw))
+            assert got.tobytes() == want.tobytes()
+            if interp:
+                assert got[..., 0].min() >= 0.0 and got[..., 0].max() <= 1.0 and got[..., 1].max() > 1.0
+
+
+def test_zero_params_identity(fx):
+    for dt, interp, flags in itertools.product(("u1", "u2", "u4", "f4", "f8"), (0, 1, 2), (0, 1)):
+        img = orc.synth_image(150, 300, 3, dt, 21)
+        got = fx.correct(img, fx.FixCaParams(interpolation=interp, lens_x=150, lens_y=75), flags=flags)
+        assert (got == img).all(), (dt, interp, flags)
+
+
+# ---------------------------------------------------------------------------------------------
+# drop-in semantics of the region call
+# ---------------------------------------------------------------------------------------------
+def test_band_call_writes_only_its_rows(fx, checker):
+    img = orc.synth_image(333, 411, 4, "u2", 31)
+    kw = dict(KW, lens_x=200, lens_y=100, interpolation=2)
+    full = checker.region(img, orc.Params(**kw))
+    dst = np.full_like(img, 0xABCD)
+    fx.fix_ca_region(img, dst, 411, 333, 8, 2, fx.FixCaParams(**kw), 0, 411, 100, 177, True)
+    assert (dst[100:177] == full[100:177]).all()
+    assert (dst[:100] == 0xABCD).all() and (dst[177:] == 0xABCD).all()
+    # single row, first row, last row
+    for y in (0, 166, 332):
+        d2 = np.zeros_like(img)
+        fx.fix_ca_region(img, d2, 411, 333, 8, 2, fx.FixCaParams(**kw), 0, 411, y, y + 1, False)
+        assert (d2[y] == full[y]).all()
+
+
+def test_progress_protocol_matches_reference(fx):
+    # fix-ca.c:1022-1023, 1331-1332, 1335-1336
+    img = orc.synth_image(50, 64, 3, "u1", 2)
+    calls = []
+    fx.set_progress(lambda kind, frac: calls.append((kind, frac)))
+    try:
+        fx.correct(img, fx.FixCaParams(blue=1.0, lens_x=32, lens_y=25), y1=3, y2=45)
+    finally:
+        fx.set_progress(None)
+    assert calls[0] == (0, 0.0)
+    want = [(1, (y - 3) / 42.0) for y in range(3, 45) if (y - 3) % 8 == 0] + [(1, 0.0)]
+    assert calls[1:] == want
+
+
+def test_multi_device_bands_and_frames(fx, checker):
+    img = orc.synth_image(500, 700, 3, "u2", 41)
+    kw = dict(KW, lens_x=350, lens_y=250, interpolation=2)
+    want = checker.region(img, orc.Params(**kw))
+    ndev = fx.device_count()
+    # several bands on whatever devices exist (the same device may serve more than one band)
+    for bands in (1, 2, 3):
+        devs = [i % ndev for i in range(bands)]
+        got = fx.correct(img, fx.FixCaParams(**kw), devices=devs)
+        assert got.tobytes() == want.tobytes(), bands
+    frames = [orc.synth_image(120, 200, 3, "u1", 100 + k) for k in range(7)]
+    outs = fx.correct_frames(frames, fx.FixCaParams(**kw), flags=fx.PRECISION_EXACT)
+    for f, o in zip(frames, outs):
+        assert o.tobytes() == checker.region(f, orc.Params(**kw)).tobytes()
+
+
+def test_device_resident_entry_with_torch_buffers(fx, checker):
+    import torch
+
+    h, w = 257, 640                       # 640*6 bytes: pitch is a multiple of 16 -> tiled kernel
+    img = orc.synth_image(h, w, 3, "u2", 51)
+    kw = dict(KW, lens_x=300, lens_y=128, interpolation=2)
+    want = checker.region(img, orc.Params(**kw))
+    src = torch.from_numpy(img.view(np.int16)).cuda()
+    dst = torch.zeros_like(src)
+    stream = torch.cuda.current_stream().cuda_stream
+    fx.fix_ca_region_dev(src.data_ptr(), w * 6, 0, h, dst.data_ptr(), w * 6, 0, w, h, 6, 2, fx.FixCaParams(**kw), 0, h,
+                         fx.PRECISION_EXACT, stream)
+    torch.cuda.synchronize()
+    assert fx.last_kernel().startswith("tiled")
+    assert dst.cpu().numpy().view(np.uint16).tobytes() == want.tobytes()
+    # a band whose source rows are a sub-range of the image (what one rank of a multi-GPU run holds)
+    lo, hi = fx.band_source_rows(w, h, fx.FixCaParams(**kw), 100, 180)
+    sub = src[lo:hi + 1].contiguous()
+    out = torch.zeros((80, w, 3), dtype=torch.int16, device="cuda")
+    fx.fix_ca_region_dev(sub.data_ptr(), w * 6, lo, hi - lo + 1, out.data_ptr(), w * 6, 100, w, h, 6, 2,
+                         fx.FixCaParams(**kw), 100, 180, fx.PRECISION_EXACT, stream)
+    torch.cuda.synchronize()
+    assert out.cpu().numpy().view(np.uint16).tobytes() == want[100:180].tobytes()
+    # missing halo rows are refused, not read out of bounds
+    with pytest.raises(fx.FixCaError):
+        fx.fix_ca_region_dev(sub.data_ptr(), w * 6, lo + 1, hi - lo, out.data_ptr(), w * 6, 100, w, h, 6, 2,
+                             fx.FixCaParams(**kw), 100, 180, fx.PRECISION_EXACT, stream)
+    # odd width: rows are not 16-byte multiples -> the direct kernel takes over, still exact
+    h2, w2 = 100, 333
+    img2 = orc.synth_image(h2, w2, 3, "u1", 52)
+    want2 = checker.region(img2, orc.Params(**kw))
+    s2 = torch.from_numpy(img2).cuda()
+    d2 = torch.zeros_like(s2)
+    fx.fix_ca_region_dev(s2.data_ptr(), w2 * 3, 0, h2, d2.data_ptr(), w2 * 3, 0, w2, h2, 3, 1, fx.FixCaParams(**kw), 0, h2,
+                         fx.PRECISION_EXACT, stream)
+    torch.cuda.synchronize()
+    assert fx.last_kernel().startswith("direct") and d2.cpu().numpy().tobytes() == want2.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes: size-independent properties + oracle on sampled bands
+# ---------------------------------------------------------------------------------------------
+FULL = [  # (name, h, w, ch, dtype, params)  -- SURVEY.md 8(d)
+    ("cfg2-24MP-rgb8-linear", 4000, 6000, 3, "u1", dict(blue=1.0, red=-1.5, lens_x=3000, lens_y=2000, interpolation=1)),
+    ("cfg3-8K-rgba16-cubic", 4320, 7680, 4, "u2", dict(blue=6.0, red=-2.4, lens_x=658, lens_y=1280, interpolation=2)),
+    ("target-100MP-rgb16-cubic", 8192, 12288, 3, "u2", dict(KW, lens_x=6144, lens_y=4096, interpolation=2)),
+]
+
+
+@pytest.mark.parametrize("name,h,w,ch,dtype,kw", FULL, ids=[f[0] for f in FULL])
+def test_full_size_properties(fx, checker, name, h, w, ch, dtype, kw):
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, np.iinfo(dtype).max, size=(h, w, ch), dtype=dtype, endpoint=True)
+    p = fx.FixCaParams(**kw)
+    full = fx.correct(img, p)
+    assert fx.last_kernel().startswith("tiled")
+    # green / alpha untouched everywhere
+    assert (full[..., 1] == img[..., 1]).all() and (ch == 3 or (full[..., 3] == img[..., 3]).all())
+    # oracle on sampled bands (top edge, an interior band straddling chunk borders, bottom edge)
+    for y1, y2 in ((0, 96), (h // 2 - 40, h // 2 + 56), (h - 96, h)):
+        want = np.zeros_like(img)
+        checker.region(img, orc.Params(**kw), y1, y2, dst=want)
+        assert (full[y1:y2] == want[y1:y2]).all(), (name, y1, y2)
+    # band-split invariance: two half calls write the same bytes as the full call
+    halves = np.zeros_like(img)
+    fx.correct(img, p, y1=0, y2=h // 3, out=halves)
+    fx.correct(img, p, y1=h // 3, y2=h, out=halves)
+    assert md5(halves) == md5(full)
+    # fast arithmetic: within 1 LSB of the exact result on the whole image
+    fast = fx.correct(img, p, flags=fx.PRECISION_FAST)
+    d = np.abs(fast.astype(np.int32) - full.astype(np.int32))
+    assert d.max() <= FAST_LSB_TOL
+    print("%s: fast-vs-exact mismatch fraction %.2e" % (name, float((d != 0).mean())))
+    # identity with zero amounts at full size
+    ident = fx.correct(img, fx.FixCaParams(lens_x=kw["lens_x"], lens_y=kw["lens_y"], interpolation=kw["interpolation"]),
+                       flags=fx.PRECISION_FAST)
+    assert md5(ident) == md5(img)
