@@ -465,7 +465,9 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 	chunk_rows = std::min(chunk_rows, y2 - y1);
 	const int nchunks = (y2 - y1 + chunk_rows - 1) / chunk_rows;
 
-	const bool src_pinned = is_pinned(src), dst_pinned = is_pinned(dst);
+	// look at the first rows actually touched: callers may pass a whole-image base pointer of
+	// which only this band's rows are backed by memory
+	const bool src_pinned = is_pinned(src + (size_t)band_lo * row_bytes), dst_pinned = is_pinned(dst + (size_t)y1 * row_bytes);
 	// Pageable callers go through pinned rings (2 slots per direction).
 	const int ring = 2;
 	size_t in_slot = 0, out_slot = 0;
