@@ -163,7 +163,9 @@ static int smem_limit(int dev)
 }
 
 // Largest source window (bytes per row, rows) any tile of a th-row grid needs.
-static void window_extent(const Geometry &g, int bpp, int y1, int y2, int tw, int th, int &max_wbytes, int &max_rows)
+// `slack` widens every tile's column range by that many pixels per side (strip kernel:
+// the shared-sample windows of its P-column groups), clamped to the image.
+static void window_extent(const Geometry &g, int bpp, int y1, int y2, int tw, int th, int slack, int &max_wbytes, int &max_rows)
 {
 	max_wbytes = 0;
 	max_rows = 0;
@@ -171,6 +173,8 @@ static void window_extent(const Geometry &g, int bpp, int y1, int y2, int tw, in
 		const int xl = std::min(x0 + tw, g.width) - 1;
 		int lo, hi;
 		span_needed(g.x[CH_RED], g.x[CH_BLUE], g.interp, x0, xl, lo, hi);
+		lo = std::max(lo - slack, 0);
+		hi = std::min(hi + slack, g.width - 1);
 		const int b0 = (lo * bpp) & ~15, b1 = ((hi + 1) * bpp + 15) & ~15;
 		max_wbytes = std::max(max_wbytes, b1 - b0);
 	}
@@ -220,7 +224,7 @@ static int make_plan(const Format &f, const Geometry &g, const void *d_src, size
 		const size_t sm_total = 227 * 1024;
 		int best_th = 0;
 		size_t best_smem = 0;
-		int best_wb = 0, best_rows = 0, best_off[3] = {0, 0, 0};
+		int best_wb = 0, best_rows = 0, best_off[5] = {0, 0, 0, 0, 0};
 		for (int pass = 0; pass < 2 && !best_th; ++pass) {
 			for (int th : th_choices) {
 				if (forced_th && th != forced_th)
@@ -228,15 +232,26 @@ static int make_plan(const Format &f, const Geometry &g, const void *d_src, size
 				if (th > 8 && th >= 2 * (y2 - y1) && !forced_th)
 					continue;	// tile much taller than the band
 				int wb, rows;
-				window_extent(g, f.bpp, y1, y2, k->tw, th, wb, rows);
+				window_extent(g, f.bpp, y1, y2, k->tw, th, k->strip_p, wb, rows);
 				const size_t off_ytab = align_up(sizeof(TileHeader), 16);
-				const size_t off_win = align_up(off_ytab + (size_t)2 * th * k->ycoef_bytes, 128);
-				const size_t off_out = align_up(off_win + (size_t)wb * rows, 128);
+				size_t off_nemit = 0, ne_pitch = 0, off_win, win_rows = (size_t)rows;
+				if (k->strip_p) {
+					// [header | float4 ytab[2][th] | u8 nemit[2][ne_pitch] | window (+3 rows the
+					//  4-row-unrolled walker may touch on either side) | staging tile]
+					ne_pitch = align_up((size_t)rows + 3 + 4, 4);
+					off_nemit = off_ytab + (size_t)2 * th * 16;
+					off_win = align_up(off_nemit + 2 * ne_pitch, 128);
+					win_rows = (size_t)rows + 6;	// 3 phase-alignment rows in front, 3 unroll-slack rows behind
+				} else {
+					off_win = align_up(off_ytab + (size_t)2 * th * k->ycoef_bytes, 128);
+				}
+				const size_t off_out = align_up(off_win + (size_t)wb * win_rows, 128);
 				const size_t total = off_out + (size_t)th * k->tw * f.bpp;
 				const size_t budget = pass == 0 ? (sm_total / target_ctas - 1024) : (size_t)limit;
 				if (total <= budget && total <= (size_t)limit) {
 					best_th = th; best_smem = total; best_wb = wb; best_rows = rows;
 					best_off[0] = (int)off_ytab; best_off[1] = (int)off_win; best_off[2] = (int)off_out;
+					best_off[3] = (int)off_nemit; best_off[4] = (int)ne_pitch;
 					break;
 				}
 			}
@@ -249,8 +264,10 @@ static int make_plan(const Format &f, const Geometry &g, const void *d_src, size
 			a.off_ytab = best_off[0];
 			a.off_win = best_off[1];
 			a.off_out = best_off[2];
+			a.off_nemit = best_off[3];
+			a.ne_pitch = best_off[4];
 			pl.smem = best_smem;
-			pl.block = dim3(2 * k->tw);
+			pl.block = dim3(k->strip_p ? 2 * k->tw / k->strip_p : 2 * k->tw);
 			pl.grid = dim3((g.width + k->tw - 1) / k->tw, (y2 - y1 + best_th - 1) / best_th);
 			if (pl.grid.y > 65535)
 				want_tiled = false;

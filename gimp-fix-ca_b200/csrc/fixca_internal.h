@@ -4,6 +4,7 @@
 
 #include <cstddef>
 #include "fixca_kernels.cuh"
+#include "fixca_strip.cuh"
 
 namespace fixca {
 
@@ -19,6 +20,7 @@ struct KernelEntry {
 	int         tw;		// tile width (0 for direct kernels)
 	int         ycoef_bytes;// per-row table entry size (tiled)
 	int         sample_bytes;
+	int         strip_p;	// > 0: strip_kernel with this many columns per thread (blockDim = 2 * tw / strip_p)
 };
 
 constexpr int TILE_W = 128;

@@ -54,6 +54,9 @@ struct KernelArgs {
 	int  win_pitch;			// shared-memory window row pitch, bytes (multiple of 16)
 	int  win_rows;			// window rows allocated
 	int  off_ytab, off_win, off_out;// byte offsets into dynamic shared memory
+	// strip kernel only
+	int  off_nemit;			// per-source-row emit counts, u8[2][ne_pitch]
+	int  ne_pitch;			// multiple of 4, >= win_rows + 4
 };
 
 // ---------------------------------------------------------------------------

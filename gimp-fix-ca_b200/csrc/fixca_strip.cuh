@@ -1,0 +1,342 @@
+// fixca_strip.cuh -- the FAST (FP32) Linear / Cubic kernel for sm_100a.
+//
+// Same job as tiled_kernel (fix_ca_region's row loop, fix-ca.c:1122-1320, in
+// the separable form of SURVEY.md App. A), rebuilt around what the first ncu
+// capture showed (profiles/r01_ncu_tiled_cubic_u16x3_a.md): the pass is bound
+// by instruction issue and by shared-memory wavefronts, not by HBM.
+//
+//   * One CTA per TW x TH output tile.  TMA bulk copies bring in (a) the source
+//     window (tile + halo reachable through the affine map, fix-ca.c:801/:813)
+//     and (b) the tile's own pixels straight into the staging tile, so green /
+//     alpha pass through (fix-ca.c:1094-1098) without a single instruction.
+//   * A thread owns P adjacent output columns of ONE channel (red or blue) and
+//     walks down the SOURCE rows of the window.  Per source row it loads
+//     NS = P + NW - 1 consecutive samples once and forms the P horizontal
+//     results with NW = T + 1 weights each: the extra weight absorbs the
+//     one-sample drift between neighbouring columns' tap windows (scale != 1),
+//     so register indexing stays static and 5 loads replace 8 (Cubic, P = 2).
+//     P is chosen per pixel format so that the lane stride in shared memory
+//     (P * bytes-per-pixel) is conflict-free.
+//   * The vertical pass keeps the last four horizontal rows in a ring of
+//     registers.  The per-output-row weights are stored in shared memory
+//     already permuted into ring-slot order (clamped edge taps folded in), so
+//     the ring never shifts: 4 FMAs per output, no register moves.
+//   * Output rows are emitted when their last tap row has been produced; the
+//     per-source-row emit counts come from a small table built with the row
+//     coefficients.  float -> integer conversion saturates in hardware
+//     (cvt.rni.sat), which is clip_d + round in one instruction.
+//   * Columns whose tap windows are bent by the clamp-to-edge rules
+//     (fix-ca.c:1271-1298) cannot use consecutive samples; their warps take a
+//     per-tap path (same ring, same emission), exact in the same sense.
+//
+// Results are within +-1 LSB of the reference for u8 / u16 and ~2 ulp(1.0) for
+// float; FAST mode assumes finite float samples (a
+// zero weight times an Inf/NaN neighbour is NaN).
+#pragma once
+
+#include <type_traits>
+
+#include "fixca_kernels.cuh"
+
+namespace fixca {
+
+
+// fp32 tap weights from the fraction t (fix-ca.c:891-892 Linear, :905-907 Cubic, per tap).
+template <int INTERP>
+__device__ __forceinline__ void tap_weights(float t, float (&w)[4])
+{
+	if (INTERP == 1) {
+		w[0] = 1.0f - t; w[1] = t; w[2] = 0.f; w[3] = 0.f;
+	} else {
+		w[0] = ((2.0f - t) * t - 1.0f) * t * 0.5f;
+		w[1] = ((3.0f * t - 5.0f) * t * t + 2.0f) * 0.5f;
+		w[2] = ((4.0f - 3.0f * t) * t + 1.0f) * t * 0.5f;
+		w[3] = (t - 1.0f) * t * t * 0.5f;
+	}
+}
+
+template <class S> struct StripCodec;
+template <> struct StripCodec<uint8_t> {
+	__device__ __forceinline__ static float load(const unsigned char *p) { return (float)*p; }
+	__device__ __forceinline__ static void store(unsigned char *p, float v)
+	{
+		unsigned r;
+		asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+		*p = (unsigned char)r;
+	}
+};
+template <> struct StripCodec<uint16_t> {
+	__device__ __forceinline__ static float load(const unsigned char *p) { return (float)*reinterpret_cast<const uint16_t *>(p); }
+	__device__ __forceinline__ static void store(unsigned char *p, float v)
+	{
+		unsigned short r;
+		asm("cvt.rni.sat.u16.f32 %0, %1;" : "=h"(r) : "f"(v));
+		*reinterpret_cast<uint16_t *>(p) = r;
+	}
+};
+template <> struct StripCodec<float> {
+	__device__ __forceinline__ static float load(const unsigned char *p) { return *reinterpret_cast<const float *>(p); }
+	__device__ __forceinline__ static void store(unsigned char *p, float v)
+	{
+		// clip_d's order: <= 0 first, then >= 1; NaN passes (fix-ca.c:873-880)
+		*reinterpret_cast<float *>(p) = (v <= 0.f) ? 0.f : ((v >= 1.f) ? 1.f : v);
+	}
+};
+
+// S      sample type (uint8_t, uint16_t, float)
+// NCH    3 or 4 samples per pixel
+// INTERP 1 Linear, 2 Cubic
+// P      adjacent output columns per thread
+// TW     tile width in pixels; blockDim.x == 2 * TW / P (red half, blue half)
+//
+// Dynamic shared memory: [TileHeader | ytab float4[2][th] | nemit u8[2][ne_pitch] | window | staging tile]
+template <class S, int NCH, int INTERP, int P, int TW>
+__global__ void __launch_bounds__(2 * TW / P) strip_kernel(const __grid_constant__ KernelArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	constexpr int BPP = NCH * (int)sizeof(S);
+	constexpr int OUT_PITCH = TW * BPP;
+	constexpr int T = INTERP == 1 ? 2 : 4;		// taps per axis
+	constexpr int OFF = INTERP == 1 ? 0 : 1;	// first tap = base index - OFF
+	constexpr int NW = P == 1 ? T : T + 1;		// weights per output
+	constexpr int NS = P + NW - 1;			// consecutive samples a thread loads per source row
+	constexpr int NT = 2 * TW / P;			// threads per CTA
+	constexpr int HALF = TW / P;			// threads per channel
+	static_assert(HALF % 32 == 0, "a warp must not straddle the two channels");
+	typedef StripCodec<S> Codec;
+
+	TileHeader *hdr = reinterpret_cast<TileHeader *>(smem);
+	float4 *ytab = reinterpret_cast<float4 *>(smem + a.off_ytab);		// [2][th]
+	unsigned char *nemit = smem + a.off_nemit;				// [2][ne_pitch]
+	unsigned char *win = smem + a.off_win;
+	unsigned char *stage = smem + a.off_out;
+
+	const int tid = threadIdx.x;
+	const int c = tid / HALF;		// 0 red, 1 blue: uniform per warp
+	const int lt = tid - c * HALF;
+	const int W = a.g.width, H = a.g.height;
+	const int x0 = blockIdx.x * TW;
+	const int y0 = a.y1 + blockIdx.y * a.th;
+	const int xl = min(x0 + TW, W) - 1;
+	const int yl = min(y0 + a.th, a.y2) - 1;
+	const int nrows_out = yl - y0 + 1;
+
+	// ---- 1. window extent (tap ranges at the tile corners) ----
+	if (tid == 0) {
+		mbar_init(reinterpret_cast<uint64_t *>(&hdr->bar), 1);
+		fence_mbar_init();
+	}
+	if (tid < 8) {
+		const int ch = tid & 1, last = (tid >> 1) & 1, isrow = tid >> 2;
+		const Axis &ax = isrow ? a.g.y[ch] : a.g.x[ch];
+		const int i = isrow ? (last ? yl : y0) : (last ? xl : x0);
+		int lo, hi;
+		tap_range(ax, INTERP, i, lo, hi);
+		(isrow ? hdr->row_lo : hdr->col_lo)[tid & 3] = lo;
+		(isrow ? hdr->row_hi : hdr->col_hi)[tid & 3] = hi;
+	}
+	for (int k = tid; k < 2 * a.ne_pitch / 4; k += NT)
+		reinterpret_cast<int *>(nemit)[k] = 0;
+	__syncthreads();
+
+	int col_lo = x0, col_hi = xl, row_lo = y0, row_hi = yl;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		col_lo = min(col_lo, hdr->col_lo[k]);
+		col_hi = max(col_hi, hdr->col_hi[k]);
+		row_lo = min(row_lo, hdr->row_lo[k]);
+		row_hi = max(row_hi, hdr->row_hi[k]);
+	}
+	// slack columns for the shared-sample windows of the P-column groups
+	col_lo = max(col_lo - P, 0);
+	col_hi = min(col_hi + P, W - 1);
+	const int wb0 = (col_lo * BPP) & ~15;
+	const int wbytes = (((col_hi + 1) * BPP + 15) & ~15) - wb0;
+	const int wrows = row_hi - row_lo + 1;
+	const int wpitch = a.win_pitch;
+	// Ring phase and window slots are tied to ABSOLUTE source rows (slot = row & 3, window row
+	// index = row - row_base), so a row's arithmetic does not depend on where tiles or bands start.
+	const int row_base = row_lo & ~3;
+
+	// ---- 2. TMA: window rows, and the tile's own pixels into the staging tile ----
+	uint64_t *bar = reinterpret_cast<uint64_t *>(&hdr->bar);
+	const int tile_bytes = ((xl - x0 + 1) * BPP + 15) & ~15;
+	if (tid < 32) {
+		if (tid == 0)
+			mbar_arrive_expect_tx(bar, (uint32_t)(wrows * wbytes + nrows_out * tile_bytes));
+		__syncwarp();
+		const unsigned char *g = a.src + (long long)(row_lo - a.src_row0) * a.src_pitch + wb0;
+		for (int r = tid; r < wrows; r += 32)
+			bulk_load(win + (r + row_lo - row_base) * wpitch, g + (long long)r * a.src_pitch, (uint32_t)wbytes, bar);
+		const unsigned char *t = a.src + (long long)(y0 - a.src_row0) * a.src_pitch + (long long)x0 * BPP;
+		for (int r = tid; r < nrows_out; r += 32)
+			bulk_load(stage + r * OUT_PITCH, t + (long long)r * a.src_pitch, (uint32_t)tile_bytes, bar);
+	}
+
+	// rows [row_base, row_lo) are walked but not loaded: zero them (finite values for the zero weights)
+	for (int k = tid; k < (row_lo - row_base) * (wbytes >> 4); k += NT) {
+		const int r = k / (wbytes >> 4), v = k - r * (wbytes >> 4);
+		*reinterpret_cast<int4 *>(win + r * wpitch + v * 16) = make_int4(0, 0, 0, 0);
+	}
+
+	// ---- 3. per-row coefficients in ring-slot order + emit counts (overlaps the copies) ----
+	for (int k = tid; k < 2 * nrows_out; k += NT) {
+		const int ch = k >= nrows_out;
+		const int r = k - ch * nrows_out;
+		double td;
+		const int i0 = base_index(a.g.y[ch], y0 + r, td);
+		float w[4];
+		tap_weights<INTERP>((float)td, w);
+		float slot[4] = {0.f, 0.f, 0.f, 0.f};
+		int last = 0;
+#pragma unroll
+		for (int j = 0; j < T; ++j) {
+			const int q = clampi(i0 - OFF + j, 0, H - 1);
+			last = q;
+			const int sl = q & 3;
+#pragma unroll
+			for (int m = 0; m < 4; ++m)
+				slot[m] += (sl == m) ? w[j] : 0.f;
+		}
+		ytab[ch * a.th + r] = make_float4(slot[0], slot[1], slot[2], slot[3]);
+		// emitted once source row `last` (its highest tap row) has been produced
+		atomicAdd(reinterpret_cast<unsigned int *>(nemit + ch * a.ne_pitch + ((last - row_base) & ~3)),
+			  1u << (8 * (last & 3)));
+	}
+
+	// ---- 4. per-thread column state ----
+	float wt[P][NW];	// fast path: weights over the NS shared samples.  slow path: [k][j<T] tap weights
+	int cidx[P];		// base index of each column (slow path)
+	int colbase;		// byte offset of shared sample 0 from the window row start
+	bool regular;
+	{
+		int idx0[P];
+		float w[P][4];
+		int bmin = INT_MAX;
+#pragma unroll
+		for (int k = 0; k < P; ++k) {
+			const int x = min(x0 + lt * P + k, xl);
+			double td;
+			cidx[k] = base_index(a.g.x[c], x, td);
+			tap_weights<INTERP>((float)td, w[k]);
+			idx0[k] = cidx[k] - OFF - k;		// first tap minus k (unclamped)
+			bmin = min(bmin, idx0[k]);
+		}
+		// regular: every tap of column k sits at shared sample k + j', 0 <= j' < NW, without clamping
+		regular = bmin >= col_lo && bmin + NS - 1 <= col_hi;
+#pragma unroll
+		for (int k = 0; k < P; ++k)
+			regular = regular && (idx0[k] - bmin + T - 1 <= NW - 1);
+		regular = __all_sync(0xffffffffu, regular);
+#pragma unroll
+		for (int k = 0; k < P; ++k)
+#pragma unroll
+			for (int j = 0; j < NW; ++j) {
+				if (regular) {
+					const int d = j - (idx0[k] - bmin);	// tap number landing on shared sample k + j
+					float v = 0.f;
+#pragma unroll
+					for (int m = 0; m < T; ++m)
+						v = (d == m) ? w[k][m] : v;
+					wt[k][j] = v;
+				} else {
+					wt[k][j] = j < T ? w[k][j] : 0.f;
+				}
+			}
+		colbase = bmin * BPP + 2 * c * (int)sizeof(S) - wb0;
+	}
+
+	// walk bounds for this channel: first and last source row any output row of the tile taps
+	int s_first, s_last;
+	{
+		double td;
+		const int i0a = base_index(a.g.y[c], y0, td);
+		const int i0b = base_index(a.g.y[c], yl, td);
+		s_first = max(i0a - OFF, 0);
+		s_last = min(i0b + T - 1 - OFF, H - 1);
+		s_first &= ~3;				// ring phase: slot = row & 3
+	}
+
+	__syncthreads();	// ytab / nemit complete
+	mbar_wait(bar, 0);	// window + pass-through tile have landed
+
+	// ---- 5. walk down the source rows ----
+	{
+		float hr[4][P];
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+#pragma unroll
+			for (int k = 0; k < P; ++k)
+				hr[u][k] = 0.f;
+		const unsigned char *prow = win + (s_first - row_base) * wpitch;
+		unsigned char *q = stage + lt * P * BPP + 2 * c * (int)sizeof(S);
+		const float4 *wy = ytab + c * a.th;
+		const unsigned int *ne = reinterpret_cast<const unsigned int *>(nemit + c * a.ne_pitch + (s_first - row_base));
+		const int choff = 2 * c * (int)sizeof(S) - wb0;
+
+		// one instantiation per path so that the choice is made once, not per source row
+		auto walk = [&](auto fast_path) {
+			constexpr bool FAST = decltype(fast_path)::value;
+			for (int s = s_first; s <= s_last; s += 4) {
+				const unsigned int ne4 = *ne++;
+#pragma unroll
+				for (int u = 0; u < 4; ++u) {
+					if (FAST) {
+						float smp[NS];
+#pragma unroll
+						for (int m = 0; m < NS; ++m)
+							smp[m] = Codec::load(prow + colbase + m * BPP);
+#pragma unroll
+						for (int k = 0; k < P; ++k) {
+							float v = wt[k][0] * smp[k];
+#pragma unroll
+							for (int j = 1; j < NW; ++j)
+								v = fmaf(wt[k][j], smp[k + j], v);
+							hr[u][k] = v;
+						}
+					} else {
+#pragma unroll
+						for (int k = 0; k < P; ++k) {
+							float v = 0.f;
+#pragma unroll
+							for (int j = 0; j < T; ++j) {
+								const int ix = clampi(cidx[k] - OFF + j, 0, W - 1);
+								v = fmaf(wt[k][j], Codec::load(prow + ix * BPP + choff), v);
+							}
+							hr[u][k] = v;
+						}
+					}
+					prow += wpitch;
+					// usually exactly one output row completes per source row (scale ~ 1)
+#pragma unroll 1
+					for (int n = (ne4 >> (8 * u)) & 0xff; n > 0; --n) {
+						const float4 w = *wy++;
+#pragma unroll
+						for (int k = 0; k < P; ++k) {
+							const float v = fmaf(w.w, hr[3][k], fmaf(w.z, hr[2][k], fmaf(w.y, hr[1][k], w.x * hr[0][k])));
+							Codec::store(q + k * BPP, v);
+						}
+						q += OUT_PITCH;
+					}
+				}
+			}
+		};
+		if (regular)
+			walk(std::true_type());
+		else
+			walk(std::false_type());
+	}
+
+	// ---- 6. staging tile -> global, one bulk store per row ----
+	fence_proxy_async_smem();
+	__syncthreads();
+	if (tid < 32) {
+		unsigned char *g = a.dst + (long long)(y0 - a.dst_row0) * a.dst_pitch + (long long)x0 * BPP;
+		for (int r = tid; r < nrows_out; r += 32)
+			bulk_store(g + (long long)r * a.dst_pitch, stage + r * OUT_PITCH, (uint32_t)tile_bytes);
+		bulk_commit();
+		bulk_wait_read_all();
+	}
+}
+
+} // namespace fixca

@@ -1,23 +1,48 @@
-// kernels_fast.cu -- Linear / Cubic in FP32 on raw sample values (FastF32):
-// within +-1 LSB of the reference for u8 / u16, ~2 ulp(1.0) for float.
+// kernels_fast.cu -- Linear / Cubic in FP32 on raw sample values: within +-1 LSB
+// of the reference for u8 / u16, ~2 ulp(1.0) for float.
+//
+//   strip_kernel  (fixca_strip.cuh)  the fast path: P columns per thread, ring-buffered rows
+//   tiled_kernel  (FastF32)          the first-round one-column-per-thread kernel, kept for A/B
+//   direct_kernel (FastF32)          per-pixel gather, any geometry
+#include <cstdlib>
 #include "fixca_internal.h"
 
 namespace fixca {
 
 #define FAST_ENTRIES(S, TAG)                                                                                  \
-	{ (kernel_fn)tiled_kernel<S, 3, 1, FastF32, TILE_W>, "tiled/linear/f32/" TAG "x3", TILE_W, (int)sizeof(FastF32::YCoef), (int)sizeof(S) }, \
-	{ (kernel_fn)tiled_kernel<S, 4, 1, FastF32, TILE_W>, "tiled/linear/f32/" TAG "x4", TILE_W, (int)sizeof(FastF32::YCoef), (int)sizeof(S) }, \
-	{ (kernel_fn)tiled_kernel<S, 3, 2, FastF32, TILE_W>, "tiled/cubic/f32/" TAG "x3", TILE_W, (int)sizeof(FastF32::YCoef), (int)sizeof(S) },  \
-	{ (kernel_fn)tiled_kernel<S, 4, 2, FastF32, TILE_W>, "tiled/cubic/f32/" TAG "x4", TILE_W, (int)sizeof(FastF32::YCoef), (int)sizeof(S) },  \
-	{ (kernel_fn)direct_kernel<S, 3, 1, FastF32>, "direct/linear/f32/" TAG "x3", 0, 0, (int)sizeof(S) },  \
-	{ (kernel_fn)direct_kernel<S, 4, 1, FastF32>, "direct/linear/f32/" TAG "x4", 0, 0, (int)sizeof(S) },  \
-	{ (kernel_fn)direct_kernel<S, 3, 2, FastF32>, "direct/cubic/f32/" TAG "x3", 0, 0, (int)sizeof(S) },   \
-	{ (kernel_fn)direct_kernel<S, 4, 2, FastF32>, "direct/cubic/f32/" TAG "x4", 0, 0, (int)sizeof(S) }
+	{ (kernel_fn)tiled_kernel<S, 3, 1, FastF32, TILE_W>, "tiled/linear/f32/" TAG "x3", TILE_W, (int)sizeof(FastF32::YCoef), (int)sizeof(S), 0 }, \
+	{ (kernel_fn)tiled_kernel<S, 4, 1, FastF32, TILE_W>, "tiled/linear/f32/" TAG "x4", TILE_W, (int)sizeof(FastF32::YCoef), (int)sizeof(S), 0 }, \
+	{ (kernel_fn)tiled_kernel<S, 3, 2, FastF32, TILE_W>, "tiled/cubic/f32/" TAG "x3", TILE_W, (int)sizeof(FastF32::YCoef), (int)sizeof(S), 0 },  \
+	{ (kernel_fn)tiled_kernel<S, 4, 2, FastF32, TILE_W>, "tiled/cubic/f32/" TAG "x4", TILE_W, (int)sizeof(FastF32::YCoef), (int)sizeof(S), 0 },  \
+	{ (kernel_fn)direct_kernel<S, 3, 1, FastF32>, "direct/linear/f32/" TAG "x3", 0, 0, (int)sizeof(S), 0 },  \
+	{ (kernel_fn)direct_kernel<S, 4, 1, FastF32>, "direct/linear/f32/" TAG "x4", 0, 0, (int)sizeof(S), 0 },  \
+	{ (kernel_fn)direct_kernel<S, 3, 2, FastF32>, "direct/cubic/f32/" TAG "x3", 0, 0, (int)sizeof(S), 0 },   \
+	{ (kernel_fn)direct_kernel<S, 4, 2, FastF32>, "direct/cubic/f32/" TAG "x4", 0, 0, (int)sizeof(S), 0 }
 
 static const KernelEntry fast_table[] = {
 	FAST_ENTRIES(uint8_t, "u8"),
 	FAST_ENTRIES(uint16_t, "u16"),
 	FAST_ENTRIES(float, "f32"),
+};
+
+// Columns per thread are picked so that the lane stride in shared memory, P * bytes-per-pixel,
+// is conflict-free (an odd number of 32-bit words) or as close as the format allows.
+#define STRIP_ENTRIES(S, TAG, P3, TW3, P4, TW4)                                                               \
+	{ (kernel_fn)strip_kernel<S, 3, 1, P3, TW3>, "strip/linear/f32/" TAG "x3", TW3, 16, (int)sizeof(S), P3 }, \
+	{ (kernel_fn)strip_kernel<S, 4, 1, P4, TW4>, "strip/linear/f32/" TAG "x4", TW4, 16, (int)sizeof(S), P4 }, \
+	{ (kernel_fn)strip_kernel<S, 3, 2, P3, TW3>, "strip/cubic/f32/" TAG "x3", TW3, 16, (int)sizeof(S), P3 },  \
+	{ (kernel_fn)strip_kernel<S, 4, 2, P4, TW4>, "strip/cubic/f32/" TAG "x4", TW4, 16, (int)sizeof(S), P4 }
+
+static const KernelEntry strip_table[] = {
+	STRIP_ENTRIES(uint8_t, "u8", 4, 256, 1, 128),
+	STRIP_ENTRIES(uint16_t, "u16", 2, 256, 1, 128),
+	STRIP_ENTRIES(float, "f32", 1, 128, 1, 128),
+};
+
+// narrower-tile variants of the headline format, for tuning (FIXCA_STRIP_TW=128)
+static const KernelEntry strip_u16x3_tw128[] = {
+	{ (kernel_fn)strip_kernel<uint16_t, 3, 1, 2, 128>, "strip/linear/f32/u16x3/tw128", 128, 16, 2, 2 },
+	{ (kernel_fn)strip_kernel<uint16_t, 3, 2, 2, 128>, "strip/cubic/f32/u16x3/tw128", 128, 16, 2, 2 },
 };
 
 const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled)
@@ -31,6 +56,15 @@ const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled)
 	}
 	if ((nch != 3 && nch != 4) || (interp != 1 && interp != 2))
 		return nullptr;
+	if (tiled) {
+		const char *e = getenv("FIXCA_FAST_KERNEL");
+		if (!(e && e[0] == 't')) {
+			const char *tw = getenv("FIXCA_STRIP_TW");
+			if (kind == SK_U16 && nch == 3 && tw && atoi(tw) == 128)
+				return &strip_u16x3_tw128[interp - 1];
+			return &strip_table[s * 4 + (interp - 1) * 2 + (nch - 3)];
+		}
+	}
 	return &fast_table[s * 8 + (tiled ? 0 : 4) + (interp - 1) * 2 + (nch - 3)];
 }
 

@@ -111,6 +111,37 @@ def test_matrix_exact(fx, checker, dtype, ch):
             assert got.tobytes() == want.tobytes(), (h, w, dtype, ch, interp, lens, fx.last_kernel())
 
 
+FAST_SHAPES = [(1, 1), (2, 3), (5, 40), (7, 129), (129, 7), (64, 128), (65, 257), (33, 513), (301, 517), (97, 1000), (40, 2051)]
+
+
+@pytest.mark.parametrize("dtype,ch", [("u1", 3), ("u1", 4), ("u2", 3), ("u2", 4), ("f4", 3), ("f4", 4)])
+def test_matrix_fast(fx, checker, dtype, ch):
+    """FAST (FP32) arithmetic, strip kernel: every format it serves x Linear/Cubic x awkward shapes
+    (tiles narrower than a warp's column group, widths that are not a multiple of the tile) x
+    lens positions x scales on both sides of 1, against the checker within the stated tolerance."""
+    tol = FLOAT_ABS_TOL if dtype == "f4" else FAST_LSB_TOL
+    n, kernels = 0, set()
+    for (h, w), interp, lens, amounts in itertools.product(
+            FAST_SHAPES, (1, 2), ("c", (0, 0), (-1, -1)), ((3.0, -2.0), (-6.0, 2.4), (0.0, 0.0), (30.0, -30.0))):
+        n += 1
+        lx, ly = (w // 2, h // 2) if lens == "c" else lens
+        kw = dict(KW, blue=amounts[0], red=amounts[1], lens_x=lx, lens_y=ly, interpolation=interp)
+        m = max_dim(w, h, lx, ly)
+        if m + kw["blue"] <= 0 or m + kw["red"] <= 0:
+            continue        # infinite / negative scale: covered by the direct-kernel tests
+        img = orc.synth_image(h, w, ch, dtype, seed=5000 + n)
+        want = checker.region(img, orc.Params(**kw))
+        got = fx.correct(img, fx.FixCaParams(**kw), flags=fx.PRECISION_FAST)
+        kernels.add(fx.last_kernel().split("/")[0])
+        d, frac = lsb_diff(got, want)
+        assert d <= tol, (h, w, dtype, ch, interp, lens, amounts, d, frac, fx.last_kernel())
+        # pass-through channels are byte copies in every mode (fix-ca.c:1094-1098)
+        assert np.array_equal(got[..., 1], img[..., 1])
+        if ch == 4:
+            assert np.array_equal(got[..., 3], img[..., 3])
+    assert "strip" in kernels, kernels
+
+
 def test_none_is_bit_exact_for_every_sample_size_including_nan_payloads(fx, checker):
     rng = np.random.default_rng(3)
     for dt, ch in itertools.product(("u1", "u2", "u4", "u8"), (3, 4)):
@@ -291,3 +322,30 @@ def test_full_size_properties(fx, checker, name, h, w, ch, dtype, kw):
     ident = fx.correct(img, fx.FixCaParams(lens_x=kw["lens_x"], lens_y=kw["lens_y"], interpolation=kw["interpolation"]),
                        flags=fx.PRECISION_FAST)
     assert md5(ident) == md5(img)
+
+
+@pytest.mark.parametrize("name,h,w,ch,dtype,kw", FULL, ids=[f[0] for f in FULL])
+def test_full_size_fast_within_one_lsb(fx, checker, name, h, w, ch, dtype, kw):
+    """The bench configuration itself (FAST arithmetic, strip kernel) at BASELINE.json's sizes:
+    +-1 LSB on sampled bands, pass-through channels identical, and band-split invariance."""
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, np.iinfo(dtype).max, size=(h, w, ch), dtype=dtype, endpoint=True)
+    p = fx.FixCaParams(**kw)
+    full = fx.correct(img, p, flags=fx.PRECISION_FAST)
+    assert fx.last_kernel().startswith("strip")
+    assert (full[..., 1] == img[..., 1]).all() and (ch == 3 or (full[..., 3] == img[..., 3]).all())
+    worst, nbad, ntot = 0, 0, 0
+    for y1, y2 in ((0, 96), (h // 2 - 40, h // 2 + 56), (h - 96, h)):
+        want = np.zeros_like(img)
+        checker.region(img, orc.Params(**kw), y1, y2, dst=want)
+        d = np.abs(full[y1:y2].astype(np.int64) - want[y1:y2].astype(np.int64))
+        worst = max(worst, int(d.max()))
+        nbad += int((d != 0).sum())
+        ntot += d.size
+    assert worst <= FAST_LSB_TOL, (name, worst)
+    assert nbad / ntot < 5e-3, (name, nbad / ntot)      # SURVEY.md App. A item 13: ~2e-3 of u16 samples
+    # a band computed on its own equals the same rows of the full call (row-band independence)
+    y1, y2 = h // 3, h // 3 + 77
+    band = np.zeros_like(img)
+    fx.correct(img, p, y1=y1, y2=y2, out=band, flags=fx.PRECISION_FAST)
+    assert (band[y1:y2] == full[y1:y2]).all()
