@@ -55,32 +55,47 @@ __device__ __forceinline__ void tap_weights(float t, float (&w)[4])
 	}
 }
 
+// Sample codecs.  The integer <-> float conversions are kept off the XU pipe (I2F.U16 / F2I run
+// there at 16 lanes/clk/SM and were the top pipe of the first strip kernel, profiles/r01_*_d.md):
+//   load   ld.shared.u8/u16 zero-extends into a 32-bit register; cvt.rn.f32.u32 -> I2FP (ALU pipe)
+//   store  the vertical weights are pre-scaled by 1/max so the last FMA saturates to [0,1] (FFMA.SAT
+//          = clip_d, fix-ca.c:873-880); one more FMA with 1.5 * 2^23 rounds max * r to nearest-even in
+//          the low mantissa bits, which st.shared.u8/u16 then stores.
 template <class S> struct StripCodec;
 template <> struct StripCodec<uint8_t> {
-	__device__ __forceinline__ static float load(const unsigned char *p) { return (float)*p; }
-	__device__ __forceinline__ static void store(unsigned char *p, float v)
+	static constexpr float kInvMax = (float)(1.0 / 255.0);
+	__device__ __forceinline__ static float load(const unsigned char *p)
 	{
-		unsigned r;
-		asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
-		*p = (unsigned char)r;
+		unsigned v;
+		float f;
+		asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)));
+		asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
+		return f;
+	}
+	__device__ __forceinline__ static void store(unsigned char *p, float sat01)
+	{
+		*p = (unsigned char)__float_as_uint(fmaf(sat01, 255.0f, 12582912.0f));
 	}
 };
 template <> struct StripCodec<uint16_t> {
-	__device__ __forceinline__ static float load(const unsigned char *p) { return (float)*reinterpret_cast<const uint16_t *>(p); }
-	__device__ __forceinline__ static void store(unsigned char *p, float v)
+	static constexpr float kInvMax = (float)(1.0 / 65535.0);
+	__device__ __forceinline__ static float load(const unsigned char *p)
 	{
-		unsigned short r;
-		asm("cvt.rni.sat.u16.f32 %0, %1;" : "=h"(r) : "f"(v));
-		*reinterpret_cast<uint16_t *>(p) = r;
+		unsigned v;
+		float f;
+		asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)));
+		asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
+		return f;
+	}
+	__device__ __forceinline__ static void store(unsigned char *p, float sat01)
+	{
+		*reinterpret_cast<uint16_t *>(p) = (uint16_t)__float_as_uint(fmaf(sat01, 65535.0f, 12582912.0f));
 	}
 };
 template <> struct StripCodec<float> {
+	static constexpr float kInvMax = 1.0f;
 	__device__ __forceinline__ static float load(const unsigned char *p) { return *reinterpret_cast<const float *>(p); }
-	__device__ __forceinline__ static void store(unsigned char *p, float v)
-	{
-		// clip_d's order: <= 0 first, then >= 1; NaN passes (fix-ca.c:873-880)
-		*reinterpret_cast<float *>(p) = (v <= 0.f) ? 0.f : ((v >= 1.f) ? 1.f : v);
-	}
+	__device__ __forceinline__ static void store(unsigned char *p, float sat01) { *reinterpret_cast<float *>(p) = sat01; }
 };
 
 // S      sample type (uint8_t, uint16_t, float)
@@ -187,6 +202,9 @@ __global__ void __launch_bounds__(2 * TW / P) strip_kernel(const __grid_constant
 		const int i0 = base_index(a.g.y[ch], y0 + r, td);
 		float w[4];
 		tap_weights<INTERP>((float)td, w);
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			w[j] *= Codec::kInvMax;	// the vertical pass lands in [0,1] units
 		float slot[4] = {0.f, 0.f, 0.f, 0.f};
 		int last = 0;
 #pragma unroll
@@ -313,7 +331,7 @@ __global__ void __launch_bounds__(2 * TW / P) strip_kernel(const __grid_constant
 						const float4 w = *wy++;
 #pragma unroll
 						for (int k = 0; k < P; ++k) {
-							const float v = fmaf(w.w, hr[3][k], fmaf(w.z, hr[2][k], fmaf(w.y, hr[1][k], w.x * hr[0][k])));
+							const float v = __saturatef(fmaf(w.w, hr[3][k], fmaf(w.z, hr[2][k], fmaf(w.y, hr[1][k], w.x * hr[0][k]))));
 							Codec::store(q + k * BPP, v);
 						}
 						q += OUT_PITCH;

@@ -58,6 +58,15 @@ if __name__ == "__main__":
         run("50MP rgb f32 cubic fast", 6144, 8192, 3, torch.float32, -4, 2, F)
         run("50MP rgb f32 cubic exact", 6144, 8192, 3, torch.float32, -4, 2, E)
         run("4K rgb8 cubic fast", 2160, 3840, 3, torch.uint8, 1, 2, F)
+    if which == "quick":
+        for th in sys.argv[2:] or ["16"]:
+            os.environ["FIXCA_TILE_H"] = th
+            run("100MP rgb16 cubic fast", 8192, 12288, 3, torch.int16, 2, 2, F)
+            run("100MP rgb16 linear fast", 8192, 12288, 3, torch.int16, 2, 1, F)
+            run("24MP rgb8 cubic fast", 4000, 6000, 3, torch.uint8, 1, 2, F)
+            run("24MP rgb8 linear fast", 4000, 6000, 3, torch.uint8, 1, 1, F)
+            run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
+            run("50MP rgb f32 cubic fast", 6144, 8192, 3, torch.float32, -4, 2, F)
     if which == "strip":
         for tw in ("256", "128"):
             os.environ["FIXCA_STRIP_TW"] = tw
