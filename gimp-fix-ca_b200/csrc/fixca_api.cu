@@ -192,6 +192,28 @@ static int env_int(const char *name, int dflt)
 	return (s && *s) ? atoi(s) : dflt;
 }
 
+static int g_sm_count[64];	// per device, 0 = not queried
+
+static int sm_count(int dev)
+{
+	if (dev < 0 || dev >= 64)
+		return 148;
+	if (!g_sm_count[dev]) {
+		int v = 0;
+		if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+			v = 148;
+		g_sm_count[dev] = v;
+	}
+	return g_sm_count[dev];
+}
+
+struct Plan;
+// Streaming kernel: every CTA takes one tw-column strip and one segment of rows; the grid is sized
+// so that all CTAs are resident at once (strips x segments ~ SMs x CTAs per SM).  Fills the
+// kernel-specific parts of `pl` and returns true, or returns false when the window ring for D + 1
+// chunks does not fit in shared memory.
+static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g, int y1, int y2, int dev, int limit, Plan &pl);
+
 static int make_plan(const Format &f, const Geometry &g, const void *d_src, size_t src_pitch, int src_row0,
 		     void *d_dst, size_t dst_pitch, int dst_row0, int y1, int y2, unsigned flags, int dev, Plan &pl)
 {
@@ -217,6 +239,12 @@ static int make_plan(const Format &f, const Geometry &g, const void *d_src, size
 		if (!k)
 			return fail(FIXCA_ERR_FORMAT, "no tiled kernel for this format");
 		const int limit = smem_limit(dev);
+		if (k->stream) {
+			if (plan_stream(k, f, g, y1, y2, dev, limit, pl))
+				return FIXCA_OK;
+			// the ring does not fit (huge shifts): fall back to per-tile windows
+			k = lookup_fast_variant(f.kind, f.nch, g.interp, 2);
+		}
 		// Prefer the tallest tile that still leaves room for `want` CTAs per SM.
 		const int target_ctas = env_int("FIXCA_TILE_CTAS", 3);
 		const int forced_th = env_int("FIXCA_TILE_H", 0);
@@ -290,6 +318,57 @@ static int make_plan(const Format &f, const Geometry &g, const void *d_src, size
 	if (pl.grid.y > 65535)
 		return fail(FIXCA_ERR_ARG, "band of %d rows is too tall for one launch", y2 - y1);
 	return FIXCA_OK;
+}
+
+static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g, int y1, int y2, int dev, int limit, Plan &pl)
+{
+	const int CH = STREAM_CH, span = (STREAM_D + 1) * CH;
+	int wb, rows_unused;
+	window_extent(g, f.bpp, y1, y2, k->tw, y2 - y1, k->strip_p, wb, rows_unused);
+	// ring capacity: the source rows D + 1 consecutive chunks can have live at once, for any chunk start
+	int max_rows = 0;
+	for (int y0 = y1; y0 < y2; y0 += CH) {
+		const int yl = std::min(y0 + span, y2) - 1;
+		int lo, hi;
+		span_needed(g.y[CH_RED], g.y[CH_BLUE], g.interp, y0, yl, lo, hi);
+		max_rows = std::max(max_rows, hi - lo + 1);
+	}
+	const size_t ring_rows = align_up((size_t)max_rows, 4);
+	const size_t off_meta = align_up(sizeof(StreamHeader), 16);
+	const size_t off_win = align_up(off_meta + STREAM_NF * sizeof(StreamMeta), 128);
+	const size_t off_out = align_up(off_win + ring_rows * (size_t)wb, 128);
+	const size_t total = off_out + (size_t)STREAM_NSTG * CH * k->tw * f.bpp;
+	if (total > (size_t)limit)
+		return false;
+	const int threads = 2 * k->tw / k->strip_p + 32;
+	int per_sm = (int)((227 * 1024) / (total + 1024));
+	per_sm = std::max(1, std::min(per_sm, 2048 / threads));
+	per_sm = std::min(per_sm, env_int("FIXCA_STREAM_CTAS", 8));
+	const int strips = (g.width + k->tw - 1) / k->tw;
+	const int rows = y2 - y1;
+	int segs = std::max(1, sm_count(dev) * per_sm / strips);
+	const int forced = env_int("FIXCA_STREAM_SEGS", 0);
+	if (forced > 0)
+		segs = forced;
+	int seg_rows = (int)align_up((size_t)(rows + segs - 1) / segs, CH);
+	seg_rows = std::max(seg_rows, CH);
+	segs = (rows + seg_rows - 1) / seg_rows;
+	if (segs > 65535)
+		return false;
+	KernelArgs &a = pl.args;
+	pl.k = k;
+	a.th = CH;
+	a.win_pitch = wb;
+	a.win_rows = (int)ring_rows;
+	a.ring_rows = (int)ring_rows;
+	a.seg_rows = seg_rows;
+	a.off_ytab = (int)off_meta;
+	a.off_win = (int)off_win;
+	a.off_out = (int)off_out;
+	pl.smem = total;
+	pl.block = dim3(threads);
+	pl.grid = dim3(strips, segs);
+	return true;
 }
 
 static int launch_plan(const Plan &pl, cudaStream_t stream)

@@ -5,6 +5,7 @@
 #include <cstddef>
 #include "fixca_kernels.cuh"
 #include "fixca_strip.cuh"
+#include "fixca_stream.cuh"
 
 namespace fixca {
 
@@ -21,6 +22,7 @@ struct KernelEntry {
 	int         ycoef_bytes;// per-row table entry size (tiled)
 	int         sample_bytes;
 	int         strip_p;	// > 0: strip_kernel with this many columns per thread (blockDim = 2 * tw / strip_p)
+	int         stream;	// != 0: stream_kernel (blockDim = 2 * tw / strip_p + 32, grid = strips x segments)
 };
 
 constexpr int TILE_W = 128;
@@ -31,5 +33,7 @@ const KernelEntry *lookup_none(int sample_bytes, int nch, bool tiled);
 const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled);
 // kind in {SK_U8,SK_U16,SK_F32}; interp in {1,2}
 const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled);
+// variant: 0 direct, 1 first-round tiled, 2 strip, 3 stream
+const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int variant);
 
 } // namespace fixca

@@ -57,6 +57,9 @@ struct KernelArgs {
 	// strip kernel only
 	int  off_nemit;			// per-source-row emit counts, u8[2][ne_pitch]
 	int  ne_pitch;			// multiple of 4, >= win_rows + 4
+	// stream kernel only (off_ytab = metadata ring, off_win = window ring, off_out = staging ring)
+	int  seg_rows;			// output rows per CTA (multiple of the chunk height)
+	int  ring_rows;			// window ring capacity in rows (multiple of 4)
 };
 
 // ---------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 //   tiled_kernel  (FastF32)          the first-round one-column-per-thread kernel, kept for A/B
 //   direct_kernel (FastF32)          per-pixel gather, any geometry
 #include <cstdlib>
+#include <cstring>
 #include "fixca_internal.h"
 
 namespace fixca {
@@ -39,13 +40,31 @@ static const KernelEntry strip_table[] = {
 	STRIP_ENTRIES(float, "f32", 1, 128, 1, 128),
 };
 
+#define STREAM_ENTRIES(S, TAG, P3, TW3, P4, TW4)                                                              \
+	{ (kernel_fn)stream_kernel<S, 3, 1, P3, TW3>, "stream/linear/f32/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1 }, \
+	{ (kernel_fn)stream_kernel<S, 4, 1, P4, TW4>, "stream/linear/f32/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1 }, \
+	{ (kernel_fn)stream_kernel<S, 3, 2, P3, TW3>, "stream/cubic/f32/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1 },  \
+	{ (kernel_fn)stream_kernel<S, 4, 2, P4, TW4>, "stream/cubic/f32/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1 }
+
+static const KernelEntry stream_table[] = {
+	STREAM_ENTRIES(uint8_t, "u8", 4, 256, 1, 128),
+	STREAM_ENTRIES(uint16_t, "u16", 2, 256, 1, 128),
+	STREAM_ENTRIES(float, "f32", 1, 128, 1, 128),
+};
+
+static const KernelEntry stream_u16x3_tw128[] = {
+	{ (kernel_fn)stream_kernel<uint16_t, 3, 1, 2, 128>, "stream/linear/f32/u16x3/tw128", 128, 0, 2, 2, 1 },
+	{ (kernel_fn)stream_kernel<uint16_t, 3, 2, 2, 128>, "stream/cubic/f32/u16x3/tw128", 128, 0, 2, 2, 1 },
+};
+
 // narrower-tile variants of the headline format, for tuning (FIXCA_STRIP_TW=128)
 static const KernelEntry strip_u16x3_tw128[] = {
 	{ (kernel_fn)strip_kernel<uint16_t, 3, 1, 2, 128>, "strip/linear/f32/u16x3/tw128", 128, 16, 2, 2 },
 	{ (kernel_fn)strip_kernel<uint16_t, 3, 2, 2, 128>, "strip/cubic/f32/u16x3/tw128", 128, 16, 2, 2 },
 };
 
-const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled)
+// variant: 0 direct, 1 first-round tiled, 2 strip, 3 stream
+const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int variant)
 {
 	int s;
 	switch (kind) {
@@ -56,16 +75,26 @@ const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled)
 	}
 	if ((nch != 3 && nch != 4) || (interp != 1 && interp != 2))
 		return nullptr;
-	if (tiled) {
-		const char *e = getenv("FIXCA_FAST_KERNEL");
-		if (!(e && e[0] == 't')) {
-			const char *tw = getenv("FIXCA_STRIP_TW");
-			if (kind == SK_U16 && nch == 3 && tw && atoi(tw) == 128)
-				return &strip_u16x3_tw128[interp - 1];
-			return &strip_table[s * 4 + (interp - 1) * 2 + (nch - 3)];
-		}
+	const char *tw = getenv("FIXCA_STRIP_TW");	// tuning: narrower tiles for the headline format
+	const bool tw128 = kind == SK_U16 && nch == 3 && tw && atoi(tw) == 128;
+	switch (variant) {
+	case 3: return tw128 ? &stream_u16x3_tw128[interp - 1] : &stream_table[s * 4 + (interp - 1) * 2 + (nch - 3)];
+	case 2: return tw128 ? &strip_u16x3_tw128[interp - 1] : &strip_table[s * 4 + (interp - 1) * 2 + (nch - 3)];
+	case 1: return &fast_table[s * 8 + (interp - 1) * 2 + (nch - 3)];
+	default: return &fast_table[s * 8 + 4 + (interp - 1) * 2 + (nch - 3)];
 	}
-	return &fast_table[s * 8 + (tiled ? 0 : 4) + (interp - 1) * 2 + (nch - 3)];
+}
+
+const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled)
+{
+	if (!tiled)
+		return lookup_fast_variant(kind, nch, interp, 0);
+	const char *e = getenv("FIXCA_FAST_KERNEL");	// "tiled" | "strip" | "stream" (default), for A/B runs
+	if (e && !strcmp(e, "tiled"))
+		return lookup_fast_variant(kind, nch, interp, 1);
+	if (e && !strcmp(e, "strip"))
+		return lookup_fast_variant(kind, nch, interp, 2);
+	return lookup_fast_variant(kind, nch, interp, 3);
 }
 
 } // namespace fixca

@@ -114,11 +114,13 @@ def test_matrix_exact(fx, checker, dtype, ch):
 FAST_SHAPES = [(1, 1), (2, 3), (5, 40), (7, 129), (129, 7), (64, 128), (65, 257), (33, 513), (301, 517), (97, 1000), (40, 2051)]
 
 
+@pytest.mark.parametrize("variant", ["stream", "strip"])
 @pytest.mark.parametrize("dtype,ch", [("u1", 3), ("u1", 4), ("u2", 3), ("u2", 4), ("f4", 3), ("f4", 4)])
-def test_matrix_fast(fx, checker, dtype, ch):
-    """FAST (FP32) arithmetic, strip kernel: every format it serves x Linear/Cubic x awkward shapes
+def test_matrix_fast(fx, checker, dtype, ch, variant, monkeypatch):
+    """FAST (FP32) arithmetic, streaming kernel and its per-tile fallback (strip): every format x Linear/Cubic x awkward shapes
     (tiles narrower than a warp's column group, widths that are not a multiple of the tile) x
     lens positions x scales on both sides of 1, against the checker within the stated tolerance."""
+    monkeypatch.setenv("FIXCA_FAST_KERNEL", variant)
     tol = FLOAT_ABS_TOL if dtype == "f4" else FAST_LSB_TOL
     n, kernels = 0, set()
     for (h, w), interp, lens, amounts in itertools.product(
@@ -139,7 +141,7 @@ def test_matrix_fast(fx, checker, dtype, ch):
         assert np.array_equal(got[..., 1], img[..., 1])
         if ch == 4:
             assert np.array_equal(got[..., 3], img[..., 3])
-    assert "strip" in kernels, kernels
+    assert variant in kernels, kernels
 
 
 def test_none_is_bit_exact_for_every_sample_size_including_nan_payloads(fx, checker):
@@ -325,14 +327,14 @@ def test_full_size_properties(fx, checker, name, h, w, ch, dtype, kw):
 
 
 @pytest.mark.parametrize("name,h,w,ch,dtype,kw", FULL, ids=[f[0] for f in FULL])
-def test_full_size_fast_within_one_lsb(fx, checker, name, h, w, ch, dtype, kw):
+def test_full_size_fast_within_one_lsb(fx, checker, name, h, w, ch, dtype, kw, monkeypatch):
     """The bench configuration itself (FAST arithmetic, strip kernel) at BASELINE.json's sizes:
     +-1 LSB on sampled bands, pass-through channels identical, and band-split invariance."""
     rng = np.random.default_rng(5)
     img = rng.integers(0, np.iinfo(dtype).max, size=(h, w, ch), dtype=dtype, endpoint=True)
     p = fx.FixCaParams(**kw)
     full = fx.correct(img, p, flags=fx.PRECISION_FAST)
-    assert fx.last_kernel().startswith("strip")
+    assert fx.last_kernel().startswith("stream")
     assert (full[..., 1] == img[..., 1]).all() and (ch == 3 or (full[..., 3] == img[..., 3]).all())
     worst, nbad, ntot = 0, 0, 0
     for y1, y2 in ((0, 96), (h // 2 - 40, h // 2 + 56), (h - 96, h)):
@@ -349,3 +351,7 @@ def test_full_size_fast_within_one_lsb(fx, checker, name, h, w, ch, dtype, kw):
     band = np.zeros_like(img)
     fx.correct(img, p, y1=y1, y2=y2, out=band, flags=fx.PRECISION_FAST)
     assert (band[y1:y2] == full[y1:y2]).all()
+    # the per-tile fallback kernel shares the arithmetic (same weights, same FMA order): same bytes
+    monkeypatch.setenv("FIXCA_FAST_KERNEL", "strip")
+    fx.correct(img, p, y1=y1, y2=y2, out=band, flags=fx.PRECISION_FAST)
+    assert fx.last_kernel().startswith("strip") and (band[y1:y2] == full[y1:y2]).all()
