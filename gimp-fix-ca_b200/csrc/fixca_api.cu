@@ -16,6 +16,7 @@
 #include <thread>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/fixca_cuda.h"
@@ -134,6 +135,9 @@ struct Plan {
 	KernelArgs args;
 	dim3 grid, block;
 	size_t smem = 0;
+	// stream kernel: TMA tensor maps of the source (window groups, pass-through tiles) and destination
+	CUtensorMap tm_win, tm_tile, tm_out;
+	int src_rows_avail = 0;	// rows of the source band present at args.src
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -186,6 +190,22 @@ static void window_extent(const Geometry &g, int bpp, int y1, int y2, int tw, in
 	}
 }
 
+// Widest window (bytes) any strip of the streaming kernel needs; the slack is NOT clamped to the image
+// (the kernel's TMA tiles are zero-filled outside it).
+static void window_extent_stream(const Geometry &g, int bpp, int tw, int slack, int &max_wbytes)
+{
+	max_wbytes = 0;
+	for (int x0 = 0; x0 < g.width; x0 += tw) {
+		const int xl = std::min(x0 + tw, g.width) - 1;
+		int lo, hi;
+		span_needed(g.x[CH_RED], g.x[CH_BLUE], g.interp, x0, xl, lo, hi);
+		lo -= slack;
+		hi += slack;
+		const int b0 = (lo * bpp) & ~15, b1 = ((hi + 1) * bpp + 15) & ~15;
+		max_wbytes = std::max(max_wbytes, b1 - b0);
+	}
+}
+
 static int env_int(const char *name, int dflt)
 {
 	const char *s = getenv(name);
@@ -214,7 +234,7 @@ struct Plan;
 // chunks does not fit in shared memory.
 static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g, int y1, int y2, int dev, int limit, Plan &pl);
 
-static int make_plan(const Format &f, const Geometry &g, const void *d_src, size_t src_pitch, int src_row0,
+static int make_plan(const Format &f, const Geometry &g, const void *d_src, size_t src_pitch, int src_row0, int src_rows,
 		     void *d_dst, size_t dst_pitch, int dst_row0, int y1, int y2, unsigned flags, int dev, Plan &pl)
 {
 	pl = Plan();
@@ -229,6 +249,7 @@ static int make_plan(const Format &f, const Geometry &g, const void *d_src, size
 	a.y1 = y1;
 	a.y2 = y2;
 	a.g = g;
+	pl.src_rows_avail = src_rows;
 
 	const bool tma_ok = g.monotone && (src_pitch % 16 == 0) && (dst_pitch % 16 == 0) &&
 			    ((uintptr_t)d_src % 16 == 0) && ((uintptr_t)d_dst % 16 == 0);
@@ -320,30 +341,86 @@ static int make_plan(const Format &f, const Geometry &g, const void *d_src, size
 	return FIXCA_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda).
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+				    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+				    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn encode_tiled()
+{
+	static encode_tiled_fn fn = nullptr;
+	static std::once_flag once;
+	std::call_once(once, []() {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+		    q == cudaDriverEntryPointSuccess)
+			fn = (encode_tiled_fn)p;
+		else
+			cudaGetLastError();
+	});
+	return fn;
+}
+
+// A 2-D map of 8-byte elements over `rows` rows of `row_bytes` (multiple of 16) bytes at `pitch`;
+// boxes of box_bytes x box_rows.  Out-of-range parts of a box are zero-filled on load, dropped on store.
+static bool make_tensor_map(CUtensorMap &tm, const void *base, size_t pitch, size_t row_bytes, size_t rows,
+			    unsigned box_bytes, unsigned box_rows)
+{
+	encode_tiled_fn enc = encode_tiled();
+	if (!enc || box_bytes % 16 || box_bytes / 8 > 256 || box_rows > 256 || rows == 0 || row_bytes % 16)
+		return false;
+	const cuuint64_t dims[2] = {row_bytes / 8, rows};
+	const cuuint64_t strides[1] = {pitch};
+	const cuuint32_t box[2] = {box_bytes / 8, box_rows};
+	const cuuint32_t estr[2] = {1, 1};
+	return enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void *>(base), dims, strides, box, estr,
+		   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g, int y1, int y2, int dev, int limit, Plan &pl)
 {
-	const int CH = STREAM_CH, span = (STREAM_D + 1) * CH;
-	int wb, rows_unused;
-	window_extent(g, f.bpp, y1, y2, k->tw, y2 - y1, k->strip_p, wb, rows_unused);
-	// ring capacity: the source rows D + 1 consecutive chunks can have live at once, for any chunk start
-	int max_rows = 0;
-	for (int y0 = y1; y0 < y2; y0 += CH) {
-		const int yl = std::min(y0 + span, y2) - 1;
-		int lo, hi;
-		span_needed(g.y[CH_RED], g.y[CH_BLUE], g.interp, y0, yl, lo, hi);
-		max_rows = std::max(max_rows, hi - lo + 1);
+	const int CH = STREAM_CH;
+	int wb;
+	window_extent_stream(g, f.bpp, k->tw, STREAM_COL_SLACK(k->strip_p), wb);
+	wb = (int)align_up((size_t)wb, 32);	// the window box: 4 * wb must keep ring groups 128-byte aligned
+	if (wb > 2048 || k->tw * f.bpp > 2048)
+		return false;			// TMA boxes are at most 256 elements (of 8 bytes) wide
+	const int threads = 2 * k->tw / k->strip_p + 64;
+	const int want_ctas = std::max(1, env_int("FIXCA_STREAM_CTAS", 2));
+	const int forced_d = env_int("FIXCA_STREAM_DEPTH", 0);
+	// Deepest pipeline that still lets `want_ctas` CTAs share an SM; at least depth 1 in whatever fits.
+	size_t total = 0, off_meta = 0, off_win = 0, off_out = 0, ring_rows = 0;
+	int depth = 0;
+	for (int d = forced_d > 0 ? std::min(forced_d, STREAM_MAX_D) : STREAM_MAX_D; d >= 1; --d) {
+		// ring capacity: the source rows d + 1 consecutive chunks can have live at once, for any chunk start
+		const int span = (d + 1) * CH;
+		int max_rows = 0;
+		for (int y0 = y1; y0 < y2; y0 += CH) {
+			const int yl = std::min(y0 + span, y2) - 1;
+			int lo, hi;
+			span_needed(g.y[CH_RED], g.y[CH_BLUE], g.interp, y0, yl, lo, hi);
+			max_rows = std::max(max_rows, hi - lo + 1);
+		}
+		ring_rows = align_up((size_t)max_rows, 4) + 8;	// whole 4-row groups at both ends
+		off_meta = align_up(sizeof(StreamHeader), 16);
+		off_win = align_up(off_meta + (size_t)(d + 1) * sizeof(StreamMeta), 128);
+		off_out = align_up(off_win + ring_rows * (size_t)wb, 128);
+		total = off_out + (size_t)STREAM_NSTG * CH * k->tw * f.bpp;
+		const size_t budget = (d == 1 || forced_d > 0) ? (size_t)limit : std::min<size_t>(limit, (227 * 1024) / want_ctas - 1024);
+		if (total <= budget) {
+			depth = d;
+			break;
+		}
+		if (forced_d > 0)
+			break;
 	}
-	const size_t ring_rows = align_up((size_t)max_rows, 4);
-	const size_t off_meta = align_up(sizeof(StreamHeader), 16);
-	const size_t off_win = align_up(off_meta + STREAM_NF * sizeof(StreamMeta), 128);
-	const size_t off_out = align_up(off_win + ring_rows * (size_t)wb, 128);
-	const size_t total = off_out + (size_t)STREAM_NSTG * CH * k->tw * f.bpp;
-	if (total > (size_t)limit)
+	if (!depth)
 		return false;
-	const int threads = 2 * k->tw / k->strip_p + 32;
 	int per_sm = (int)((227 * 1024) / (total + 1024));
 	per_sm = std::max(1, std::min(per_sm, 2048 / threads));
-	per_sm = std::min(per_sm, env_int("FIXCA_STREAM_CTAS", 8));
+	per_sm = std::min(per_sm, want_ctas);
 	const int strips = (g.width + k->tw - 1) / k->tw;
 	const int rows = y2 - y1;
 	int segs = std::max(1, sm_count(dev) * per_sm / strips);
@@ -362,12 +439,24 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	a.win_rows = (int)ring_rows;
 	a.ring_rows = (int)ring_rows;
 	a.seg_rows = seg_rows;
+	a.depth = depth;
+	a.debug = env_int("FIXCA_STREAM_DEBUG", 0);
 	a.off_ytab = (int)off_meta;
 	a.off_win = (int)off_win;
 	a.off_out = (int)off_out;
 	pl.smem = total;
 	pl.block = dim3(threads);
 	pl.grid = dim3(strips, segs);
+	if (env_int("FIXCA_VERBOSE", 0))
+		fprintf(stderr, "fixca: %s grid %d x %d, %d threads, smem %zu B (ring %zu rows x %d B, depth %d), seg %d rows, %d CTA/SM\n",
+			k->name, strips, segs, threads, total, ring_rows, wb, depth, seg_rows, per_sm);
+	// rows as the kernels see them: align16(width * bpp) bytes (they may touch the padding bytes)
+	const size_t row_bytes = align_up((size_t)g.width * f.bpp, 16);
+	const size_t src_rows = (size_t)pl.src_rows_avail, dst_rows = (size_t)(y2 - a.dst_row0);
+	if (!make_tensor_map(pl.tm_win, a.src, (size_t)a.src_pitch, row_bytes, src_rows, (unsigned)wb, 4) ||
+	    !make_tensor_map(pl.tm_tile, a.src, (size_t)a.src_pitch, row_bytes, src_rows, (unsigned)(k->tw * f.bpp), CH) ||
+	    !make_tensor_map(pl.tm_out, a.dst, (size_t)a.dst_pitch, row_bytes, dst_rows, (unsigned)(k->tw * f.bpp), CH))
+		return false;
 	return true;
 }
 
@@ -378,7 +467,8 @@ static int launch_plan(const Plan &pl, cudaStream_t stream)
 		CUDA_TRY(cudaFuncSetAttribute((const void *)pl.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
 	}
 	KernelArgs a = pl.args;
-	void *params[] = {&a};
+	CUtensorMap tm[3] = {pl.tm_win, pl.tm_tile, pl.tm_out};
+	void *params[] = {&a, &tm[0], &tm[1], &tm[2]};	// the tensor maps are only declared by stream kernels
 	CUDA_TRY(cudaLaunchKernel((const void *)pl.k->fn, pl.grid, pl.block, params, pl.smem, stream));
 	g_launches.fetch_add(1);
 	snprintf(tl_kernel, sizeof tl_kernel, "%s", pl.k->name);
@@ -444,7 +534,7 @@ extern "C" int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int sr
 	int dev;
 	if ((rc = current_device_or(-1, dev))) return rc;
 	Plan pl;
-	if ((rc = make_plan(f, g, d_src, src_pitch, src_row0, d_dst, dst_pitch, dst_row0, y1, y2, flags, dev, pl))) return rc;
+	if ((rc = make_plan(f, g, d_src, src_pitch, src_row0, src_rows, d_dst, dst_pitch, dst_row0, y1, y2, flags, dev, pl))) return rc;
 	return launch_plan(pl, (cudaStream_t)stream);
 }
 
@@ -636,7 +726,7 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 		CUDA_TRY(cudaEventRecord(e_up, cx.s_up));
 		CUDA_TRY(cudaStreamWaitEvent(cx.s_run, e_up, 0));
 		Plan pl;
-		if ((rc = make_plan(f, g, cx.d_src, pitch, band_lo, cx.d_dst, pitch, y1, c1, c2, flags, dev, pl))) return rc;
+		if ((rc = make_plan(f, g, cx.d_src, pitch, band_lo, src_rows, cx.d_dst, pitch, y1, c1, c2, flags, dev, pl))) return rc;
 		if ((rc = launch_plan(pl, cx.s_run))) return rc;
 		CUDA_TRY(cudaEventRecord(e_run, cx.s_run));
 		CUDA_TRY(cudaStreamWaitEvent(cx.s_down, e_run, 0));
@@ -817,7 +907,7 @@ extern "C" int fixca_cuda_frames(const unsigned char *const *src_frames, unsigne
 			unsigned char *to = is_pinned(dst_frames[i]) ? dst_frames[i] : s.h_out;
 			CUDA_TRY(cudaMemcpy2DAsync(s.d_src, pitch, from, row_bytes, row_bytes, height, cudaMemcpyHostToDevice, s.s));
 			Plan pl;
-			if ((r = make_plan(f, g, s.d_src, pitch, 0, s.d_dst, pitch, 0, 0, height, flags, dev, pl))) return r;
+			if ((r = make_plan(f, g, s.d_src, pitch, 0, height, s.d_dst, pitch, 0, 0, height, flags, dev, pl))) return r;
 			if ((r = launch_plan(pl, s.s))) return r;
 			CUDA_TRY(cudaMemcpy2DAsync(to, row_bytes, s.d_dst, pitch, row_bytes, height, cudaMemcpyDeviceToHost, s.s));
 			s.frame = i;

@@ -60,6 +60,8 @@ struct KernelArgs {
 	// stream kernel only (off_ytab = metadata ring, off_win = window ring, off_out = staging ring)
 	int  seg_rows;			// output rows per CTA (multiple of the chunk height)
 	int  ring_rows;			// window ring capacity in rows (multiple of 4)
+	int  depth;			// chunks prefetched ahead (pipeline depth D)
+	int  debug;			// bit 0: skip the arithmetic (timing experiments only)
 };
 
 // ---------------------------------------------------------------------------

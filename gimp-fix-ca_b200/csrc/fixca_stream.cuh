@@ -18,9 +18,15 @@
 //     from global memory once per strip), the pass-through pixels of the next
 //     output chunk land in a staging buffer, finished chunks leave with TMA bulk
 //     stores; D chunks are in flight ahead of the compute warps;
-//   * the producer warp's idle lanes compute the per-row vertical weights of the
-//     chunks it prefetches (FP64 coordinates, fix-ca.c:813-820, weights folded
-//     into ring-slot order), so the compute warps never touch FP64;
+//     Copies are TMA *tensor* tiles (cp.async.bulk.tensor.2d over CUtensorMaps of the source and
+//     destination images): one instruction moves a 4-row group of the window, one the 8 x TW
+//     pass-through tile, one stores a finished chunk; rows and columns outside the image are
+//     zero-filled / clipped by the TMA unit.  (A first version issued one bulk copy per row --
+//     24 per chunk -- and the producer's own instruction stream, ~1.9 us per chunk, was the
+//     critical path of the whole kernel: profiles/r01_stream_pipe_sweep_i.md.)
+//   * a second helper warp computes the per-row vertical weights of the chunks ahead (FP64
+//     coordinates, fix-ca.c:813-820, weights folded into ring-slot order), so the compute
+//     warps never touch FP64 and the TMA warp never waits for arithmetic;
 //   * the 8 compute warps (4 red, 4 blue) never meet at a CTA barrier: they wait
 //     on "full" mbarriers and arrive on "done" mbarriers.
 //
@@ -30,26 +36,33 @@
 
 #include <type_traits>
 
+#include <cuda.h>	// CUtensorMap (the maps are encoded on the host, fixca_api.cu)
+
 #include "fixca_strip.cuh"
 
 namespace fixca {
 
 constexpr int STREAM_CH = 8;	// output rows per chunk
-constexpr int STREAM_D = 2;	// chunks prefetched ahead of the compute warps
-constexpr int STREAM_NF = STREAM_D + 1;		// chunks with live "full"/"done" barriers and metadata
-constexpr int STREAM_NSTG = STREAM_D + 2;	// staging buffers: D loading, 1 computing, 1 draining
+// Pipeline depth D (KernelArgs::depth, chosen by the host from the shared memory left): chunks whose
+// window rows are requested ahead of the compute warps -- these come from HBM and carry the
+// latency.  D + 1 chunks have live "full"/"done" barriers and metadata.  The pass-through tile of a
+// chunk is an L2 hit (its rows went through the window a moment ago) and is requested only one
+// chunk ahead, so three staging buffers suffice: one loading, one computing, one draining.
+constexpr int STREAM_MAX_D = 8;
+constexpr int STREAM_MAX_NF = STREAM_MAX_D + 1;
+constexpr int STREAM_NSTG = 3;
+#define STREAM_COL_SLACK(P) ((P) + 4)	// >= NS = P + taps: pixels of window slack per side (host and device)
 
 struct StreamMeta {
 	float4 wy[2][STREAM_CH];	// vertical weights per output row, ring-slot order, pre-scaled by 1/max
 	int    last[2][STREAM_CH + 1];	// highest tap row of each output row (INT_MAX after the chunk's last row)
 	int    s_end[2];		// = last[c][nrows - 1]
-	int    nrows;
-	int    pad;
+	int    simple[2];		// full chunk whose rows finish on CH consecutive source rows (the usual case)
 };
 
 struct StreamHeader {
-	unsigned long long full[STREAM_NF];
-	unsigned long long done[STREAM_NF];
+	unsigned long long full[STREAM_MAX_NF];
+	unsigned long long done[STREAM_MAX_NF];
 	int col_lo[2], col_hi[2];
 };
 
@@ -57,18 +70,59 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Wait with a suspend-time hint: the helper warps are far ahead of the data and must not burn
+// issue slots polling.
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity, uint32_t hint_ns)
+{
+	uint32_t done;
+	do {
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+			"selp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(done)
+			: "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+			: "memory");
+	} while (!done);
+}
 template <int N>
 __device__ __forceinline__ void bulk_wait_read()
 {
 	asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 2-D tensor tile, global -> shared; coordinates in elements of the map (c0: 8-byte units, c1: rows)
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+		     ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+		     : "memory");
+}
+// 2-D tensor tile, shared -> global (clipped to the tensor's extent)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, int c0, int c1, const void *smem_src)
+{
+	asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+		     ::"l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
+		     : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *tm)
+{
+	asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
 
-// Dynamic shared memory: [StreamHeader | StreamMeta[NF] | window ring (ring_rows x win_pitch) |
-//                         staging (NSTG x CH x TW x BPP)]
-// blockDim.x == 2 * TW / P compute threads + 32 (the producer warp).
+// Dynamic shared memory: [StreamHeader | StreamMeta[D + 1] | window ring (ring_rows x win_pitch) |
+//                         staging (3 x CH x TW x BPP)]
+// blockDim.x == 2 * TW / P compute threads + 64 (the TMA warp and the row-coefficient warp).
+//
+// tm_win   source image, box = win_pitch bytes x 4 rows     (window ring groups)
+// tm_tile  source image, box = TW * BPP bytes x CH rows      (pass-through pixels of a chunk)
+// tm_out   destination rows [dst_row0, y2), same box         (finished chunks; clipped at y2 and at the row end)
+// All three are maps of 8-byte elements over rows of align16(width * BPP) bytes; row coordinates are
+// relative to src_row0 / dst_row0.
 template <class S, int NCH, int INTERP, int P, int TW>
-__global__ void __launch_bounds__(2 * TW / P + 32) stream_kernel(const __grid_constant__ KernelArgs a)
+__global__ void __launch_bounds__(2 * TW / P + 64)
+stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUtensorMap tm_win,
+	      const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ CUtensorMap tm_out)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	constexpr int BPP = NCH * (int)sizeof(S);
@@ -80,7 +134,9 @@ __global__ void __launch_bounds__(2 * TW / P + 32) stream_kernel(const __grid_co
 	constexpr int NS = P + NW - 1;
 	constexpr int NTC = 2 * TW / P;		// compute threads
 	constexpr int HALF = TW / P;
-	constexpr int CH = STREAM_CH, NF = STREAM_NF, NSTG = STREAM_NSTG, D = STREAM_D;
+	constexpr int CH = STREAM_CH;
+	constexpr int NSTG = STREAM_NSTG;
+	const int D = a.depth, NF = D + 1;
 	static_assert(HALF % 32 == 0, "a warp must not straddle the two channels");
 	static_assert(2 * CH <= 32, "one producer lane per (channel, row) of a chunk");
 	typedef StripCodec<S> Codec;
@@ -102,9 +158,8 @@ __global__ void __launch_bounds__(2 * TW / P + 32) stream_kernel(const __grid_co
 
 	// ---- one-time: barriers and the strip's column extent ----
 	if (tid == 0) {
-#pragma unroll
 		for (int i = 0; i < NF; ++i) {
-			mbar_init(reinterpret_cast<uint64_t *>(&hdr->full[i]), 1);
+			mbar_init(reinterpret_cast<uint64_t *>(&hdr->full[i]), 3);	// window rows, pass-through tile, row coefficients
 			mbar_init(reinterpret_cast<uint64_t *>(&hdr->done[i]), NTC);
 		}
 		fence_mbar_init();
@@ -118,96 +173,127 @@ __global__ void __launch_bounds__(2 * TW / P + 32) stream_kernel(const __grid_co
 	__syncthreads();
 	int col_lo = min(x0, min(hdr->col_lo[0], hdr->col_lo[1]));
 	int col_hi = max(xl, max(hdr->col_hi[0], hdr->col_hi[1]));
-	col_lo = max(col_lo - P, 0);
-	col_hi = min(col_hi + P, W - 1);
-	const int wb0 = (col_lo * BPP) & ~15;
-	const int wbytes = (((col_hi + 1) * BPP + 15) & ~15) - wb0;
-	const int tile_bytes = ((xl - x0 + 1) * BPP + 15) & ~15;
+	// Slack for the shared-sample windows of the P-column groups.  NOT clamped to the image: the TMA
+	// unit zero-fills columns outside it, and the clamp-to-edge rule is folded into the weights (a
+	// tap that would fall outside lands on the edge column; the zero-filled samples get weight 0).
+	col_lo -= STREAM_COL_SLACK(P);
+	col_hi += STREAM_COL_SLACK(P);
+	const int wb0 = (col_lo * BPP) & ~15;	// may be negative
 	uint64_t *full = reinterpret_cast<uint64_t *>(hdr->full);
 	uint64_t *done = reinterpret_cast<uint64_t *>(hdr->done);
 
+	if (tid >= NTC + 32) {
+		// =====================================================================
+		// row-coefficient warp: vertical weights and bookkeeping of the chunks ahead
+		// =====================================================================
+		const int lane = tid - NTC - 32;
+		int inf = 0, ipar = 0;	// i % NF, (i / NF) & 1
+		for (int i = 0; i < nchunks; ++i) {
+			if (i >= NF)	// the slot's previous tenant (chunk i - NF) must be finished
+				mbar_wait_sleepy(&done[inf], (uint32_t)(ipar ^ 1), 2000u);
+			const int y_first = ya + i * CH;
+			const int nr = min(CH, yb - y_first);
+			StreamMeta &m = meta[inf];
+			const int ch = (lane / CH) & 1, r = lane % CH;
+			const bool mine = lane < 2 * CH && r < nr;
+			int last = 0;
+			if (mine) {
+				double td;
+				const int i0 = base_index(a.g.y[ch], y_first + r, td);
+				float w[4];
+				tap_weights<INTERP>((float)td, w);
+				float slot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+				for (int j = 0; j < T; ++j) {
+					const int q = clampi(i0 - OFF + j, 0, H - 1);
+					last = q;
+#pragma unroll
+					for (int s = 0; s < 4; ++s)
+						slot[s] += ((q & 3) == s) ? w[j] * Codec::kInvMax : 0.f;
+				}
+				m.wy[ch][r] = make_float4(slot[0], slot[1], slot[2], slot[3]);
+				m.last[ch][r] = last;
+				if (r == nr - 1) {
+					m.last[ch][nr] = INT_MAX;
+					m.s_end[ch] = last;
+				}
+			}
+			// "simple": a full chunk in which every row completes exactly one source row after
+			// the previous one -- one horizontal row in, one output row out, CH times
+			const int prev = __shfl_up_sync(0xffffffffu, last, 1);
+			const bool ok = mine && (r == 0 || last == prev + 1);
+			const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+			if (lane < 2) {
+				const unsigned want = ((1u << CH) - 1u) << (lane * CH);
+				m.simple[lane] = (nr == CH) && ((okmask & want) == want);
+			}
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(&full[inf]);	// release: the metadata above is visible to the waiters
+			if (++inf == NF) { inf = 0; ipar ^= 1; }
+		}
+		return;
+	}
 	if (tid >= NTC) {
 		// =====================================================================
-		// producer warp
+		// TMA warp (one elected lane): window groups and pass-through tiles in, finished chunks out
 		// =====================================================================
-		const int lane = tid - NTC;
-		int loaded_hi;		// highest source row already requested
+		if (tid != NTC)
+			return;
+		prefetch_tensormap(&tm_win);
+		prefetch_tensormap(&tm_tile);
+		prefetch_tensormap(&tm_out);
+		const int NRG = NR >> 2;		// ring capacity in 4-row groups
+		const int group_bytes = 4 * wpitch;
+		const int c0_win = wb0 >> 3, c0_tile = (x0 * BPP) >> 3;
+		int loaded_g;				// highest 4-row group already requested
 		{
 			double td;
 			const int fr = max(base_index(a.g.y[0], ya, td) - OFF, 0);
 			const int fb = max(base_index(a.g.y[1], ya, td) - OFF, 0);
-			loaded_hi = min(fr, fb) - 1;
+			loaded_g = (min(fr, fb) >> 2) - 1;
 		}
-		auto produce = [&](int i) {
-			const int y_first = ya + i * CH;
-			const int nr = min(CH, yb - y_first);
-			StreamMeta &m = meta[i % NF];
-			if (lane < 2 * CH) {
-				const int ch = lane / CH, r = lane - ch * CH;
-				if (r < nr) {
-					double td;
-					const int i0 = base_index(a.g.y[ch], y_first + r, td);
-					float w[4];
-					tap_weights<INTERP>((float)td, w);
-					float slot[4] = {0.f, 0.f, 0.f, 0.f};
-					int last = 0;
-#pragma unroll
-					for (int j = 0; j < T; ++j) {
-						const int q = clampi(i0 - OFF + j, 0, H - 1);
-						last = q;
-#pragma unroll
-						for (int s = 0; s < 4; ++s)
-							slot[s] += ((q & 3) == s) ? w[j] * Codec::kInvMax : 0.f;
-					}
-					m.wy[ch][r] = make_float4(slot[0], slot[1], slot[2], slot[3]);
-					m.last[ch][r] = last;
-					if (r == nr - 1) {
-						m.last[ch][nr] = INT_MAX;
-						m.s_end[ch] = last;
-					}
-				}
+		int gslot = (loaded_g + 1) % NRG;	// ring slot of group loaded_g + 1
+		int wnf = 0;				// window requests: i % NF
+		auto request_window = [&](int i) {	// the source rows chunk i adds to the ring
+			const int y_last = min(ya + i * CH + CH, yb) - 1;
+			double td;
+			const int hr_ = min(base_index(a.g.y[0], y_last, td) + T - 1 - OFF, H - 1);
+			const int hb_ = min(base_index(a.g.y[1], y_last, td) + T - 1 - OFF, H - 1);
+			const int hi_g = max(max(hr_, hb_) >> 2, loaded_g);
+			uint64_t *bar = &full[wnf];
+			mbar_arrive_expect_tx(bar, (uint32_t)((hi_g - loaded_g) * group_bytes));
+			for (int g = loaded_g + 1; g <= hi_g; ++g) {
+				tma_load_2d(win + gslot * group_bytes, &tm_win, c0_win, 4 * g - a.src_row0, bar);
+				gslot = gslot + 1 == NRG ? 0 : gslot + 1;
 			}
-			if (lane == 0)
-				m.nrows = nr;
-			int hi;
-			{
-				double td;
-				const int hr_ = min(base_index(a.g.y[0], y_first + nr - 1, td) + T - 1 - OFF, H - 1);
-				const int hb_ = min(base_index(a.g.y[1], y_first + nr - 1, td) + T - 1 - OFF, H - 1);
-				hi = max(max(hr_, hb_), loaded_hi);
-			}
-			const int n_new = hi - loaded_hi;
-			// the staging buffer's previous tenant (chunk i - NSTG) must have been read out
+			loaded_g = hi_g;
+			wnf = wnf + 1 == NF ? 0 : wnf + 1;
+		};
+		int tnf = 0, tstg = 0;			// tile requests: i % NF, i % NSTG
+		auto request_tile = [&](int i) {	// chunk i's own pixels -> its staging buffer
+			// the buffer's previous tenant (chunk i - NSTG) was stored two iterations ago
 			bulk_wait_read<1>();
-			__syncwarp();
-			uint64_t *bar = &full[i % NF];
-			if (lane == 0)
-				mbar_arrive_expect_tx(bar, (uint32_t)(n_new * wbytes + nr * tile_bytes));
-			__syncwarp();
-			for (int r = lane; r < n_new; r += 32) {
-				const int q = loaded_hi + 1 + r;
-				bulk_load(win + (q % NR) * wpitch,
-					  a.src + (long long)(q - a.src_row0) * a.src_pitch + wb0, (uint32_t)wbytes, bar);
-			}
-			unsigned char *st = stage + (i % NSTG) * STAGE_BYTES;
-			const unsigned char *t = a.src + (long long)(y_first - a.src_row0) * a.src_pitch + (long long)x0 * BPP;
-			for (int r = lane; r < nr; r += 32)
-				bulk_load(st + r * OUT_PITCH, t + (long long)r * a.src_pitch, (uint32_t)tile_bytes, bar);
-			loaded_hi = hi;
+			uint64_t *bar = &full[tnf];
+			mbar_arrive_expect_tx(bar, (uint32_t)STAGE_BYTES);
+			tma_load_2d(stage + tstg * STAGE_BYTES, &tm_tile, c0_tile, ya + i * CH - a.src_row0, bar);
+			tnf = tnf + 1 == NF ? 0 : tnf + 1;
+			tstg = tstg + 1 == NSTG ? 0 : tstg + 1;
 		};
 		for (int i = 0; i < D && i < nchunks; ++i)
-			produce(i);
+			request_window(i);
+		request_tile(0);
+		int jnf = 0, jstg = 0, jpar = 0;	// j % NF, j % NSTG, (j / NF) & 1
 		for (int j = 0; j < nchunks; ++j) {
 			if (j + D < nchunks)
-				produce(j + D);
-			mbar_wait(&done[j % NF], (uint32_t)((j / NF) & 1));
-			const int y_first = ya + j * CH;
-			const int nr = min(CH, yb - y_first);
-			const unsigned char *st = stage + (j % NSTG) * STAGE_BYTES;
-			unsigned char *g = a.dst + (long long)(y_first - a.dst_row0) * a.dst_pitch + (long long)x0 * BPP;
-			for (int r = lane; r < nr; r += 32)
-				bulk_store(g + (long long)r * a.dst_pitch, st + r * OUT_PITCH, (uint32_t)tile_bytes);
+				request_window(j + D);
+			if (j + 1 < nchunks)
+				request_tile(j + 1);
+			mbar_wait_sleepy(&done[jnf], (uint32_t)jpar, 500u);
+			tma_store_2d(&tm_out, c0_tile, ya + j * CH - a.dst_row0, stage + jstg * STAGE_BYTES);
 			bulk_commit();
+			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
+			jstg = jstg + 1 == NSTG ? 0 : jstg + 1;
 		}
 		bulk_wait_all();
 		return;
@@ -219,41 +305,49 @@ __global__ void __launch_bounds__(2 * TW / P + 32) stream_kernel(const __grid_co
 	const int c = tid / HALF;		// 0 red, 1 blue: uniform per warp
 	const int lt = tid - c * HALF;
 
-	float wt[P][NW];
-	int cidx[P];
-	int colbase;
+	float wt[P][NW];	// regular: weights over the NS shared samples.  otherwise [k][j < T]: plain tap weights
+	int cidx[P];		// base index of each column (per-tap path)
+	int colbase;		// byte offset of shared sample 0 from the window row start
 	bool regular;
 	{
-		int idx0[P];
 		float w[P][4];
+		int tap[P][T];	// clamp-to-edge tap columns minus k (fix-ca.c:1271-1298)
 		int bmin = INT_MAX;
 #pragma unroll
 		for (int k = 0; k < P; ++k) {
-			const int x = min(x0 + lt * P + k, xl);
+			// columns past the tile's last one are computed like any other (their results are
+			// clipped by the TMA store); past the image the coordinate clamps to W - 1
 			double td;
-			cidx[k] = base_index(a.g.x[c], x, td);
+			cidx[k] = base_index(a.g.x[c], x0 + lt * P + k, td);
 			tap_weights<INTERP>((float)td, w[k]);
-			idx0[k] = cidx[k] - OFF - k;
-			bmin = min(bmin, idx0[k]);
+#pragma unroll
+			for (int j = 0; j < T; ++j) {
+				tap[k][j] = clampi(cidx[k] - OFF + j, 0, W - 1) - k;
+				if (w[k][j] != 0.f)
+					bmin = min(bmin, tap[k][j]);
+			}
 		}
+		// regular: every tap that carries weight sits at shared sample k + j', 0 <= j' < NW, and the
+		// NS samples lie inside the window
 		regular = bmin >= col_lo && bmin + NS - 1 <= col_hi;
 #pragma unroll
 		for (int k = 0; k < P; ++k)
-			regular = regular && (idx0[k] - bmin + T - 1 <= NW - 1);
+#pragma unroll
+			for (int j = 0; j < T; ++j)
+				regular = regular && (w[k][j] == 0.f || tap[k][j] - bmin <= NW - 1);
 		regular = __all_sync(0xffffffffu, regular);
 #pragma unroll
 		for (int k = 0; k < P; ++k)
 #pragma unroll
-			for (int j = 0; j < NW; ++j) {
+			for (int jj = 0; jj < NW; ++jj) {
 				if (regular) {
-					const int d = j - (idx0[k] - bmin);
 					float v = 0.f;
 #pragma unroll
-					for (int m = 0; m < T; ++m)
-						v = (d == m) ? w[k][m] : v;
-					wt[k][j] = v;
+					for (int j = 0; j < T; ++j)
+						v += (w[k][j] != 0.f && tap[k][j] - bmin == jj) ? w[k][j] : 0.f;
+					wt[k][jj] = v;
 				} else {
-					wt[k][j] = j < T ? w[k][j] : 0.f;
+					wt[k][jj] = jj < T ? w[k][jj] : 0.f;
 				}
 			}
 		colbase = bmin * BPP + 2 * c * (int)sizeof(S) - wb0;
@@ -277,14 +371,18 @@ __global__ void __launch_bounds__(2 * TW / P + 32) stream_kernel(const __grid_co
 
 	auto run = [&](auto fast_path) {
 		constexpr bool FAST = decltype(fast_path)::value;
+		int jnf = 0, jstg = 0, jpar = 0;	// j % NF, j % NSTG, (j / NF) & 1
 		for (int j = 0; j < nchunks; ++j) {
-			mbar_wait(&full[j % NF], (uint32_t)((j / NF) & 1));
-			const StreamMeta &m = meta[j % NF];
+			mbar_wait(&full[jnf], (uint32_t)jpar);
+			const StreamMeta &m = meta[jnf];
+			uint64_t *const done_bar = &done[jnf];
+			unsigned char *q = stage + jstg * STAGE_BYTES + qoff;
+			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
+			jstg = jstg + 1 == NSTG ? 0 : jstg + 1;
 			const int s_end = m.s_end[c];
 			const float4 *wy = m.wy[c];
 			const int *lastp = m.last[c];
 			int next_last = lastp[0];
-			unsigned char *q = stage + (j % NSTG) * STAGE_BYTES + qoff;
 
 #define FIXCA_EMIT()                                                                                          \
 	do {                                                                                                  \
@@ -329,6 +427,63 @@ __global__ void __launch_bounds__(2 * TW / P + 32) stream_kernel(const __grid_co
 		_Pragma("unroll 1") while (next_last <= s_done) FIXCA_EMIT();                                 \
 	} while (0)
 
+			if (a.debug & 1) {	// timing experiment: memory pipeline only (results are wrong)
+				s_done = s_end;
+				prow = win + ((s_done + 1) % NR) * wpitch;
+				fence_proxy_async_smem();
+				mbar_arrive(done_bar);
+				continue;
+			}
+			if (FAST && m.simple[c] && next_last == s_done + 1) {
+				// Steady state: CH source rows in, CH output rows out, fully unrolled.  The ring
+				// slot of every row is static per entry phase; the next row's samples are loaded
+				// before the current row's arithmetic (the loads never wait on the stores).
+				auto simple = [&](auto phase) {
+					constexpr int PH = decltype(phase)::value;
+					float smp[2][NS];
+#pragma unroll
+					for (int mm = 0; mm < NS; ++mm)
+						smp[0][mm] = Codec::load(prow + colbase + mm * BPP);
+#pragma unroll
+					for (int u = 0; u < CH; ++u) {
+						const unsigned char *pnext = prow + wpitch;
+						if (((PH + u) & 3) == 3 && pnext == win_end)
+							pnext = win;
+						if (u + 1 < CH) {
+#pragma unroll
+							for (int mm = 0; mm < NS; ++mm)
+								smp[(u + 1) & 1][mm] = Codec::load(pnext + colbase + mm * BPP);
+						}
+#pragma unroll
+						for (int k = 0; k < P; ++k) {
+							float v = wt[k][0] * smp[u & 1][k];
+#pragma unroll
+							for (int jj = 1; jj < NW; ++jj)
+								v = fmaf(wt[k][jj], smp[u & 1][k + jj], v);
+							hr[(PH + u) & 3][k] = v;
+						}
+						const float4 w_ = wy[u];
+#pragma unroll
+						for (int k = 0; k < P; ++k) {
+							const float v_ = __saturatef(fmaf(w_.w, hr[3][k], fmaf(w_.z, hr[2][k],
+									 fmaf(w_.y, hr[1][k], w_.x * hr[0][k]))));
+							Codec::store(q + u * OUT_PITCH + k * BPP, v_);
+						}
+						prow = pnext;
+					}
+				};
+				switch ((s_done + 1) & 3) {
+				case 0: simple(std::integral_constant<int, 0>()); break;
+				case 1: simple(std::integral_constant<int, 1>()); break;
+				case 2: simple(std::integral_constant<int, 2>()); break;
+				default: simple(std::integral_constant<int, 3>()); break;
+				}
+				s_done += CH;
+				fence_proxy_async_smem();
+				mbar_arrive(done_bar);
+				continue;
+			}
+
 			// rows of this chunk whose taps were all produced while walking the previous chunk
 #pragma unroll 1
 			while (next_last <= s_done)
@@ -355,7 +510,7 @@ __global__ void __launch_bounds__(2 * TW / P + 32) stream_kernel(const __grid_co
 #undef FIXCA_EMIT
 			// staging writes -> visible to the TMA store the producer issues after this barrier
 			fence_proxy_async_smem();
-			mbar_arrive(&done[j % NF]);
+			mbar_arrive(done_bar);
 		}
 	};
 	if (regular)

@@ -67,6 +67,17 @@ if __name__ == "__main__":
             run("24MP rgb8 linear fast", 4000, 6000, 3, torch.uint8, 1, 1, F)
             run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
             run("50MP rgb f32 cubic fast", 6144, 8192, 3, torch.float32, -4, 2, F)
+    if which == "pipe":
+        for ctas in ("1", "2"):
+            for d in ("1", "2", "3", "4", "6", "8"):
+                os.environ["FIXCA_STREAM_CTAS"] = ctas
+                os.environ["FIXCA_STREAM_DEPTH"] = d
+                for dbg in ("0", "1"):
+                    os.environ["FIXCA_STREAM_DEBUG"] = dbg
+                    try:
+                        run("cubic ctas%s D%s dbg%s" % (ctas, d, dbg), 8192, 12288, 3, torch.int16, 2, 2, F, reps=5)
+                    except fixca.FixCaError as e:
+                        print("ctas", ctas, "D", d, str(e)[:80])
     if which == "strip":
         for tw in ("256", "128"):
             os.environ["FIXCA_STRIP_TW"] = tw
