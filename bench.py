@@ -118,7 +118,7 @@ class ClockSampler:
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
                 return
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def start(self):
         if self.nv is not None:
@@ -449,8 +449,8 @@ def cpu_baseline(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=("cuda", "reference"), default="cuda")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
     ap.add_argument("--exact", action="store_true", help="FP64 bit-exact arithmetic instead of fast FP32")

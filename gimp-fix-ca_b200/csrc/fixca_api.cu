@@ -234,8 +234,8 @@ struct Plan;
 // chunks does not fit in shared memory.
 static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g, int y1, int y2, int dev, int limit, Plan &pl);
 
-static int make_plan(const Format &f, const Geometry &g, const void *d_src, size_t src_pitch, int src_row0, int src_rows,
-		     void *d_dst, size_t dst_pitch, int dst_row0, int y1, int y2, unsigned flags, int dev, Plan &pl)
+static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_src, size_t src_pitch, int src_row0, int src_rows,
+			      void *d_dst, size_t dst_pitch, int dst_row0, int y1, int y2, unsigned flags, int dev, Plan &pl)
 {
 	pl = Plan();
 	KernelArgs &a = pl.args;
@@ -460,11 +460,93 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	return true;
 }
 
+// Planning costs tens of microseconds (window scans in FP64, three tensor-map encodes), a third of
+// the kernel itself; callers that repeat a call (frame streams, benchmarks, the chunks of a band) hit
+// a small per-thread cache instead.  The key holds every input of make_plan_uncached, including the
+// tuning environment.
+struct PlanKey {
+	int kind, nch, bpp, interp, width, height, monotone;
+	int axis_center[4], axis_size[4];
+	double axis_scale[4], axis_shift[4];
+	const void *src, *dst;
+	size_t src_pitch, dst_pitch;
+	int src_row0, src_rows, dst_row0, y1, y2, dev;
+	unsigned flags;
+	unsigned env;
+};
+
+static unsigned env_signature()
+{
+	static const char *const names[] = {"FIXCA_FAST_KERNEL", "FIXCA_STRIP_TW", "FIXCA_TILE_H", "FIXCA_TILE_CTAS",
+					    "FIXCA_STREAM_CTAS", "FIXCA_STREAM_DEPTH", "FIXCA_STREAM_SEGS",
+					    "FIXCA_STREAM_DEBUG", "FIXCA_VERBOSE"};
+	unsigned h = 2166136261u;
+	for (const char *n : names) {
+		const char *v = getenv(n);
+		for (; v && *v; ++v)
+			h = (h ^ (unsigned char)*v) * 16777619u;
+		h = (h ^ 0xffu) * 16777619u;
+	}
+	return h;
+}
+
+static int make_plan(const Format &f, const Geometry &g, const void *d_src, size_t src_pitch, int src_row0, int src_rows,
+		     void *d_dst, size_t dst_pitch, int dst_row0, int y1, int y2, unsigned flags, int dev, Plan &pl)
+{
+	PlanKey k;
+	memset(&k, 0, sizeof k);
+	k.kind = f.kind; k.nch = f.nch; k.bpp = f.bpp;
+	k.interp = g.interp; k.width = g.width; k.height = g.height; k.monotone = g.monotone;
+	const Axis *ax[4] = {&g.x[0], &g.x[1], &g.y[0], &g.y[1]};
+	for (int i = 0; i < 4; ++i) {
+		k.axis_center[i] = ax[i]->center; k.axis_size[i] = ax[i]->size;
+		k.axis_scale[i] = ax[i]->scale; k.axis_shift[i] = ax[i]->shift;
+	}
+	k.src = d_src; k.dst = d_dst; k.src_pitch = src_pitch; k.dst_pitch = dst_pitch;
+	k.src_row0 = src_row0; k.src_rows = src_rows; k.dst_row0 = dst_row0; k.y1 = y1; k.y2 = y2; k.dev = dev;
+	k.flags = flags;
+	k.env = env_signature();
+	constexpr int SLOTS = 8;
+	static thread_local PlanKey keys[SLOTS];
+	static thread_local Plan plans[SLOTS];
+	static thread_local bool used[SLOTS];
+	static thread_local int next = 0;
+	for (int i = 0; i < SLOTS; ++i)
+		if (used[i] && !memcmp(&keys[i], &k, sizeof k)) {
+			pl = plans[i];
+			return FIXCA_OK;
+		}
+	const int rc = make_plan_uncached(f, g, d_src, src_pitch, src_row0, src_rows, d_dst, dst_pitch, dst_row0, y1, y2, flags, dev, pl);
+	if (rc == FIXCA_OK) {
+		keys[next] = k;
+		plans[next] = pl;
+		used[next] = true;
+		next = (next + 1) % SLOTS;
+	}
+	return rc;
+}
+
 static int launch_plan(const Plan &pl, cudaStream_t stream)
 {
 	if (pl.smem > 48 * 1024) {
-		// Opt in once per kernel function (per device context the attribute sticks).
-		CUDA_TRY(cudaFuncSetAttribute((const void *)pl.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+		// Opt in to large dynamic shared memory; the attribute sticks per function and device, so
+		// only raise it when a plan needs more than what was already granted.
+		static std::mutex mu;
+		static std::vector<std::pair<std::pair<const void *, int>, size_t>> granted;
+		int dev = 0;
+		cudaGetDevice(&dev);
+		std::lock_guard<std::mutex> lock(mu);
+		size_t *have = nullptr;
+		for (auto &e : granted)
+			if (e.first.first == (const void *)pl.k->fn && e.first.second == dev)
+				have = &e.second;
+		if (!have || *have < pl.smem) {
+			CUDA_TRY(cudaFuncSetAttribute((const void *)pl.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+			if (have)
+				*have = pl.smem;
+			else
+				granted.push_back({{(const void *)pl.k->fn, dev}, pl.smem});
+		}
 	}
 	KernelArgs a = pl.args;
 	CUtensorMap tm[3] = {pl.tm_win, pl.tm_tile, pl.tm_out};
