@@ -279,9 +279,9 @@ def run_cuda(args):
     lx, ly = (W // 2, H // 2) if lens == "centre" else lens
     p = fixca.FixCaParams(interpolation=interp, lens_x=float(lx), lens_y=float(ly), **kw)
     flags = fixca.PRECISION_EXACT if args.exact else fixca.PRECISION_FAST
-    y1, y2 = fixca.split_bands(0, H, world)[rank]
-    lo, hi = fixca.band_source_rows(W, H, p, y1, y2)
-    src_rows = hi - lo + 1
+    from fixca import bands
+    plan = bands.plan_band(W, H, p, rank, world)     # this rank's rows + the halo rows it must hold
+    y1, y2, lo, hi, src_rows = plan.y1, plan.y2, plan.src_lo, plan.src_hi, plan.src_rows
     row_bytes = W * bpp
     pitch = (row_bytes + 127) // 128 * 128
 
@@ -296,8 +296,7 @@ def run_cuda(args):
     stream = torch.cuda.current_stream()
 
     def step():
-        fixca.fix_ca_region_dev(d_src.data_ptr(), pitch, lo, src_rows, d_dst.data_ptr(), pitch, y1,
-                                W, H, bpp, bpc, p, y1, y2, flags, stream.cuda_stream)
+        bands.run_band_device(plan, d_src.data_ptr(), pitch, d_dst.data_ptr(), pitch, bpp, bpc, p, flags, stream.cuda_stream)
 
     sampler = ClockSampler(_nvml_index(local))
     for _ in range(max(3, args.warmup)):

@@ -1,0 +1,88 @@
+"""fixca.bands -- one-process-per-GPU row banding.
+
+Output row y of the correction pass depends only on (y, params, source rows near the mapped
+coordinate) -- fix-ca.c:1091-1329 -- so an image splits into contiguous full-width row bands that are
+computed independently; a band needs its own rows plus the halo rows `band_source_rows()` reports.
+There is no data-path collective.  `gather_bands()` reassembles the image on one rank when a caller
+wants that (NCCL over NVLink on GPUs, gloo in the CPU tests).
+
+Nothing here computes pixels: `BandPlan.run()` calls the CUDA library; the CPU tests pass their own
+`compute` callable (the oracle) to exercise the sharding logic without a GPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import FixCaParams, band_source_rows, bpc_of, fix_ca_region_dev, split_bands, PRECISION_EXACT
+
+
+@dataclass
+class BandPlan:
+    """What one rank of `world` holds for a height x width image."""
+
+    rank: int
+    world: int
+    width: int
+    height: int
+    y1: int           # output rows [y1, y2) this rank produces
+    y2: int
+    src_lo: int       # source rows [src_lo, src_hi] it must hold (band + halo), inclusive
+    src_hi: int
+
+    @property
+    def src_rows(self) -> int:
+        return self.src_hi - self.src_lo + 1
+
+    @property
+    def halo_rows(self) -> int:
+        return self.src_rows - (self.y2 - self.y1)
+
+
+def plan_band(width: int, height: int, params: FixCaParams, rank: int, world: int, y1: int = 0, y2: int | None = None) -> BandPlan:
+    y2 = height if y2 is None else y2
+    b1, b2 = split_bands(y1, y2, world)[rank]
+    if b1 == b2:
+        return BandPlan(rank, world, width, height, b1, b2, b1, b1 - 1)
+    lo, hi = band_source_rows(width, height, params, b1, b2)
+    return BandPlan(rank, world, width, height, b1, b2, lo, hi)
+
+
+def run_band_device(plan: BandPlan, d_src_ptr: int, src_pitch: int, d_dst_ptr: int, dst_pitch: int, bytes_per_pixel: int,
+                    bpc: int, params: FixCaParams, flags: int = PRECISION_EXACT, stream: int = 0) -> None:
+    """Launch this rank's band on its GPU: d_src holds rows [src_lo, src_hi], d_dst receives rows [y1, y2)."""
+    if plan.y1 == plan.y2:
+        return
+    fix_ca_region_dev(d_src_ptr, src_pitch, plan.src_lo, plan.src_rows, d_dst_ptr, dst_pitch, plan.y1,
+                      plan.width, plan.height, bytes_per_pixel, bpc, params, plan.y1, plan.y2, flags, stream)
+
+
+def gather_bands(band, plan: BandPlan, dst_rank: int = 0, group=None):
+    """Reassemble the image on `dst_rank` from every rank's band (a torch tensor of its rows [y1, y2)).
+
+    Bands may differ by one row in height, so each rank sends its own shape; returns the full tensor on
+    dst_rank and None elsewhere.  One message per rank: the only inter-GPU traffic of the whole pass."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    rows = torch.tensor([band.shape[0]], dtype=torch.int64, device=band.device)
+    all_rows = [torch.zeros_like(rows) for _ in range(world)]
+    dist.all_gather(all_rows, rows, group=group)
+    sizes = [int(r.item()) for r in all_rows]
+    if rank == dst_rank:
+        parts = [torch.empty((n,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device) for n in sizes]
+        reqs = []
+        for r in range(world):
+            if r == rank:
+                parts[r].copy_(band)
+            elif sizes[r]:
+                reqs.append(dist.irecv(parts[r], src=r, group=group))
+        for q in reqs:
+            q.wait()
+        return torch.cat(parts, dim=0)
+    if band.shape[0]:
+        dist.send(band.contiguous(), dst=dst_rank, group=group)
+    return None
