@@ -388,7 +388,11 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	if (wb > 2048 || k->tw * f.bpp > 2048)
 		return false;			// TMA boxes are at most 256 elements (of 8 bytes) wide
 	const int threads = 2 * k->tw / k->strip_p + 64;
-	const int want_ctas = std::max(1, env_int("FIXCA_STREAM_CTAS", 2));
+	// As many CTAs per SM as shared memory allows up to ~32 compute warps: the narrow pixel formats are
+	// instruction-bound and have small CTAs (measured: RGB8 0.086 -> 0.062 ms, RGBA16 0.155 -> 0.131 ms
+	// going from 2 to 4 CTAs per SM); the 3-channel 16-bit / float strips fit 2 per SM at depth 2.
+	const int compute_warps = 2 * k->tw / k->strip_p / 32;
+	const int want_ctas = std::max(1, env_int("FIXCA_STREAM_CTAS", std::max(2, 32 / compute_warps)));
 	const int forced_d = env_int("FIXCA_STREAM_DEPTH", 0);
 	// Deepest pipeline that still lets `want_ctas` CTAs share an SM; at least depth 1 in whatever fits.
 	size_t total = 0, off_meta = 0, off_win = 0, off_out = 0, ring_rows = 0;

@@ -71,6 +71,19 @@ if __name__ == "__main__":
             run("24MP rgb8 linear fast", 4000, 6000, 3, torch.uint8, 1, 1, F)
             run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
             run("50MP rgb f32 cubic fast", 6144, 8192, 3, torch.float32, -4, 2, F)
+    if which == "narrow":
+        for ctas in ("2", "4", "6"):
+            os.environ["FIXCA_STREAM_CTAS"] = ctas
+            run("24MP rgb8 cubic ctas" + ctas, 4000, 6000, 3, torch.uint8, 1, 2, F)
+            run("24MP rgb8 linear ctas" + ctas, 4000, 6000, 3, torch.uint8, 1, 1, F)
+            run("4K rgb8 cubic ctas" + ctas, 2160, 3840, 3, torch.uint8, 1, 2, F)
+            run("8K rgba16 cubic ctas" + ctas, 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
+            run("33MP rgba8 cubic ctas" + ctas, 4320, 7680, 4, torch.uint8, 1, 2, F)
+        os.environ["FIXCA_STREAM_DEBUG"] = "1"
+        for ctas in ("2", "4"):
+            os.environ["FIXCA_STREAM_CTAS"] = ctas
+            run("24MP rgb8 cubic NOCOMPUTE ctas" + ctas, 4000, 6000, 3, torch.uint8, 1, 2, F)
+            run("8K rgba16 cubic NOCOMPUTE ctas" + ctas, 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
     if which == "pipe":
         for ctas in ("1", "2"):
             for d in ("1", "2", "3", "4", "6", "8"):
