@@ -394,31 +394,45 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	const int compute_warps = 2 * k->tw / k->strip_p / 32;
 	const int want_ctas = std::max(1, env_int("FIXCA_STREAM_CTAS", std::max(2, 32 / compute_warps)));
 	const int forced_d = env_int("FIXCA_STREAM_DEPTH", 0);
-	// Deepest pipeline that still lets `want_ctas` CTAs share an SM; at least depth 1 in whatever fits.
 	size_t total = 0, off_meta = 0, off_win = 0, off_out = 0, ring_rows = 0;
 	int depth = 0;
-	for (int d = forced_d > 0 ? std::min(forced_d, STREAM_MAX_D) : STREAM_MAX_D; d >= 1; --d) {
+	// first / last source row each chunk touches (one scan; the map is monotone, so a chunk's extremes
+	// sit at its first and last output row)
+	const int nchunks_all = (y2 - y1 + CH - 1) / CH;
+	std::vector<int> c_lo(nchunks_all), c_hi(nchunks_all);
+	for (int j = 0; j < nchunks_all; ++j) {
+		const int y0 = y1 + j * CH, yl = std::min(y0 + CH, y2) - 1;
+		span_needed(g.y[CH_RED], g.y[CH_BLUE], g.interp, y0, yl, c_lo[j], c_hi[j]);
+	}
+	// shared memory of a CTA at pipeline depth d
+	auto layout = [&](int d) {
 		// ring capacity: the source rows d + 1 consecutive chunks can have live at once, for any chunk start
-		const int span = (d + 1) * CH;
 		int max_rows = 0;
-		for (int y0 = y1; y0 < y2; y0 += CH) {
-			const int yl = std::min(y0 + span, y2) - 1;
-			int lo, hi;
-			span_needed(g.y[CH_RED], g.y[CH_BLUE], g.interp, y0, yl, lo, hi);
-			max_rows = std::max(max_rows, hi - lo + 1);
-		}
+		for (int j = 0; j < nchunks_all; ++j)
+			max_rows = std::max(max_rows, c_hi[std::min(j + d, nchunks_all - 1)] - c_lo[j] + 1);
 		ring_rows = align_up((size_t)max_rows, 4) + 8;	// whole 4-row groups at both ends
 		off_meta = align_up(sizeof(StreamHeader), 16);
 		off_win = align_up(off_meta + (size_t)(d + 1) * sizeof(StreamMeta), 128);
 		off_out = align_up(off_win + ring_rows * (size_t)wb, 128);
 		total = off_out + (size_t)STREAM_NSTG * CH * k->tw * f.bpp;
-		const size_t budget = (d == 1 || forced_d > 0) ? (size_t)limit : std::min<size_t>(limit, (227 * 1024) / want_ctas - 1024);
-		if (total <= budget) {
-			depth = d;
-			break;
+	};
+	if (forced_d > 0) {
+		layout(std::min(forced_d, STREAM_MAX_D));
+		if (total <= (size_t)limit)
+			depth = std::min(forced_d, STREAM_MAX_D);
+	} else {
+		// Most CTAs per SM that still leave a pipeline depth of 2 (the HBM latency needs ~2 chunks in
+		// flight per CTA); then the deepest pipeline that fits beside them.
+		for (int want = want_ctas; want >= 1 && !depth; --want) {
+			const size_t budget = std::min<size_t>(limit, (227 * 1024) / want - 1024);
+			for (int d = STREAM_MAX_D; d >= (want > 1 ? 2 : 1); --d) {
+				layout(d);
+				if (total <= budget) {
+					depth = d;
+					break;
+				}
+			}
 		}
-		if (forced_d > 0)
-			break;
 	}
 	if (!depth)
 		return false;
@@ -731,9 +745,12 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 	if ((rc = cx.reserve_dev(cx.d_src, cx.d_src_cap, pitch * src_rows))) return rc;
 	if ((rc = cx.reserve_dev(cx.d_dst, cx.d_dst_cap, pitch * (size_t)(y2 - y1)))) return rc;
 
-	// Chunking: ~32 MB of rows per chunk, at least 64 rows, at most 64 chunks.
-	int chunk_rows = (int)std::max<size_t>(64, (32u << 20) / std::max<size_t>(row_bytes, 1));
-	chunk_rows = std::max(chunk_rows, (y2 - y1 + 63) / 64);
+	// Chunking: ~32 MB of rows per chunk (FIXCA_CHUNK_MB), at least 64 rows, a multiple of 8 rows (the
+	// streaming kernel's chunk height, so every launch of the band shares one chunk grid), at most 256 chunks.
+	const size_t chunk_bytes = (size_t)std::max(1, env_int("FIXCA_CHUNK_MB", 32)) << 20;
+	int chunk_rows = (int)std::max<size_t>(64, chunk_bytes / std::max<size_t>(row_bytes, 1));
+	chunk_rows = std::max(chunk_rows, (y2 - y1 + 255) / 256);
+	chunk_rows = (chunk_rows + 7) & ~7;
 	chunk_rows = std::min(chunk_rows, y2 - y1);
 	const int nchunks = (y2 - y1 + chunk_rows - 1) / chunk_rows;
 

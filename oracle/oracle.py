@@ -54,7 +54,8 @@ class Params:
 def build(force: bool = False) -> None:
     """Run oracle/Makefile (restatement always; _ref only where the reference is mounted)."""
     if force or not os.path.exists(RESTATEMENT_SO) or (
-            os.path.exists("/root/reference/fix-ca.c") and not os.path.exists(REFERENCE_SO)):
+            os.path.exists("/root/reference/fix-ca.c") and not (os.path.exists(REFERENCE_SO) and os.path.exists(
+                os.path.join(HERE, "_ref", "libfixca_plugin_cuda.so")))):
         subprocess.run(["make", "-C", HERE, "-s"], check=True,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
@@ -190,6 +191,31 @@ class Reference:
         a, b = ctypes.c_double(lx), ctypes.c_double(ly)
         self.lib.ref_dialog_lens(w, h, ctypes.byref(a), ctypes.byref(b))
         return a.value, b.value
+
+
+PLUGIN_CUDA_SO = os.path.join(HERE, "_ref", "libfixca_plugin_cuda.so")
+
+
+class PatchedPlugin(Reference):
+    """The reference plug-in with INTEGRATION.md's patch applied (oracle/patch_plugin.py): the same
+    run() / fix_ca() code, behind the same fake GIMP, but its final-render call goes through
+    fixca_cuda_region() when a GPU is present.  Used to prove the drop-in at the real call site."""
+
+    kind = "reference+cuda"
+
+    @staticmethod
+    def available() -> bool:
+        build()
+        return os.path.exists(PLUGIN_CUDA_SO)
+
+    def __init__(self):
+        build()
+        so = REFERENCE_SO
+        try:
+            globals()["REFERENCE_SO"] = PLUGIN_CUDA_SO
+            Reference.__init__(self)
+        finally:
+            globals()["REFERENCE_SO"] = so
 
 
 def best_checker():

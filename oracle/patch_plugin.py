@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""oracle/patch_plugin.py -- TEST INFRASTRUCTURE ONLY.
+
+Applies the INTEGRATION.md patch to a scratch copy of the reference plug-in source so that the
+reference's own run() / fix_ca() can be driven (behind the fake GIMP of ref_harness.c) with its row
+loop replaced by fixca_cuda_region().  The reference source is read where it lies and the patched
+text is written to the path given (a temporary file: it is compiled into
+oracle/_ref/libfixca_plugin_cuda.so and deleted; no reference source enters this repository).
+
+    python oracle/patch_plugin.py /root/reference/fix-ca.c /tmp/fix-ca-cuda.c
+"""
+import re
+import sys
+
+INCLUDE_BLOCK = r'''
+#ifdef HAVE_FIXCA_CUDA
+#include <fixca_cuda.h>	/* B200 correction pass; FixCaParams is layout-identical to fixca_params */
+static void fixca_progress (int kind, double fraction, void *user)
+{
+	(void) user;
+	if (kind == 0)
+		gimp_progress_init (_("Shifting pixel components..."));
+	else
+		gimp_progress_update (fraction);
+}
+#endif
+'''
+
+CALL_BLOCK = r'''
+#ifdef HAVE_FIXCA_CUDA
+	fixca_cuda_set_progress (fixca_progress, NULL);
+	if (x == 0 && width == xImg && fixca_cuda_device_count () > 0) {
+		if (fixca_cuda_region (srcImg, destImg, xImg, yImg, bppImg, bpcImg,
+				       (const fixca_params *) params,
+				       x, x + width, y, y + height, TRUE) != 0) {
+			g_message ("%s", fixca_cuda_last_error ());
+			g_free (destImg);
+			g_free (srcImg);
+			g_object_unref (destBuf);
+			g_object_unref (srcBuf);
+			return -1;
+		}
+	} else
+#endif
+'''
+
+
+def patch(text: str) -> str:
+    # (1) the binding, in front of fix_ca() (fix-ca.c:332), i.e. after the gettext macros it uses
+    m = re.search(r'\nstatic int fix_ca \(gint32 drawable_ID', text)
+    if not m:
+        raise SystemExit("patch_plugin: fix_ca() not found")
+    text = text[:m.start()] + "\n" + INCLUDE_BLOCK + text[m.start():]
+    # (2) the final-render call in fix_ca() (fix-ca.c:373-374): the one call that passes TRUE
+    calls = list(re.finditer(r'\n([ \t]*)fix_ca_region \(srcImg, destImg,[^;]*?TRUE\);', text, re.S))
+    if len(calls) != 1:
+        raise SystemExit("patch_plugin: expected exactly one final-render call, found %d" % len(calls))
+    c = calls[0]
+    text = text[:c.start()] + "\n" + CALL_BLOCK.strip("\n") + text[c.start():]
+    return text
+
+
+if __name__ == "__main__":
+    src, dst = sys.argv[1], sys.argv[2]
+    with open(src) as f:
+        out = patch(f.read())
+    with open(dst, "w") as f:
+        f.write(out)

@@ -1,0 +1,80 @@
+"""The drop-in at the real call site: the reference plug-in's own run() -> fix_ca(), behind the fake
+GIMP backend of oracle/ref_harness.c, with INTEGRATION.md's patch applied (oracle/patch_plugin.py) so
+that fix-ca.c:373-374 calls fixca_cuda_region().  Compared with the unpatched plug-in on the same
+drawable and PDB arguments: pixels, PDB status, progress protocol and messages must be identical.
+
+CPU part: the patched plug-in builds, loads and (no GPU) keeps its own row loop.
+GPU part (-m gpu): the same calls, now served by the CUDA library (its launch counter moves)."""
+import numpy as np
+import pytest
+
+import oracle as orc
+
+NONINTERACTIVE, INTERACTIVE, WITH_LAST_VALS = 1, 0, 2
+PDB_SUCCESS, PDB_CALLING_ERROR = 3, 1
+
+DRAWABLES = [
+    # shape, dtype, babl format name
+    ((120, 200, 3), "u1", "R'G'B' u8"),
+    ((97, 131, 4), "u2", "R'G'B'A u16"),
+    ((64, 160, 3), "f4", "RGB float"),
+    ((33, 48, 4), "u4", "R'G'B'A u32"),
+    ((40, 56, 3), "f8", "RGB double"),
+]
+
+CALLS = [
+    dict(run_mode=NONINTERACTIVE, nparams=12, blue=6.0, red=-2.4, lens_x=658.0, lens_y=1280.0, interpolation=1),
+    dict(run_mode=NONINTERACTIVE, nparams=12, blue=3.0, red=-2.0, lens_x=50.0, lens_y=30.0, interpolation=2,
+         x_blue=0.7, x_red=-0.4, y_blue=0.3, y_red=-0.9),
+    dict(run_mode=NONINTERACTIVE, nparams=12, blue=-4.0, red=5.0, interpolation=0, x_blue=2.0, y_red=-3.0),
+    dict(run_mode=NONINTERACTIVE, nparams=5, blue=2.0, red=-1.0),                 # missing args take defaults
+    dict(run_mode=NONINTERACTIVE, nparams=12, blue=31.0, red=0.0, interpolation=1),   # out of range -> calling error
+    dict(run_mode=INTERACTIVE, nparams=3, dialog_ok=True),                          # dialog path, lens reset
+]
+
+
+@pytest.fixture(scope="module")
+def plugins():
+    if not orc.Reference.available() or not orc.PatchedPlugin.available():
+        pytest.skip("oracle/_ref plug-in builds missing (they need /root/reference at build time)")
+    return orc.Reference(), orc.PatchedPlugin()
+
+
+def _drive(plugin, pixels, fmt, call):
+    px = pixels.copy()
+    kw = {k: v for k, v in call.items()}
+    status = plugin.run(px, fmt, kw.pop("run_mode"), kw.pop("nparams"), **kw)
+    # the fake backend zeroes its counters when the drawable is installed (start of run())
+    return px, status, [plugin.counter(i) for i in range(5)], plugin.last_message()
+
+
+def _compare(plugins, expect_gpu):
+    import fixca
+
+    ref, patched = plugins
+    n = 0
+    for (shape, dt, fmt), call in [(d, c) for d in DRAWABLES for c in CALLS]:
+        n += 1
+        img = orc.synth_image(shape[0], shape[1], shape[2], dt, seed=7000 + n)
+        want_px, want_status, want_counts, _ = _drive(ref, img, fmt, call)
+        launches = fixca.launch_count()
+        got_px, got_status, got_counts, msg = _drive(patched, img, fmt, call)
+        assert got_status == want_status, (fmt, call, msg)
+        assert got_px.tobytes() == want_px.tobytes(), (fmt, call)
+        assert got_counts == want_counts, (fmt, call, got_counts, want_counts)    # progress init/update, messages, merge, flush
+        if expect_gpu and want_status == PDB_SUCCESS:
+            assert fixca.launch_count() > launches, "the patched plug-in did not reach the CUDA library"
+        if not expect_gpu:
+            assert fixca.launch_count() == launches
+
+
+def test_patched_plugin_without_gpu_keeps_its_cpu_loop(plugins, fx):
+    if fx.device_count() > 0:
+        pytest.skip("a GPU is present; covered by the gpu test")
+    _compare(plugins, expect_gpu=False)
+
+
+@pytest.mark.gpu
+def test_patched_plugin_runs_on_the_gpu_bit_identically(plugins, fx):
+    assert fx.device_count() > 0
+    _compare(plugins, expect_gpu=True)
