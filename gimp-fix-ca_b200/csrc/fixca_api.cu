@@ -633,9 +633,18 @@ extern "C" int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int sr
 		return fail(FIXCA_ERR_ARG, "dst_row0 %d is past the first output row %d", dst_row0, y1);
 	int dev;
 	if ((rc = current_device_or(-1, dev))) return rc;
+	if ((flags & FIXCA_PREVIEW_OVERLAY) && f.kind == SK_U64 && params->saturation != 0.0)
+		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples: the preview's saturation boost needs 80-bit long double arithmetic (fix-ca.c:728-733)");
 	Plan pl;
 	if ((rc = make_plan(f, g, d_src, src_pitch, src_row0, src_rows, d_dst, dst_pitch, dst_row0, y1, y2, flags, dev, pl))) return rc;
-	return launch_plan(pl, (cudaStream_t)stream);
+	if ((rc = launch_plan(pl, (cudaStream_t)stream))) return rc;
+	if (flags & FIXCA_PREVIEW_OVERLAY) {
+		// fix-ca.c:1322-1327: saturate (iff saturation != 0) and centerline on every finished row
+		CUDA_TRY(launch_preview(f.kind, f.nch, (unsigned char *)d_dst, (long long)dst_pitch, dst_row0, y1, y2, width,
+					(int)params->lens_x, (int)params->lens_y, params->saturation, (cudaStream_t)stream));
+		g_launches.fetch_add(1);
+	}
+	return FIXCA_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -831,6 +840,11 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 		Plan pl;
 		if ((rc = make_plan(f, g, cx.d_src, pitch, band_lo, src_rows, cx.d_dst, pitch, y1, c1, c2, flags, dev, pl))) return rc;
 		if ((rc = launch_plan(pl, cx.s_run))) return rc;
+		if (flags & FIXCA_PREVIEW_OVERLAY) {
+			CUDA_TRY(launch_preview(f.kind, f.nch, cx.d_dst, (long long)pitch, y1, c1, c2, width,
+						(int)params->lens_x, (int)params->lens_y, params->saturation, cx.s_run));
+			g_launches.fetch_add(1);
+		}
 		CUDA_TRY(cudaEventRecord(e_run, cx.s_run));
 		CUDA_TRY(cudaStreamWaitEvent(cx.s_down, e_run, 0));
 		unsigned char *to = dst_pinned ? dst + (size_t)c1 * row_bytes : cx.h_out + (size_t)(i % ring) * out_slot;
@@ -844,7 +858,6 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 	if (progress && g_progress)
 		g_progress(1, 0.0, g_progress_user);
 	(void)height;
-	(void)params;
 	return FIXCA_OK;
 }
 
@@ -873,6 +886,10 @@ extern "C" int fixca_cuda_region_ex(const unsigned char *src, unsigned char *dst
 	if ((rc = current_device_or(device, dev))) return rc;
 	if (y1 == y2)
 		return FIXCA_OK;
+	if (!show_progress)	// the preview call (fix-ca.c:656-657): saturation boost + centre lines on top
+		flags |= FIXCA_PREVIEW_OVERLAY;
+	if ((flags & FIXCA_PREVIEW_OVERLAY) && f.kind == SK_U64 && params->saturation != 0.0)
+		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples: the preview's saturation boost needs 80-bit long double arithmetic (fix-ca.c:728-733)");
 	int prev = -1;
 	cudaGetDevice(&prev);
 	rc = region_host_band(dev, src, dst, width, height, f, params, g, y1, y2, flags, show_progress != 0);

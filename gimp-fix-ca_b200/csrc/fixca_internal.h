@@ -36,4 +36,8 @@ const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled)
 // variant: 0 direct, 1 first-round tiled, 2 strip, 3 stream
 const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int variant);
 
+// kernels_preview.cu: saturate() + centerline() on destination rows [y1, y2) (fix-ca.c:1322-1327)
+cudaError_t launch_preview(int kind, int nch, unsigned char *dst, long long pitch, int dst_row0, int y1, int y2, int width,
+			   int xc, int yc, double saturation, cudaStream_t st);
+
 } // namespace fixca

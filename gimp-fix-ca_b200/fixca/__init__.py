@@ -26,6 +26,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfixca_cuda.so")
 INTERP_NONE, INTERP_LINEAR, INTERP_CUBIC = 0, 1, 2
 PRECISION_EXACT, PRECISION_FAST = 0x0, 0x1
 FORCE_DIRECT, FORCE_TILED = 0x10, 0x20
+PREVIEW_OVERLAY = 0x40      # saturate() + centerline() on the rows written (the show_progress=False call)
 INPUT_MAX = 30.0
 
 OK = 0

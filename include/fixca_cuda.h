@@ -98,6 +98,11 @@ typedef struct fixca_params {
 /* Kernel selection, for tests and profiling (default: tiled when it fits). */
 #define FIXCA_FORCE_DIRECT     0x10u	/* per-pixel global-memory gather kernel */
 #define FIXCA_FORCE_TILED      0x20u	/* fail instead of falling back to direct */
+/* The preview epilogue of fix_ca_region(..., show_progress = FALSE) (fix-ca.c:1322-1327): after the
+ * correction, saturate() (iff params->saturation != 0, fix-ca.c:922-943) and centerline() (the dashed
+ * lens cross and diagonals, fix-ca.c:945-996) are applied to every row written.  Set automatically by
+ * fixca_cuda_region*() when show_progress == 0; pass it to fixca_cuda_region_dev() to get the same. */
+#define FIXCA_PREVIEW_OVERLAY  0x40u
 
 /* ------------------------------------------------------------------------- */
 /* The pass, host buffers: replaces fix_ca_region()                           */
@@ -114,9 +119,11 @@ typedef struct fixca_params {
  *
  * show_progress != 0 issues the reference's progress sequence through the
  * callback installed with fixca_cuda_set_progress().  show_progress == 0 is
- * the preview call: the reference then also draws its saturation boost and
- * centre-line overlay (fix-ca.c:1322-1327); those are NOT applied here (they
- * never reach the final image) -- the corrected rows are returned as is.
+ * the dialog's preview call (fix-ca.c:656-657): as in the reference, the
+ * saturation boost (params->saturation) and the centre-line overlay are then
+ * drawn into the rows written (FIXCA_PREVIEW_OVERLAY) and no progress is
+ * reported.  The HSV conversion behind the saturation boost is libgimpcolor's,
+ * restated (it is not part of the reference tree).
  */
 FIXCA_API int fixca_cuda_region(const unsigned char *src, unsigned char *dst,
 				int width, int height, int bytes, int bpc,

@@ -326,3 +326,148 @@ EXPORT void fixca_oracle_resolve_lens (int width, int height, double *lens_x, do
 	if (*lens_x <= 0 || *lens_x >= width) *lens_x = round (width / 2);
 	if (*lens_y <= 0 || *lens_y >= height) *lens_y = round (height / 2);
 }
+
+/* ------------------------------------------------------------------------- */
+/* Preview epilogue: what fix_ca_region() does to a finished row when it is   */
+/* called with show_progress == FALSE (fix-ca.c:1322-1327)                    */
+/* ------------------------------------------------------------------------- */
+
+/* set_pixel() WITHOUT clip_d (fix-ca.c:748-774): saturate() and centerline() call it directly */
+static void put_sample (unsigned char *p, double d, int bpc)
+{
+	switch (bpc) {
+	case 1: *p = round (d * 255); break;
+	case 2: { uint16_t v = round (d * 65535); memcpy (p, &v, 2); break; }
+	case 4: { uint32_t v = round (d * 4294967295); memcpy (p, &v, 4); break; }
+	case 8: { uint64_t v = roundl (d * 18446744073709551615UL); memcpy (p, &v, 8); break; }
+	case -8: memcpy (p, &d, 8); break;
+	case -4: { float v = (float) d; memcpy (p, &v, 4); break; }
+	default: break;
+	}
+}
+
+/* gimp_rgb_to_hsv / gimp_hsv_to_rgb of libgimpcolor 2.10 (gimpcolorspace.c) -- a dependency that is
+ * NOT in the reference tree: restated from the published algorithm, PARITY UNPINNED for this pair. */
+static void rgb_to_hsv (double r, double g, double b, double *h, double *s, double *v)
+{
+	double max = r > g ? (r > b ? r : b) : (g > b ? g : b);
+	double min = r < g ? (r < b ? r : b) : (g < b ? g : b);
+	double delta = max - min;
+	*v = max;
+	if (delta > 0.0001) {
+		*s = delta / max;
+		if (r == max) {
+			*h = (g - b) / delta;
+			if (*h < 0.0)
+				*h += 6.0;
+		} else if (g == max) {
+			*h = 2.0 + (b - r) / delta;
+		} else {
+			*h = 4.0 + (r - g) / delta;
+		}
+		*h /= 6.0;
+	} else {
+		*s = 0.0;
+		*h = 0.0;
+	}
+}
+
+static void hsv_to_rgb (double h, double s, double v, double *r, double *g, double *b)
+{
+	if (s == 0.0) {
+		*r = *g = *b = v;
+	} else {
+		double hue = h, f, w, q, t;
+		int i;
+		if (hue == 1.0)
+			hue = 0.0;
+		hue *= 6.0;
+		i = (int) hue;
+		f = hue - i;
+		w = v * (1.0 - s);
+		q = v * (1.0 - (s * f));
+		t = v * (1.0 - (s * (1.0 - f)));
+		switch (i) {
+		case 0: *r = v; *g = t; *b = w; break;
+		case 1: *r = q; *g = v; *b = w; break;
+		case 2: *r = w; *g = v; *b = t; break;
+		case 3: *r = w; *g = q; *b = v; break;
+		case 4: *r = t; *g = w; *b = v; break;
+		case 5: *r = v; *g = w; *b = q; break;
+		default: break;	/* out-of-range hue: the reference leaves rgb untouched */
+		}
+	}
+}
+
+/* saturate(), fix-ca.c:922-943, on one row */
+static void saturate_row (unsigned char *row, int width, int bytes, int bpc, double s_scale)
+{
+	int b = bpc < 0 ? -bpc : bpc, x;
+	for (x = 0; x < width; ++x) {
+		unsigned char *px = row + (size_t) x * bytes;
+		double r = decode (px, bpc), g = decode (px + b, bpc), bl = decode (px + 2 * b, bpc);
+		double h, s, v;
+		rgb_to_hsv (r, g, bl, &h, &s, &v);
+		s *= s_scale;
+		if (s > 1.0)
+			s = 1.0;
+		hsv_to_rgb (h, s, v, &r, &g, &bl);
+		put_sample (px, r, bpc);
+		put_sample (px + b, g, bpc);
+		put_sample (px + 2 * b, bl, bpc);
+	}
+}
+
+static void put_rgb (unsigned char *px, double c, int b, int bpc)
+{
+	put_sample (px, c, bpc);
+	put_sample (px + b, c, bpc);
+	put_sample (px + 2 * b, c, bpc);
+}
+
+/* centerline(), fix-ca.c:945-996, on row y (x1 == 0): dashed horizontal line through the lens row,
+ * dashed vertical line and the two diagonals elsewhere */
+static void centerline_row (unsigned char *row, int width, int bytes, int bpc, int y, int xc, int yc)
+{
+	int b = bpc < 0 ? -bpc : bpc, i, x;
+	double c = 1.0;
+	if (y == yc) {
+		i = (xc < 0 ? -xc : xc) % 16;
+		if (i < 8) c = 0.0;
+		for (x = 0; x < width; ++x) {
+			put_rgb (row + (size_t) x * bytes, c, b, bpc);
+			if (i-- < 0) {
+				i = 7;
+				c = c > 0 ? 0.0 : 1.0;
+			}
+		}
+		return;
+	}
+	y = y <= yc ? yc - y : y - yc;
+	i = (y < 0 ? -y : y) % 16;
+	if (i < 8) c = 0.0;
+	if (xc >= 0 && xc < width)
+		put_rgb (row + (size_t) xc * bytes, c, b, bpc);
+	x = xc - y;
+	if (x >= 0 && x < width)
+		put_rgb (row + (size_t) x * bytes, c, b, bpc);
+	x = xc + y;
+	if (x >= 0 && x < width)
+		put_rgb (row + (size_t) x * bytes, c, b, bpc);
+}
+
+/* fix_ca_region (..., show_progress = FALSE): the pass, then per row saturate (iff saturation != 0)
+ * and centerline (fix-ca.c:1322-1327). */
+EXPORT int fixca_oracle_region_preview (const unsigned char *src, unsigned char *dst, int width, int height,
+					int bytes, int bpc, const double *p, int y1, int y2)
+{
+	int y, rc = fixca_oracle_region (src, dst, width, height, bytes, bpc, p, 0, width, y1, y2);
+	if (rc) return rc;
+	for (y = y1; y < y2; ++y) {
+		unsigned char *row = dst + (size_t) y * width * bytes;
+		if (p[P_SAT] != 0.0)
+			saturate_row (row, width, bytes, bpc, 1 + p[P_SAT] / 100);
+		centerline_row (row, width, bytes, bpc, y, (int) p[P_LENS_X], (int) p[P_LENS_Y]);
+	}
+	return 0;
+}

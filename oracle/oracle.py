@@ -79,19 +79,25 @@ class Restatement:
         self.lib.fixca_oracle_region.restype = _c_int
         self.lib.fixca_oracle_region_mt.argtypes = [_c_vp, _c_vp] + [_c_int] * 4 + [_c_dp] + [_c_int] * 3
         self.lib.fixca_oracle_region_mt.restype = _c_int
+        self.lib.fixca_oracle_region_preview.argtypes = [_c_vp, _c_vp] + [_c_int] * 4 + [_c_dp] + [_c_int] * 2
+        self.lib.fixca_oracle_region_preview.restype = _c_int
         self.lib.fixca_oracle_axis.argtypes = [_c_int, _c_int, _c_dp, _c_int, _c_int, _c_vp, _c_vp]
         self.lib.fixca_oracle_axis.restype = _c_int
         self.lib.fixca_oracle_resolve_lens.argtypes = [_c_int, _c_int, _c_dp, _c_dp]
 
     kind = "port"
 
-    def region(self, src: np.ndarray, p: Params, y1=None, y2=None, dst=None, threads: int = 1):
+    def region(self, src: np.ndarray, p: Params, y1=None, y2=None, dst=None, threads: int = 1, preview: bool = False):
+        """preview=True is the call with show_progress == FALSE: saturation boost + centre lines on top."""
         h, w, bytes_, bpc = _img_args(src)
         y1 = 0 if y1 is None else y1
         y2 = h if y2 is None else y2
         if dst is None:
             dst = np.zeros_like(src)
-        if threads > 1:
+        if preview:
+            rc = self.lib.fixca_oracle_region_preview(src.ctypes.data, dst.ctypes.data, w, h, bytes_, bpc,
+                                                      p.as_array(), y1, y2)
+        elif threads > 1:
             rc = self.lib.fixca_oracle_region_mt(src.ctypes.data, dst.ctypes.data, w, h, bytes_, bpc,
                                                  p.as_array(), y1, y2, threads)
         else:
@@ -149,19 +155,21 @@ class Reference:
         L.ref_run.argtypes = [ctypes.c_char_p, _c_int, _c_int, _c_dp, _c_int]
         L.ref_run.restype = _c_int
         L.ref_dialog_lens.argtypes = [_c_int, _c_int, _c_dp, _c_dp]
+        L.ref_preview_update.argtypes = [_c_int] * 4 + [_c_dp, _c_vp]
+        L.ref_preview_update.restype = _c_int
 
-    def region(self, src: np.ndarray, p: Params, y1=None, y2=None, dst=None, threads: int = 1):
+    def region(self, src: np.ndarray, p: Params, y1=None, y2=None, dst=None, threads: int = 1, preview: bool = False):
         h, w, bytes_, bpc = _img_args(src)
         y1 = 0 if y1 is None else y1
         y2 = h if y2 is None else y2
         if dst is None:
             dst = np.zeros_like(src)
-        if threads > 1:
+        if threads > 1 and not preview:
             self.lib.ref_fix_ca_region_mt(src.ctypes.data, dst.ctypes.data, w, h, bytes_, bpc,
                                           p.as_array(), y1, y2, threads)
         else:
             self.lib.ref_fix_ca_region(src.ctypes.data, dst.ctypes.data, w, h, bytes_, bpc,
-                                       p.as_array(), 0, w, y1, y2, 1)
+                                       p.as_array(), 0, w, y1, y2, 0 if preview else 1)
         return dst
 
     def color_size(self, name: str, bpp: int) -> int:
@@ -180,6 +188,16 @@ class Reference:
         self.lib.ref_fake_set_dialog_response(1 if dialog_ok else 0)
         f = (ctypes.c_double * 8)(blue, red, lens_x, lens_y, x_blue, x_red, y_blue, y_red)
         return self.lib.ref_run(proc_name.encode(), run_mode, nparams, f, interpolation)
+
+    def preview_update(self, pixels: np.ndarray, fmt: str, x: int, y: int, w: int, h: int, p: Params):
+        """The dialog's preview refresh (fix-ca.c:617-679) of window (x, y, w, h): returns the 8-bit buffer
+        the plug-in draws, shape (h, w, channels)."""
+        hh, ww, ch = pixels.shape
+        self.lib.ref_fake_set_drawable(ww, hh, ch * pixels.dtype.itemsize, fmt.encode(), pixels.ctypes.data)
+        out = np.zeros((h, w, ch), dtype=np.uint8)
+        stride = self.lib.ref_preview_update(x, y, w, h, p.as_array(), out.ctypes.data)
+        assert stride == w * ch, (stride, w, ch)
+        return out
 
     def last_message(self) -> str:
         return self.lib.ref_fake_last_message().decode()

@@ -45,6 +45,18 @@ CALL_BLOCK = r'''
 '''
 
 
+PREVIEW_BLOCK = r'''
+#ifdef HAVE_FIXCA_CUDA
+	/* show_progress = FALSE: the library draws the saturation boost and the centre lines as well */
+	if (fixca_cuda_device_count () > 0 &&
+	    fixca_cuda_region (srcImg, destImg, xImg, yImg, bppImg, bpcImg, (const fixca_params *) params,
+			       0, xImg, y, y + height, FALSE) == 0)
+		;
+	else
+#endif
+'''
+
+
 def patch(text: str) -> str:
     # (1) the binding, in front of fix_ca() (fix-ca.c:332), i.e. after the gettext macros it uses
     m = re.search(r'\nstatic int fix_ca \(gint32 drawable_ID', text)
@@ -57,6 +69,12 @@ def patch(text: str) -> str:
         raise SystemExit("patch_plugin: expected exactly one final-render call, found %d" % len(calls))
     c = calls[0]
     text = text[:c.start()] + "\n" + CALL_BLOCK.strip("\n") + text[c.start():]
+    # (3) the preview call in preview_update() (fix-ca.c:656-657): the one call that passes FALSE
+    calls = list(re.finditer(r'\n([ \t]*)fix_ca_region \(srcImg, destImg,[^;]*?FALSE\);', text, re.S))
+    if len(calls) != 1:
+        raise SystemExit("patch_plugin: expected exactly one preview call, found %d" % len(calls))
+    c = calls[0]
+    text = text[:c.start()] + "\n" + PREVIEW_BLOCK.strip("\n") + text[c.start():]
     return text
 
 

@@ -181,10 +181,65 @@ gboolean gimp_progress_init (const gchar *msg) { (void) msg; G.n_progress_init++
 gboolean gimp_progress_update (gdouble f) { G.n_progress_update++; G.last_progress = f; return TRUE; }
 void gimp_message (const gchar *msg) { g_message ("%s", msg); }
 
-/* libgimpcolor is not part of the reference tree; only the preview-only
- * saturate() (fix-ca.c:922-943) reaches these.  Out of scope: trap loudly. */
-void gimp_rgb_to_hsv (const GimpRGB *rgb, GimpHSV *hsv) { (void) rgb; (void) hsv; abort (); }
-void gimp_hsv_to_rgb (const GimpHSV *hsv, GimpRGB *rgb) { (void) hsv; (void) rgb; abort (); }
+/* libgimpcolor (GIMP 2.10, libgimpcolor/gimpcolorspace.c) is a dependency that is NOT part of the
+ * reference tree; only the preview-only saturate() (fix-ca.c:922-943) reaches these two.  They are
+ * RESTATED here from the published GIMP 2.10 algorithm -- PARITY UNPINNED for this pair: nothing in
+ * the reference's tests or fixtures exercises them.  Everything around them (get_pixel, the s *= scale
+ * clamp, set_pixel, centerline) is the reference's own compiled code. */
+void gimp_rgb_to_hsv (const GimpRGB *rgb, GimpHSV *hsv)
+{
+	gdouble max, min, delta;
+	max = rgb->r > rgb->g ? (rgb->r > rgb->b ? rgb->r : rgb->b) : (rgb->g > rgb->b ? rgb->g : rgb->b);
+	min = rgb->r < rgb->g ? (rgb->r < rgb->b ? rgb->r : rgb->b) : (rgb->g < rgb->b ? rgb->g : rgb->b);
+	hsv->v = max;
+	delta = max - min;
+	if (delta > 0.0001) {
+		hsv->s = delta / max;
+		if (rgb->r == max) {
+			hsv->h = (rgb->g - rgb->b) / delta;
+			if (hsv->h < 0.0)
+				hsv->h += 6.0;
+		} else if (rgb->g == max) {
+			hsv->h = 2.0 + (rgb->b - rgb->r) / delta;
+		} else {
+			hsv->h = 4.0 + (rgb->r - rgb->g) / delta;
+		}
+		hsv->h /= 6.0;
+	} else {
+		hsv->s = 0.0;
+		hsv->h = 0.0;
+	}
+	hsv->a = rgb->a;
+}
+void gimp_hsv_to_rgb (const GimpHSV *hsv, GimpRGB *rgb)
+{
+	gint    i;
+	gdouble f, w, q, t, hue;
+	if (hsv->s == 0.0) {
+		rgb->r = hsv->v;
+		rgb->g = hsv->v;
+		rgb->b = hsv->v;
+	} else {
+		hue = hsv->h;
+		if (hue == 1.0)
+			hue = 0.0;
+		hue *= 6.0;
+		i = (gint) hue;
+		f = hue - i;
+		w = hsv->v * (1.0 - hsv->s);
+		q = hsv->v * (1.0 - (hsv->s * f));
+		t = hsv->v * (1.0 - (hsv->s * (1.0 - f)));
+		switch (i) {
+		case 0: rgb->r = hsv->v; rgb->g = t;      rgb->b = w;      break;
+		case 1: rgb->r = q;      rgb->g = hsv->v; rgb->b = w;      break;
+		case 2: rgb->r = w;      rgb->g = hsv->v; rgb->b = t;      break;
+		case 3: rgb->r = w;      rgb->g = q;      rgb->b = hsv->v; break;
+		case 4: rgb->r = t;      rgb->g = w;      rgb->b = hsv->v; break;
+		case 5: rgb->r = hsv->v; rgb->g = w;      rgb->b = q;      break;
+		}
+	}
+	rgb->a = hsv->a;
+}
 
 /* ---- inert GTK ---- */
 static GtkWidget the_widget = { &the_widget };
@@ -364,6 +419,21 @@ EXPORT void ref_dialog_lens (int width, int height, double *lens_x, double *lens
 }
 
 EXPORT void ref_query (void) { query (); }
+
+/* The dialog's preview refresh, preview_update() (fix-ca.c:617-679), on the drawable installed with
+ * ref_fake_set_drawable(): the visible window is (x, y, w, h); `out` receives the 8-bit buffer the
+ * reference hands to gimp_preview_draw_buffer() (w * h * bpp / |bpc| bytes); returns its row stride. */
+EXPORT int ref_preview_update (int x, int y, int w, int h, const double *p, unsigned char *out)
+{
+	FixCaParams fp;
+	fill_params (&fp, p);
+	G.preview_x = x; G.preview_y = y; G.preview_w = w; G.preview_h = h;
+	G.preview_out = out;
+	G.preview_rowstride = 0;
+	preview_update (&the_widget, &fp);
+	G.preview_out = NULL;
+	return G.preview_rowstride;
+}
 
 /* The reference's function on `nthreads` disjoint full-width row bands, one
  * thread per band: legal because fix_ca_region() only uses locals and g_new

@@ -72,8 +72,30 @@ def cases():
                    lens_x=float(lx), lens_y=float(ly), **pk)
 
 
+PREVIEW_SHAPES = [(1, 1), (7, 40), (64, 64), (90, 131), (150, 203)]
+PREVIEW_FORMATS = [("u1", 3), ("u1", 4), ("u2", 3), ("u2", 4), ("u4", 3), ("f4", 3), ("f4", 4), ("f8", 3)]
+PREVIEW_SATURATION = (0.0, 35.0, -50.0, 100.0, -100.0)
+
+
+def preview_cases():
+    """The show_progress = FALSE call (fix-ca.c:656-657, :1322-1327): correction + saturate + centerline."""
+    n = 0
+    for (h, w), (dt, ch), sat, (lname, lens), interp in itertools.product(
+            PREVIEW_SHAPES, PREVIEW_FORMATS, PREVIEW_SATURATION, LENSES.items(), (0, 1, 2)):
+        n += 1
+        if n % 5:
+            continue
+        lx, ly = (w // 2, h // 2) if lens is None else lens
+        m = max_dim(w, h, lx, ly)
+        if m + 3.0 == 0 or m - 2.0 == 0:
+            continue
+        yield dict(name="preview-%dx%d-%sx%d-sat%g-%s-i%d" % (w, h, dt, ch, sat, lname, interp), h=h, w=w, ch=ch,
+                   dtype=dt, seed=50000 + n, wide=(dt[0] == "f" and n % 2 == 0), interpolation=interp,
+                   lens_x=float(lx), lens_y=float(ly), saturation=sat, blue=3.0, red=-2.0, x_blue=0.7, y_red=-0.9)
+
+
 def case_params(c) -> orc.Params:
-    keys = ("blue", "red", "lens_x", "lens_y", "interpolation", "x_blue", "x_red", "y_blue", "y_red")
+    keys = ("blue", "red", "lens_x", "lens_y", "interpolation", "saturation", "x_blue", "x_red", "y_blue", "y_red")
     return orc.Params(**{k: c[k] for k in keys if k in c})
 
 
@@ -114,9 +136,18 @@ def main():
         c["md5"] = hashlib.md5(got.tobytes()).hexdigest()
         suite.append(c)
     out["suite"] = suite
+    # --- preview suite: the reference's own saturate()/centerline() on top of its pass; the HSV pair behind
+    #     saturate() is libgimpcolor's, restated in oracle/ref_harness.c (parity unpinned for that pair) ---
+    preview = []
+    for c in preview_cases():
+        src = orc.synth_image(c["h"], c["w"], c["ch"], c["dtype"], c["seed"], c["wide"])
+        got = ref.region(src, case_params(c), preview=True)
+        c["md5"] = hashlib.md5(got.tobytes()).hexdigest()
+        preview.append(c)
+    out["preview"] = preview
     with open(GOLDEN_JSON, "w") as f:
         json.dump(out, f, indent=0, separators=(",", ":"))
-    print("wrote %s: %d synthetic cases + fixture chain (%s)" % (GOLDEN_JSON, len(suite), want_bmp))
+    print("wrote %s: %d synthetic cases + %d preview cases + fixture chain (%s)" % (GOLDEN_JSON, len(suite), len(preview), want_bmp))
 
 
 if __name__ == "__main__":

@@ -22,7 +22,7 @@ def golden():
     return _golden
 
 
-PKEYS = ("blue", "red", "lens_x", "lens_y", "interpolation", "x_blue", "x_red", "y_blue", "y_red")
+PKEYS = ("blue", "red", "lens_x", "lens_y", "interpolation", "saturation", "x_blue", "x_red", "y_blue", "y_red")
 
 
 def oracle_params(c) -> orc.Params:

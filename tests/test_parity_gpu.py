@@ -213,7 +213,7 @@ def test_band_call_writes_only_its_rows(fx, checker):
     # single row, first row, last row
     for y in (0, 166, 332):
         d2 = np.zeros_like(img)
-        fx.fix_ca_region(img, d2, 411, 333, 8, 2, fx.FixCaParams(**kw), 0, 411, y, y + 1, False)
+        fx.fix_ca_region(img, d2, 411, 333, 8, 2, fx.FixCaParams(**kw), 0, 411, y, y + 1, True)
         assert (d2[y] == full[y]).all()
 
 
@@ -355,3 +355,40 @@ def test_full_size_fast_within_one_lsb(fx, checker, name, h, w, ch, dtype, kw, m
     monkeypatch.setenv("FIXCA_FAST_KERNEL", "strip")
     fx.correct(img, p, y1=y1, y2=y2, out=band, flags=fx.PRECISION_FAST)
     assert fx.last_kernel().startswith("strip") and (band[y1:y2] == full[y1:y2]).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# the preview call: show_progress = FALSE (fix-ca.c:656-657, :1322-1327)
+# ---------------------------------------------------------------------------------------------
+def test_preview_call_matches_golden(fx):
+    """fixca_cuda_region(..., show_progress = 0): correction + saturate() + centerline(), bit-exact against digests
+    made by the reference's own code (HSV pair restated, see oracle/ref_harness.c)."""
+    bad = []
+    for c in golden()["preview"]:
+        img = case_image(c)
+        out = np.zeros_like(img)
+        fx.fix_ca_region(img, out, c["w"], c["h"], img.shape[2] * img.dtype.itemsize, fx.bpc_of(img.dtype),
+                         fx_params(fx, c), 0, c["w"], 0, c["h"], False)
+        if md5(out) != c["md5"]:
+            bad.append(c["name"])
+    assert not bad, "%d of %d preview cases differ, first: %s" % (len(bad), len(golden()["preview"]), bad[:6])
+
+
+def test_preview_band_and_device_flag(fx, checker):
+    """The dialog previews a row band of the whole drawable (fix-ca.c:656-657); the device-resident entry takes
+    FIXCA_PREVIEW_OVERLAY for the same result."""
+    import torch
+
+    img = orc.synth_image(300, 640, 3, "u2", 77)
+    kw = dict(KW, lens_x=300, lens_y=140, interpolation=1, saturation=40.0)
+    want = np.zeros_like(img)
+    checker.region(img, orc.Params(**kw), 120, 190, dst=want, preview=True)
+    got = np.zeros_like(img)
+    fx.fix_ca_region(img, got, 640, 300, 6, 2, fx.FixCaParams(**kw), 0, 640, 120, 190, False)
+    assert got.tobytes() == want.tobytes()
+    src = torch.from_numpy(img.view(np.int16)).cuda()
+    dst = torch.zeros_like(src)
+    fx.fix_ca_region_dev(src.data_ptr(), 640 * 6, 0, 300, dst.data_ptr(), 640 * 6, 0, 640, 300, 6, 2, fx.FixCaParams(**kw),
+                         120, 190, fx.PRECISION_EXACT | fx.PREVIEW_OVERLAY, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert dst.cpu().numpy().view(np.uint16)[120:190].tobytes() == want[120:190].tobytes()

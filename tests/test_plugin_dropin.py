@@ -68,13 +68,45 @@ def _compare(plugins, expect_gpu):
             assert fixca.launch_count() == launches
 
 
+PREVIEWS = [
+    # window (x, y, w, h) of the drawable the dialog shows, saturation, interpolation, lens
+    ((0, 0, 64, 48), 0.0, 1, (30.0, 20.0)),
+    ((17, 23, 80, 33), 35.0, 2, (60.0, 40.0)),
+    ((5, 60, 100, 30), -60.0, 0, (-1.0, -1.0)),
+]
+
+
+def _compare_previews(plugins, expect_gpu):
+    """preview_update() (fix-ca.c:617-679): whole-drawable fetch, the pass on the visible row band with
+    show_progress = FALSE (overlay + saturation), 8-bit down-conversion, gimp_preview_draw_buffer()."""
+    import fixca
+
+    ref, patched = plugins
+    n = 0
+    for (shape, dt, fmt), (win, sat, interp, lens) in [(d, c) for d in DRAWABLES[:3] for c in PREVIEWS]:
+        n += 1
+        h, w = shape[0], shape[1]
+        x, y, ww, hh = win
+        ww, hh = min(ww, w - x), min(hh, h - y)
+        img = orc.synth_image(h, w, shape[2], dt, seed=8000 + n)
+        P = orc.Params(blue=3.0, red=-2.0, lens_x=lens[0], lens_y=lens[1], interpolation=interp, saturation=sat,
+                       x_blue=0.7, y_red=-0.9)
+        want = ref.preview_update(img.copy(), fmt, x, y, ww, hh, P)
+        launches = fixca.launch_count()
+        got = patched.preview_update(img.copy(), fmt, x, y, ww, hh, P)
+        assert got.tobytes() == want.tobytes(), (fmt, win, sat, interp)
+        assert (fixca.launch_count() > launches) == expect_gpu
+
+
 def test_patched_plugin_without_gpu_keeps_its_cpu_loop(plugins, fx):
     if fx.device_count() > 0:
         pytest.skip("a GPU is present; covered by the gpu test")
     _compare(plugins, expect_gpu=False)
+    _compare_previews(plugins, expect_gpu=False)
 
 
 @pytest.mark.gpu
 def test_patched_plugin_runs_on_the_gpu_bit_identically(plugins, fx):
     assert fx.device_count() > 0
     _compare(plugins, expect_gpu=True)
+    _compare_previews(plugins, expect_gpu=True)
