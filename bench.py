@@ -221,7 +221,7 @@ def run_reference(args):
         "e2e": {"value": round(mps, 3), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=args.out, flush=True)
     return 0
 
 
@@ -255,6 +255,7 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    _bind_to_gpu_numa_node(_nvml_index(local))     # pinned host buffers should be local to the GPU's root port
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -349,7 +350,32 @@ def run_cuda(args):
         torch.cuda.synchronize()
         dt_e2e = max_over_ranks(time.perf_counter() - t0)
         barrier()
+        # the floor of any end-to-end number on this host: the same bytes moved by plain copies, upload and
+        # download concurrently on two streams, no kernel
+        s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+        d_in = torch.empty((src_rows, row_bytes), dtype=torch.uint8, device=dev)
+        d_out = torch.empty((y2 - y1, row_bytes), dtype=torch.uint8, device=dev)
+
+        def copy_only():
+            with torch.cuda.stream(s_up):
+                d_in.copy_(h_src, non_blocking=True)
+            with torch.cuda.stream(s_down):
+                h_dst.copy_(d_out, non_blocking=True)
+            s_up.synchronize()
+            s_down.synchronize()
+
+        dst_keep = h_dst.clone()
+        copy_only()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            copy_only()
+        dt_copy = max_over_ranks(time.perf_counter() - t0)
+        h_dst.copy_(dst_keep)
+        del d_in, d_out, dst_keep
+        barrier()
         e2e = {"value": round(total_mp_step * e2e_steps / dt_e2e, 1), "unit": "MP/s",
+               "copy_only_ms_per_step": round(dt_copy / e2e_steps * 1e3, 3),
                "h2d_bytes_per_step": int(src_rows * row_bytes) * world, "d2h_bytes_per_step": int((y2 - y1) * row_bytes) * world,
                "steps": e2e_steps, "ms_per_step": round(dt_e2e / e2e_steps * 1e3, 3),
                "api": "fixca_cuda_region_ex (host pointers, pinned), synchronous"}
@@ -380,10 +406,19 @@ def run_cuda(args):
         }
         if parity is not None:
             line["parity"] = parity
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _bind_to_gpu_numa_node(index: int) -> None:
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception:
+        pass
 
 
 def _nvml_index(local: int) -> int:
@@ -445,6 +480,16 @@ def cpu_baseline(args):
             "single_thread_value": None if one is None else round(one, 2)}
 
 
+def _stdout_to_stderr():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner with NCCL_DEBUG=VERSION), so everything but the final line is sent to stderr: fd 1 is pointed at
+    fd 2 for the run and the saved descriptor is used for the result."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -460,6 +505,7 @@ def main():
     ap.add_argument("--quick-cpu", action="store_true")
     args = ap.parse_args()
     args.steps = max(1, args.steps)
+    args.out = _stdout_to_stderr()
     if args.impl == "reference":
         return run_reference(args)
     return run_cuda(args)
