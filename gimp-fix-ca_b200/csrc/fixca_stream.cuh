@@ -440,36 +440,47 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				// before the current row's arithmetic (the loads never wait on the stores).
 				auto simple = [&](auto phase) {
 					constexpr int PH = decltype(phase)::value;
+					// UNR rows are unrolled (a multiple of 4, so ring slots stay static); wide column
+					// groups unroll less to keep one phase variant within the instruction cache
+					// (ncu on RGB8, P = 4, 8 rows unrolled: "no instruction" was the top stall)
+					constexpr int UNR = P >= 4 ? 4 : CH;
+					static_assert(CH % UNR == 0 && UNR % 4 == 0, "unroll must divide the chunk and cover whole ring turns");
 					float smp[2][NS];
 #pragma unroll
 					for (int mm = 0; mm < NS; ++mm)
 						smp[0][mm] = Codec::load(prow + colbase + mm * BPP);
+					const float4 *wyp = wy;
+					unsigned char *qp = q;
+#pragma unroll 1
+					for (int it = 0; it < CH / UNR; ++it) {
 #pragma unroll
-					for (int u = 0; u < CH; ++u) {
-						const unsigned char *pnext = prow + wpitch;
-						if (((PH + u) & 3) == 3 && pnext == win_end)
-							pnext = win;
-						if (u + 1 < CH) {
+						for (int u = 0; u < UNR; ++u) {
+							const unsigned char *pnext = prow + wpitch;
+							if (((PH + u) & 3) == 3 && pnext == win_end)
+								pnext = win;
+							// the next row's samples (after the chunk's last row they are simply dropped)
 #pragma unroll
 							for (int mm = 0; mm < NS; ++mm)
 								smp[(u + 1) & 1][mm] = Codec::load(pnext + colbase + mm * BPP);
-						}
 #pragma unroll
-						for (int k = 0; k < P; ++k) {
-							float v = wt[k][0] * smp[u & 1][k];
+							for (int k = 0; k < P; ++k) {
+								float v = wt[k][0] * smp[u & 1][k];
 #pragma unroll
-							for (int jj = 1; jj < NW; ++jj)
-								v = fmaf(wt[k][jj], smp[u & 1][k + jj], v);
-							hr[(PH + u) & 3][k] = v;
-						}
-						const float4 w_ = wy[u];
+								for (int jj = 1; jj < NW; ++jj)
+									v = fmaf(wt[k][jj], smp[u & 1][k + jj], v);
+								hr[(PH + u) & 3][k] = v;
+							}
+							const float4 w_ = wyp[u];
 #pragma unroll
-						for (int k = 0; k < P; ++k) {
-							const float v_ = __saturatef(fmaf(w_.w, hr[3][k], fmaf(w_.z, hr[2][k],
-									 fmaf(w_.y, hr[1][k], w_.x * hr[0][k]))));
-							Codec::store(q + u * OUT_PITCH + k * BPP, v_);
+							for (int k = 0; k < P; ++k) {
+								const float v_ = __saturatef(fmaf(w_.w, hr[3][k], fmaf(w_.z, hr[2][k],
+										 fmaf(w_.y, hr[1][k], w_.x * hr[0][k]))));
+								Codec::store(qp + u * OUT_PITCH + k * BPP, v_);
+							}
+							prow = pnext;
 						}
-						prow = pnext;
+						wyp += UNR;
+						qp += UNR * OUT_PITCH;
 					}
 				};
 				switch ((s_done + 1) & 3) {
