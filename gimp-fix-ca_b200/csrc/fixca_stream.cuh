@@ -25,13 +25,13 @@
 //     24 per chunk -- and the producer's own instruction stream, ~1.9 us per chunk, was the
 //     critical path of the whole kernel: profiles/r01_stream_pipe_sweep_i.md.)
 //   * a second helper warp computes the per-row vertical weights of the chunks ahead (FP64
-//     coordinates, fix-ca.c:813-820, weights folded into ring-slot order), so the compute
+//     coordinates, fix-ca.c:813-820, weights ordered by tap position), so the compute
 //     warps never touch FP64 and the TMA warp never waits for arithmetic;
 //   * the 8 compute warps (4 red, 4 blue) never meet at a CTA barrier: they wait
 //     on "full" mbarriers and arrive on "done" mbarriers.
 //
-// Arithmetic is identical to strip_kernel (same weights, same FMA order, ring
-// phase tied to absolute source rows), so both produce the same bytes.
+// Arithmetic is identical to strip_kernel (same weights, same FMA order: taps oldest -> newest,
+// whatever the ring phase), so both produce the same bytes for any tiling, segment or band split.
 #pragma once
 
 #include <type_traits>
@@ -54,7 +54,7 @@ constexpr int STREAM_NSTG = 3;
 #define STREAM_COL_SLACK(P) ((P) + 4)	// >= NS = P + taps: pixels of window slack per side (host and device)
 
 struct StreamMeta {
-	float4 wy[2][STREAM_CH];	// vertical weights per output row, ring-slot order, pre-scaled by 1/max
+	float4 wy[STREAM_CH][2];	// vertical weights per output row and channel, by tap position (position_weights)
 	int    last[2][STREAM_CH + 1];	// highest tap row of each output row (INT_MAX after the chunk's last row)
 	int    s_end[2];		// = last[c][nrows - 1]
 	int    simple[2];		// full chunk whose rows finish on CH consecutive source rows (the usual case)
@@ -119,8 +119,8 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *tm)
 // tm_out   destination rows [dst_row0, y2), same box         (finished chunks; clipped at y2 and at the row end)
 // All three are maps of 8-byte elements over rows of align16(width * BPP) bytes; row coordinates are
 // relative to src_row0 / dst_row0.
-template <class S, int NCH, int INTERP, int P, int TW>
-__global__ void __launch_bounds__(2 * TW / P + 64)
+template <class S, int NCH, int INTERP, int P, int TW, bool ALT = false>
+__global__ void __launch_bounds__(2 * TW / P + 64, (2 * TW / P + 64) <= 192 ? 4 : 2)	// register budget: 4 (2) resident CTAs
 stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUtensorMap tm_win,
 	      const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ CUtensorMap tm_out)
 {
@@ -137,7 +137,8 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	constexpr int CH = STREAM_CH;
 	constexpr int NSTG = STREAM_NSTG;
 	const int D = a.depth, NF = D + 1;
-	static_assert(HALF % 32 == 0, "a warp must not straddle the two channels");
+	static_assert(ALT || HALF % 32 == 0, "a warp must not straddle the two channels");
+	static_assert(NTC % 32 == 0, "whole compute warps");
 	static_assert(2 * CH <= 32, "one producer lane per (channel, row) of a chunk");
 	typedef StripCodec<S> Codec;
 
@@ -198,20 +199,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			const bool mine = lane < 2 * CH && r < nr;
 			int last = 0;
 			if (mine) {
-				double td;
-				const int i0 = base_index(a.g.y[ch], y_first + r, td);
-				float w[4];
-				tap_weights<INTERP>((float)td, w);
-				float slot[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-				for (int j = 0; j < T; ++j) {
-					const int q = clampi(i0 - OFF + j, 0, H - 1);
-					last = q;
-#pragma unroll
-					for (int s = 0; s < 4; ++s)
-						slot[s] += ((q & 3) == s) ? w[j] * Codec::kInvMax : 0.f;
-				}
-				m.wy[ch][r] = make_float4(slot[0], slot[1], slot[2], slot[3]);
+				m.wy[r][ch] = position_weights<INTERP>(a.g.y[ch], y_first + r, H, Codec::kInvMax, last);
 				m.last[ch][r] = last;
 				if (r == nr - 1) {
 					m.last[ch][nr] = INT_MAX;
@@ -302,31 +290,44 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	// =========================================================================
 	// compute warps
 	// =========================================================================
-	const int c = tid / HALF;		// 0 red, 1 blue: uniform per warp
-	const int lt = tid - c * HALF;
+	// ALT (4-channel formats): even lanes red, odd lanes blue of the same pixel, so that a warp's
+	// samples span 32 * BPP / 2 bytes of a row instead of 32 * BPP (half the shared-memory
+	// wavefronts for 8- and 16-byte pixels).  Otherwise the channel is uniform per warp.
+	const int c = ALT ? (tid & 1) : tid / HALF;	// 0 red, 1 blue
+	const int lt = ALT ? (tid >> 1) : tid - c * HALF;
 
-	float wt[P][NW];	// regular: weights over the NS shared samples.  otherwise [k][j < T]: plain tap weights
-	int cidx[P];		// base index of each column (per-tap path)
+	// regular: the P columns share one window of NS consecutive samples; wt[k][jj] weighs sample k + jj.
+	// otherwise ("bent": tap windows squeezed against an image edge, fix-ca.c:1271-1298): column k reads its
+	// own T consecutive samples from byte offset cofs[k]; wt[k][jj < T] weighs sample jj, clamped taps merged.
+	// Both forms run the same row loop without index arithmetic, so a bent warp costs about as much as a
+	// regular one (a per-tap path with clamps in the loop made every CTA of an edge strip a 1.4x straggler).
+	float wt[P][NW];
+	int cofs[P];
 	int colbase;		// byte offset of shared sample 0 from the window row start
 	bool regular;
 	{
 		float w[P][4];
-		int tap[P][T];	// clamp-to-edge tap columns minus k (fix-ca.c:1271-1298)
+		int tap[P][T];	// clamp-to-edge tap columns minus k
 		int bmin = INT_MAX;
 #pragma unroll
 		for (int k = 0; k < P; ++k) {
 			// columns past the tile's last one are computed like any other (their results are
-			// clipped by the TMA store); past the image the coordinate clamps to W - 1
+			// clipped by the TMA store); past the image the coordinate clamps to W - 1 ...
 			double td;
-			cidx[k] = base_index(a.g.x[c], x0 + lt * P + k, td);
+			const int i0 = base_index(a.g.x[c], x0 + lt * P + k, td);
 			tap_weights<INTERP>((float)td, w[k]);
+			// ... with zero weights, so that they do not bend a warp of the last strip
+			if (x0 + lt * P + k > xl)
+				w[k][0] = w[k][1] = w[k][2] = w[k][3] = 0.f;
 #pragma unroll
 			for (int j = 0; j < T; ++j) {
-				tap[k][j] = clampi(cidx[k] - OFF + j, 0, W - 1) - k;
+				tap[k][j] = clampi(i0 - OFF + j, 0, W - 1) - k;
 				if (w[k][j] != 0.f)
 					bmin = min(bmin, tap[k][j]);
 			}
 		}
+		if (bmin == INT_MAX)	// no column of this thread is inside the image
+			bmin = col_lo;
 		// regular: every tap that carries weight sits at shared sample k + j', 0 <= j' < NW, and the
 		// NS samples lie inside the window
 		regular = bmin >= col_lo && bmin + NS - 1 <= col_hi;
@@ -337,40 +338,44 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				regular = regular && (w[k][j] == 0.f || tap[k][j] - bmin <= NW - 1);
 		regular = __all_sync(0xffffffffu, regular);
 #pragma unroll
-		for (int k = 0; k < P; ++k)
+		for (int k = 0; k < P; ++k) {
 #pragma unroll
 			for (int jj = 0; jj < NW; ++jj) {
-				if (regular) {
-					float v = 0.f;
+				float v = 0.f;
 #pragma unroll
-					for (int j = 0; j < T; ++j)
-						v += (w[k][j] != 0.f && tap[k][j] - bmin == jj) ? w[k][j] : 0.f;
-					wt[k][jj] = v;
-				} else {
-					wt[k][jj] = jj < T ? w[k][jj] : 0.f;
+				for (int j = 0; j < T; ++j) {
+					const int at = regular ? tap[k][j] - bmin : tap[k][j] - tap[k][0];
+					v += (w[k][j] != 0.f && at == jj) ? w[k][j] : 0.f;
 				}
+				wt[k][jj] = v;
 			}
+			cofs[k] = (tap[k][0] + k) * BPP + 2 * c * (int)sizeof(S) - wb0;
+		}
 		colbase = bmin * BPP + 2 * c * (int)sizeof(S) - wb0;
 	}
-	const int choff = 2 * c * (int)sizeof(S) - wb0;
 
 	int s_done;	// last source row this thread has filtered horizontally
 	{
 		double td;
 		s_done = max(base_index(a.g.y[c], ya, td) - OFF, 0) - 1;
 	}
+	// Ring of the last four horizontal rows.  `ph` = slot the next source row goes to; the newest row
+	// sits in slot ph - 1, the row p below it in slot ph - 1 - p (mod 4).  The vertical weights come
+	// ordered by that distance p (position_weights), so the arithmetic is independent of ph.
 	float hr[4][P];
 #pragma unroll
 	for (int u = 0; u < 4; ++u)
 #pragma unroll
 		for (int k = 0; k < P; ++k)
 			hr[u][k] = 0.f;
+	int ph = (5 - T) & 3;	// after the T - 1 priming rows of a segment the ring is back at slot 0
 	const unsigned char *prow = win + ((s_done + 1) % NR) * wpitch;	// row s_done + 1
 	const unsigned char *const win_end = win + NR * wpitch;
 	const int qoff = lt * P * BPP + 2 * c * (int)sizeof(S);
 
-	auto run = [&](auto fast_path) {
-		constexpr bool FAST = decltype(fast_path)::value;
+	auto run = [&](auto regular_form) {
+		constexpr bool REG = decltype(regular_form)::value;
+		constexpr int NSL = REG ? NS : P * T;	// samples a thread loads per source row
 		int jnf = 0, jstg = 0, jpar = 0;	// j % NF, j % NSTG, (j / NF) & 1
 		for (int j = 0; j < nchunks; ++j) {
 			mbar_wait(&full[jnf], (uint32_t)jpar);
@@ -380,52 +385,9 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
 			jstg = jstg + 1 == NSTG ? 0 : jstg + 1;
 			const int s_end = m.s_end[c];
-			const float4 *wy = m.wy[c];
+			const float4 *wy = &m.wy[0][c];		// [row][channel]: stride 2
 			const int *lastp = m.last[c];
 			int next_last = lastp[0];
-
-#define FIXCA_EMIT()                                                                                          \
-	do {                                                                                                  \
-		const float4 w_ = *wy++;                                                                      \
-		_Pragma("unroll") for (int k = 0; k < P; ++k)                                                 \
-		{                                                                                             \
-			const float v_ = __saturatef(fmaf(w_.w, hr[3][k], fmaf(w_.z, hr[2][k],                \
-							 fmaf(w_.y, hr[1][k], w_.x * hr[0][k]))));            \
-			Codec::store(q + k * BPP, v_);                                                        \
-		}                                                                                             \
-		q += OUT_PITCH;                                                                               \
-		next_last = *++lastp;                                                                         \
-	} while (0)
-
-#define FIXCA_STEP(U)                                                                                         \
-	do {                                                                                                  \
-		if (FAST) {                                                                                   \
-			float smp[NS];                                                                        \
-			_Pragma("unroll") for (int mm = 0; mm < NS; ++mm)                                     \
-				smp[mm] = Codec::load(prow + colbase + mm * BPP);                             \
-			_Pragma("unroll") for (int k = 0; k < P; ++k)                                         \
-			{                                                                                     \
-				float v = wt[k][0] * smp[k];                                                  \
-				_Pragma("unroll") for (int jj = 1; jj < NW; ++jj)                             \
-					v = fmaf(wt[k][jj], smp[k + jj], v);                                  \
-				hr[U][k] = v;                                                                 \
-			}                                                                                     \
-		} else {                                                                                      \
-			_Pragma("unroll") for (int k = 0; k < P; ++k)                                         \
-			{                                                                                     \
-				float v = 0.f;                                                                \
-				_Pragma("unroll") for (int jj = 0; jj < T; ++jj)                              \
-				{                                                                             \
-					const int ix = clampi(cidx[k] - OFF + jj, 0, W - 1);                  \
-					v = fmaf(wt[k][jj], Codec::load(prow + ix * BPP + choff), v);         \
-				}                                                                             \
-				hr[U][k] = v;                                                                 \
-			}                                                                                     \
-		}                                                                                             \
-		++s_done;                                                                                     \
-		prow += wpitch;                                                                               \
-		_Pragma("unroll 1") while (next_last <= s_done) FIXCA_EMIT();                                 \
-	} while (0)
 
 			if (a.debug & 1) {	// timing experiment: memory pipeline only (results are wrong)
 				s_done = s_end;
@@ -434,91 +396,154 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				mbar_arrive(done_bar);
 				continue;
 			}
-			if (FAST && m.simple[c] && next_last == s_done + 1) {
-				// Steady state: CH source rows in, CH output rows out, fully unrolled.  The ring
-				// slot of every row is static per entry phase; the next row's samples are loaded
-				// before the current row's arithmetic (the loads never wait on the stores).
-				auto simple = [&](auto phase) {
-					constexpr int PH = decltype(phase)::value;
-					// UNR rows are unrolled (a multiple of 4, so ring slots stay static); wide column
-					// groups unroll less to keep one phase variant within the instruction cache
-					// (ncu on RGB8, P = 4, 8 rows unrolled: "no instruction" was the top stall)
-					constexpr int UNR = P >= 4 ? 4 : CH;
-					static_assert(CH % UNR == 0 && UNR % 4 == 0, "unroll must divide the chunk and cover whole ring turns");
-					float smp[2][NS];
+
+			// a source row's samples / the P horizontal results from them, in either form
+			auto load_row = [&](const unsigned char *p, float (&smp)[NSL]) {
+				if (REG) {
 #pragma unroll
 					for (int mm = 0; mm < NS; ++mm)
-						smp[0][mm] = Codec::load(prow + colbase + mm * BPP);
-					const float4 *wyp = wy;
-					unsigned char *qp = q;
+						smp[mm] = Codec::load(p + colbase + mm * BPP);
+				} else {
+#pragma unroll
+					for (int k = 0; k < P; ++k)
+#pragma unroll
+						for (int jj = 0; jj < T; ++jj)
+							smp[k * T + jj] = Codec::load(p + cofs[k] + jj * BPP);
+				}
+			};
+			auto hfilter = [&](const float (&smp)[NSL], float (&out)[P]) {
+#pragma unroll
+				for (int k = 0; k < P; ++k) {
+					float v = wt[k][0] * smp[REG ? k : k * T];
+#pragma unroll
+					for (int jj = 1; jj < (REG ? NW : T); ++jj)
+						v = fmaf(wt[k][jj], smp[REG ? k + jj : k * T + jj], v);
+					out[k] = v;
+				}
+			};
+			// one source row through the horizontal filter into ring slot U
+			auto hrow = [&](auto slot) {
+				constexpr int U = decltype(slot)::value;
+				float smp[NSL];
+				load_row(prow, smp);
+				hfilter(smp, hr[U]);
+				++s_done;
+				prow += wpitch;
+				if (prow == win_end)
+					prow = win;
+			};
+			// the output rows completed by the newest row (slot U)
+			auto emit = [&](auto slot) {
+				constexpr int U = decltype(slot)::value;
 #pragma unroll 1
-					for (int it = 0; it < CH / UNR; ++it) {
-#pragma unroll
-						for (int u = 0; u < UNR; ++u) {
-							const unsigned char *pnext = prow + wpitch;
-							if (((PH + u) & 3) == 3 && pnext == win_end)
-								pnext = win;
-							// the next row's samples (after the chunk's last row they are simply dropped)
-#pragma unroll
-							for (int mm = 0; mm < NS; ++mm)
-								smp[(u + 1) & 1][mm] = Codec::load(pnext + colbase + mm * BPP);
-#pragma unroll
-							for (int k = 0; k < P; ++k) {
-								float v = wt[k][0] * smp[u & 1][k];
-#pragma unroll
-								for (int jj = 1; jj < NW; ++jj)
-									v = fmaf(wt[k][jj], smp[u & 1][k + jj], v);
-								hr[(PH + u) & 3][k] = v;
-							}
-							const float4 w_ = wyp[u];
-#pragma unroll
-							for (int k = 0; k < P; ++k) {
-								const float v_ = __saturatef(fmaf(w_.w, hr[3][k], fmaf(w_.z, hr[2][k],
-										 fmaf(w_.y, hr[1][k], w_.x * hr[0][k]))));
-								Codec::store(qp + u * OUT_PITCH + k * BPP, v_);
-							}
-							prow = pnext;
-						}
-						wyp += UNR;
-						qp += UNR * OUT_PITCH;
+				while (next_last <= s_done) {
+					vertical_emit<INTERP, U, P, BPP, Codec>(hr, *wy, q);
+					wy += 2;
+					q += OUT_PITCH;
+					next_last = *++lastp;
+				}
+			};
+			// general walk: source rows up to `upto`, emitting whatever they complete
+			auto walk = [&](const int upto) {
+#pragma unroll 1
+				while (s_done < upto) {
+					switch (ph) {
+					case 0:
+						hrow(std::integral_constant<int, 0>());
+						emit(std::integral_constant<int, 0>());
+						ph = 1;
+						if (s_done >= upto) break;
+					case 1:
+						hrow(std::integral_constant<int, 1>());
+						emit(std::integral_constant<int, 1>());
+						ph = 2;
+						if (s_done >= upto) break;
+					case 2:
+						hrow(std::integral_constant<int, 2>());
+						emit(std::integral_constant<int, 2>());
+						ph = 3;
+						if (s_done >= upto) break;
+					default:
+						hrow(std::integral_constant<int, 3>());
+						emit(std::integral_constant<int, 3>());
+						ph = 0;
 					}
-				};
-				switch ((s_done + 1) & 3) {
-				case 0: simple(std::integral_constant<int, 0>()); break;
-				case 1: simple(std::integral_constant<int, 1>()); break;
-				case 2: simple(std::integral_constant<int, 2>()); break;
-				default: simple(std::integral_constant<int, 3>()); break;
+				}
+			};
+
+			if (m.simple[c] && next_last > s_done) {
+				// Steady state: CH consecutive source rows in, CH output rows out.  Rows below the
+				// first output's newest tap (a segment's first chunk: T - 1 of them) only prime the ring.
+				walk(next_last - 1);
+				if (ph != 0) {	// bring the ring to slot 0 (after a general chunk; rare)
+					auto rotate = [&](auto by) {
+						constexpr int N = decltype(by)::value;
+						float t[4][P];
+#pragma unroll
+						for (int u = 0; u < 4; ++u)
+#pragma unroll
+							for (int k = 0; k < P; ++k)
+								t[u][k] = hr[(u + N) & 3][k];
+#pragma unroll
+						for (int u = 0; u < 4; ++u)
+#pragma unroll
+							for (int k = 0; k < P; ++k)
+								hr[u][k] = t[u][k];
+					};
+					switch (ph) {
+					case 1: rotate(std::integral_constant<int, 1>()); break;
+					case 2: rotate(std::integral_constant<int, 2>()); break;
+					default: rotate(std::integral_constant<int, 3>()); break;
+					}
+					ph = 0;
+				}
+				// UNR rows unrolled (whole ring turns, so slots stay static); the next row's samples are
+				// loaded before the current row's arithmetic (the loads never wait on the stores).
+				// Wide column groups unroll one ring turn only: 8 rows of P = 4 are 8 KB of code and
+				// "no instruction" became the top stall (profiles/r01_ncu_stream_narrow_A.md).
+				constexpr int UNR = P >= 4 ? 4 : CH;
+				static_assert(CH % UNR == 0 && UNR % 4 == 0, "unroll must divide the chunk and cover whole ring turns");
+				// (bent warps load and filter row by row: their P * T samples are not double-buffered)
+				float smp[REG ? 2 : 1][NSL];
+				if (REG)
+					load_row(prow, smp[0]);
+#pragma unroll 1
+				for (int it = 0; it < CH / UNR; ++it) {
+#pragma unroll
+					for (int u = 0; u < UNR; ++u) {
+						const unsigned char *pnext = prow + wpitch;
+						if (pnext == win_end)
+							pnext = win;
+						// (after the chunk's last row the samples are simply dropped)
+						if (REG)
+							load_row(pnext, smp[REG ? (u + 1) & 1 : 0]);
+						else
+							load_row(prow, smp[0]);
+						hfilter(smp[REG ? u & 1 : 0], hr[u & 3]);
+						switch (u & 3) {
+						case 0: vertical_emit<INTERP, 0, P, BPP, Codec>(hr, wy[2 * u], q + u * OUT_PITCH); break;
+						case 1: vertical_emit<INTERP, 1, P, BPP, Codec>(hr, wy[2 * u], q + u * OUT_PITCH); break;
+						case 2: vertical_emit<INTERP, 2, P, BPP, Codec>(hr, wy[2 * u], q + u * OUT_PITCH); break;
+						default: vertical_emit<INTERP, 3, P, BPP, Codec>(hr, wy[2 * u], q + u * OUT_PITCH); break;
+						}
+						prow = pnext;
+					}
+					wy += 2 * UNR;
+					q += UNR * OUT_PITCH;
 				}
 				s_done += CH;
-				fence_proxy_async_smem();
-				mbar_arrive(done_bar);
-				continue;
-			}
-
-			// rows of this chunk whose taps were all produced while walking the previous chunk
-#pragma unroll 1
-			while (next_last <= s_done)
-				FIXCA_EMIT();
-#pragma unroll 1
-			while (s_done < s_end) {
-				switch ((s_done + 1) & 3) {	// ring slot of the next source row: static per case
-				case 0:
-					FIXCA_STEP(0);
-					if (s_done >= s_end) break;
-				case 1:
-					FIXCA_STEP(1);
-					if (s_done >= s_end) break;
-				case 2:
-					FIXCA_STEP(2);
-					if (s_done >= s_end) break;
-				default:
-					FIXCA_STEP(3);
-					if (prow == win_end)	// ring_rows % 4 == 0: the ring only wraps after slot 3
-						prow = win;
+			} else {
+				// rows of this chunk whose taps were all produced while walking the previous chunk
+				if (next_last <= s_done) {
+					switch (ph) {
+					case 1: emit(std::integral_constant<int, 0>()); break;
+					case 2: emit(std::integral_constant<int, 1>()); break;
+					case 3: emit(std::integral_constant<int, 2>()); break;
+					default: emit(std::integral_constant<int, 3>()); break;
+					}
 				}
+				walk(s_end);
 			}
-#undef FIXCA_STEP
-#undef FIXCA_EMIT
 			// staging writes -> visible to the TMA store the producer issues after this barrier
 			fence_proxy_async_smem();
 			mbar_arrive(done_bar);

@@ -18,9 +18,12 @@
 //     P is chosen per pixel format so that the lane stride in shared memory
 //     (P * bytes-per-pixel) is conflict-free.
 //   * The vertical pass keeps the last four horizontal rows in a ring of
-//     registers.  The per-output-row weights are stored in shared memory
-//     already permuted into ring-slot order (clamped edge taps folded in), so
-//     the ring never shifts: 4 FMAs per output, no register moves.
+//     registers whose slots are static in the unrolled row loop.  The
+//     per-output-row weights are stored in shared memory by tap POSITION
+//     (distance below the output row's newest tap row, clamped edge taps
+//     folded in) and the FMA chain runs oldest -> newest, so a sample's
+//     arithmetic does not depend on ring phase, tile, segment or band:
+//     4 FMAs per Cubic output, 2 per Linear output, no register moves.
 //   * Output rows are emitted when their last tap row has been produced; the
 //     per-source-row emit counts come from a small table built with the row
 //     coefficients.  float -> integer conversion saturates in hardware
@@ -98,6 +101,53 @@ template <> struct StripCodec<float> {
 	__device__ __forceinline__ static void store(unsigned char *p, float sat01) { *reinterpret_cast<float *>(p) = sat01; }
 };
 
+// Vertical weights of output row y of one channel, ordered by tap position: .w weighs the newest
+// tap row `last` (the row whose arrival completes the output), .z row last - 1, .y last - 2, .x
+// last - 3.  Clamp-to-edge taps (fix-ca.c:1219-1256, :1149-1158) land on the same row and their
+// weights add up; positions that hold no tap get weight 0.  Pre-scaled by inv_max so that the
+// vertical pass lands in [0,1] units.
+template <int INTERP>
+__device__ __forceinline__ float4 position_weights(const Axis &ay, int y, int H, float inv_max, int &last)
+{
+	constexpr int T = INTERP == 1 ? 2 : 4;
+	constexpr int OFF = INTERP == 1 ? 0 : 1;
+	double td;
+	const int i0 = base_index(ay, y, td);
+	float w[4];
+	tap_weights<INTERP>((float)td, w);
+	last = clampi(i0 - OFF + T - 1, 0, H - 1);
+	float pos[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+	for (int j = 0; j < T; ++j) {
+		const int p = last - clampi(i0 - OFF + j, 0, H - 1);
+#pragma unroll
+		for (int m = 0; m < 4; ++m)
+			pos[m] += (p == m) ? w[j] * inv_max : 0.f;
+	}
+	return make_float4(pos[3], pos[2], pos[1], pos[0]);
+}
+
+// One output row of P columns from the ring of horizontal rows; U = ring slot of the newest row.
+// Chain order oldest -> newest; the last FMA saturates (clip_d, fix-ca.c:873-880).  Linear has taps
+// at the two newest positions only.
+template <int INTERP, int U, int P, int BPP, class Codec>
+__device__ __forceinline__ void vertical_emit(const float (&hr)[4][P], const float4 w, unsigned char *q)
+{
+#pragma unroll
+	for (int k = 0; k < P; ++k) {
+		float v;
+		if (INTERP == 1) {
+			v = w.z * hr[(U + 3) & 3][k];
+		} else {
+			v = w.x * hr[(U + 1) & 3][k];
+			v = fmaf(w.y, hr[(U + 2) & 3][k], v);
+			v = fmaf(w.z, hr[(U + 3) & 3][k], v);
+		}
+		v = __saturatef(fmaf(w.w, hr[U][k], v));
+		Codec::store(q + k * BPP, v);
+	}
+}
+
 // S      sample type (uint8_t, uint16_t, float)
 // NCH    3 or 4 samples per pixel
 // INTERP 1 Linear, 2 Cubic
@@ -169,8 +219,8 @@ __global__ void __launch_bounds__(2 * TW / P) strip_kernel(const __grid_constant
 	const int wbytes = (((col_hi + 1) * BPP + 15) & ~15) - wb0;
 	const int wrows = row_hi - row_lo + 1;
 	const int wpitch = a.win_pitch;
-	// Ring phase and window slots are tied to ABSOLUTE source rows (slot = row & 3, window row
-	// index = row - row_base), so a row's arithmetic does not depend on where tiles or bands start.
+	// The walker's ring slot and window row index are tied to absolute source rows (slot = row & 3,
+	// window row index = row - row_base); the arithmetic is phase-free (tap-position weights).
 	const int row_base = row_lo & ~3;
 
 	// ---- 2. TMA: window rows, and the tile's own pixels into the staging tile ----
@@ -194,29 +244,12 @@ __global__ void __launch_bounds__(2 * TW / P) strip_kernel(const __grid_constant
 		*reinterpret_cast<int4 *>(win + r * wpitch + v * 16) = make_int4(0, 0, 0, 0);
 	}
 
-	// ---- 3. per-row coefficients in ring-slot order + emit counts (overlaps the copies) ----
+	// ---- 3. per-row coefficients by tap position + emit counts (overlaps the copies) ----
 	for (int k = tid; k < 2 * nrows_out; k += NT) {
 		const int ch = k >= nrows_out;
 		const int r = k - ch * nrows_out;
-		double td;
-		const int i0 = base_index(a.g.y[ch], y0 + r, td);
-		float w[4];
-		tap_weights<INTERP>((float)td, w);
-#pragma unroll
-		for (int j = 0; j < 4; ++j)
-			w[j] *= Codec::kInvMax;	// the vertical pass lands in [0,1] units
-		float slot[4] = {0.f, 0.f, 0.f, 0.f};
-		int last = 0;
-#pragma unroll
-		for (int j = 0; j < T; ++j) {
-			const int q = clampi(i0 - OFF + j, 0, H - 1);
-			last = q;
-			const int sl = q & 3;
-#pragma unroll
-			for (int m = 0; m < 4; ++m)
-				slot[m] += (sl == m) ? w[j] : 0.f;
-		}
-		ytab[ch * a.th + r] = make_float4(slot[0], slot[1], slot[2], slot[3]);
+		int last;
+		ytab[ch * a.th + r] = position_weights<INTERP>(a.g.y[ch], y0 + r, H, Codec::kInvMax, last);
 		// emitted once source row `last` (its highest tap row) has been produced
 		atomicAdd(reinterpret_cast<unsigned int *>(nemit + ch * a.ne_pitch + ((last - row_base) & ~3)),
 			  1u << (8 * (last & 3)));
@@ -295,48 +328,48 @@ __global__ void __launch_bounds__(2 * TW / P) strip_kernel(const __grid_constant
 		// one instantiation per path so that the choice is made once, not per source row
 		auto walk = [&](auto fast_path) {
 			constexpr bool FAST = decltype(fast_path)::value;
-			for (int s = s_first; s <= s_last; s += 4) {
-				const unsigned int ne4 = *ne++;
+			// one source row into ring slot u (= row & 3), then the output rows it completes
+			auto row = [&](auto slot, const unsigned int ne4) {
+				constexpr int u = decltype(slot)::value;
+				if (FAST) {
+					float smp[NS];
 #pragma unroll
-				for (int u = 0; u < 4; ++u) {
-					if (FAST) {
-						float smp[NS];
+					for (int m = 0; m < NS; ++m)
+						smp[m] = Codec::load(prow + colbase + m * BPP);
 #pragma unroll
-						for (int m = 0; m < NS; ++m)
-							smp[m] = Codec::load(prow + colbase + m * BPP);
+					for (int k = 0; k < P; ++k) {
+						float v = wt[k][0] * smp[k];
 #pragma unroll
-						for (int k = 0; k < P; ++k) {
-							float v = wt[k][0] * smp[k];
-#pragma unroll
-							for (int j = 1; j < NW; ++j)
-								v = fmaf(wt[k][j], smp[k + j], v);
-							hr[u][k] = v;
-						}
-					} else {
-#pragma unroll
-						for (int k = 0; k < P; ++k) {
-							float v = 0.f;
-#pragma unroll
-							for (int j = 0; j < T; ++j) {
-								const int ix = clampi(cidx[k] - OFF + j, 0, W - 1);
-								v = fmaf(wt[k][j], Codec::load(prow + ix * BPP + choff), v);
-							}
-							hr[u][k] = v;
-						}
+						for (int j = 1; j < NW; ++j)
+							v = fmaf(wt[k][j], smp[k + j], v);
+						hr[u][k] = v;
 					}
-					prow += wpitch;
-					// usually exactly one output row completes per source row (scale ~ 1)
-#pragma unroll 1
-					for (int n = (ne4 >> (8 * u)) & 0xff; n > 0; --n) {
-						const float4 w = *wy++;
+				} else {
 #pragma unroll
-						for (int k = 0; k < P; ++k) {
-							const float v = __saturatef(fmaf(w.w, hr[3][k], fmaf(w.z, hr[2][k], fmaf(w.y, hr[1][k], w.x * hr[0][k]))));
-							Codec::store(q + k * BPP, v);
+					for (int k = 0; k < P; ++k) {
+						float v = 0.f;
+#pragma unroll
+						for (int j = 0; j < T; ++j) {
+							const int ix = clampi(cidx[k] - OFF + j, 0, W - 1);
+							v = fmaf(wt[k][j], Codec::load(prow + ix * BPP + choff), v);
 						}
-						q += OUT_PITCH;
+						hr[u][k] = v;
 					}
 				}
+				prow += wpitch;
+				// usually exactly one output row completes per source row (scale ~ 1)
+#pragma unroll 1
+				for (int n = (ne4 >> (8 * u)) & 0xff; n > 0; --n) {
+					vertical_emit<INTERP, u, P, BPP, Codec>(hr, *wy++, q);
+					q += OUT_PITCH;
+				}
+			};
+			for (int s = s_first; s <= s_last; s += 4) {
+				const unsigned int ne4 = *ne++;
+				row(std::integral_constant<int, 0>(), ne4);
+				row(std::integral_constant<int, 1>(), ne4);
+				row(std::integral_constant<int, 2>(), ne4);
+				row(std::integral_constant<int, 3>(), ne4);
 			}
 		};
 		if (regular)

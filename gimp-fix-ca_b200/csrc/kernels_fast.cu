@@ -40,16 +40,32 @@ static const KernelEntry strip_table[] = {
 	STRIP_ENTRIES(float, "f32", 1, 128, 1, 128),
 };
 
-#define STREAM_ENTRIES(S, TAG, P3, TW3, P4, TW4)                                                              \
+// ALT4: 4-channel strips put red and blue of one pixel on neighbouring lanes (half the row span
+// per warp load: no 2-way / 4-way bank conflicts for 8- and 16-byte pixels).
+#define STREAM_ENTRIES(S, TAG, P3, TW3, P4, TW4, ALT4)                                                        \
 	{ (kernel_fn)stream_kernel<S, 3, 1, P3, TW3>, "stream/linear/f32/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1 }, \
-	{ (kernel_fn)stream_kernel<S, 4, 1, P4, TW4>, "stream/linear/f32/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1 }, \
+	{ (kernel_fn)stream_kernel<S, 4, 1, P4, TW4, ALT4>, "stream/linear/f32/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1 }, \
 	{ (kernel_fn)stream_kernel<S, 3, 2, P3, TW3>, "stream/cubic/f32/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1 },  \
-	{ (kernel_fn)stream_kernel<S, 4, 2, P4, TW4>, "stream/cubic/f32/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1 }
+	{ (kernel_fn)stream_kernel<S, 4, 2, P4, TW4, ALT4>, "stream/cubic/f32/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1 }
 
 static const KernelEntry stream_table[] = {
-	STREAM_ENTRIES(uint8_t, "u8", 4, 256, 1, 128),
-	STREAM_ENTRIES(uint16_t, "u16", 2, 256, 1, 128),
-	STREAM_ENTRIES(float, "f32", 1, 128, 1, 128),
+	STREAM_ENTRIES(uint8_t, "u8", 4, 256, 1, 128, false),
+	STREAM_ENTRIES(uint16_t, "u16", 2, 256, 1, 128, true),
+	STREAM_ENTRIES(float, "f32", 1, 128, 1, 64, true),	// 16-byte pixels: 64 + halo columns fit one 2 KB TMA box
+};
+
+// channel-per-warp variants of the 4-channel strips, for A/B runs (FIXCA_STREAM_NOALT=1)
+static const KernelEntry stream_x4_noalt[] = {
+	{ (kernel_fn)stream_kernel<uint16_t, 4, 1, 1, 128>, "stream/linear/f32/u16x4/noalt", 128, 0, 2, 1, 1 },
+	{ (kernel_fn)stream_kernel<uint16_t, 4, 2, 1, 128>, "stream/cubic/f32/u16x4/noalt", 128, 0, 2, 1, 1 },
+	{ (kernel_fn)stream_kernel<float, 4, 1, 1, 128>, "stream/linear/f32/f32x4/noalt", 128, 0, 4, 1, 1 },
+	{ (kernel_fn)stream_kernel<float, 4, 2, 1, 128>, "stream/cubic/f32/f32x4/noalt", 128, 0, 4, 1, 1 },
+};
+
+// wider strips for 3-byte pixels, for tuning (FIXCA_STREAM_TW8=512): half as many helper warps per pixel
+static const KernelEntry stream_u8x3_tw512[] = {
+	{ (kernel_fn)stream_kernel<uint8_t, 3, 1, 4, 512>, "stream/linear/f32/u8x3/tw512", 512, 0, 1, 4, 1 },
+	{ (kernel_fn)stream_kernel<uint8_t, 3, 2, 4, 512>, "stream/cubic/f32/u8x3/tw512", 512, 0, 1, 4, 1 },
 };
 
 static const KernelEntry stream_u16x3_tw128[] = {
@@ -77,6 +93,16 @@ const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int
 		return nullptr;
 	const char *tw = getenv("FIXCA_STRIP_TW");	// tuning: narrower tiles for the headline format
 	const bool tw128 = kind == SK_U16 && nch == 3 && tw && atoi(tw) == 128;
+	if (variant == 3 && nch == 4 && kind != SK_U8) {
+		const char *na = getenv("FIXCA_STREAM_NOALT");
+		if (na && atoi(na))
+			return &stream_x4_noalt[(kind == SK_F32 ? 2 : 0) + interp - 1];
+	}
+	if (variant == 3 && nch == 3 && kind == SK_U8) {
+		const char *w8 = getenv("FIXCA_STREAM_TW8");
+		if (w8 && atoi(w8) == 512)
+			return &stream_u8x3_tw512[interp - 1];
+	}
 	switch (variant) {
 	case 3: return tw128 ? &stream_u16x3_tw128[interp - 1] : &stream_table[s * 4 + (interp - 1) * 2 + (nch - 3)];
 	case 2: return tw128 ? &strip_u16x3_tw128[interp - 1] : &strip_table[s * 4 + (interp - 1) * 2 + (nch - 3)];

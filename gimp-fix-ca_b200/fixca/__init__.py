@@ -21,7 +21,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfixca_cuda.so")
+# FIXCA_LIB: developer override for A/B runs of two builds of the same library (scripts/quick_bench.py)
+LIB_PATH = os.environ.get("FIXCA_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libfixca_cuda.so")
 
 INTERP_NONE, INTERP_LINEAR, INTERP_CUBIC = 0, 1, 2
 PRECISION_EXACT, PRECISION_FAST = 0x0, 0x1

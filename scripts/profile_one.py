@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run one workload a few times (for ncu): python scripts/profile_one.py <fast|exact|linear|none|rgb8> [reps]"""
+"""Run one workload a few times (for ncu): python scripts/profile_one.py <fast|exact|linear|none|rgb8|rgb8lin|rgba16|rgb8_4k> [reps]"""
 import os
 import sys
 
@@ -18,6 +18,9 @@ cfg = {
     "linear": (8192, 12288, 3, 2, 2, 1, fixca.PRECISION_FAST),
     "none":   (8192, 12288, 3, 2, 2, 0, fixca.PRECISION_EXACT),
     "rgb8":   (4000, 6000, 3, 1, 1, 2, fixca.PRECISION_FAST),
+    "rgb8lin": (4000, 6000, 3, 1, 1, 1, fixca.PRECISION_FAST),
+    "rgba16": (4320, 7680, 4, 2, 2, 2, fixca.PRECISION_FAST),
+    "rgb8_4k": (2160, 3840, 3, 1, 1, 2, fixca.PRECISION_FAST),
 }[which]
 h, w, ch, es, bpc, interp, flags = cfg
 bpp = ch * es

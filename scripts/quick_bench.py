@@ -71,6 +71,30 @@ if __name__ == "__main__":
             run("24MP rgb8 linear fast", 4000, 6000, 3, torch.uint8, 1, 1, F)
             run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
             run("50MP rgb f32 cubic fast", 6144, 8192, 3, torch.float32, -4, 2, F)
+    if which == "mix":
+        run("100MP rgb16 cubic fast", 8192, 12288, 3, torch.int16, 2, 2, F)
+        run("100MP rgb16 linear fast", 8192, 12288, 3, torch.int16, 2, 1, F)
+        run("24MP rgb8 cubic fast", 4000, 6000, 3, torch.uint8, 1, 2, F)
+        run("24MP rgb8 linear fast", 4000, 6000, 3, torch.uint8, 1, 1, F)
+        run("4K rgb8 cubic fast", 2160, 3840, 3, torch.uint8, 1, 2, F)
+        run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
+        run("8K rgba16 linear fast", 4320, 7680, 4, torch.int16, 2, 1, F, lens=(658, 1280))
+        run("33MP rgba8 cubic fast", 4320, 7680, 4, torch.uint8, 1, 2, F)
+        run("50MP rgb f32 cubic fast", 6144, 8192, 3, torch.float32, -4, 2, F)
+        run("50MP rgba f32 cubic fast", 6144, 8192, 4, torch.float32, -4, 2, F)
+    if which == "rgb8":
+        for _ in range(2):
+            run("24MP rgb8 cubic fast", 4000, 6000, 3, torch.uint8, 1, 2, F)
+            run("24MP rgb8 linear fast", 4000, 6000, 3, torch.uint8, 1, 1, F)
+            run("4K rgb8 cubic fast", 2160, 3840, 3, torch.uint8, 1, 2, F)
+    if which == "widths":
+        for w in (6144, 6000, 5888, 6100):
+            run("rgb8 cubic w=%d" % w, 4000, w, 3, torch.uint8, 1, 2, F)
+            run("rgb8 linear w=%d" % w, 4000, w, 3, torch.uint8, 1, 1, F)
+    if which == "x4":       # run with and without FIXCA_STREAM_NOALT=1 (separate processes: plans are cached)
+        run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
+        run("8K rgba16 linear fast", 4320, 7680, 4, torch.int16, 2, 1, F, lens=(658, 1280))
+        run("50MP rgba f32 cubic fast", 6144, 8192, 4, torch.float32, -4, 2, F)
     if which == "narrow":
         for ctas in ("2", "4", "6"):
             os.environ["FIXCA_STREAM_CTAS"] = ctas
