@@ -263,6 +263,10 @@ static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_
 		if (k->stream) {
 			if (plan_stream(k, f, g, y1, y2, dev, limit, pl))
 				return FIXCA_OK;
+			// the window is wider than a TMA box: narrower strips if the format has them
+			const KernelEntry *k2 = lookup_fast_variant(f.kind, f.nch, g.interp, 4);
+			if (k2 && plan_stream(k2, f, g, y1, y2, dev, limit, pl))
+				return FIXCA_OK;
 			// the ring does not fit (huge shifts): fall back to per-tile windows
 			k = lookup_fast_variant(f.kind, f.nch, g.interp, 2);
 		}

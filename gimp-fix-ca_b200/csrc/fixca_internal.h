@@ -33,7 +33,7 @@ const KernelEntry *lookup_none(int sample_bytes, int nch, bool tiled);
 const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled);
 // kind in {SK_U8,SK_U16,SK_F32}; interp in {1,2}
 const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled);
-// variant: 0 direct, 1 first-round tiled, 2 strip, 3 stream
+// variant: 0 direct, 1 first-round tiled, 2 strip, 3 stream, 4 narrower stream (may be nullptr)
 const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int variant);
 
 // kernels_preview.cu: saturate() + centerline() on destination rows [y1, y2) (fix-ca.c:1322-1327)

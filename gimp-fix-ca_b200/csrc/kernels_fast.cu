@@ -49,9 +49,16 @@ static const KernelEntry strip_table[] = {
 	{ (kernel_fn)stream_kernel<S, 4, 2, P4, TW4, ALT4>, "stream/cubic/f32/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1 }
 
 static const KernelEntry stream_table[] = {
-	STREAM_ENTRIES(uint8_t, "u8", 4, 256, 1, 128, false),
-	STREAM_ENTRIES(uint16_t, "u16", 2, 256, 1, 128, true),
+	STREAM_ENTRIES(uint8_t, "u8", 4, 256, 3, 192, false),	// 4-byte pixels: 3 columns = 12 bytes per lane, 7 loads per 3 outputs
+	STREAM_ENTRIES(uint16_t, "u16", 2, 256, 3, 192, true),	// 8-byte pixels, lanes alternate channels: 3 columns = conflict-free, 7 loads per 3 outputs
 	STREAM_ENTRIES(float, "f32", 1, 128, 1, 64, true),	// 16-byte pixels: 64 + halo columns fit one 2 KB TMA box
+};
+
+// Narrower 16-bit RGBA strips for the calls whose window (strip + shift + slack columns) would not fit one
+// 2 KB TMA box at 192 columns (variant 4).
+static const KernelEntry stream_u16x4_tw128[] = {
+	{ (kernel_fn)stream_kernel<uint16_t, 4, 1, 1, 128, true>, "stream/linear/f32/u16x4/tw128", 128, 0, 2, 1, 1 },
+	{ (kernel_fn)stream_kernel<uint16_t, 4, 2, 1, 128, true>, "stream/cubic/f32/u16x4/tw128", 128, 0, 2, 1, 1 },
 };
 
 // channel-per-warp variants of the 4-channel strips, for A/B runs (FIXCA_STREAM_NOALT=1)
@@ -79,9 +86,11 @@ static const KernelEntry strip_u16x3_tw128[] = {
 	{ (kernel_fn)strip_kernel<uint16_t, 3, 2, 2, 128>, "strip/cubic/f32/u16x3/tw128", 128, 16, 2, 2 },
 };
 
-// variant: 0 direct, 1 first-round tiled, 2 strip, 3 stream
+// variant: 0 direct, 1 first-round tiled, 2 strip, 3 stream, 4 narrower stream (nullptr when there is none)
 const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int variant)
 {
+	if (variant == 4)
+		return (kind == SK_U16 && nch == 4 && (interp == 1 || interp == 2)) ? &stream_u16x4_tw128[interp - 1] : nullptr;
 	int s;
 	switch (kind) {
 	case SK_U8:  s = 0; break;
