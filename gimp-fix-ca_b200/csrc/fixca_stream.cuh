@@ -302,7 +302,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	// Both forms run the same row loop without index arithmetic, so a bent warp costs about as much as a
 	// regular one (a per-tap path with clamps in the loop made every CTA of an edge strip a 1.4x straggler).
 	float wt[P][NW];
-	int cofs[P];
+	int cofs[P];		// ... relative to colbase
 	int colbase;		// byte offset of shared sample 0 from the window row start
 	bool regular;
 	{
@@ -349,7 +349,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				}
 				wt[k][jj] = v;
 			}
-			cofs[k] = (tap[k][0] + k) * BPP + 2 * c * (int)sizeof(S) - wb0;
+			cofs[k] = (tap[k][0] + k - bmin) * BPP;
 		}
 		colbase = bmin * BPP + 2 * c * (int)sizeof(S) - wb0;
 	}
@@ -369,8 +369,10 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		for (int k = 0; k < P; ++k)
 			hr[u][k] = 0.f;
 	int ph = (5 - T) & 3;	// after the T - 1 priming rows of a segment the ring is back at slot 0
-	const unsigned char *prow = win + ((s_done + 1) % NR) * wpitch;	// row s_done + 1
-	const unsigned char *const win_end = win + NR * wpitch;
+	// the thread's view of the window ring: every row pointer already carries its column offset
+	const unsigned char *const win_c = win + colbase;
+	const unsigned char *const win_end = win_c + NR * wpitch;
+	const unsigned char *prow = win_c + ((s_done + 1) % NR) * wpitch;	// shared sample 0 of row s_done + 1
 	const int qoff = lt * P * BPP + 2 * c * (int)sizeof(S);
 
 	auto run = [&](auto regular_form) {
@@ -391,7 +393,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 
 			if (a.debug & 1) {	// timing experiment: memory pipeline only (results are wrong)
 				s_done = s_end;
-				prow = win + ((s_done + 1) % NR) * wpitch;
+				prow = win_c + ((s_done + 1) % NR) * wpitch;
 				fence_proxy_async_smem();
 				mbar_arrive(done_bar);
 				continue;
@@ -402,7 +404,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				if (REG) {
 #pragma unroll
 					for (int mm = 0; mm < NS; ++mm)
-						smp[mm] = Codec::load(p + colbase + mm * BPP);
+						smp[mm] = Codec::load(p + mm * BPP);
 				} else {
 #pragma unroll
 					for (int k = 0; k < P; ++k)
@@ -430,7 +432,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				++s_done;
 				prow += wpitch;
 				if (prow == win_end)
-					prow = win;
+					prow = win_c;
 			};
 			// the output rows completed by the newest row (slot U)
 			auto emit = [&](auto slot) {
@@ -513,7 +515,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 					for (int u = 0; u < UNR; ++u) {
 						const unsigned char *pnext = prow + wpitch;
 						if (pnext == win_end)
-							pnext = win;
+							pnext = win_c;
 						// (after the chunk's last row the samples are simply dropped)
 						if (REG)
 							load_row(pnext, smp[REG ? (u + 1) & 1 : 0]);
