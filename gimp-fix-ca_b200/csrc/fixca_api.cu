@@ -260,6 +260,11 @@ static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_
 		if (!k)
 			return fail(FIXCA_ERR_FORMAT, "no tiled kernel for this format");
 		const int limit = smem_limit(dev);
+		if (g.interp == 0) {
+			const KernelEntry *ks = lookup_none_stream(f.sample_bytes, f.nch);
+			if (ks && plan_stream(ks, f, g, y1, y2, dev, limit, pl))
+				return FIXCA_OK;
+		}
 		if (k->stream) {
 			if (plan_stream(k, f, g, y1, y2, dev, limit, pl))
 				return FIXCA_OK;
@@ -501,7 +506,8 @@ static unsigned env_signature()
 {
 	static const char *const names[] = {"FIXCA_FAST_KERNEL", "FIXCA_STRIP_TW", "FIXCA_TILE_H", "FIXCA_TILE_CTAS",
 					    "FIXCA_STREAM_CTAS", "FIXCA_STREAM_DEPTH", "FIXCA_STREAM_SEGS",
-					    "FIXCA_STREAM_DEBUG", "FIXCA_VERBOSE"};
+					    "FIXCA_STREAM_DEBUG", "FIXCA_VERBOSE", "FIXCA_NONE_KERNEL", "FIXCA_STREAM_NOALT",
+					    "FIXCA_STREAM_TW8"};
 	unsigned h = 2166136261u;
 	for (const char *n : names) {
 		const char *v = getenv(n);

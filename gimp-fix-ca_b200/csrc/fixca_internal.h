@@ -29,6 +29,8 @@ constexpr int TILE_W = 128;
 
 // sample_bytes in {1,2,4,8}; nch in {3,4}
 const KernelEntry *lookup_none(int sample_bytes, int nch, bool tiled);
+// the streaming None kernel for this format, or nullptr (8-byte samples, FIXCA_NONE_KERNEL=tiled)
+const KernelEntry *lookup_none_stream(int sample_bytes, int nch);
 // kind in {SK_U8,SK_U16,SK_U32,SK_F32,SK_F64}; interp in {1,2}
 const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled);
 // kind in {SK_U8,SK_U16,SK_F32}; interp in {1,2}

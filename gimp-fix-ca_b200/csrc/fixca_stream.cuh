@@ -128,8 +128,8 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	constexpr int BPP = NCH * (int)sizeof(S);
 	constexpr int OUT_PITCH = TW * BPP;
 	constexpr int STAGE_BYTES = STREAM_CH * OUT_PITCH;
-	constexpr int T = INTERP == 1 ? 2 : 4;
-	constexpr int OFF = INTERP == 1 ? 0 : 1;
+	constexpr int T = INTERP == 0 ? 1 : INTERP == 1 ? 2 : 4;	// taps per axis (None: the nearest sample)
+	constexpr int OFF = INTERP == 2 ? 1 : 0;
 	constexpr int NW = P == 1 ? T : T + 1;
 	constexpr int NS = P + NW - 1;
 	constexpr int NTC = 2 * TW / P;		// compute threads
@@ -140,8 +140,6 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	static_assert(ALT || HALF % 32 == 0, "a warp must not straddle the two channels");
 	static_assert(NTC % 32 == 0, "whole compute warps");
 	static_assert(2 * CH <= 32, "one producer lane per (channel, row) of a chunk");
-	typedef StripCodec<S> Codec;
-
 	StreamHeader *hdr = reinterpret_cast<StreamHeader *>(smem);
 	StreamMeta *meta = reinterpret_cast<StreamMeta *>(smem + a.off_ytab);
 	unsigned char *win = smem + a.off_win;
@@ -183,6 +181,24 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	uint64_t *full = reinterpret_cast<uint64_t *>(hdr->full);
 	uint64_t *done = reinterpret_cast<uint64_t *>(hdr->done);
 
+	// first / last source row output row y of channel ch touches (fix-ca.c:1105-1106 None, :1219-1256 Cubic)
+	auto first_tap_row = [&](int ch, int y) {
+		if constexpr (INTERP == 0) {
+			return nearest_index(a.g.y[ch], y);
+		} else {
+			double td;
+			return max(base_index(a.g.y[ch], y, td) - OFF, 0);
+		}
+	};
+	auto last_tap_row = [&](int ch, int y) {
+		if constexpr (INTERP == 0) {
+			return nearest_index(a.g.y[ch], y);
+		} else {
+			double td;
+			return min(base_index(a.g.y[ch], y, td) + T - 1 - OFF, H - 1);
+		}
+	};
+
 	if (tid >= NTC + 32) {
 		// =====================================================================
 		// row-coefficient warp: vertical weights and bookkeeping of the chunks ahead
@@ -198,8 +214,19 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			const int ch = (lane / CH) & 1, r = lane % CH;
 			const bool mine = lane < 2 * CH && r < nr;
 			int last = 0;
+			if constexpr (INTERP == 0) {
+				// None: the ring offset of the one source row each output row copies from (rows past
+				// the band's end repeat its last row: the copy loop is not predicated, the store clips)
+				if (lane < 2 * CH) {
+					const int src = nearest_index(a.g.y[ch], min(y_first + r, yb - 1));
+					m.wy[r][ch] = make_float4(__int_as_float((src % NR) * wpitch), 0.f, 0.f, 0.f);
+				}
+			}
 			if (mine) {
-				m.wy[r][ch] = position_weights<INTERP>(a.g.y[ch], y_first + r, H, Codec::kInvMax, last);
+				if constexpr (INTERP == 0)
+					last = nearest_index(a.g.y[ch], y_first + r);
+				else
+					m.wy[r][ch] = position_weights<INTERP>(a.g.y[ch], y_first + r, H, StripCodec<S>::kInvMax, last);
 				m.last[ch][r] = last;
 				if (r == nr - 1) {
 					m.last[ch][nr] = INT_MAX;
@@ -235,20 +262,12 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		const int group_bytes = 4 * wpitch;
 		const int c0_win = wb0 >> 3, c0_tile = (x0 * BPP) >> 3;
 		int loaded_g;				// highest 4-row group already requested
-		{
-			double td;
-			const int fr = max(base_index(a.g.y[0], ya, td) - OFF, 0);
-			const int fb = max(base_index(a.g.y[1], ya, td) - OFF, 0);
-			loaded_g = (min(fr, fb) >> 2) - 1;
-		}
+		loaded_g = (min(first_tap_row(0, ya), first_tap_row(1, ya)) >> 2) - 1;
 		int gslot = (loaded_g + 1) % NRG;	// ring slot of group loaded_g + 1
 		int wnf = 0;				// window requests: i % NF
 		auto request_window = [&](int i) {	// the source rows chunk i adds to the ring
 			const int y_last = min(ya + i * CH + CH, yb) - 1;
-			double td;
-			const int hr_ = min(base_index(a.g.y[0], y_last, td) + T - 1 - OFF, H - 1);
-			const int hb_ = min(base_index(a.g.y[1], y_last, td) + T - 1 - OFF, H - 1);
-			const int hi_g = max(max(hr_, hb_) >> 2, loaded_g);
+			const int hi_g = max(max(last_tap_row(0, y_last), last_tap_row(1, y_last)) >> 2, loaded_g);
 			uint64_t *bar = &full[wnf];
 			mbar_arrive_expect_tx(bar, (uint32_t)((hi_g - loaded_g) * group_bytes));
 			for (int g = loaded_g + 1; g <= hi_g; ++g) {
@@ -295,6 +314,44 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	// wavefronts for 8- and 16-byte pixels).  Otherwise the channel is uniform per warp.
 	const int c = ALT ? (tid & 1) : tid / HALF;	// 0 red, 1 blue
 	const int lt = ALT ? (tid >> 1) : tid - c * HALF;
+	const int qoff = lt * P * BPP + 2 * c * (int)sizeof(S);
+
+	if constexpr (INTERP == 0) {
+		// ---- None (fix-ca.c:1100-1121): dst.c = src[nearest row][nearest column].c as raw sample bytes,
+		// exact for every payload; green / alpha are already in the staging buffer (pass-through tile)
+		int cofs[P];
+#pragma unroll
+		for (int k = 0; k < P; ++k)
+			cofs[k] = nearest_index(a.g.x[c], x0 + lt * P + k) * BPP + 2 * c * (int)sizeof(S) - wb0;
+		int jnf = 0, jstg = 0, jpar = 0;	// j % NF, j % NSTG, (j / NF) & 1
+		for (int j = 0; j < nchunks; ++j) {
+			mbar_wait(&full[jnf], (uint32_t)jpar);
+			const StreamMeta &m = meta[jnf];
+			uint64_t *const done_bar = &done[jnf];
+			unsigned char *q = stage + jstg * STAGE_BYTES + qoff;
+			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
+			jstg = jstg + 1 == NSTG ? 0 : jstg + 1;
+			if (!(a.debug & 1)) {
+				// rows past the band's end (last chunk) repeat valid offsets and are clipped by the store
+				S v[CH][P];
+#pragma unroll
+				for (int r = 0; r < CH; ++r) {
+					const unsigned char *prow = win + __float_as_int(m.wy[r][c].x);
+#pragma unroll
+					for (int k = 0; k < P; ++k)
+						v[r][k] = *reinterpret_cast<const S *>(prow + cofs[k]);
+				}
+#pragma unroll
+				for (int r = 0; r < CH; ++r)
+#pragma unroll
+					for (int k = 0; k < P; ++k)
+						*reinterpret_cast<S *>(q + r * OUT_PITCH + k * BPP) = v[r][k];
+			}
+			fence_proxy_async_smem();
+			mbar_arrive(done_bar);
+		}
+	} else {
+	typedef StripCodec<S> Codec;
 
 	// regular: the P columns share one window of NS consecutive samples; wt[k][jj] weighs sample k + jj.
 	// otherwise ("bent": tap windows squeezed against an image edge, fix-ca.c:1271-1298): column k reads its
@@ -304,6 +361,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	float wt[P][NW];
 	int cofs[P];		// ... relative to colbase
 	int colbase;		// byte offset of shared sample 0 from the window row start
+	int cmax;		// bent form: offset of the image's last column (samples past it carry no weight)
 	bool regular;
 	{
 		float w[P][4];
@@ -331,6 +389,12 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		// regular: every tap that carries weight sits at shared sample k + j', 0 <= j' < NW, and the
 		// NS samples lie inside the window
 		regular = bmin >= col_lo && bmin + NS - 1 <= col_hi;
+		// Float samples: a zero weight does not silence a NaN.  Columns left of the image and right of
+		// its 16-byte-aligned row end are zero-filled by the TMA unit, but the bytes between width * BPP
+		// and that row end are whatever the caller's pitch padding holds: such windows go the bent way,
+		// which clamps its sample offsets to the last column.
+		if (std::is_floating_point<S>::value)
+			regular = regular && bmin + NS - 1 <= W - 1;
 #pragma unroll
 		for (int k = 0; k < P; ++k)
 #pragma unroll
@@ -352,6 +416,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			cofs[k] = (tap[k][0] + k - bmin) * BPP;
 		}
 		colbase = bmin * BPP + 2 * c * (int)sizeof(S) - wb0;
+		cmax = (W - 1 - bmin) * BPP;
 	}
 
 	int s_done;	// last source row this thread has filtered horizontally
@@ -373,7 +438,6 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	const unsigned char *const win_c = win + colbase;
 	const unsigned char *const win_end = win_c + NR * wpitch;
 	const unsigned char *prow = win_c + ((s_done + 1) % NR) * wpitch;	// shared sample 0 of row s_done + 1
-	const int qoff = lt * P * BPP + 2 * c * (int)sizeof(S);
 
 	auto run = [&](auto regular_form) {
 		constexpr bool REG = decltype(regular_form)::value;
@@ -410,7 +474,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 					for (int k = 0; k < P; ++k)
 #pragma unroll
 						for (int jj = 0; jj < T; ++jj)
-							smp[k * T + jj] = Codec::load(p + cofs[k] + jj * BPP);
+							smp[k * T + jj] = Codec::load(p + min(cofs[k] + jj * BPP, cmax));
 				}
 			};
 			auto hfilter = [&](const float (&smp)[NSL], float (&out)[P]) {
@@ -555,6 +619,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		run(std::true_type());
 	else
 		run(std::false_type());
+	}	// INTERP != 0
 }
 
 } // namespace fixca

@@ -91,6 +91,12 @@ if __name__ == "__main__":
         for w in (6144, 6000, 5888, 6100):
             run("rgb8 cubic w=%d" % w, 4000, w, 3, torch.uint8, 1, 2, F)
             run("rgb8 linear w=%d" % w, 4000, w, 3, torch.uint8, 1, 1, F)
+    if which == "none":
+        run("100MP rgb16 none", 8192, 12288, 3, torch.int16, 2, 0, E)
+        run("24MP rgb8 none", 4000, 6000, 3, torch.uint8, 1, 0, E)
+        run("8K rgba16 none", 4320, 7680, 4, torch.int16, 2, 0, E, lens=(658, 1280))
+        run("50MP rgb f32 none", 6144, 8192, 3, torch.float32, -4, 0, E)
+        run("50MP rgba f32 none", 6144, 8192, 4, torch.float32, -4, 0, E)
     if which == "x4":       # run with and without FIXCA_STREAM_NOALT=1 (separate processes: plans are cached)
         run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
         run("8K rgba16 linear fast", 4320, 7680, 4, torch.int16, 2, 1, F, lens=(658, 1280))

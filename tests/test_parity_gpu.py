@@ -114,6 +114,35 @@ def test_matrix_exact(fx, checker, dtype, ch):
 FAST_SHAPES = [(1, 1), (2, 3), (5, 40), (7, 129), (129, 7), (64, 128), (65, 257), (33, 513), (301, 517), (97, 1000), (40, 2051)]
 
 
+@pytest.mark.parametrize("dtype,ch", [("u1", 3), ("u1", 4), ("u2", 3), ("u2", 4), ("u4", 3), ("u4", 4)])
+def test_matrix_none_stream(fx, checker, dtype, ch):
+    """interpolation = None on the streaming kernel: every sample size x awkward shapes (strips narrower than
+    a warp's column group, widths that are not a multiple of the strip, bands that end inside a chunk) x lens
+    positions x scales on both sides of 1: identical bytes (fix-ca.c:1100-1121)."""
+    n, kernels = 0, set()
+    rng = np.random.default_rng(77)
+    for (h, w), lens, amounts in itertools.product(FAST_SHAPES, ("c", (0, 0), (-1, -1)),
+                                                   ((3.0, -2.0), (-6.0, 2.4), (0.0, 0.0), (30.0, -30.0))):
+        n += 1
+        lx, ly = (w // 2, h // 2) if lens == "c" else lens
+        kw = dict(KW, blue=amounts[0], red=amounts[1], lens_x=lx, lens_y=ly, interpolation=0)
+        m = max_dim(w, h, lx, ly)
+        if m + kw["blue"] <= 0 or m + kw["red"] <= 0:
+            continue
+        img = rng.integers(0, np.iinfo(dtype).max, size=(h, w, ch), dtype=dtype, endpoint=True)
+        want = checker.region(img, orc.Params(**kw))
+        got = fx.correct(img, fx.FixCaParams(**kw))
+        kernels.add(fx.last_kernel().split("/")[0])
+        assert got.tobytes() == want.tobytes(), (h, w, dtype, ch, lens, amounts, fx.last_kernel())
+        # a band that starts and ends inside chunks, into a poisoned buffer: only its rows change
+        if h >= 6:
+            y1, y2 = h // 3 + 1, max(h // 3 + 2, 2 * h // 3 - 1)
+            out = np.full_like(img, 0x5A)
+            fx.correct(img, fx.FixCaParams(**kw), y1=y1, y2=y2, out=out)
+            assert out[y1:y2].tobytes() == want[y1:y2].tobytes() and (out[:y1] == 0x5A).all() and (out[y2:] == 0x5A).all()
+    assert "stream" in kernels, kernels
+
+
 @pytest.mark.parametrize("variant", ["stream", "strip"])
 @pytest.mark.parametrize("dtype,ch", [("u1", 3), ("u1", 4), ("u2", 3), ("u2", 4), ("f4", 3), ("f4", 4)])
 def test_matrix_fast(fx, checker, dtype, ch, variant, monkeypatch):
@@ -144,13 +173,17 @@ def test_matrix_fast(fx, checker, dtype, ch, variant, monkeypatch):
     assert variant in kernels, kernels
 
 
-def test_none_is_bit_exact_for_every_sample_size_including_nan_payloads(fx, checker):
+@pytest.mark.parametrize("variant", ["stream", "tiled"])
+def test_none_is_bit_exact_for_every_sample_size_including_nan_payloads(fx, checker, variant, monkeypatch):
+    monkeypatch.setenv("FIXCA_NONE_KERNEL", variant)
     rng = np.random.default_rng(3)
     for dt, ch in itertools.product(("u1", "u2", "u4", "u8"), (3, 4)):
         img = rng.integers(0, np.iinfo(dt).max, size=(131, 259, ch), dtype=dt, endpoint=True)
         kw = dict(KW, lens_x=100, lens_y=60, interpolation=0)
         want = checker.region(img, orc.Params(**kw))
         assert fx.correct(img, fx.FixCaParams(**kw)).tobytes() == want.tobytes()
+        # 8-byte samples have no streaming kernel (a strip of them exceeds a TMA box)
+        assert fx.last_kernel().startswith("tiled" if dt == "u8" else variant), fx.last_kernel()
         # the same bits viewed as floats (NaN payloads, infinities) must pass through untouched
         if dt in ("u4", "u8"):
             fimg = img.view("f4" if dt == "u4" else "f8")
