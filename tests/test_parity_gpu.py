@@ -319,6 +319,29 @@ def test_device_resident_entry_with_torch_buffers(fx, checker):
     assert fx.last_kernel().startswith("direct") and d2.cpu().numpy().tobytes() == want2.tobytes()
 
 
+def test_float_pitch_padding_is_never_sampled(fx, checker):
+    """FAST float kernels weigh out-of-image samples with 0, and 0 * NaN is NaN: the bytes between width * bpp
+    and the 16-byte row end (caller's pitch padding, not zero-filled by the TMA unit) must not be read.
+    Device-resident call with the padding of every row set to NaN bit patterns, widths around strip ends."""
+    import torch
+    stream = torch.cuda.current_stream().cuda_stream
+    for (h, w, ch), interp in itertools.product(((129, 7, 3), (40, 131, 3), (33, 517, 4), (70, 257, 3)), (1, 2)):
+        kw = dict(KW, lens_x=w // 2, lens_y=h // 2, interpolation=interp)
+        img = orc.synth_image(h, w, ch, "f4", seed=900 + w)
+        want = checker.region(img, orc.Params(**kw))
+        bpp, pitch = ch * 4, (w * ch * 4 + 127) // 128 * 128
+        src = torch.full((h, pitch), 0xFF, dtype=torch.uint8, device="cuda")          # 0xFFFFFFFF = NaN
+        src[:, :w * bpp] = torch.from_numpy(img.view(np.uint8).reshape(h, w * bpp)).cuda()
+        dst = torch.zeros_like(src)
+        fx.fix_ca_region_dev(src.data_ptr(), pitch, 0, h, dst.data_ptr(), pitch, 0, w, h, bpp, -4,
+                             fx.FixCaParams(**kw), 0, h, fx.PRECISION_FAST, stream)
+        torch.cuda.synchronize()
+        got = dst[:, :w * bpp].cpu().numpy().view(np.float32).reshape(h, w, ch)
+        assert fx.last_kernel().startswith("stream")
+        assert np.isfinite(got).all()
+        assert np.abs(got.astype(np.float64) - want).max() <= FLOAT_ABS_TOL, (h, w, ch, interp)
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json's full sizes: size-independent properties + oracle on sampled bands
 # ---------------------------------------------------------------------------------------------
