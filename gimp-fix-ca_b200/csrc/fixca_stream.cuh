@@ -435,9 +435,11 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			hr[u][k] = 0.f;
 	int ph = (5 - T) & 3;	// after the T - 1 priming rows of a segment the ring is back at slot 0
 	// the thread's view of the window ring: every row pointer already carries its column offset
-	const unsigned char *const win_c = win + colbase;
-	const unsigned char *const win_end = win_c + NR * wpitch;
-	const unsigned char *prow = win_c + ((s_done + 1) % NR) * wpitch;	// shared sample 0 of row s_done + 1
+	// (32-bit shared-window addresses: one add / compare / select per row; with generic pointers the
+	// compiler kept a second, converted copy of the chain for the ld.shared operands)
+	const uint32_t win_c = smem_u32(win) + (uint32_t)colbase;
+	const uint32_t win_end = win_c + (uint32_t)(NR * wpitch);
+	uint32_t prow = win_c + (uint32_t)(((s_done + 1) % NR) * wpitch);	// shared sample 0 of row s_done + 1
 
 	// form 0: bent; 1: regular, NW weights per column; 2: regular and no column group of the warp
 	// straddles a drift of the tap window (the usual case: the map drifts one sample every
@@ -462,24 +464,24 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 
 			if (a.debug & 1) {	// timing experiment: memory pipeline only (results are wrong)
 				s_done = s_end;
-				prow = win_c + ((s_done + 1) % NR) * wpitch;
+				prow = win_c + (uint32_t)(((s_done + 1) % NR) * wpitch);
 				fence_proxy_async_smem();
 				mbar_arrive(done_bar);
 				continue;
 			}
 
 			// a source row's samples / the P horizontal results from them, in either form
-			auto load_row = [&](const unsigned char *p, float (&smp)[NSL]) {
+			auto load_row = [&](const uint32_t p, float (&smp)[NSL]) {
 				if (REG) {
 #pragma unroll
 					for (int mm = 0; mm < NSL; ++mm)
-						smp[mm] = Codec::load(p + mm * BPP);
+						smp[mm] = Codec::load_at(p + mm * BPP);
 				} else {
 #pragma unroll
 					for (int k = 0; k < P; ++k)
 #pragma unroll
 						for (int jj = 0; jj < T; ++jj)
-							smp[k * T + jj] = Codec::load(p + min(cofs[k] + jj * BPP, cmax));
+							smp[k * T + jj] = Codec::load_at(p + (uint32_t)min(cofs[k] + jj * BPP, cmax));
 				}
 			};
 			auto hfilter = [&](const float (&smp)[NSL], float (&out)[P]) {
@@ -499,7 +501,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				load_row(prow, smp);
 				hfilter(smp, hr[U]);
 				++s_done;
-				prow += wpitch;
+				prow += (uint32_t)wpitch;
 				if (prow == win_end)
 					prow = win_c;
 			};
@@ -582,7 +584,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				for (int it = 0; it < CH / UNR; ++it) {
 #pragma unroll
 					for (int u = 0; u < UNR; ++u) {
-						const unsigned char *pnext = prow + wpitch;
+						uint32_t pnext = prow + (uint32_t)wpitch;
 						if (pnext == win_end)
 							pnext = win_c;
 						// (after the chunk's last row the samples are simply dropped)

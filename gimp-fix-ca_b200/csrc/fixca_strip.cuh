@@ -75,6 +75,14 @@ template <> struct StripCodec<uint8_t> {
 		asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
 		return f;
 	}
+	__device__ __forceinline__ static float load_at(uint32_t saddr)	// 32-bit shared-window address
+	{
+		unsigned v;
+		float f;
+		asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+		asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
+		return f;
+	}
 	__device__ __forceinline__ static void store(unsigned char *p, float sat01)
 	{
 		*p = (unsigned char)__float_as_uint(fmaf(sat01, 255.0f, 12582912.0f));
@@ -90,6 +98,14 @@ template <> struct StripCodec<uint16_t> {
 		asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
 		return f;
 	}
+	__device__ __forceinline__ static float load_at(uint32_t saddr)
+	{
+		unsigned v;
+		float f;
+		asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+		asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
+		return f;
+	}
 	__device__ __forceinline__ static void store(unsigned char *p, float sat01)
 	{
 		*reinterpret_cast<uint16_t *>(p) = (uint16_t)__float_as_uint(fmaf(sat01, 65535.0f, 12582912.0f));
@@ -98,6 +114,12 @@ template <> struct StripCodec<uint16_t> {
 template <> struct StripCodec<float> {
 	static constexpr float kInvMax = 1.0f;
 	__device__ __forceinline__ static float load(const unsigned char *p) { return *reinterpret_cast<const float *>(p); }
+	__device__ __forceinline__ static float load_at(uint32_t saddr)
+	{
+		float f;
+		asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f) : "r"(saddr));
+		return f;
+	}
 	__device__ __forceinline__ static void store(unsigned char *p, float sat01) { *reinterpret_cast<float *>(p) = sat01; }
 };
 
