@@ -54,6 +54,10 @@ WORKLOADS = {
     "cfg4_50mp_rgbf32_cubic": (8192, 6144, 3, "f4", 2, dict(blue=3.0, red=-2.0, **DIRECTIONAL), "centre"),
     "cfg5_4k_rgb8_cubic": (3840, 2160, 3, "u1", 2, dict(blue=1.0, red=-1.5, **DIRECTIONAL), "centre"),
 }
+# BASELINE configs[4]: a batch of frames per GPU (frames sharded by index, no communication): the step is ONE
+# fixca_cuda_frames_dev launch over every frame this rank holds
+WORKLOADS["cfg5_batch_4k_rgb8_cubic"] = WORKLOADS["cfg5_4k_rgb8_cubic"]
+WORKLOAD_FRAMES = {"cfg5_batch_4k_rgb8_cubic": 128}
 DEFAULT_WORKLOAD = "target_100mp_rgb16_cubic"
 INTERP_NAME = {0: "none", 1: "linear", 2: "cubic"}
 
@@ -240,6 +244,110 @@ def workload_config(name, n, extra=None):
 # ---------------------------------------------------------------------------------------------
 # the CUDA path
 # ---------------------------------------------------------------------------------------------
+def run_cuda_batch(args, torch, dist, fixca, rank, world, local, dev, barrier, max_over_ranks):
+    """Frame batches (BASELINE configs[4]): every rank holds `frames` device-resident frames; a step is one launch
+    over all of them.  e2e: the host-frame stream API (pinned H2D / kernel / D2H ring) on a few frames."""
+    import ctypes
+    W, H, ch, dts, interp, kw, lens = WORKLOADS[args.workload]
+    F = WORKLOAD_FRAMES[args.workload]
+    dt = np.dtype(dts)
+    bpp, bpc = ch * dt.itemsize, bpc_of(dt)
+    lx, ly = (W // 2, H // 2) if lens == "centre" else lens
+    p = fixca.FixCaParams(interpolation=interp, lens_x=float(lx), lens_y=float(ly), **kw)
+    flags = fixca.PRECISION_EXACT if args.exact else fixca.PRECISION_FAST
+    row_bytes = W * bpp
+    pitch = (row_bytes + 127) // 128 * 128
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    d_src = torch.randint(0, 256, (F, H, pitch), dtype=torch.uint8, device=dev, generator=g)
+    d_dst = torch.empty_like(d_src)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        fixca.fix_ca_frames_dev(d_src.data_ptr(), pitch, pitch * H, d_dst.data_ptr(), pitch, pitch * H, F, W, H, bpp, bpc, p,
+                                flags, stream.cuda_stream)
+
+    sampler = ClockSampler(_nvml_index(local))
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    n0 = fixca.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    sampler.stop()
+    launches = fixca.launch_count() - n0
+    kernel = fixca.last_kernel()
+    ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    total_mp_step = W * H * F * world / 1e6
+    local_ms = e0.elapsed_time(e1) / args.steps
+    alg_bytes = 2.0 * bpp * W * H * F
+    achieved = alg_bytes / (local_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+
+    e2e = parity = None
+    if not args.no_e2e:
+        nf = 16
+        h_src = torch.empty((nf, H, row_bytes), dtype=torch.uint8, pin_memory=True)
+        h_dst = torch.empty((nf, H, row_bytes), dtype=torch.uint8, pin_memory=True)
+        h_src.copy_(d_src[:nf, :, :row_bytes])
+        torch.cuda.synchronize()
+        vp = ctypes.c_void_p
+        srcs = (vp * nf)(*[h_src[k].data_ptr() for k in range(nf)])
+        dsts = (vp * nf)(*[h_dst[k].data_ptr() for k in range(nf)])
+        L = fixca.load()
+
+        def e2e_step():
+            rc = L.fixca_cuda_frames(srcs, dsts, nf, W, H, bpp, bpc, ctypes.byref(p), flags, local)
+            if rc:
+                raise RuntimeError("fixca_cuda_frames: %d" % rc)
+
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        dt_e2e = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e = {"value": round(W * H * nf * world * e2e_steps / 1e6 / dt_e2e, 1), "unit": "MP/s",
+               "h2d_bytes_per_step": int(nf * H * row_bytes) * world, "d2h_bytes_per_step": int(nf * H * row_bytes) * world,
+               "steps": e2e_steps, "ms_per_step": round(dt_e2e / e2e_steps * 1e3, 3),
+               "api": "fixca_cuda_frames (%d pinned host frames per step, H2D / kernel / D2H ring), synchronous" % nf}
+        if rank == 0 and not args.no_check:
+            parity = spot_check(args, h_src[0], h_dst[0], W, H, ch, dt, p, 0, 0, kw, interp, lx, ly)
+    if rank == 0:
+        cfg = workload_config(args.workload, 1, "arithmetic %s; kernel %s" % (
+            "exact FP64 (bit-identical)" if args.exact else "fast FP32 (+-1 LSB of the reference)", kernel))
+        cfg.update({"frames_per_gpu": F, "image": "%dx%d x %d frames" % (W, H, F * world),
+                    "parallelism": "frames sharded by index over %d GPU(s), no collective" % world,
+                    "cache": "inputs larger than L2 (%.0f MB in + %.0f MB out per GPU vs 126 MB L2)"
+                             % (F * H * row_bytes / 1e6, F * H * row_bytes / 1e6)})
+        cfg.pop("rows_per_gpu", None)
+        line = {
+            "metric": "megapixels/sec (cubic, lateral+directional)" if interp == 2 else "megapixels/sec",
+            "value": round(total_mp_step / (ms_step * 1e-3), 1), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.exact else "f32", "data": "synthetic",
+            "config": cfg,
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload, kernel),
+                         "peak_source": peak_src, "kernel": kernel,
+                         "algorithmic_bytes_per_launch": int(alg_bytes), "launch_ms": round(local_ms, 5)},
+            "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.report(),
+        }
+        if parity is not None:
+            line["parity"] = parity
+        print(json.dumps(line), file=args.out, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -272,6 +380,8 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if args.workload in WORKLOAD_FRAMES:
+        return run_cuda_batch(args, torch, dist, fixca, rank, world, local, dev, barrier, max_over_ranks)
     W, Hr, ch, dts, interp, kw, lens = WORKLOADS[args.workload]
     dt = np.dtype(dts)
     bpp = ch * dt.itemsize

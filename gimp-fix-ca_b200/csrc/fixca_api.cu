@@ -138,6 +138,15 @@ struct Plan {
 	// stream kernel: TMA tensor maps of the source (window groups, pass-through tiles) and destination
 	CUtensorMap tm_win, tm_tile, tm_out;
 	int src_rows_avail = 0;	// rows of the source band present at args.src
+	// a batch of equal frames in one launch (stream kernels: grid.z = frame, 3-D tensor maps)
+	int nframes = 1;
+	size_t src_frame_stride = 0, dst_frame_stride = 0;
+};
+
+// frames of a batch: frame i starts src_stride / dst_stride bytes after frame i - 1
+struct Batch {
+	int nframes = 1;
+	size_t src_stride = 0, dst_stride = 0;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -235,9 +244,13 @@ struct Plan;
 static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g, int y1, int y2, int dev, int limit, Plan &pl);
 
 static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_src, size_t src_pitch, int src_row0, int src_rows,
-			      void *d_dst, size_t dst_pitch, int dst_row0, int y1, int y2, unsigned flags, int dev, Plan &pl)
+			      void *d_dst, size_t dst_pitch, int dst_row0, int y1, int y2, unsigned flags, int dev, Plan &pl,
+			      const Batch &batch)
 {
 	pl = Plan();
+	pl.nframes = batch.nframes;
+	pl.src_frame_stride = batch.src_stride;
+	pl.dst_frame_stride = batch.dst_stride;
 	KernelArgs &a = pl.args;
 	memset(&a, 0, sizeof a);
 	a.src = (const unsigned char *)d_src;
@@ -252,8 +265,12 @@ static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_
 	pl.src_rows_avail = src_rows;
 
 	const bool tma_ok = g.monotone && (src_pitch % 16 == 0) && (dst_pitch % 16 == 0) &&
-			    ((uintptr_t)d_src % 16 == 0) && ((uintptr_t)d_dst % 16 == 0);
+			    ((uintptr_t)d_src % 16 == 0) && ((uintptr_t)d_dst % 16 == 0) &&
+			    (batch.nframes <= 1 || (batch.src_stride % 16 == 0 && batch.dst_stride % 16 == 0));
 	bool want_tiled = tma_ok && !(flags & FIXCA_FORCE_DIRECT);
+	// only the streaming kernels take a batch in one launch; every other plan is for one frame and the
+	// caller loops (pl.nframes tells which)
+	struct OneFrame { Plan &p; ~OneFrame() { if (!p.k || !p.k->stream) { p.nframes = 1; p.src_frame_stride = p.dst_frame_stride = 0; } } } one_frame{pl};
 
 	if (want_tiled) {
 		const KernelEntry *k = pick_kernel(f, g.interp, flags, true);
@@ -371,19 +388,21 @@ static encode_tiled_fn encode_tiled()
 	return fn;
 }
 
-// A 2-D map of 8-byte elements over `rows` rows of `row_bytes` (multiple of 16) bytes at `pitch`;
-// boxes of box_bytes x box_rows.  Out-of-range parts of a box are zero-filled on load, dropped on store.
+// A 3-D map of 8-byte elements over `frames` frames (frame_stride bytes apart) of `rows` rows of `row_bytes`
+// (multiple of 16) bytes at `pitch`; boxes of box_bytes x box_rows x 1.  Out-of-range parts of a box are
+// zero-filled on load, dropped on store.
 static bool make_tensor_map(CUtensorMap &tm, const void *base, size_t pitch, size_t row_bytes, size_t rows,
-			    unsigned box_bytes, unsigned box_rows)
+			    size_t frames, size_t frame_stride, unsigned box_bytes, unsigned box_rows)
 {
 	encode_tiled_fn enc = encode_tiled();
-	if (!enc || box_bytes % 16 || box_bytes / 8 > 256 || box_rows > 256 || rows == 0 || row_bytes % 16)
+	if (!enc || box_bytes % 16 || box_bytes / 8 > 256 || box_rows > 256 || rows == 0 || row_bytes % 16 || frames == 0 ||
+	    frame_stride % 16 || pitch % 16)
 		return false;
-	const cuuint64_t dims[2] = {row_bytes / 8, rows};
-	const cuuint64_t strides[1] = {pitch};
-	const cuuint32_t box[2] = {box_bytes / 8, box_rows};
-	const cuuint32_t estr[2] = {1, 1};
-	return enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void *>(base), dims, strides, box, estr,
+	const cuuint64_t dims[3] = {row_bytes / 8, rows, frames};
+	const cuuint64_t strides[2] = {pitch, frame_stride};
+	const cuuint32_t box[3] = {box_bytes / 8, box_rows, 1};
+	const cuuint32_t estr[3] = {1, 1, 1};
+	return enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(base), dims, strides, box, estr,
 		   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
 		   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -451,6 +470,12 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	const int strips = (g.width + k->tw - 1) / k->tw;
 	const int rows = y2 - y1;
 	int segs = std::max(1, sm_count(dev) * per_sm / strips);
+	if (pl.nframes > 1) {
+		// a batch fills the GPU with frames x strips x segments CTAs: long segments (>= 256 rows) so that
+		// a CTA's set-up and ring priming are spread over many chunks, as long as every SM slot gets a CTA
+		const int fill = (sm_count(dev) * per_sm + strips * pl.nframes - 1) / (strips * pl.nframes);
+		segs = std::max(fill, (rows + 255) / 256);
+	}
 	const int forced = env_int("FIXCA_STREAM_SEGS", 0);
 	if (forced > 0)
 		segs = forced;
@@ -473,16 +498,21 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	a.off_out = (int)off_out;
 	pl.smem = total;
 	pl.block = dim3(threads);
-	pl.grid = dim3(strips, segs);
+	pl.grid = dim3(strips, segs, pl.nframes);
+	if (pl.nframes > 65535)
+		return false;
 	if (env_int("FIXCA_VERBOSE", 0))
 		fprintf(stderr, "fixca: %s grid %d x %d, %d threads, smem %zu B (ring %zu rows x %d B, depth %d), seg %d rows, %d CTA/SM\n",
 			k->name, strips, segs, threads, total, ring_rows, wb, depth, seg_rows, per_sm);
 	// rows as the kernels see them: align16(width * bpp) bytes (they may touch the padding bytes)
 	const size_t row_bytes = align_up((size_t)g.width * f.bpp, 16);
 	const size_t src_rows = (size_t)pl.src_rows_avail, dst_rows = (size_t)(y2 - a.dst_row0);
-	if (!make_tensor_map(pl.tm_win, a.src, (size_t)a.src_pitch, row_bytes, src_rows, (unsigned)wb, 4) ||
-	    !make_tensor_map(pl.tm_tile, a.src, (size_t)a.src_pitch, row_bytes, src_rows, (unsigned)(k->tw * f.bpp), CH) ||
-	    !make_tensor_map(pl.tm_out, a.dst, (size_t)a.dst_pitch, row_bytes, dst_rows, (unsigned)(k->tw * f.bpp), CH))
+	const size_t nf = (size_t)pl.nframes;
+	const size_t sfs = nf > 1 ? pl.src_frame_stride : (size_t)a.src_pitch * src_rows;
+	const size_t dfs = nf > 1 ? pl.dst_frame_stride : (size_t)a.dst_pitch * dst_rows;
+	if (!make_tensor_map(pl.tm_win, a.src, (size_t)a.src_pitch, row_bytes, src_rows, nf, sfs, (unsigned)wb, 4) ||
+	    !make_tensor_map(pl.tm_tile, a.src, (size_t)a.src_pitch, row_bytes, src_rows, nf, sfs, (unsigned)(k->tw * f.bpp), CH) ||
+	    !make_tensor_map(pl.tm_out, a.dst, (size_t)a.dst_pitch, row_bytes, dst_rows, nf, dfs, (unsigned)(k->tw * f.bpp), CH))
 		return false;
 	return true;
 }
@@ -500,6 +530,8 @@ struct PlanKey {
 	int src_row0, src_rows, dst_row0, y1, y2, dev;
 	unsigned flags;
 	unsigned env;
+	int nframes;
+	size_t src_frame_stride, dst_frame_stride;
 };
 
 static unsigned env_signature()
@@ -519,7 +551,8 @@ static unsigned env_signature()
 }
 
 static int make_plan(const Format &f, const Geometry &g, const void *d_src, size_t src_pitch, int src_row0, int src_rows,
-		     void *d_dst, size_t dst_pitch, int dst_row0, int y1, int y2, unsigned flags, int dev, Plan &pl)
+		     void *d_dst, size_t dst_pitch, int dst_row0, int y1, int y2, unsigned flags, int dev, Plan &pl,
+		     const Batch &batch = Batch())
 {
 	PlanKey k;
 	memset(&k, 0, sizeof k);
@@ -534,6 +567,7 @@ static int make_plan(const Format &f, const Geometry &g, const void *d_src, size
 	k.src_row0 = src_row0; k.src_rows = src_rows; k.dst_row0 = dst_row0; k.y1 = y1; k.y2 = y2; k.dev = dev;
 	k.flags = flags;
 	k.env = env_signature();
+	k.nframes = batch.nframes; k.src_frame_stride = batch.src_stride; k.dst_frame_stride = batch.dst_stride;
 	constexpr int SLOTS = 8;
 	static thread_local PlanKey keys[SLOTS];
 	static thread_local Plan plans[SLOTS];
@@ -544,7 +578,7 @@ static int make_plan(const Format &f, const Geometry &g, const void *d_src, size
 			pl = plans[i];
 			return FIXCA_OK;
 		}
-	const int rc = make_plan_uncached(f, g, d_src, src_pitch, src_row0, src_rows, d_dst, dst_pitch, dst_row0, y1, y2, flags, dev, pl);
+	const int rc = make_plan_uncached(f, g, d_src, src_pitch, src_row0, src_rows, d_dst, dst_pitch, dst_row0, y1, y2, flags, dev, pl, batch);
 	if (rc == FIXCA_OK) {
 		keys[next] = k;
 		plans[next] = pl;
@@ -658,6 +692,51 @@ extern "C" int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int sr
 }
 
 // ---------------------------------------------------------------------------
+// device-resident batch of frames
+// ---------------------------------------------------------------------------
+extern "C" int fixca_cuda_frames_dev(const void *d_src, size_t src_pitch, size_t src_frame_stride,
+				     void *d_dst, size_t dst_pitch, size_t dst_frame_stride, int nframes,
+				     int width, int height, int bytes, int bpc,
+				     const fixca_params *params, unsigned flags, void *stream)
+{
+	if (nframes < 0)
+		return fail(FIXCA_ERR_ARG, "negative frame count");
+	if (nframes == 0)
+		return FIXCA_OK;
+	int rc = check_common(d_src, d_dst, width, height, params, 0, height);
+	if (rc) return rc;
+	Format f;
+	if ((rc = parse_format(bytes, bpc, f))) return rc;
+	if (f.kind == SK_U64 && params->interpolation != 0)
+		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples with Linear/Cubic need 80-bit long double arithmetic (fix-ca.c:728-733)");
+	if (flags & FIXCA_PREVIEW_OVERLAY)
+		return fail(FIXCA_ERR_UNSUPPORTED, "the preview overlay is a single-frame call (fixca_cuda_region_dev)");
+	Geometry g;
+	if ((rc = make_geometry(width, height, params, g))) return rc;
+	const size_t row = (size_t)width * bytes;
+	if (src_pitch < row || dst_pitch < row)
+		return fail(FIXCA_ERR_ARG, "pitch smaller than a row (%zu / %zu < %zu)", src_pitch, dst_pitch, row);
+	if (nframes > 1 && (src_frame_stride < src_pitch * (size_t)(height - 1) + row || dst_frame_stride < dst_pitch * (size_t)(height - 1) + row))
+		return fail(FIXCA_ERR_ARG, "frame stride smaller than a frame");
+	int dev;
+	if ((rc = current_device_or(-1, dev))) return rc;
+	const unsigned char *sp = (const unsigned char *)d_src;
+	unsigned char *dp = (unsigned char *)d_dst;
+	for (int first = 0; first < nframes;) {
+		Batch b;
+		b.nframes = std::min(nframes - first, 65535);
+		b.src_stride = src_frame_stride;
+		b.dst_stride = dst_frame_stride;
+		Plan pl;
+		if ((rc = make_plan(f, g, sp + (size_t)first * src_frame_stride, src_pitch, 0, height,
+				    dp + (size_t)first * dst_frame_stride, dst_pitch, 0, 0, height, flags, dev, pl, b))) return rc;
+		if ((rc = launch_plan(pl, (cudaStream_t)stream))) return rc;
+		first += pl.nframes;	// 1 when the plan's kernel has no batch form
+	}
+	return FIXCA_OK;
+}
+
+// ---------------------------------------------------------------------------
 // host region driver
 // ---------------------------------------------------------------------------
 namespace {
@@ -728,6 +807,33 @@ struct DeviceCtx {
 };
 
 DeviceCtx g_ctx[16];
+
+// fixca_cuda_frames: per-device ring of frame slots, kept between calls
+struct FrameRing {
+	static constexpr int SLOTS = 3;
+	struct Slot {
+		cudaStream_t s = nullptr;
+		unsigned char *d_src = nullptr, *d_dst = nullptr, *h_in = nullptr, *h_out = nullptr;
+		size_t dev_cap = 0, h_in_cap = 0, h_out_cap = 0;
+		int frame = -1;
+		bool staged_out = false;
+	};
+	std::mutex mu;
+	int dev = -1;
+	Slot slot[SLOTS];
+	void release()
+	{
+		for (Slot &s : slot) {
+			if (s.s) { cudaStreamSynchronize(s.s); cudaStreamDestroy(s.s); }
+			if (s.d_src) cudaFree(s.d_src);
+			if (s.d_dst) cudaFree(s.d_dst);
+			if (s.h_in) cudaFreeHost(s.h_in);
+			if (s.h_out) cudaFreeHost(s.h_out);
+			s = Slot();
+		}
+	}
+};
+FrameRing g_frame_ring[16];
 
 bool is_pinned(const void *p)
 {
@@ -990,51 +1096,66 @@ extern "C" int fixca_cuda_frames(const unsigned char *const *src_frames, unsigne
 	cudaGetDevice(&prev);
 	CUDA_TRY(cudaSetDevice(dev));
 
-	// A ring of 3 slots, each with its own stream, device frame pair and pinned pair.
-	const int ring = std::min(3, nframes);
+	// A ring of 3 slots, each with its own stream, device frame pair and (only for pageable caller memory)
+	// pinned pair.  The ring lives as long as the library (fixca_cuda_release frees it): allocating streams,
+	// device frames and pinned frames per call cost ~200 ms, 20x the PCIe time of a 16-frame 4K batch.
 	const size_t row_bytes = (size_t)width * bytes, pitch = align_up(row_bytes, 128);
 	const size_t frame_bytes = row_bytes * height, dev_bytes = pitch * height;
-	struct Slot { cudaStream_t s; unsigned char *d_src, *d_dst, *h_in, *h_out; int frame; };
-	std::vector<Slot> slots(ring);
-	auto cleanup = [&]() {
-		for (Slot &s : slots) {
-			if (s.s) { cudaStreamSynchronize(s.s); cudaStreamDestroy(s.s); }
-			if (s.d_src) cudaFree(s.d_src);
-			if (s.d_dst) cudaFree(s.d_dst);
-			if (s.h_in) cudaFreeHost(s.h_in);
-			if (s.h_out) cudaFreeHost(s.h_out);
-		}
+	if (dev >= 16) {
 		if (prev >= 0) cudaSetDevice(prev);
-	};
-	for (Slot &s : slots) { s.s = nullptr; s.d_src = s.d_dst = s.h_in = s.h_out = nullptr; s.frame = -1; }
+		return fail(FIXCA_ERR_NO_DEVICE, "device %d: the frame ring serves devices 0..15", dev);
+	}
+	FrameRing &fr = g_frame_ring[dev];
+	std::lock_guard<std::mutex> lock(fr.mu);
+	const int ring = std::min(FrameRing::SLOTS, nframes);
 	auto body = [&]() -> int {
-		for (Slot &s : slots) {
-			CUDA_TRY(cudaStreamCreateWithFlags(&s.s, cudaStreamNonBlocking));
-			CUDA_TRY(cudaMalloc(&s.d_src, dev_bytes));
-			CUDA_TRY(cudaMalloc(&s.d_dst, dev_bytes));
-			CUDA_TRY(cudaHostAlloc(&s.h_in, frame_bytes, cudaHostAllocDefault));
-			CUDA_TRY(cudaHostAlloc(&s.h_out, frame_bytes, cudaHostAllocDefault));
+		for (int k = 0; k < ring; ++k) {
+			FrameRing::Slot &s = fr.slot[k];
+			if (!s.s)
+				CUDA_TRY(cudaStreamCreateWithFlags(&s.s, cudaStreamNonBlocking));
+			if (s.dev_cap < dev_bytes) {
+				if (s.d_src) cudaFree(s.d_src);
+				if (s.d_dst) cudaFree(s.d_dst);
+				s.d_src = s.d_dst = nullptr;
+				s.dev_cap = 0;
+				CUDA_TRY(cudaMalloc(&s.d_src, dev_bytes));
+				CUDA_TRY(cudaMalloc(&s.d_dst, dev_bytes));
+				s.dev_cap = dev_bytes;
+			}
+			s.frame = -1;
 		}
-		auto retire = [&](Slot &s) -> int {
+		auto pinned_buf = [&](unsigned char *&p, size_t &cap) -> int {
+			if (cap >= frame_bytes) return FIXCA_OK;
+			if (p) cudaFreeHost(p);
+			p = nullptr;
+			cap = 0;
+			CUDA_TRY(cudaHostAlloc(&p, frame_bytes, cudaHostAllocDefault));
+			cap = frame_bytes;
+			return FIXCA_OK;
+		};
+		auto retire = [&](FrameRing::Slot &s) -> int {
 			if (s.frame < 0) return FIXCA_OK;
 			CUDA_TRY(cudaStreamSynchronize(s.s));
-			if (!is_pinned(dst_frames[s.frame]))
+			if (s.staged_out)
 				memcpy(dst_frames[s.frame], s.h_out, frame_bytes);
 			s.frame = -1;
 			return FIXCA_OK;
 		};
 		for (int i = 0; i < nframes; ++i) {
-			Slot &s = slots[i % ring];
+			FrameRing::Slot &s = fr.slot[i % ring];
 			int r = retire(s);
 			if (r) return r;
 			if (!src_frames[i] || !dst_frames[i])
 				return fail(FIXCA_ERR_ARG, "frame %d is NULL", i);
 			const unsigned char *from = src_frames[i];
 			if (!is_pinned(from)) {
+				if ((r = pinned_buf(s.h_in, s.h_in_cap))) return r;
 				memcpy(s.h_in, from, frame_bytes);
 				from = s.h_in;
 			}
-			unsigned char *to = is_pinned(dst_frames[i]) ? dst_frames[i] : s.h_out;
+			s.staged_out = !is_pinned(dst_frames[i]);
+			if (s.staged_out && (r = pinned_buf(s.h_out, s.h_out_cap))) return r;
+			unsigned char *to = s.staged_out ? s.h_out : dst_frames[i];
 			CUDA_TRY(cudaMemcpy2DAsync(s.d_src, pitch, from, row_bytes, row_bytes, height, cudaMemcpyHostToDevice, s.s));
 			Plan pl;
 			if ((r = make_plan(f, g, s.d_src, pitch, 0, height, s.d_dst, pitch, 0, 0, height, flags, dev, pl))) return r;
@@ -1042,14 +1163,17 @@ extern "C" int fixca_cuda_frames(const unsigned char *const *src_frames, unsigne
 			CUDA_TRY(cudaMemcpy2DAsync(to, row_bytes, s.d_dst, pitch, row_bytes, height, cudaMemcpyDeviceToHost, s.s));
 			s.frame = i;
 		}
-		for (Slot &s : slots) {
-			int r = retire(s);
+		for (int k = 0; k < ring; ++k) {
+			int r = retire(fr.slot[k]);
 			if (r) return r;
 		}
 		return FIXCA_OK;
 	};
 	rc = body();
-	cleanup();
+	if (rc)		// leave no copy in flight behind an error
+		for (int k = 0; k < FrameRing::SLOTS; ++k)
+			if (fr.slot[k].s) cudaStreamSynchronize(fr.slot[k].s);
+	if (prev >= 0) cudaSetDevice(prev);
 	return rc;
 }
 
@@ -1163,6 +1287,17 @@ extern "C" void fixca_cuda_release(void)
 		std::lock_guard<std::mutex> lock(c.mu);
 		c.release();
 	}
+	int prev = -1;
+	cudaGetDevice(&prev);
+	for (int d = 0; d < 16; ++d) {
+		std::lock_guard<std::mutex> lock(g_frame_ring[d].mu);
+		bool any = false;
+		for (const FrameRing::Slot &s : g_frame_ring[d].slot)
+			any = any || s.s || s.d_src;
+		if (any && cudaSetDevice(d) == cudaSuccess)
+			g_frame_ring[d].release();
+	}
+	if (prev >= 0) cudaSetDevice(prev);
 }
 
 extern "C" const char *fixca_version(void) { return "fixca-b200 0.1 (sm_100a)"; }

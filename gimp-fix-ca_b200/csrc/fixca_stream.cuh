@@ -91,18 +91,19 @@ __device__ __forceinline__ void bulk_wait_read()
 	asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// 2-D tensor tile, global -> shared; coordinates in elements of the map (c0: 8-byte units, c1: rows)
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar)
+// Tensor tile of one frame, global -> shared; coordinates in elements of the map (c0: 8-byte units, c1: rows,
+// c2: frame of the batch)
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar)
 {
-	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-		     ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+		     ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
 		     : "memory");
 }
-// 2-D tensor tile, shared -> global (clipped to the tensor's extent)
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, int c0, int c1, const void *smem_src)
+// Tensor tile, shared -> global (clipped to the tensor's extent)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, int c0, int c1, int c2, const void *smem_src)
 {
-	asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-		     ::"l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
+	asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+		     ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(smem_src))
 		     : "memory");
 }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *tm)
@@ -117,8 +118,8 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *tm)
 // tm_win   source image, box = win_pitch bytes x 4 rows     (window ring groups)
 // tm_tile  source image, box = TW * BPP bytes x CH rows      (pass-through pixels of a chunk)
 // tm_out   destination rows [dst_row0, y2), same box         (finished chunks; clipped at y2 and at the row end)
-// All three are maps of 8-byte elements over rows of align16(width * BPP) bytes; row coordinates are
-// relative to src_row0 / dst_row0.
+// All three are 3-D maps (8-byte elements x rows x frames of a batch, blockIdx.z = frame) over rows of
+// align16(width * BPP) bytes; row coordinates are relative to src_row0 / dst_row0.
 template <class S, int NCH, int INTERP, int P, int TW, bool ALT = false>
 __global__ void __launch_bounds__(2 * TW / P + 64, (2 * TW / P + 64) <= 192 ? 4 : 2)	// register budget: 4 (2) resident CTAs
 stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUtensorMap tm_win,
@@ -261,6 +262,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		const int NRG = NR >> 2;		// ring capacity in 4-row groups
 		const int group_bytes = 4 * wpitch;
 		const int c0_win = wb0 >> 3, c0_tile = (x0 * BPP) >> 3;
+		const int frame = blockIdx.z;		// a batch of equal frames: one grid layer per frame
 		int loaded_g;				// highest 4-row group already requested
 		loaded_g = (min(first_tap_row(0, ya), first_tap_row(1, ya)) >> 2) - 1;
 		int gslot = (loaded_g + 1) % NRG;	// ring slot of group loaded_g + 1
@@ -271,7 +273,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			uint64_t *bar = &full[wnf];
 			mbar_arrive_expect_tx(bar, (uint32_t)((hi_g - loaded_g) * group_bytes));
 			for (int g = loaded_g + 1; g <= hi_g; ++g) {
-				tma_load_2d(win + gslot * group_bytes, &tm_win, c0_win, 4 * g - a.src_row0, bar);
+				tma_load_3d(win + gslot * group_bytes, &tm_win, c0_win, 4 * g - a.src_row0, frame, bar);
 				gslot = gslot + 1 == NRG ? 0 : gslot + 1;
 			}
 			loaded_g = hi_g;
@@ -283,7 +285,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			bulk_wait_read<1>();
 			uint64_t *bar = &full[tnf];
 			mbar_arrive_expect_tx(bar, (uint32_t)STAGE_BYTES);
-			tma_load_2d(stage + tstg * STAGE_BYTES, &tm_tile, c0_tile, ya + i * CH - a.src_row0, bar);
+			tma_load_3d(stage + tstg * STAGE_BYTES, &tm_tile, c0_tile, ya + i * CH - a.src_row0, frame, bar);
 			tnf = tnf + 1 == NF ? 0 : tnf + 1;
 			tstg = tstg + 1 == NSTG ? 0 : tstg + 1;
 		};
@@ -297,7 +299,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			if (j + 1 < nchunks)
 				request_tile(j + 1);
 			mbar_wait_sleepy(&done[jnf], (uint32_t)jpar, 500u);
-			tma_store_2d(&tm_out, c0_tile, ya + j * CH - a.dst_row0, stage + jstg * STAGE_BYTES);
+			tma_store_3d(&tm_out, c0_tile, ya + j * CH - a.dst_row0, frame, stage + jstg * STAGE_BYTES);
 			bulk_commit();
 			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
 			jstg = jstg + 1 == NSTG ? 0 : jstg + 1;

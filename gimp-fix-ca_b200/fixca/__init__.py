@@ -37,7 +37,7 @@ ERR_RANGE, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -6, -7, -8, -9,
 # Every symbol include/fixca_cuda.h declares.
 EXPORTS = (
     "fixca_cuda_region", "fixca_cuda_region_ex", "fixca_cuda_region_multi", "fixca_cuda_region_dev",
-    "fixca_cuda_frames", "fixca_band_source_rows", "fixca_split_bands", "fixca_resolve_lens",
+    "fixca_cuda_frames", "fixca_cuda_frames_dev", "fixca_band_source_rows", "fixca_split_bands", "fixca_resolve_lens",
     "fixca_check_params", "fixca_color_size", "fixca_params_default", "fixca_cuda_set_progress",
     "fixca_cuda_last_error", "fixca_strerror", "fixca_cuda_device_count", "fixca_cuda_last_kernel",
     "fixca_cuda_launch_count", "fixca_cuda_release", "fixca_version",
@@ -95,6 +95,8 @@ def load() -> ctypes.CDLL:
     L.fixca_cuda_region_dev.argtypes = [vp, ctypes.c_size_t, i, i, vp, ctypes.c_size_t, i, i, i, i, i, pp, i, i,
                                         ctypes.c_uint, vp]
     L.fixca_cuda_frames.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), i, i, i, i, i, pp, ctypes.c_uint, i]
+    L.fixca_cuda_frames_dev.argtypes = [vp, ctypes.c_size_t, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.c_size_t, i,
+                                        i, i, i, i, pp, ctypes.c_uint, vp]
     L.fixca_band_source_rows.argtypes = [i, i, pp, i, i, ctypes.POINTER(i), ctypes.POINTER(i)]
     L.fixca_split_bands.argtypes = [i, i, i, ctypes.POINTER(i), ctypes.POINTER(i)]
     L.fixca_resolve_lens.argtypes = [i, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
@@ -175,6 +177,15 @@ def fix_ca_region_dev(d_src: int, src_pitch: int, src_row0: int, src_rows: int, 
     """Device-resident pass (raw CUDA pointers, asynchronous on ``stream``)."""
     _check(load().fixca_cuda_region_dev(d_src, src_pitch, src_row0, src_rows, d_dst, dst_pitch, dst_row0,
                                         width, height, bytes, bpc, ctypes.byref(params), y1, y2, flags, stream))
+
+
+def fix_ca_frames_dev(d_src: int, src_pitch: int, src_frame_stride: int, d_dst: int, dst_pitch: int,
+                      dst_frame_stride: int, nframes: int, width: int, height: int, bytes: int, bpc: int,
+                      params: FixCaParams, flags: int = PRECISION_EXACT, stream: int = 0) -> None:
+    """A batch of equal device-resident frames (raw CUDA pointers, frame i at base + i * frame_stride), one launch
+    for the whole batch on the streaming kernels; asynchronous on ``stream``."""
+    _check(load().fixca_cuda_frames_dev(d_src, src_pitch, src_frame_stride, d_dst, dst_pitch, dst_frame_stride, nframes,
+                                        width, height, bytes, bpc, ctypes.byref(params), flags, stream))
 
 
 def correct_frames(frames, params: FixCaParams, flags=PRECISION_EXACT, device=-1):

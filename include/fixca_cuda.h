@@ -171,6 +171,19 @@ FIXCA_API int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int src
 				    unsigned flags, void *stream);
 
 /*
+ * A batch of `nframes` equal-sized device-resident frames, same parameters (BASELINE
+ * "batch stream of frames": fix-ca.c has no such call; it is fix_ca_region() over every
+ * frame, :373-374).  Frame i starts at d_src + i * src_frame_stride (bytes; strides and
+ * pitches multiples of 16 for the streaming kernels).  The streaming kernels take the
+ * whole batch in ONE launch (a grid layer per frame, long row segments); other kernels
+ * are launched per frame.  Asynchronous on `stream`.
+ */
+FIXCA_API int fixca_cuda_frames_dev(const void *d_src, size_t src_pitch, size_t src_frame_stride,
+				    void *d_dst, size_t dst_pitch, size_t dst_frame_stride, int nframes,
+				    int width, int height, int bytes, int bpc,
+				    const fixca_params *params, unsigned flags, void *stream);
+
+/*
  * A stream of `nframes` equal-sized host frames (tight rows), same parameters:
  * frames are pipelined H2D / kernel / D2H over a ring of pinned staging
  * buffers on `device`.  src_frames[i] / dst_frames[i] are host pointers.

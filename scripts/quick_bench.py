@@ -44,6 +44,36 @@ def run(name, h, w, ch, tdtype, bpc, interp, flags, reps=10, lens=None):
           % (name, fixca.last_kernel(), os.environ.get("FIXCA_TILE_H", "auto"), best, med, mp / (med * 1e-3), gbs, 100 * gbs / PEAK, PEAK), flush=True)
 
 
+def run_batch(name, nf, h, w, ch, tdtype, bpc, interp, flags, reps=5):
+    es = torch.empty((), dtype=tdtype).element_size()
+    bpp = ch * es
+    pitch = (w * bpp + 127) // 128 * 128
+    src = torch.randint(0, 255, (nf, h, pitch), dtype=torch.uint8, device="cuda")
+    dst = torch.empty_like(src)
+    p = fixca.FixCaParams(interpolation=interp, lens_x=w // 2, lens_y=h // 2, **KW)
+    st = torch.cuda.current_stream().cuda_stream
+    batch = lambda: fixca.fix_ca_frames_dev(src.data_ptr(), pitch, pitch * h, dst.data_ptr(), pitch, pitch * h, nf, w, h, bpp, bpc, p, flags, st)
+
+    def loop():
+        for k in range(nf):
+            fixca.fix_ca_region_dev(src[k].data_ptr(), pitch, 0, h, dst[k].data_ptr(), pitch, 0, w, h, bpp, bpc, p, 0, h, flags, st)
+    for label, call in (("one launch", batch), ("per frame", loop)):
+        for _ in range(2):
+            call()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); call(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        med = ts[len(ts) // 2]
+        mp = nf * h * w / 1e6
+        gbs = mp * 1e6 * 2 * bpp / (med * 1e-3) / 1e9
+        print("%-30s %-12s %-26s %d frames  med %.3f ms = %.4f ms/frame  %9.0f MP/s  %6.0f GB/s  %.1f%% of %.0f"
+              % (name, label, fixca.last_kernel(), nf, med, med / nf, mp / (med * 1e-3), gbs, 100 * gbs / PEAK, PEAK), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     F, E = fixca.PRECISION_FAST, fixca.PRECISION_EXACT
@@ -97,6 +127,11 @@ if __name__ == "__main__":
         run("8K rgba16 none", 4320, 7680, 4, torch.int16, 2, 0, E, lens=(658, 1280))
         run("50MP rgb f32 none", 6144, 8192, 3, torch.float32, -4, 0, E)
         run("50MP rgba f32 none", 6144, 8192, 4, torch.float32, -4, 0, E)
+    if which == "batch":
+        run_batch("4K rgb8 cubic", 128, 2160, 3840, 3, torch.uint8, 1, 2, F)
+        run_batch("4K rgb8 linear", 128, 2160, 3840, 3, torch.uint8, 1, 1, F)
+        run_batch("4K rgb16 cubic", 64, 2160, 3840, 3, torch.int16, 2, 2, F)
+        run_batch("1080p rgba8 cubic", 256, 1080, 1920, 4, torch.uint8, 1, 2, F)
     if which == "x4":       # run with and without FIXCA_STREAM_NOALT=1 (separate processes: plans are cached)
         run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
         run("8K rgba16 linear fast", 4320, 7680, 4, torch.int16, 2, 1, F, lens=(658, 1280))

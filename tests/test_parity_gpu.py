@@ -319,6 +319,41 @@ def test_device_resident_entry_with_torch_buffers(fx, checker):
     assert fx.last_kernel().startswith("direct") and d2.cpu().numpy().tobytes() == want2.tobytes()
 
 
+def test_device_batch_of_frames_matches_single_frames(fx, checker):
+    """fixca_cuda_frames_dev: a batch in one launch (grid layer per frame, long segments) gives every frame the
+    bytes of its own single-frame call; formats without a streaming kernel are looped per frame."""
+    import torch
+    stream = torch.cuda.current_stream().cuda_stream
+    launches = fx.load().fixca_cuda_launch_count
+    for (h, w, ch, dt, interp, flags, nf) in ((270, 517, 3, "u1", 2, fx.PRECISION_FAST, 5), (64, 300, 4, "u2", 1, fx.PRECISION_FAST, 3),
+                                              (130, 259, 3, "u2", 0, fx.PRECISION_EXACT, 4), (33, 100, 3, "f4", 2, fx.PRECISION_FAST, 2),
+                                              (40, 64, 3, "u2", 2, fx.PRECISION_EXACT, 3)):
+        kw = dict(KW, lens_x=w // 2 - 3, lens_y=h // 2 + 5, interpolation=interp)
+        p = fx.FixCaParams(**kw)
+        frames = [orc.synth_image(h, w, ch, dt, seed=300 + k) for k in range(nf)]
+        es = np.dtype(dt).itemsize
+        bpp, bpc = ch * es, (-es if dt.startswith("f") else es)
+        pitch = (w * bpp + 127) // 128 * 128
+        fstride = pitch * h + 256       # frames need not be back to back
+        src = torch.zeros(nf * fstride, dtype=torch.uint8, device="cuda")
+        dst = torch.full((nf * fstride,), 0x5A, dtype=torch.uint8, device="cuda")
+        for k, fr in enumerate(frames):
+            v = src[k * fstride:k * fstride + pitch * h].view(h, pitch)
+            v[:, :w * bpp] = torch.from_numpy(fr.view(np.uint8).reshape(h, w * bpp)).cuda()
+        n0 = launches()
+        fx.fix_ca_frames_dev(src.data_ptr(), pitch, fstride, dst.data_ptr(), pitch, fstride, nf, w, h, bpp, bpc, p, flags, stream)
+        torch.cuda.synchronize()
+        streaming = fx.last_kernel().startswith("stream")
+        assert launches() - n0 == (1 if streaming else nf), (fx.last_kernel(), launches() - n0)
+        for k, fr in enumerate(frames):
+            got = dst[k * fstride:k * fstride + pitch * h].view(h, pitch)[:, :w * bpp].cpu().numpy().view(fr.dtype).reshape(h, w, ch)
+            single = fx.correct(fr, p, flags=flags)
+            assert got.tobytes() == single.tobytes(), (dt, ch, interp, k, fx.last_kernel())
+        # the gaps between frames are not written
+        gap = dst[pitch * h:fstride].cpu().numpy()
+        assert (gap == 0x5A).all()
+
+
 def test_float_pitch_padding_is_never_sampled(fx, checker):
     """FAST float kernels weigh out-of-image samples with 0, and 0 * NaN is NaN: the bytes between width * bpp
     and the 16-byte row end (caller's pitch padding, not zero-filled by the TMA unit) must not be read.
