@@ -85,8 +85,21 @@ struct ExactF64 {
 	__device__ __forceinline__ static XCoef make_x(double t, int /*interp*/) { return XCoef{t}; }
 	__device__ __forceinline__ static YCoef make_y(int i0, double t, int /*interp*/) { return YCoef{i0, 0, t}; }
 
-	__device__ __forceinline__ static double decode(uint8_t v)  { return __ddiv_rn((double)v, 255.0); }
-	__device__ __forceinline__ static double decode(uint16_t v) { return __ddiv_rn((double)v, 65535.0); }
+	// get_pixel's true division v / max (fix-ca.c:717-722) without the division subroutine: q0 = v * RN(1/max),
+	// one exact residual, one correction (Markstein).  Correctly rounded for EVERY 8- and 16-bit sample:
+	// tests/test_host_logic.py checks all 256 + 65536 values against IEEE division in exact rational arithmetic.
+	// The sample becomes a double through the 2^52 trick (no I2F.F64 on the XU pipe).
+	template <int MAX>
+	__device__ __forceinline__ static double div_by_max(unsigned v)
+	{
+		const double x = __dsub_rn(__hiloint2double(0x43300000, (int)v), 4503599627370496.0);	// exact: 2^52 + v - 2^52
+		constexpr double r = 1.0 / (double)MAX;		// correctly rounded reciprocal
+		const double q0 = __dmul_rn(x, r);
+		const double e = __fma_rn(-(double)MAX, q0, x);	// exact residual
+		return __fma_rn(e, r, q0);
+	}
+	__device__ __forceinline__ static double decode(uint8_t v)  { return div_by_max<255>(v); }
+	__device__ __forceinline__ static double decode(uint16_t v) { return div_by_max<65535>(v); }
 	__device__ __forceinline__ static double decode(uint32_t v) { return __ddiv_rn((double)v, 4294967295.0); }
 	__device__ __forceinline__ static double decode(float v)    { return (double)v; }
 	__device__ __forceinline__ static double decode(double v)   { return v; }

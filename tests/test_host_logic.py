@@ -138,3 +138,19 @@ def test_color_size_matches_reference(fx, reference):
     for name in ("R'G'B' u8", "RGBA u16", "RGB u32", "RGB float", "RGBA double", "RGB half", "RGB u15", "CMYK u8", "RGB u8 double"):
         for bpp in (1, 2, 3, 4, 6, 8, 11, 12, 16, 23, 24, 32, 33):
             assert fx.color_size(name, bpp) == reference.color_size(name, bpp), (name, bpp)
+
+
+def test_exact_decode_division_is_correctly_rounded_for_every_8_and_16_bit_sample():
+    """ExactF64::div_by_max (csrc/fixca_kernels.cuh) replaces get_pixel's v / max (fix-ca.c:717-722) by
+    q0 = RN(v * r), e = fma(-max, q0, v), q = fma(e, r, q0) with r = RN(1 / max).  Evaluated here in exact rational
+    arithmetic (Fraction -> float rounds to nearest-even, like the device's _rn operations) for every sample
+    value: the result equals IEEE division, so EXACT mode stays bit-identical to the reference."""
+    from fractions import Fraction as Fr
+    for m in (255, 65535):
+        r = float(Fr(1, m))
+        assert r == 1.0 / m
+        for v in range(m + 1):
+            q0 = float(Fr(v) * Fr(r))
+            e = float(Fr(v) - Fr(m) * Fr(q0))
+            assert Fr(e) == Fr(v) - Fr(m) * Fr(q0)        # the residual is exact
+            assert float(Fr(q0) + Fr(e) * Fr(r)) == v / float(m), (m, v)
