@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -847,6 +848,80 @@ bool is_pinned(const void *p)
 
 } // namespace
 
+// Pageable caller memory (the plug-in's g_new buffers, fix-ca.c:366-367) goes through pinned rings; one thread
+// copies at ~12 GB/s, a quarter of what the PCIe link moves in both directions, so the staging copies are split
+// over a few worker threads that live for the duration of one call (FIXCA_COPY_THREADS, default min(8, cores/2)).
+class CopyPool {
+public:
+	explicit CopyPool(int nthreads)
+	{
+		for (int i = 1; i < nthreads; ++i)
+			workers_.emplace_back([this]() { run(); });
+	}
+	~CopyPool()
+	{
+		{
+			std::lock_guard<std::mutex> lock(mu_);
+			quit_ = true;
+		}
+		cv_.notify_all();
+		for (std::thread &t : workers_)
+			t.join();
+	}
+	// blocking; slices of >= 1 MB, 64-byte aligned cuts
+	void copy(void *dst, const void *src, size_t n)
+	{
+		const size_t parts = std::min<size_t>(workers_.size() + 1, std::max<size_t>(1, n >> 20));
+		if (parts <= 1) {
+			memcpy(dst, src, n);
+			return;
+		}
+		const size_t slice = ((n + parts - 1) / parts + 63) & ~(size_t)63;
+		{
+			std::lock_guard<std::mutex> lock(mu_);
+			for (size_t off = slice; off < n; off += slice) {
+				tasks_.push_back({(unsigned char *)dst + off, (const unsigned char *)src + off, std::min(slice, n - off)});
+				++pending_;
+			}
+		}
+		cv_.notify_all();
+		memcpy(dst, src, std::min(slice, n));
+		std::unique_lock<std::mutex> lock(mu_);
+		done_.wait(lock, [this]() { return pending_ == 0; });
+	}
+
+private:
+	struct Task { unsigned char *d; const unsigned char *s; size_t n; };
+	void run()
+	{
+		std::unique_lock<std::mutex> lock(mu_);
+		for (;;) {
+			cv_.wait(lock, [this]() { return quit_ || !tasks_.empty(); });
+			if (tasks_.empty())
+				return;
+			const Task t = tasks_.back();
+			tasks_.pop_back();
+			lock.unlock();
+			memcpy(t.d, t.s, t.n);
+			lock.lock();
+			if (--pending_ == 0)
+				done_.notify_all();
+		}
+	}
+	std::vector<std::thread> workers_;
+	std::vector<Task> tasks_;
+	std::mutex mu_;
+	std::condition_variable cv_, done_;
+	size_t pending_ = 0;
+	bool quit_ = false;
+};
+
+static int copy_threads()
+{
+	const int hw = (int)std::thread::hardware_concurrency();
+	return std::max(1, env_int("FIXCA_COPY_THREADS", std::min(8, std::max(1, hw / 2))));
+}
+
 // One band [y1,y2) of a host image on one device: upload the source rows the
 // band reads, run, download.  Rows move in chunks so that H2D of chunk i+1,
 // the kernel of chunk i and D2H of chunk i-1 overlap (PCIe is full duplex).
@@ -870,18 +945,20 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 	if ((rc = cx.reserve_dev(cx.d_src, cx.d_src_cap, pitch * src_rows))) return rc;
 	if ((rc = cx.reserve_dev(cx.d_dst, cx.d_dst_cap, pitch * (size_t)(y2 - y1)))) return rc;
 
-	// Chunking: ~32 MB of rows per chunk (FIXCA_CHUNK_MB), at least 64 rows, a multiple of 8 rows (the
+	// Chunking: ~32 MB (pinned caller) / ~16 MB (pageable caller) of rows per chunk (FIXCA_CHUNK_MB), at least 64 rows, a multiple of 8 rows (the
 	// streaming kernel's chunk height, so every launch of the band shares one chunk grid), at most 256 chunks.
-	const size_t chunk_bytes = (size_t)std::max(1, env_int("FIXCA_CHUNK_MB", 32)) << 20;
+	// look at the first rows actually touched: callers may pass a whole-image base pointer of
+	// which only this band's rows are backed by memory
+	const bool src_pinned = is_pinned(src + (size_t)band_lo * row_bytes), dst_pinned = is_pinned(dst + (size_t)y1 * row_bytes);
+	// (pageable callers: smaller chunks, the staging copies of a chunk are not overlapped with its own transfers;
+	// measured on 100 MP RGB16: 16 MB 27.3 ms, 32 MB 28.7 ms, 64 MB 41.9 ms)
+	const size_t chunk_bytes = (size_t)std::max(1, env_int("FIXCA_CHUNK_MB", (src_pinned && dst_pinned) ? 32 : 16)) << 20;
 	int chunk_rows = (int)std::max<size_t>(64, chunk_bytes / std::max<size_t>(row_bytes, 1));
 	chunk_rows = std::max(chunk_rows, (y2 - y1 + 255) / 256);
 	chunk_rows = (chunk_rows + 7) & ~7;
 	chunk_rows = std::min(chunk_rows, y2 - y1);
 	const int nchunks = (y2 - y1 + chunk_rows - 1) / chunk_rows;
 
-	// look at the first rows actually touched: callers may pass a whole-image base pointer of
-	// which only this band's rows are backed by memory
-	const bool src_pinned = is_pinned(src + (size_t)band_lo * row_bytes), dst_pinned = is_pinned(dst + (size_t)y1 * row_bytes);
 	// Pageable callers go through pinned rings (2 slots per direction).
 	const int ring = 2;
 	size_t in_slot = 0, out_slot = 0;
@@ -904,6 +981,10 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 		if ((rc = cx.reserve_pinned(cx.h_out, cx.h_out_cap, out_slot * ring))) return rc;
 	}
 
+	// worker threads for the staging copies of pageable callers (none for pinned callers or small bands)
+	const bool staged = (!src_pinned || !dst_pinned) && (size_t)(y2 - y1) * row_bytes >= ((size_t)8 << 20);
+	CopyPool pool(staged ? copy_threads() : 1);
+
 	if (progress && g_progress)
 		g_progress(0, 0.0, g_progress_user);
 
@@ -917,7 +998,7 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 		CUDA_TRY(cudaEventSynchronize(e_down));
 		if (!dst_pinned) {
 			const unsigned char *slot = cx.h_out + (size_t)(i % ring) * out_slot;
-			memcpy(dst + (size_t)chunk_y1[i] * row_bytes, slot, (size_t)(chunk_y2[i] - chunk_y1[i]) * row_bytes);
+			pool.copy(dst + (size_t)chunk_y1[i] * row_bytes, slot, (size_t)(chunk_y2[i] - chunk_y1[i]) * row_bytes);
 		}
 		if (progress && g_progress)
 			for (int y = chunk_y1[i]; y < chunk_y2[i]; ++y)
@@ -944,7 +1025,7 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 			const unsigned char *from = src + (size_t)r0 * row_bytes;
 			if (!src_pinned) {
 				unsigned char *slot = cx.h_in + (size_t)(i % ring) * in_slot;
-				memcpy(slot, from, (size_t)nr * row_bytes);
+				pool.copy(slot, from, (size_t)nr * row_bytes);
 				from = slot;
 			}
 			CUDA_TRY(cudaMemcpy2DAsync(cx.d_src + (size_t)(r0 - band_lo) * pitch, pitch, from, row_bytes,
