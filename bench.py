@@ -484,8 +484,23 @@ def run_cuda(args):
         h_dst.copy_(dst_keep)
         del d_in, d_out, dst_keep
         barrier()
+        # the call exactly as the plug-in makes it: pageable buffers (g_new, fix-ca.c:366-367), staged through
+        # the library's pinned rings by its copy threads (rank 0 of a single-GPU run only; reported, not the e2e value)
+        pageable_ms = None
+        if world == 1:
+            p_src = np.empty((src_rows, row_bytes), dtype=np.uint8)
+            p_dst = np.empty((y2 - y1, row_bytes), dtype=np.uint8)
+            p_src[:] = h_src.numpy()
+            ps, pd = p_src.ctypes.data - lo * row_bytes, p_dst.ctypes.data - y1 * row_bytes
+            fixca.fix_ca_region(ps, pd, W, H, bpp, bpc, p, 0, W, y1, y2, True, flags, local)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                fixca.fix_ca_region(ps, pd, W, H, bpp, bpc, p, 0, W, y1, y2, True, flags, local)
+            pageable_ms = round((time.perf_counter() - t0) / 2 * 1e3, 3)
+            del p_src, p_dst
         e2e = {"value": round(total_mp_step * e2e_steps / dt_e2e, 1), "unit": "MP/s",
                "copy_only_ms_per_step": round(dt_copy / e2e_steps * 1e3, 3),
+               "pageable_caller_ms_per_step": pageable_ms,
                "h2d_bytes_per_step": int(src_rows * row_bytes) * world, "d2h_bytes_per_step": int((y2 - y1) * row_bytes) * world,
                "steps": e2e_steps, "ms_per_step": round(dt_e2e / e2e_steps * 1e3, 3),
                "api": "fixca_cuda_region_ex (host pointers, pinned), synchronous"}
