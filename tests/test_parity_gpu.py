@@ -354,6 +354,48 @@ def test_device_batch_of_frames_matches_single_frames(fx, checker):
         assert (gap == 0x5A).all()
 
 
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_fuzz_small_images_all_modes(fx, checker, seed):
+    """Seeded random shapes (1..700 px, strips and chunks cut anywhere), formats, lens positions (inside, on the
+    border, outside, the -1 reset value), lateral amounts and directional shifts over the plug-in's full +-30
+    range, random row bands: None and EXACT must equal the reference's bytes, FAST must stay within tolerance,
+    the pass-through channels must be copies, and rows outside the band must stay untouched."""
+    rng = np.random.default_rng(seed)
+    kernels = set()
+    for it in range(70):
+        h = int(rng.choice([1, 2, 3, 5, 9, 17, 40, 97, 130, 260, 517]))
+        w = int(rng.choice([1, 2, 4, 7, 31, 64, 129, 255, 256, 257, 400, 700]))
+        dt = str(rng.choice(["u1", "u2", "f4"]))
+        ch = int(rng.choice([3, 4]))
+        interp = int(rng.integers(0, 3))
+        lens = [(w // 2, h // 2), (0, 0), (-1, -1), (w - 1, h - 1), (w + 13, -7), (3, h + 40)][int(rng.integers(0, 6))]
+        amt = [float(rng.uniform(-30, 30)) if rng.random() < 0.5 else float(rng.uniform(-4, 4)) for _ in range(2)]
+        sh = [float(rng.uniform(-30, 30)) if rng.random() < 0.3 else float(rng.uniform(-2, 2)) for _ in range(4)]
+        kw = dict(blue=amt[0], red=amt[1], x_blue=sh[0], x_red=sh[1], y_blue=sh[2], y_red=sh[3],
+                  lens_x=lens[0], lens_y=lens[1], interpolation=interp)
+        m = max_dim(w, h, lens[0], lens[1])
+        if m + amt[0] <= 0.5 or m + amt[1] <= 0.5:
+            continue        # degenerate / negative scale: the direct-kernel tests
+        img = orc.synth_image(h, w, ch, dt, seed=int(rng.integers(1 << 30)))
+        want = checker.region(img, orc.Params(**kw))
+        y1 = int(rng.integers(0, h))
+        y2 = int(rng.integers(y1 + 1, h + 1))
+        for flags in ((fx.PRECISION_EXACT,) if interp == 0 else (fx.PRECISION_EXACT, fx.PRECISION_FAST)):
+            out = np.full_like(img, 0x5A) if dt != "f4" else np.full_like(img, 7.0)
+            fx.correct(img, fx.FixCaParams(**kw), y1=y1, y2=y2, out=out, flags=flags)
+            kernels.add(fx.last_kernel().split("/")[0] + "/" + fx.last_kernel().split("/")[1])
+            ctx = (seed, it, h, w, dt, ch, kw, y1, y2, flags, fx.last_kernel())
+            if flags == fx.PRECISION_EXACT:
+                assert out[y1:y2].tobytes() == want[y1:y2].tobytes(), ctx
+            else:
+                d, _ = lsb_diff(out[y1:y2], want[y1:y2])
+                assert d <= (FLOAT_ABS_TOL if dt == "f4" else FAST_LSB_TOL), ctx + (d,)
+                assert np.array_equal(out[y1:y2, :, 1], img[y1:y2, :, 1]), ctx
+            fill = 7.0 if dt == "f4" else 0x5A
+            assert (out[:y1] == fill).all() and (out[y2:] == fill).all(), ctx
+    assert {"stream/none", "stream/linear", "stream/cubic"} <= kernels, kernels
+
+
 def test_float_pitch_padding_is_never_sampled(fx, checker):
     """FAST float kernels weigh out-of-image samples with 0, and 0 * NaN is NaN: the bytes between width * bpp
     and the 16-byte row end (caller's pitch padding, not zero-filled by the TMA unit) must not be read.
