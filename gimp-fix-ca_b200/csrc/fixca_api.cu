@@ -614,7 +614,23 @@ static int launch_plan(const Plan &pl, cudaStream_t stream)
 	KernelArgs a = pl.args;
 	CUtensorMap tm[3] = {pl.tm_win, pl.tm_tile, pl.tm_out};
 	void *params[] = {&a, &tm[0], &tm[1], &tm[2]};	// the tensor maps are only declared by stream kernels
-	CUDA_TRY(cudaLaunchKernel((const void *)pl.k->fn, pl.grid, pl.block, params, pl.smem, stream));
+	if (pl.k->stream && !env_int("FIXCA_NO_PDL", 0)) {
+		// programmatic dependent launch (see griddep_wait() in fixca_stream.cuh): back-to-back launches in one
+		// stream overlap the next grid's set-up with this grid's tail; memory ordering is unchanged
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = pl.grid;
+		cfg.blockDim = pl.block;
+		cfg.dynamicSmemBytes = pl.smem;
+		cfg.stream = stream;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr;
+		cfg.numAttrs = 1;
+		CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)pl.k->fn, params));
+	} else {
+		CUDA_TRY(cudaLaunchKernel((const void *)pl.k->fn, pl.grid, pl.block, params, pl.smem, stream));
+	}
 	g_launches.fetch_add(1);
 	snprintf(tl_kernel, sizeof tl_kernel, "%s", pl.k->name);
 	return FIXCA_OK;

@@ -106,6 +106,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, int c0, int 
 		     ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(smem_src))
 		     : "memory");
 }
+// Programmatic dependent launch: stream kernels are launched with programmatic stream serialization, so the
+// CTAs of the next launch in the stream may become resident (and run their set-up) while the last CTAs of this
+// one drain; nothing touches global memory before griddep_wait(), which returns once the previous grid has
+// completed and its writes are visible.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *tm)
 {
 	asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
@@ -256,6 +262,8 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		// =====================================================================
 		if (tid != NTC)
 			return;
+		griddep_launch_dependents();
+		griddep_wait();		// the only thread of the CTA that reads or writes global memory
 		prefetch_tensormap(&tm_win);
 		prefetch_tensormap(&tm_tile);
 		prefetch_tensormap(&tm_out);
