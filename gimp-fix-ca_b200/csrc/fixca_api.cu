@@ -540,7 +540,7 @@ static unsigned env_signature()
 	static const char *const names[] = {"FIXCA_FAST_KERNEL", "FIXCA_STRIP_TW", "FIXCA_TILE_H", "FIXCA_TILE_CTAS",
 					    "FIXCA_STREAM_CTAS", "FIXCA_STREAM_DEPTH", "FIXCA_STREAM_SEGS",
 					    "FIXCA_STREAM_DEBUG", "FIXCA_VERBOSE", "FIXCA_NONE_KERNEL", "FIXCA_STREAM_NOALT",
-					    "FIXCA_STREAM_TW8", "FIXCA_NO_PDL"};
+					    "FIXCA_NO_PDL"};
 	unsigned h = 2166136261u;
 	for (const char *n : names) {
 		const char *v = getenv(n);

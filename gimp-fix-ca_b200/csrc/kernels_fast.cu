@@ -69,12 +69,6 @@ static const KernelEntry stream_x4_noalt[] = {
 	{ (kernel_fn)stream_kernel<float, 4, 2, 1, 128>, "stream/cubic/f32/f32x4/noalt", 128, 0, 4, 1, 1 },
 };
 
-// wider strips for 3-byte pixels, for tuning (FIXCA_STREAM_TW8=512): half as many helper warps per pixel
-static const KernelEntry stream_u8x3_tw512[] = {
-	{ (kernel_fn)stream_kernel<uint8_t, 3, 1, 4, 512>, "stream/linear/f32/u8x3/tw512", 512, 0, 1, 4, 1 },
-	{ (kernel_fn)stream_kernel<uint8_t, 3, 2, 4, 512>, "stream/cubic/f32/u8x3/tw512", 512, 0, 1, 4, 1 },
-};
-
 static const KernelEntry stream_u16x3_tw128[] = {
 	{ (kernel_fn)stream_kernel<uint16_t, 3, 1, 2, 128>, "stream/linear/f32/u16x3/tw128", 128, 0, 2, 2, 1 },
 	{ (kernel_fn)stream_kernel<uint16_t, 3, 2, 2, 128>, "stream/cubic/f32/u16x3/tw128", 128, 0, 2, 2, 1 },
@@ -106,11 +100,6 @@ const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int
 		const char *na = getenv("FIXCA_STREAM_NOALT");
 		if (na && atoi(na))
 			return &stream_x4_noalt[(kind == SK_F32 ? 2 : 0) + interp - 1];
-	}
-	if (variant == 3 && nch == 3 && kind == SK_U8) {
-		const char *w8 = getenv("FIXCA_STREAM_TW8");
-		if (w8 && atoi(w8) == 512)
-			return &stream_u8x3_tw512[interp - 1];
 	}
 	switch (variant) {
 	case 3: return tw128 ? &stream_u16x3_tw128[interp - 1] : &stream_table[s * 4 + (interp - 1) * 2 + (nch - 3)];
