@@ -1,4 +1,5 @@
-// fixca_stream.cuh -- the streaming form of the FAST (FP32) Linear / Cubic kernel.
+// fixca_stream.cuh -- the streaming kernel: None, FAST (FP32) Linear and FAST Cubic (fix_ca_region's row
+// loop, fix-ca.c:1091-1320), the path bench.py measures.
 //
 // strip_kernel (fixca_strip.cuh) pays per 16-row tile for: the FP64 column / row
 // setup, re-priming its 4-row ring (3 halo rows of horizontal work per channel),
@@ -9,7 +10,7 @@
 //
 // stream_kernel keeps the row loop and amortises everything else:
 //
-//   * a CTA owns a TW-column strip and a long run of rows (a "segment"); the
+//   * a CTA owns a TW-column strip and a long run of rows (a "segment") of one frame (blockIdx.z); the
 //     per-column weights and the ring of horizontal rows live in registers for
 //     the whole segment, so every source row is filtered horizontally once per
 //     channel and nothing is re-primed;
@@ -18,8 +19,8 @@
 //     from global memory once per strip), the pass-through pixels of the next
 //     output chunk land in a staging buffer, finished chunks leave with TMA bulk
 //     stores; D chunks are in flight ahead of the compute warps;
-//     Copies are TMA *tensor* tiles (cp.async.bulk.tensor.2d over CUtensorMaps of the source and
-//     destination images): one instruction moves a 4-row group of the window, one the 8 x TW
+//     Copies are TMA *tensor* tiles (cp.async.bulk.tensor.3d over CUtensorMaps of the source and
+//     destination frames): one instruction moves a 4-row group of the window, one the 8 x TW
 //     pass-through tile, one stores a finished chunk; rows and columns outside the image are
 //     zero-filled / clipped by the TMA unit.  (A first version issued one bulk copy per row --
 //     24 per chunk -- and the producer's own instruction stream, ~1.9 us per chunk, was the
@@ -27,11 +28,17 @@
 //   * a second helper warp computes the per-row vertical weights of the chunks ahead (FP64
 //     coordinates, fix-ca.c:813-820, weights ordered by tap position), so the compute
 //     warps never touch FP64 and the TMA warp never waits for arithmetic;
-//   * the 8 compute warps (4 red, 4 blue) never meet at a CTA barrier: they wait
-//     on "full" mbarriers and arrive on "done" mbarriers.
+//   * the compute warps never meet at a CTA barrier: they wait on "full" mbarriers and arrive on
+//     "done" mbarriers.
 //
-// Arithmetic is identical to strip_kernel (same weights, same FMA order: taps oldest -> newest,
-// whatever the ring phase), so both produce the same bytes for any tiling, segment or band split.
+// Row loop: per warp one of three horizontal forms -- narrow (T weights over P + T - 1 shared
+// samples), regular (T + 1 weights: the extra one absorbs the drift of the tap window), bent (per-column
+// samples, tap windows squeezed against an image edge) -- then a vertical pass over a register ring whose
+// weights are ordered by tap position, so the arithmetic does not depend on ring phase, tile, segment, band or
+// batch layout; strip_kernel computes the same bytes.  4-channel 16/32-bit strips put red and blue of a pixel
+// on neighbouring lanes (ALT).  INTERP = 0 copies raw sample bytes instead (bit-exact None).  The kernel is
+// launched with programmatic stream serialization: only the TMA lane touches global memory, after
+// griddep_wait().
 #pragma once
 
 #include <type_traits>
