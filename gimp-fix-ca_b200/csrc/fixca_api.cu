@@ -69,8 +69,9 @@ static int parse_format(int bytes, int bpc, Format &f)
 	case 8:  f.kind = SK_U64; f.sample_bytes = 8; break;
 	case -4: f.kind = SK_F32; f.sample_bytes = 4; break;
 	case -8: f.kind = SK_F64; f.sample_bytes = 8; break;
+	case -2: f.kind = SK_F16; f.sample_bytes = 2; break;	// extension: the reference's commented-out half branch
 	default:
-		return fail(FIXCA_ERR_FORMAT, "unsupported bpc %d (the reference handles 1,2,4,8,-4,-8; fix-ca.c:688-707)", bpc);
+		return fail(FIXCA_ERR_FORMAT, "unsupported bpc %d (the reference handles 1,2,4,8,-4,-8, and -2 in commented-out code; fix-ca.c:688-707)", bpc);
 	}
 	if (bytes == 3 * f.sample_bytes)
 		f.nch = 3;
@@ -157,7 +158,7 @@ static const KernelEntry *pick_kernel(const Format &f, int interp, unsigned flag
 	if (interp == 0)
 		return lookup_none(f.sample_bytes, f.nch, tiled);
 	const bool fast = (flags & FIXCA_PRECISION_MASK) == FIXCA_PRECISION_FAST &&
-			  (f.kind == SK_U8 || f.kind == SK_U16 || f.kind == SK_F32);
+			  (f.kind == SK_U8 || f.kind == SK_U16 || f.kind == SK_F32 || f.kind == SK_F16);
 	return fast ? lookup_fast(f.kind, f.nch, interp, tiled) : lookup_exact(f.kind, f.nch, interp, tiled);
 }
 
@@ -1327,6 +1328,15 @@ extern "C" int fixca_color_size(const char *name, int bpp)
 	if (bpp >= 6) return 2;
 	if (bpp >= 3) return 1;
 	return FIXCA_BPC_UNSUPPORTED;
+}
+
+extern "C" int fixca_color_size_half(const char *name, int bpp)
+{
+	// color_size() with the reference's commented-out half line (fix-ca.c:692-693) enabled, in its place:
+	// after "double" and "float", before the unsigned-integer names
+	if (name && !strstr(name, "double") && !strstr(name, "float") && strstr(name, "half"))
+		return -2;
+	return fixca_color_size(name, bpp);
 }
 
 extern "C" void fixca_params_default(fixca_params *p)

@@ -9,7 +9,8 @@
 
 namespace fixca {
 
-enum SampleKind { SK_U8 = 0, SK_U16, SK_U32, SK_U64, SK_F32, SK_F64, SK_COUNT };
+// SK_F16 (bpc = -2) is the extension of SURVEY.md 8(f) #4: the reference carries it as commented-out code
+enum SampleKind { SK_U8 = 0, SK_U16, SK_U32, SK_U64, SK_F32, SK_F64, SK_F16, SK_COUNT };
 enum ArithKind  { AR_COPY = 0, AR_EXACT = 1, AR_FAST = 2 };
 
 // Every kernel has the signature  __global__ void k(const KernelArgs).
@@ -31,9 +32,9 @@ constexpr int TILE_W = 128;
 const KernelEntry *lookup_none(int sample_bytes, int nch, bool tiled);
 // the streaming None kernel for this format, or nullptr (8-byte samples, FIXCA_NONE_KERNEL=tiled)
 const KernelEntry *lookup_none_stream(int sample_bytes, int nch);
-// kind in {SK_U8,SK_U16,SK_U32,SK_F32,SK_F64}; interp in {1,2}
+// kind in {SK_U8,SK_U16,SK_U32,SK_F32,SK_F64,SK_F16}; interp in {1,2}
 const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled);
-// kind in {SK_U8,SK_U16,SK_F32}; interp in {1,2}
+// kind in {SK_U8,SK_U16,SK_F32,SK_F16}; interp in {1,2}
 const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled);
 // variant: 0 direct, 1 first-round tiled, 2 strip, 3 stream, 4 narrower stream (may be nullptr)
 const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int variant);

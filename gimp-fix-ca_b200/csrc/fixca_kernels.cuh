@@ -34,6 +34,7 @@
 
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 #include "fixca_geometry.h"
 
@@ -103,6 +104,8 @@ struct ExactF64 {
 	__device__ __forceinline__ static double decode(uint32_t v) { return __ddiv_rn((double)v, 4294967295.0); }
 	__device__ __forceinline__ static double decode(float v)    { return (double)v; }
 	__device__ __forceinline__ static double decode(double v)   { return v; }
+	// half: the reference's commented-out branch `ret += *p` (fix-ca.c:740-742): an exact widening
+	__device__ __forceinline__ static double decode(__half v)   { return (double)__half2float(v); }
 
 	__device__ __forceinline__ static double clip(double d)
 	{
@@ -115,6 +118,8 @@ struct ExactF64 {
 	__device__ __forceinline__ static void encode(uint32_t &o, double d) { o = __double2uint_rz(round(__dmul_rn(clip(d), 4294967295.0))); }
 	__device__ __forceinline__ static void encode(float &o, double d)    { o = __double2float_rn(clip(d)); }
 	__device__ __forceinline__ static void encode(double &o, double d)   { o = clip(d); }
+	// `*p = d` (fix-ca.c:768-770, commented out there): one rounding, double -> half, nearest-even
+	__device__ __forceinline__ static void encode(__half &o, double d)   { o = __double2half(clip(d)); }
 
 	// p0 + t * (p1 - p0)
 	__device__ __forceinline__ static double hlin(double p0, double p1, const XCoef &c)
@@ -176,11 +181,13 @@ struct FastF32 {
 	__device__ __forceinline__ static float decode(uint8_t v)  { return (float)v; }
 	__device__ __forceinline__ static float decode(uint16_t v) { return (float)v; }
 	__device__ __forceinline__ static float decode(float v)    { return v; }
+	__device__ __forceinline__ static float decode(__half v)   { return __half2float(v); }
 
 	// clip_d's order: <= 0 first, then >= max; NaN passes (float images only).
 	__device__ __forceinline__ static void encode(uint8_t &o, float d)  { o = (uint8_t)__float2uint_rn(fminf(fmaxf(d, 0.f), 255.f)); }
 	__device__ __forceinline__ static void encode(uint16_t &o, float d) { o = (uint16_t)__float2uint_rn(fminf(fmaxf(d, 0.f), 65535.f)); }
 	__device__ __forceinline__ static void encode(float &o, float d)    { o = (d <= 0.f) ? 0.f : ((d >= 1.f) ? 1.f : d); }
+	__device__ __forceinline__ static void encode(__half &o, float d)   { o = __float2half_rn((d <= 0.f) ? 0.f : ((d >= 1.f) ? 1.f : d)); }
 
 	__device__ __forceinline__ static float hlin(float p0, float p1, const XCoef &c) { return fmaf(c.w1, p1, c.w0 * p0); }
 	__device__ __forceinline__ static float vlin(float h0, float h1, const YCoef &c) { return fmaf(c.w1, h1, c.w0 * h0); }

@@ -410,7 +410,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		// its 16-byte-aligned row end are zero-filled by the TMA unit, but the bytes between width * BPP
 		// and that row end are whatever the caller's pitch padding holds: such windows go the bent way,
 		// which clamps its sample offsets to the last column.
-		if (std::is_floating_point<S>::value)
+		if (is_float_sample<S>::value)
 			regular = regular && bmin + NS - 1 <= W - 1;
 #pragma unroll
 		for (int k = 0; k < P; ++k)

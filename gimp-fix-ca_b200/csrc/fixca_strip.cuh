@@ -123,6 +123,23 @@ template <> struct StripCodec<float> {
 	__device__ __forceinline__ static void store(unsigned char *p, float sat01) { *reinterpret_cast<float *>(p) = sat01; }
 };
 
+template <> struct StripCodec<__half> {	// bpc = -2: computed like float images, stored with one rounding to half
+	static constexpr float kInvMax = 1.0f;
+	__device__ __forceinline__ static float load(const unsigned char *p) { return __half2float(*reinterpret_cast<const __half *>(p)); }
+	__device__ __forceinline__ static float load_at(uint32_t saddr)
+	{
+		unsigned short v;
+		asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+		return __half2float(__ushort_as_half(v));
+	}
+	__device__ __forceinline__ static void store(unsigned char *p, float sat01) { *reinterpret_cast<__half *>(p) = __float2half_rn(sat01); }
+};
+
+// Samples whose bit patterns include NaN / Inf (a zero weight does not silence them)
+template <class S> struct is_float_sample { static constexpr bool value = false; };
+template <> struct is_float_sample<float> { static constexpr bool value = true; };
+template <> struct is_float_sample<__half> { static constexpr bool value = true; };
+
 // Vertical weights of output row y of one channel, ordered by tap position: .w weighs the newest
 // tap row `last` (the row whose arrival completes the output), .z row last - 1, .y last - 2, .x
 // last - 3.  Clamp-to-edge taps (fix-ca.c:1219-1256, :1149-1158) land on the same row and their

@@ -20,6 +20,7 @@ static const KernelEntry exact_table[] = {
 	EXACT_ENTRIES(uint32_t, "u32"),
 	EXACT_ENTRIES(float, "f32"),
 	EXACT_ENTRIES(double, "f64"),
+	EXACT_ENTRIES(__half, "f16"),
 };
 
 const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled)
@@ -31,6 +32,7 @@ const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled
 	case SK_U32: s = 2; break;
 	case SK_F32: s = 3; break;
 	case SK_F64: s = 4; break;
+	case SK_F16: s = 5; break;
 	default: return nullptr;
 	}
 	if ((nch != 3 && nch != 4) || (interp != 1 && interp != 2))

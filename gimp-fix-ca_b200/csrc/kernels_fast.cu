@@ -24,6 +24,7 @@ static const KernelEntry fast_table[] = {
 	FAST_ENTRIES(uint8_t, "u8"),
 	FAST_ENTRIES(uint16_t, "u16"),
 	FAST_ENTRIES(float, "f32"),
+	FAST_ENTRIES(__half, "f16"),
 };
 
 // Columns per thread are picked so that the lane stride in shared memory, P * bytes-per-pixel,
@@ -38,6 +39,7 @@ static const KernelEntry strip_table[] = {
 	STRIP_ENTRIES(uint8_t, "u8", 4, 256, 1, 128),
 	STRIP_ENTRIES(uint16_t, "u16", 2, 256, 1, 128),
 	STRIP_ENTRIES(float, "f32", 1, 128, 1, 128),
+	STRIP_ENTRIES(__half, "f16", 2, 256, 1, 128),
 };
 
 // ALT4: 4-channel strips put red and blue of one pixel on neighbouring lanes (half the row span
@@ -52,6 +54,7 @@ static const KernelEntry stream_table[] = {
 	STREAM_ENTRIES(uint8_t, "u8", 4, 256, 3, 192, false),	// 4-byte pixels: 3 columns = 12 bytes per lane, 7 loads per 3 outputs
 	STREAM_ENTRIES(uint16_t, "u16", 2, 256, 3, 192, true),	// 8-byte pixels, lanes alternate channels: 3 columns = conflict-free, 7 loads per 3 outputs
 	STREAM_ENTRIES(float, "f32", 1, 128, 1, 64, true),	// 16-byte pixels: 64 + halo columns fit one 2 KB TMA box
+	STREAM_ENTRIES(__half, "f16", 2, 256, 3, 192, true),	// 16-bit floats: the layouts of u16
 };
 
 // Narrower 16-bit RGBA strips for the calls whose window (strip + shift + slack columns) would not fit one
@@ -59,6 +62,8 @@ static const KernelEntry stream_table[] = {
 static const KernelEntry stream_u16x4_tw128[] = {
 	{ (kernel_fn)stream_kernel<uint16_t, 4, 1, 1, 128, true>, "stream/linear/f32/u16x4/tw128", 128, 0, 2, 1, 1 },
 	{ (kernel_fn)stream_kernel<uint16_t, 4, 2, 1, 128, true>, "stream/cubic/f32/u16x4/tw128", 128, 0, 2, 1, 1 },
+	{ (kernel_fn)stream_kernel<__half, 4, 1, 1, 128, true>, "stream/linear/f32/f16x4/tw128", 128, 0, 2, 1, 1 },
+	{ (kernel_fn)stream_kernel<__half, 4, 2, 1, 128, true>, "stream/cubic/f32/f16x4/tw128", 128, 0, 2, 1, 1 },
 };
 
 // channel-per-warp variants of the 4-channel strips, for A/B runs (FIXCA_STREAM_NOALT=1)
@@ -84,19 +89,21 @@ static const KernelEntry strip_u16x3_tw128[] = {
 const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int variant)
 {
 	if (variant == 4)
-		return (kind == SK_U16 && nch == 4 && (interp == 1 || interp == 2)) ? &stream_u16x4_tw128[interp - 1] : nullptr;
+		return ((kind == SK_U16 || kind == SK_F16) && nch == 4 && (interp == 1 || interp == 2))
+			       ? &stream_u16x4_tw128[(kind == SK_F16 ? 2 : 0) + interp - 1] : nullptr;
 	int s;
 	switch (kind) {
 	case SK_U8:  s = 0; break;
 	case SK_U16: s = 1; break;
 	case SK_F32: s = 2; break;
+	case SK_F16: s = 3; break;
 	default: return nullptr;
 	}
 	if ((nch != 3 && nch != 4) || (interp != 1 && interp != 2))
 		return nullptr;
 	const char *tw = getenv("FIXCA_STRIP_TW");	// tuning: narrower tiles for the headline format
 	const bool tw128 = kind == SK_U16 && nch == 3 && tw && atoi(tw) == 128;
-	if (variant == 3 && nch == 4 && kind != SK_U8) {
+	if (variant == 3 && nch == 4 && (kind == SK_U16 || kind == SK_F32)) {
 		const char *na = getenv("FIXCA_STREAM_NOALT");
 		if (na && atoi(na))
 			return &stream_x4_noalt[(kind == SK_F32 ? 2 : 0) + interp - 1];

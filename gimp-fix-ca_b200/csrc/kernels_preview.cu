@@ -43,6 +43,10 @@ template <> struct Norm<float> {
 	__device__ static double get(float v) { return (double)v; }
 	__device__ static float put(double d) { return (float)d; }
 };
+template <> struct Norm<__half> {	// the commented-out half branches of get_pixel / set_pixel (fix-ca.c:740-742, :768-770)
+	__device__ static double get(__half v) { return (double)__half2float(v); }
+	__device__ static __half put(double d) { return __double2half(d); }
+};
 template <> struct Norm<double> {
 	__device__ static double get(double v) { return v; }
 	__device__ static double put(double d) { return d; }
@@ -190,6 +194,7 @@ cudaError_t launch_preview(int kind, int nch, unsigned char *dst, long long pitc
 	case SK_U64: return launch_s<uint64_t>(nch, a, st);
 	case SK_F32: return launch_s<float>(nch, a, st);
 	case SK_F64: return launch_s<double>(nch, a, st);
+	case SK_F16: return launch_s<__half>(nch, a, st);
 	default: return cudaErrorInvalidValue;
 	}
 }

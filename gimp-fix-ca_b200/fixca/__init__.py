@@ -38,7 +38,7 @@ ERR_RANGE, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -6, -7, -8, -9,
 EXPORTS = (
     "fixca_cuda_region", "fixca_cuda_region_ex", "fixca_cuda_region_multi", "fixca_cuda_region_dev",
     "fixca_cuda_frames", "fixca_cuda_frames_dev", "fixca_band_source_rows", "fixca_split_bands", "fixca_resolve_lens",
-    "fixca_check_params", "fixca_color_size", "fixca_params_default", "fixca_cuda_set_progress",
+    "fixca_check_params", "fixca_color_size", "fixca_color_size_half", "fixca_params_default", "fixca_cuda_set_progress",
     "fixca_cuda_last_error", "fixca_strerror", "fixca_cuda_device_count", "fixca_cuda_last_kernel",
     "fixca_cuda_launch_count", "fixca_cuda_release", "fixca_version",
 )
@@ -226,6 +226,11 @@ def check_params(params: FixCaParams) -> int:
 
 def color_size(format_name: str, bytes_per_pixel: int) -> int:
     return load().fixca_color_size(format_name.encode(), bytes_per_pixel)
+
+
+def color_size_half(format_name: str, bytes_per_pixel: int) -> int:
+    """color_size() with the reference's commented-out half-precision line enabled (bpc -2 for float16)."""
+    return load().fixca_color_size_half(format_name.encode(), bytes_per_pixel)
 
 
 def device_count() -> int:

@@ -217,6 +217,12 @@ FIXCA_API int fixca_check_params(const fixca_params *params);
 /* color_size() (fix-ca.c:681-711): babl format name + bytes per pixel -> bpc code. */
 FIXCA_API int fixca_color_size(const char *babl_format_name, int bytes_per_pixel);
 
+/* Extension: color_size() with the reference's commented-out half-precision line
+ * (fix-ca.c:692-693) enabled -- "R'G'B' half" etc. give bpc = -2, which every entry point above accepts:
+ * samples are IEEE binary16, decoded exactly (`ret += *p`, :740-742), computed like float images and stored
+ * with one rounding (`*p = d`, :768-770).  Everything else answers like fixca_color_size(). */
+FIXCA_API int fixca_color_size_half(const char *babl_format_name, int bytes_per_pixel);
+
 /* Defaults of fix_ca_params_default (fix-ca.c:85-97). */
 FIXCA_API void fixca_params_default(fixca_params *params);
 

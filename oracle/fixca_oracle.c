@@ -103,6 +103,8 @@ static double decode (const unsigned char *p, int bpc)
 		  l /= 18446744073709551615UL; r = l; break; }
 	case -8: { double v; memcpy (&v, p, 8); r += v; break; }
 	case -4: { float v; memcpy (&v, p, 4); r += v; break; }
+	/* half precision: the branch the reference keeps commented out (fix-ca.c:740-742), see patch_half.py */
+	case -2: { _Float16 v; memcpy (&v, p, 2); r += v; break; }
 	default: break;
 	}
 	return r;
@@ -120,6 +122,7 @@ static void encode (unsigned char *p, double d, int bpc)
 	case 8: { uint64_t v = roundl (d * 18446744073709551615UL); memcpy (p, &v, 8); break; }
 	case -8: memcpy (p, &d, 8); break;
 	case -4: { float v = (float) d; memcpy (p, &v, 4); break; }
+	case -2: { _Float16 v = (_Float16) d; memcpy (p, &v, 2); break; }	/* fix-ca.c:768-770, commented out there */
 	default: break;
 	}
 }
@@ -216,7 +219,7 @@ static int setup (job *j, const unsigned char *src, unsigned char *dst, int W, i
 
 	b = bpc < 0 ? -bpc : bpc;
 	interp = (int) p[P_INTERP];
-	if (!(bpc == 1 || bpc == 2 || bpc == 4 || bpc == 8 || bpc == -4 || bpc == -8))
+	if (!(bpc == 1 || bpc == 2 || bpc == 4 || bpc == 8 || bpc == -4 || bpc == -8 || bpc == -2))
 		return -2;
 	if (bytes != 3 * b && bytes != 4 * b)
 		return -2;
@@ -342,6 +345,7 @@ static void put_sample (unsigned char *p, double d, int bpc)
 	case 8: { uint64_t v = roundl (d * 18446744073709551615UL); memcpy (p, &v, 8); break; }
 	case -8: memcpy (p, &d, 8); break;
 	case -4: { float v = (float) d; memcpy (p, &v, 4); break; }
+	case -2: { _Float16 v = (_Float16) d; memcpy (p, &v, 2); break; }	/* fix-ca.c:768-770, commented out there */
 	default: break;
 	}
 }

@@ -24,6 +24,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 RESTATEMENT_SO = os.path.join(HERE, "libfixca_oracle.so")
 REFERENCE_SO = os.path.join(HERE, "_ref", "libfixca_ref.so")
+REFERENCE_HALF_SO = os.path.join(HERE, "_ref", "libfixca_ref_half.so")
 
 _c_int = ctypes.c_int
 _c_dp = ctypes.POINTER(ctypes.c_double)
@@ -55,7 +56,7 @@ def build(force: bool = False) -> None:
     """Run oracle/Makefile (restatement always; _ref only where the reference is mounted)."""
     if force or not os.path.exists(RESTATEMENT_SO) or (
             os.path.exists("/root/reference/fix-ca.c") and not (os.path.exists(REFERENCE_SO) and os.path.exists(
-                os.path.join(HERE, "_ref", "libfixca_plugin_cuda.so")))):
+                REFERENCE_HALF_SO) and os.path.exists(os.path.join(HERE, "_ref", "libfixca_plugin_cuda.so")))):
         subprocess.run(["make", "-C", HERE, "-s"], check=True,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
@@ -236,9 +237,36 @@ class PatchedPlugin(Reference):
             globals()["REFERENCE_SO"] = so
 
 
+class ReferenceHalf(Reference):
+    """The reference with its own commented-out half-precision lines enabled (oracle/patch_half.py,
+    fix-ca.c:692-693, :740-742, :768-770): the checker for float16 images (bpc = -2).  For every other
+    format it computes what ``Reference`` computes."""
+
+    kind = "reference+half"
+
+    @staticmethod
+    def available() -> bool:
+        build()
+        return os.path.exists(REFERENCE_HALF_SO)
+
+    def __init__(self):
+        build()
+        so = REFERENCE_SO
+        try:
+            globals()["REFERENCE_SO"] = REFERENCE_HALF_SO
+            Reference.__init__(self)
+        finally:
+            globals()["REFERENCE_SO"] = so
+
+
 def best_checker():
     """The strongest CPU checker present: the reference's own code, else the restatement."""
     return Reference() if Reference.available() else Restatement()
+
+
+def half_checker():
+    """Checker for float16 images: the reference with its half lines enabled, else the restatement."""
+    return ReferenceHalf() if ReferenceHalf.available() else Restatement()
 
 
 def synth_image(h: int, w: int, ch: int, dtype: str, seed: int, wide: bool = False) -> np.ndarray:

@@ -11,7 +11,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden", "golden.json")
 FIXTURE_RAW = os.path.join(ROOT, "oracle", "_ref", "full-branches.rgb")
 
+GOLDEN_HALF = os.path.join(ROOT, "tests", "golden", "golden_half.json")
 _golden = None
+_golden_half = None
+
+
+def golden_half():
+    """Digests of the half-precision extension (tests/golden/make_golden_half.py)."""
+    global _golden_half
+    if _golden_half is None:
+        with open(GOLDEN_HALF) as f:
+            _golden_half = json.load(f)
+    return _golden_half
 
 
 def golden():

@@ -154,3 +154,12 @@ def test_exact_decode_division_is_correctly_rounded_for_every_8_and_16_bit_sampl
             e = float(Fr(v) - Fr(m) * Fr(q0))
             assert Fr(e) == Fr(v) - Fr(m) * Fr(q0)        # the residual is exact
             assert float(Fr(q0) + Fr(e) * Fr(r)) == v / float(m), (m, v)
+
+
+def test_color_size_half_extension(fx):
+    """fixca_color_size_half: the reference's color_size() with its commented-out half line enabled
+    (fix-ca.c:692-693); fixca_color_size keeps answering like the shipped reference."""
+    assert fx.color_size("R'G'B' half", 6) == -99 and fx.color_size_half("R'G'B' half", 6) == -2
+    assert fx.color_size_half("R'G'B'A half", 8) == -2
+    for name, bpp in (("R'G'B' u8", 3), ("R'G'B'A u16", 8), ("RGB float", 12), ("RGBA double", 32), ("R'G'B' u15", 6), ("Y u8", 1)):
+        assert fx.color_size_half(name, bpp) == fx.color_size(name, bpp)

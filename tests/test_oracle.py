@@ -10,7 +10,7 @@ import pytest
 
 import oracle as orc
 from fixture_io import encode_gimp_bmp24
-from helpers import case_image, fixture_image, golden, max_dim, md5, oracle_params
+from helpers import case_image, fixture_image, golden, golden_half, max_dim, md5, oracle_params
 
 
 def test_restatement_matches_golden_suite(restatement):
@@ -152,3 +152,30 @@ def test_preview_centerline_shape(restatement):
         assert y == 13 or x in (20, 20 - dy, 20 + dy)
         assert prev[y, x, 0] == prev[y, x, 1] == prev[y, x, 2] and prev[y, x, 0] in (0, 255)
     assert prev[13].reshape(-1, 3).min() >= 0 and set(np.unique(prev[13])) <= {0, 255}
+
+
+# ---------------------------------------------------------------------------------------------
+# half precision (bpc = -2): the reference's commented-out lines enabled (oracle/patch_half.py)
+# ---------------------------------------------------------------------------------------------
+def test_half_restatement_matches_golden(restatement):
+    g = golden_half()
+    bad = [c["name"] for c in g["suite"] if md5(restatement.region(case_image(c), oracle_params(c))) != c["md5"]]
+    bad += [c["name"] for c in g["preview"]
+            if md5(restatement.region(case_image(c), oracle_params(c), preview=True)) != c["md5"]]
+    assert not bad, "%d half cases differ, first: %s" % (len(bad), bad[:5])
+
+
+def test_half_reference_build_matches_golden_and_leaves_other_formats_alone(reference, restatement):
+    if not orc.ReferenceHalf.available():
+        pytest.skip("oracle/_ref/libfixca_ref_half.so not built (needs /root/reference at build time)")
+    half = orc.ReferenceHalf()
+    sample = golden_half()["suite"][::5]
+    bad = [c["name"] for c in sample if md5(half.region(case_image(c), oracle_params(c))) != c["md5"]]
+    assert not bad, bad[:5]
+    # the three enabled fragments are the only difference: every other format computes what the unpatched build does
+    for c in golden()["suite"][::97]:
+        assert md5(half.region(case_image(c), oracle_params(c))) == c["md5"], c["name"]
+    # color_size: -2 for half names only (fix-ca.c:692-693 enabled), -99 in the unpatched reference
+    assert half.color_size("R'G'B' half", 6) == -2 and half.color_size("R'G'B'A half", 8) == -2
+    assert reference.color_size("R'G'B' half", 6) == -99
+    assert half.color_size("R'G'B' u16", 6) == 2 and half.color_size("R'G'B' float", 12) == -4

@@ -12,7 +12,7 @@ import pytest
 
 import oracle as orc
 from fixture_io import encode_gimp_bmp24
-from helpers import case_image, fixture_image, fx_params, golden, lsb_diff, max_dim, md5, oracle_params
+from helpers import golden_half, case_image, fixture_image, fx_params, golden, lsb_diff, max_dim, md5, oracle_params
 
 pytestmark = pytest.mark.gpu
 
@@ -394,6 +394,49 @@ def test_fuzz_small_images_all_modes(fx, checker, seed):
             fill = 7.0 if dt == "f4" else 0x5A
             assert (out[:y1] == fill).all() and (out[y2:] == fill).all(), ctx
     assert {"stream/none", "stream/linear", "stream/cubic"} <= kernels, kernels
+
+
+# ---------------------------------------------------------------------------------------------
+# half precision (bpc = -2), SURVEY.md 8(f) #4: checker = the reference with its commented-out half lines enabled
+# ---------------------------------------------------------------------------------------------
+HALF_ABS_TOL = 2.0 ** -11       # one unit in the last place of a half in [0.5, 1): FAST rounds an FP32 result once
+
+
+def test_half_golden_suite_bit_exact(fx):
+    """None and EXACT Linear / Cubic on float16 images: identical bytes (266 digests + 36 preview digests)."""
+    g = golden_half()
+    bad, kernels = [], set()
+    for c in g["suite"]:
+        got = fx.correct(case_image(c), fx_params(fx, c), flags=fx.PRECISION_EXACT)
+        kernels.add(fx.last_kernel().rsplit("/", 1)[0])
+        if md5(got) != c["md5"]:
+            bad.append(c["name"])
+    for c in g["preview"]:
+        got = fx.correct(case_image(c), fx_params(fx, c), flags=fx.PRECISION_EXACT | fx.PREVIEW_OVERLAY)
+        if md5(got) != c["md5"]:
+            bad.append(c["name"])
+    assert not bad, "%d half cases differ, first: %s" % (len(bad), bad[:8])
+    assert {"stream/none/copy", "tiled/cubic/f64", "tiled/linear/f64"} <= kernels, kernels
+
+
+def test_half_fast_within_one_ulp(fx):
+    """FAST (FP32) Linear / Cubic on float16: the streaming kernel, at most one half-ulp step from the checker."""
+    chk = orc.half_checker()
+    worst, n, nbad, kernels = 0.0, 0, 0, set()
+    for (h, w), ch, interp, wide in itertools.product(((65, 257), (301, 517), (40, 2051), (7, 129)), (3, 4), (1, 2), (False, True)):
+        kw = dict(KW, lens_x=w // 2, lens_y=h // 2, interpolation=interp)
+        img = orc.synth_image(h, w, ch, "f2", seed=h + w + ch + interp, wide=wide)
+        want = chk.region(img, orc.Params(**kw))
+        got = fx.correct(img, fx.FixCaParams(**kw), flags=fx.PRECISION_FAST)
+        kernels.add(fx.last_kernel().split("/")[0])
+        d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+        worst = max(worst, float(d.max()))
+        n += d.size
+        nbad += int((d != 0).sum())
+        assert np.array_equal(got[..., 1], img[..., 1])          # pass-through is a copy, clipped or not
+    assert worst <= HALF_ABS_TOL, worst
+    assert nbad / n < 2e-3, nbad / n                              # FP32 vs FP64 before one rounding to 11 bits
+    assert kernels == {"stream"}, kernels
 
 
 def test_float_pitch_padding_is_never_sampled(fx, checker):
