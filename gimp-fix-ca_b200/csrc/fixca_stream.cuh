@@ -391,6 +391,9 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			double td;
 			const int i0 = base_index(a.g.x[c], x0 + lt * P + k, td);
 			tap_weights<INTERP>((float)td, w[k]);
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				w[k][j] += 0.f;		// -0 -> +0: the sign of an all-zero sum must not depend on the fold
 			// ... with zero weights, so that they do not bend a warp of the last strip
 			if (x0 + lt * P + k > xl)
 				w[k][0] = w[k][1] = w[k][2] = w[k][3] = 0.f;
@@ -418,20 +421,45 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			for (int j = 0; j < T; ++j)
 				regular = regular && (w[k][j] == 0.f || tap[k][j] - bmin <= NW - 1);
 		regular = __all_sync(0xffffffffu, regular);
+		// The usual thread: no tap clamped, every column's window starts 0 or 1 samples after the group's
+		// first sample -- its weights are the tap weights, shifted by that drift (20 selects instead of the
+		// P x NW x T compare-select-add fold below; the set-up is the launch ramp of every CTA).
+		bool plain = regular;
 #pragma unroll
 		for (int k = 0; k < P; ++k) {
+			const int d = tap[k][0] - bmin;
+			plain = plain && (d == 0 || (NW > T && d == 1));
 #pragma unroll
-			for (int jj = 0; jj < NW; ++jj) {
-				float v = 0.f;
-#pragma unroll
-				for (int j = 0; j < T; ++j) {
-					const int at = regular ? tap[k][j] - bmin : tap[k][j] - tap[k][0];
-					v += (w[k][j] != 0.f && at == jj) ? w[k][j] : 0.f;
-				}
-				wt[k][jj] = v;
-			}
-			cofs[k] = (tap[k][0] + k - bmin) * BPP;
+			for (int j = 1; j < T; ++j)
+				plain = plain && tap[k][j] == tap[k][0] + j;
 		}
+		if (plain) {
+#pragma unroll
+			for (int k = 0; k < P; ++k) {
+				const bool drift = tap[k][0] != bmin;
+#pragma unroll
+				for (int jj = 0; jj < NW; ++jj) {
+					const float w0 = jj < T ? w[k][jj] : 0.f, w1 = jj >= 1 ? w[k][jj - 1] : 0.f;
+					wt[k][jj] = drift ? w1 : w0;
+				}
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < P; ++k)
+#pragma unroll
+				for (int jj = 0; jj < NW; ++jj) {
+					float v = 0.f;
+#pragma unroll
+					for (int j = 0; j < T; ++j) {
+						const int at = regular ? tap[k][j] - bmin : tap[k][j] - tap[k][0];
+						v += (w[k][j] != 0.f && at == jj) ? w[k][j] : 0.f;
+					}
+					wt[k][jj] = v;
+				}
+		}
+#pragma unroll
+		for (int k = 0; k < P; ++k)
+			cofs[k] = (tap[k][0] + k - bmin) * BPP;
 		colbase = bmin * BPP + 2 * c * (int)sizeof(S) - wb0;
 		cmax = (W - 1 - bmin) * BPP;
 	}
