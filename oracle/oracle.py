@@ -56,7 +56,8 @@ def build(force: bool = False) -> None:
     """Run oracle/Makefile (restatement always; _ref only where the reference is mounted)."""
     if force or not os.path.exists(RESTATEMENT_SO) or (
             os.path.exists("/root/reference/fix-ca.c") and not (os.path.exists(REFERENCE_SO) and os.path.exists(
-                REFERENCE_HALF_SO) and os.path.exists(os.path.join(HERE, "_ref", "libfixca_plugin_cuda.so")))):
+                REFERENCE_HALF_SO) and os.path.exists(os.path.join(HERE, "_ref", "libfixca_plugin_cuda.so")) and
+                os.path.exists(os.path.join(HERE, "_ref", "libfixca_plugin_cuda_half.so")))):
         subprocess.run(["make", "-C", HERE, "-s"], check=True,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
@@ -254,6 +255,30 @@ class ReferenceHalf(Reference):
         so = REFERENCE_SO
         try:
             globals()["REFERENCE_SO"] = REFERENCE_HALF_SO
+            Reference.__init__(self)
+        finally:
+            globals()["REFERENCE_SO"] = so
+
+
+PLUGIN_CUDA_HALF_SO = os.path.join(HERE, "_ref", "libfixca_plugin_cuda_half.so")
+
+
+class PatchedPluginHalf(Reference):
+    """INTEGRATION.md's patch on top of patch_half.py: the plug-in with its half lines enabled, calling
+    fixca_cuda_region() -- drives `R'G'B' half` drawables through run() on the GPU."""
+
+    kind = "reference+half+cuda"
+
+    @staticmethod
+    def available() -> bool:
+        build()
+        return os.path.exists(PLUGIN_CUDA_HALF_SO)
+
+    def __init__(self):
+        build()
+        so = REFERENCE_SO
+        try:
+            globals()["REFERENCE_SO"] = PLUGIN_CUDA_HALF_SO
             Reference.__init__(self)
         finally:
             globals()["REFERENCE_SO"] = so

@@ -110,3 +110,35 @@ def test_patched_plugin_runs_on_the_gpu_bit_identically(plugins, fx):
     assert fx.device_count() > 0
     _compare(plugins, expect_gpu=True)
     _compare_previews(plugins, expect_gpu=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# half-precision drawables: the plug-in with its own commented-out half lines enabled (patch_half.py),
+# unpatched vs with INTEGRATION.md's patch on top
+# ---------------------------------------------------------------------------------------------
+HALF_DRAWABLES = [((90, 140, 3), "f2", "R'G'B' half"), ((61, 97, 4), "f2", "R'G'B'A half")]
+
+
+@pytest.mark.gpu
+def test_half_drawables_through_the_patched_plugin(fx):
+    import fixca
+
+    if not orc.ReferenceHalf.available() or not orc.PatchedPluginHalf.available():
+        pytest.skip("oracle/_ref half plug-in builds missing (they need /root/reference at build time)")
+    ref, patched = orc.ReferenceHalf(), orc.PatchedPluginHalf()
+    n = 0
+    for (shape, dt, fmt), call in [(d, c) for d in HALF_DRAWABLES for c in CALLS[:4]]:
+        n += 1
+        img = orc.synth_image(shape[0], shape[1], shape[2], dt, seed=9000 + n, wide=bool(n % 2))
+        want_px, want_status, want_counts, _ = _drive(ref, img, fmt, call)
+        launches = fixca.launch_count()
+        got_px, got_status, got_counts, msg = _drive(patched, img, fmt, call)
+        assert got_status == want_status == PDB_SUCCESS, (fmt, call, msg)
+        assert got_px.tobytes() == want_px.tobytes(), (fmt, call)
+        assert got_counts == want_counts
+        assert fixca.launch_count() > launches
+    # the shipped reference refuses the same drawable (color_size -> -99, fix-ca.c:692-697)
+    plain = orc.Reference()
+    img = orc.synth_image(20, 30, 3, "f2", seed=1)
+    _, status, _, _ = _drive(plain, img, "R'G'B' half", CALLS[0])
+    assert status != PDB_SUCCESS
