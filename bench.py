@@ -435,6 +435,25 @@ def run_cuda(args):
     achieved = alg_bytes / (local_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
 
+    # ---- optional: reassembly of the bands on rank 0 (NCCL send/recv over NVLink), outside the timed steps.
+    # Bands are independent, so this is the only inter-GPU traffic the pass can have; it is
+    # reported beside the step time to show why it is kept off the measured path.
+    gather = None
+    if args.gather and world > 1:
+        times = []
+        for rep in range(4):
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            full = bands.gather_bands(d_dst, plan, dst_rank=0)
+            g1.record(stream)
+            barrier()
+            if rep:
+                times.append(max_over_ranks(g0.elapsed_time(g1)))
+            del full
+        gather = {"ms": round(min(times), 3), "bytes_into_rank0": int((world - 1) * (y2 - y1) * pitch),
+                  "how": "fixca.bands.gather_bands: one NCCL send/recv per band to rank 0, best of 3"}
+
     # ---- end to end through the host C ABI: pinned host band, H2D + kernels + D2H timed ----
     e2e = None
     parity = None
@@ -531,6 +550,8 @@ def run_cuda(args):
         }
         if parity is not None:
             line["parity"] = parity
+        if gather is not None:
+            line["gather"] = gather
         print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -625,6 +646,7 @@ def main():
     ap.add_argument("--exact", action="store_true", help="FP64 bit-exact arithmetic instead of fast FP32")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="also time the reassembly of the bands on rank 0 (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--quick-cpu", action="store_true")
