@@ -362,10 +362,11 @@ def test_fuzz_small_images_all_modes(fx, checker, seed):
     the pass-through channels must be copies, and rows outside the band must stay untouched."""
     rng = np.random.default_rng(seed)
     kernels = set()
+    half = orc.half_checker()       # float16 images: the reference with its commented-out half lines enabled
     for it in range(70):
         h = int(rng.choice([1, 2, 3, 5, 9, 17, 40, 97, 130, 260, 517]))
         w = int(rng.choice([1, 2, 4, 7, 31, 64, 129, 255, 256, 257, 400, 700]))
-        dt = str(rng.choice(["u1", "u2", "f4"]))
+        dt = str(rng.choice(["u1", "u2", "f4", "f2"]))
         ch = int(rng.choice([3, 4]))
         interp = int(rng.integers(0, 3))
         lens = [(w // 2, h // 2), (0, 0), (-1, -1), (w - 1, h - 1), (w + 13, -7), (3, h + 40)][int(rng.integers(0, 6))]
@@ -377,11 +378,11 @@ def test_fuzz_small_images_all_modes(fx, checker, seed):
         if m + amt[0] <= 0.5 or m + amt[1] <= 0.5:
             continue        # degenerate / negative scale: the direct-kernel tests
         img = orc.synth_image(h, w, ch, dt, seed=int(rng.integers(1 << 30)))
-        want = checker.region(img, orc.Params(**kw))
+        want = (half if dt == "f2" else checker).region(img, orc.Params(**kw))
         y1 = int(rng.integers(0, h))
         y2 = int(rng.integers(y1 + 1, h + 1))
         for flags in ((fx.PRECISION_EXACT,) if interp == 0 else (fx.PRECISION_EXACT, fx.PRECISION_FAST)):
-            out = np.full_like(img, 0x5A) if dt != "f4" else np.full_like(img, 7.0)
+            out = np.full_like(img, 0x5A) if dt[0] != "f" else np.full_like(img, 7.0)
             fx.correct(img, fx.FixCaParams(**kw), y1=y1, y2=y2, out=out, flags=flags)
             kernels.add(fx.last_kernel().split("/")[0] + "/" + fx.last_kernel().split("/")[1])
             ctx = (seed, it, h, w, dt, ch, kw, y1, y2, flags, fx.last_kernel())
@@ -389,9 +390,9 @@ def test_fuzz_small_images_all_modes(fx, checker, seed):
                 assert out[y1:y2].tobytes() == want[y1:y2].tobytes(), ctx
             else:
                 d, _ = lsb_diff(out[y1:y2], want[y1:y2])
-                assert d <= (FLOAT_ABS_TOL if dt == "f4" else FAST_LSB_TOL), ctx + (d,)
+                assert d <= (FLOAT_ABS_TOL if dt == "f4" else HALF_ABS_TOL if dt == "f2" else FAST_LSB_TOL), ctx + (d,)
                 assert np.array_equal(out[y1:y2, :, 1], img[y1:y2, :, 1]), ctx
-            fill = 7.0 if dt == "f4" else 0x5A
+            fill = 7.0 if dt[0] == "f" else 0x5A
             assert (out[:y1] == fill).all() and (out[y2:] == fill).all(), ctx
     assert {"stream/none", "stream/linear", "stream/cubic"} <= kernels, kernels
 
