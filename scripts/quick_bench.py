@@ -132,6 +132,13 @@ if __name__ == "__main__":
         run_batch("4K rgb8 linear", 128, 2160, 3840, 3, torch.uint8, 1, 1, F)
         run_batch("4K rgb16 cubic", 64, 2160, 3840, 3, torch.int16, 2, 2, F)
         run_batch("1080p rgba8 cubic", 256, 1080, 1920, 4, torch.uint8, 1, 2, F)
+    if which == "exact":
+        run("100MP rgb16 cubic exact", 8192, 12288, 3, torch.int16, 2, 2, E, reps=5)
+        run("100MP rgb16 linear exact", 8192, 12288, 3, torch.int16, 2, 1, E, reps=5)
+        run("24MP rgb8 linear exact", 4000, 6000, 3, torch.uint8, 1, 1, E)
+        run("24MP rgb8 cubic exact", 4000, 6000, 3, torch.uint8, 1, 2, E)
+        run("8K rgba16 cubic exact", 4320, 7680, 4, torch.int16, 2, 2, E, lens=(658, 1280))
+        run("50MP rgb f32 cubic exact", 6144, 8192, 3, torch.float32, -4, 2, E)
     if which == "x4":       # run with and without FIXCA_STREAM_NOALT=1 (separate processes: plans are cached)
         run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
         run("8K rgba16 linear fast", 4320, 7680, 4, torch.int16, 2, 1, F, lens=(658, 1280))
