@@ -453,6 +453,38 @@ def run_cuda(args):
             del full
         gather = {"ms": round(min(times), 3), "bytes_into_rank0": int((world - 1) * (y2 - y1) * pitch),
                   "how": "fixca.bands.gather_bands: one NCCL send/recv per band to rank 0, best of 3"}
+        # The same reassembly folded into the pass: rank 0 owns the whole frame, every rank's kernel stores its
+        # finished chunks straight into it (TMA stores through the CUDA IPC peer mapping, NVLink): compute + gather
+        # in one kernel, timed like a step (barrier both sides, max over ranks).
+        frame = bands.PeerFrame(H, pitch, owner=0)
+
+        def peer_step():
+            bands.run_band_into_frame(plan, d_src.data_ptr(), pitch, frame, bpp, bpc, p, flags, stream.cuda_stream)
+
+        for _ in range(3):
+            peer_step()
+        ptimes = []
+        for rep in range(6):
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            peer_step()
+            g1.record(stream)
+            barrier()
+            ptimes.append(max_over_ranks(g0.elapsed_time(g1)))
+        peer_kernel = fixca.last_kernel()
+        step()
+        full = bands.gather_bands(d_dst, plan, dst_rank=0)
+        frame.sync()
+        same = None
+        if rank == 0:
+            same = bool(torch.equal(frame.as_tensor()[:, :row_bytes], full[:, :row_bytes]))
+        del full
+        frame.close()
+        gather["peer_store"] = {"ms": round(min(ptimes), 3), "median_ms": round(sorted(ptimes)[len(ptimes) // 2], 3),
+                                "identical_to_nccl_gather": same, "kernel": peer_kernel,
+                                "how": "fixca.bands.PeerFrame + run_band_into_frame: every rank's kernel writes its band "
+                                       "into rank 0's frame over NVLink (compute + gather, one kernel); max over ranks"}
 
     # ---- end to end through the host C ABI: pinned host band, H2D + kernels + D2H timed ----
     e2e = None

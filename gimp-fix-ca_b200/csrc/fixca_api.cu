@@ -710,6 +710,60 @@ extern "C" int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int sr
 }
 
 // ---------------------------------------------------------------------------
+// peer frames: a destination frame on one GPU that the kernels of every rank store into
+// ---------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == FIXCA_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+
+extern "C" int fixca_cuda_frame_alloc(size_t bytes, void **d_frame, unsigned char *handle)
+{
+	if (!d_frame || !handle || !bytes)
+		return fail(FIXCA_ERR_ARG, "fixca_cuda_frame_alloc: NULL / empty argument");
+	int dev, rc;
+	if ((rc = current_device_or(-1, dev))) return rc;
+	void *p = nullptr;
+	CUDA_TRY(cudaMalloc(&p, bytes));
+	cudaIpcMemHandle_t h;
+	cudaError_t e = cudaIpcGetMemHandle(&h, p);
+	if (e != cudaSuccess) {
+		cudaFree(p);
+		cudaGetLastError();
+		return fail(FIXCA_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+	}
+	memcpy(handle, &h, sizeof h);
+	*d_frame = p;
+	return FIXCA_OK;
+}
+
+extern "C" int fixca_cuda_frame_open(const unsigned char *handle, void **d_frame)
+{
+	if (!d_frame || !handle)
+		return fail(FIXCA_ERR_ARG, "fixca_cuda_frame_open: NULL argument");
+	int dev, rc;
+	if ((rc = current_device_or(-1, dev))) return rc;
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, sizeof h);
+	void *p = nullptr;
+	// maps the owner's allocation into this process and enables peer access to its device
+	CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	*d_frame = p;
+	return FIXCA_OK;
+}
+
+extern "C" int fixca_cuda_frame_close(void *d_frame)
+{
+	if (!d_frame) return FIXCA_OK;
+	CUDA_TRY(cudaIpcCloseMemHandle(d_frame));
+	return FIXCA_OK;
+}
+
+extern "C" int fixca_cuda_frame_free(void *d_frame)
+{
+	if (!d_frame) return FIXCA_OK;
+	CUDA_TRY(cudaFree(d_frame));
+	return FIXCA_OK;
+}
+
+// ---------------------------------------------------------------------------
 // device-resident batch of frames
 // ---------------------------------------------------------------------------
 extern "C" int fixca_cuda_frames_dev(const void *d_src, size_t src_pitch, size_t src_frame_stride,

@@ -41,7 +41,9 @@ EXPORTS = (
     "fixca_check_params", "fixca_color_size", "fixca_color_size_half", "fixca_params_default", "fixca_cuda_set_progress",
     "fixca_cuda_last_error", "fixca_strerror", "fixca_cuda_device_count", "fixca_cuda_last_kernel",
     "fixca_cuda_launch_count", "fixca_cuda_release", "fixca_version",
+    "fixca_cuda_frame_alloc", "fixca_cuda_frame_open", "fixca_cuda_frame_close", "fixca_cuda_frame_free",
 )
+IPC_HANDLE_BYTES = 64
 
 
 class FixCaParams(ctypes.Structure):
@@ -97,6 +99,10 @@ def load() -> ctypes.CDLL:
     L.fixca_cuda_frames.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), i, i, i, i, i, pp, ctypes.c_uint, i]
     L.fixca_cuda_frames_dev.argtypes = [vp, ctypes.c_size_t, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.c_size_t, i,
                                         i, i, i, i, pp, ctypes.c_uint, vp]
+    L.fixca_cuda_frame_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.fixca_cuda_frame_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.fixca_cuda_frame_close.argtypes = [vp]
+    L.fixca_cuda_frame_free.argtypes = [vp]
     L.fixca_band_source_rows.argtypes = [i, i, pp, i, i, ctypes.POINTER(i), ctypes.POINTER(i)]
     L.fixca_split_bands.argtypes = [i, i, i, ctypes.POINTER(i), ctypes.POINTER(i)]
     L.fixca_resolve_lens.argtypes = [i, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
@@ -200,6 +206,30 @@ def correct_frames(frames, params: FixCaParams, flags=PRECISION_EXACT, device=-1
     _check(load().fixca_cuda_frames(src, dst, n, w, h, ch * frames[0].dtype.itemsize, bpc_of(frames[0].dtype),
                                     ctypes.byref(params), flags, device))
     return outs
+
+
+def frame_alloc(nbytes: int):
+    """A destination frame on the current GPU that other ranks can map (fixca_cuda_frame_alloc):
+    returns (device pointer, 64-byte CUDA IPC handle)."""
+    ptr = ctypes.c_void_p()
+    handle = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+    _check(load().fixca_cuda_frame_alloc(nbytes, ctypes.byref(ptr), handle))
+    return int(ptr.value), handle.raw
+
+
+def frame_open(handle: bytes) -> int:
+    """Map another rank's frame into this process (peer access over NVLink); returns the device pointer."""
+    ptr = ctypes.c_void_p()
+    _check(load().fixca_cuda_frame_open(ctypes.create_string_buffer(bytes(handle), IPC_HANDLE_BYTES), ctypes.byref(ptr)))
+    return int(ptr.value)
+
+
+def frame_close(ptr: int) -> None:
+    _check(load().fixca_cuda_frame_close(ptr))
+
+
+def frame_free(ptr: int) -> None:
+    _check(load().fixca_cuda_frame_free(ptr))
 
 
 def band_source_rows(width: int, height: int, params: FixCaParams, y1: int, y2: int):

@@ -3,8 +3,10 @@
 Output row y of the correction pass depends only on (y, params, source rows near the mapped
 coordinate) -- fix-ca.c:1091-1329 -- so an image splits into contiguous full-width row bands that are
 computed independently; a band needs its own rows plus the halo rows `band_source_rows()` reports.
-There is no data-path collective.  `gather_bands()` reassembles the image on one rank when a caller
-wants that (NCCL over NVLink on GPUs, gloo in the CPU tests).
+There is no data-path collective.  When one rank must own the whole frame, `PeerFrame` +
+`run_band_into_frame()` make every rank's kernel store its band straight into that rank's memory (peer stores
+over NVLink, compute and gather in one kernel); `gather_bands()` is the plain collective form of the same
+(NCCL send/recv on GPUs, gloo in the CPU tests).
 
 Nothing here computes pixels: `BandPlan.run()` calls the CUDA library; the CPU tests pass their own
 `compute` callable (the oracle) to exercise the sharding logic without a GPU.
@@ -15,7 +17,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from . import FixCaParams, band_source_rows, bpc_of, fix_ca_region_dev, split_bands, PRECISION_EXACT
+from . import (FixCaParams, band_source_rows, bpc_of, fix_ca_region_dev, split_bands, PRECISION_EXACT,
+               frame_alloc, frame_open, frame_close, frame_free)
 
 
 @dataclass
@@ -55,6 +58,72 @@ def run_band_device(plan: BandPlan, d_src_ptr: int, src_pitch: int, d_dst_ptr: i
     if plan.y1 == plan.y2:
         return
     fix_ca_region_dev(d_src_ptr, src_pitch, plan.src_lo, plan.src_rows, d_dst_ptr, dst_pitch, plan.y1,
+                      plan.width, plan.height, bytes_per_pixel, bpc, params, plan.y1, plan.y2, flags, stream)
+
+
+class PeerFrame:
+    """The whole destination frame on `owner`'s GPU, mapped into every rank of the box (CUDA IPC; peer access
+    over NVLink / NVSwitch).  Each rank passes `ptr` as the destination of its band (`run_band_into_frame`):
+    the kernel's TMA stores land in the owner's memory, so computing a band and gathering it are one kernel.
+    Collective over `group`: every rank constructs it, `sync()`s before the owner reads, and `close()`s it."""
+
+    def __init__(self, rows: int, pitch: int, owner: int = 0, group=None):
+        import torch.distributed as dist
+
+        self.rows, self.pitch, self.owner, self.group = rows, pitch, owner, group
+        self.rank = dist.get_rank(group)
+        box = [None]
+        if self.rank == owner:
+            self.ptr, handle = frame_alloc(rows * pitch)
+            box[0] = handle
+        dist.broadcast_object_list(box, src=owner, group=group)
+        if self.rank != owner:
+            self.ptr = frame_open(box[0])
+        self._open = True
+
+    def sync(self) -> None:
+        """Every rank's band is in the owner's frame: each rank drains its own stream, then the ranks meet."""
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def as_tensor(self):
+        """Owner only: the frame as a (rows, pitch) uint8 torch tensor (a view of the allocation, no copy)."""
+        import torch
+
+        assert self.rank == self.owner
+
+        class _Mem:     # __cuda_array_interface__ view of the raw allocation
+            pass
+
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (self.rows, self.pitch), "typestr": "|u1", "data": (self.ptr, False),
+                                      "version": 3}
+        self._keep = m
+        return torch.as_tensor(m, device="cuda")
+
+    def close(self) -> None:
+        import torch.distributed as dist
+
+        if not self._open:
+            return
+        self._open = False
+        if self.rank != self.owner:
+            frame_close(self.ptr)
+        dist.barrier(group=self.group)      # nobody maps the frame any more
+        if self.rank == self.owner:
+            frame_free(self.ptr)
+
+
+def run_band_into_frame(plan: BandPlan, d_src_ptr: int, src_pitch: int, frame: PeerFrame, bytes_per_pixel: int,
+                        bpc: int, params: FixCaParams, flags: int = PRECISION_EXACT, stream: int = 0) -> None:
+    """Launch this rank's band with the owner's frame as its destination: rows [y1, y2) are written at their
+    place in the whole frame (dst_row0 = 0), over NVLink when the frame lives on another GPU."""
+    if plan.y1 == plan.y2:
+        return
+    fix_ca_region_dev(d_src_ptr, src_pitch, plan.src_lo, plan.src_rows, frame.ptr, frame.pitch, 0,
                       plan.width, plan.height, bytes_per_pixel, bpc, params, plan.y1, plan.y2, flags, stream)
 
 

@@ -184,6 +184,27 @@ FIXCA_API int fixca_cuda_frames_dev(const void *d_src, size_t src_pitch, size_t 
 				    const fixca_params *params, unsigned flags, void *stream);
 
 /*
+ * Peer frames: the reassembly step of a row-banded image ("reassembly is a P2P/NCCL gather
+ * over NVLink only") folded into the pass itself.  One process (the frame's owner) allocates the whole
+ * destination frame on its GPU and exports a CUDA IPC handle; every other rank of the box opens the handle
+ * (peer access over NVLink / NVSwitch is enabled by the open) and passes the mapped pointer as `d_dst` of
+ * fixca_cuda_region_dev() with dst_row0 = 0: its kernel then stores each finished chunk of its band straight
+ * into the owner's memory (the same TMA tensor stores, through the peer mapping), so the compute and the gather
+ * are ONE kernel and no staging band, second copy or concatenation exists.  The owner sees the rows once the
+ * writer's stream has completed and the ranks have met (an event / barrier of the caller's).
+ * fix-ca.c has no counterpart (one process, one buffer: destImg, :367).
+ *
+ * fixca_cuda_frame_alloc: cudaMalloc on the current device + cudaIpcGetMemHandle.
+ * fixca_cuda_frame_open:  cudaIpcOpenMemHandle in ANOTHER process (CUDA refuses the exporting process).
+ * fixca_cuda_frame_close / _free: undo them (after the ranks have met).
+ */
+#define FIXCA_IPC_HANDLE_BYTES 64
+FIXCA_API int fixca_cuda_frame_alloc(size_t bytes, void **d_frame, unsigned char handle[FIXCA_IPC_HANDLE_BYTES]);
+FIXCA_API int fixca_cuda_frame_open(const unsigned char handle[FIXCA_IPC_HANDLE_BYTES], void **d_frame);
+FIXCA_API int fixca_cuda_frame_close(void *d_frame);
+FIXCA_API int fixca_cuda_frame_free(void *d_frame);
+
+/*
  * A stream of `nframes` equal-sized host frames (tight rows), same parameters:
  * frames are pipelined H2D / kernel / D2H over a ring of pinned staging
  * buffers on `device`.  src_frames[i] / dst_frames[i] are host pointers.

@@ -119,3 +119,83 @@ def test_band_plans_cover_the_image_without_overlap():
             assert pl.y2 - pl.y1 == 8192                       # weak scaling: equal bands
             assert pl.src_lo <= pl.y1 and pl.src_hi >= pl.y2 - 1
             assert pl.halo_rows <= 2 * 64                      # halo <= ~64 rows per side
+
+
+def _peer_worker(rank, world, port, out_q):
+    """One process per GPU (NCCL): every rank's kernel stores its band into rank 0's frame (PeerFrame, CUDA IPC
+    peer mapping over NVLink); rank 0 compares the frame with the oracle's full image."""
+    for p in (os.path.join(ROOT, "gimp-fix-ca_b200"), os.path.join(ROOT, "oracle"), ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import fixca
+    import oracle as orc
+    from fixca import bands
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        chk = orc.best_checker()
+        ok = True
+        cases = [
+            (1203, 1157, 3, "u2", 2, fixca.PRECISION_FAST, 1, dict(blue=3.0, red=-2.0, lens_x=578, lens_y=601, x_blue=0.7, x_red=-0.4, y_blue=0.3, y_red=-0.9)),
+            (997, 640, 4, "u1", 1, fixca.PRECISION_EXACT, 0, dict(blue=-6.0, red=2.4, lens_x=0, lens_y=0)),
+            (1200, 900, 3, "f4", 0, fixca.PRECISION_EXACT, 0, dict(blue=30.0, red=-30.0, lens_x=450, lens_y=600, y_blue=30.0, y_red=-30.0)),
+        ]
+        for n, (h, w, ch, dt, interp, flags, tol, kw) in enumerate(cases):
+            img = orc.synth_image(h, w, ch, dt, seed=700 + n)
+            P = fixca.FixCaParams(interpolation=interp, **kw)
+            plan = bands.plan_band(w, h, P, rank, world)
+            bpp = ch * img.dtype.itemsize
+            row_bytes = w * bpp
+            pitch = (row_bytes + 127) // 128 * 128
+            # this rank holds ONLY its band + halo rows
+            mine = np.zeros((plan.src_rows, pitch), dtype=np.uint8)
+            mine[:, :row_bytes] = img[plan.src_lo:plan.src_hi + 1].view(np.uint8).reshape(plan.src_rows, row_bytes)
+            d_src = torch.from_numpy(mine).to(dev)
+            frame = bands.PeerFrame(h, pitch, owner=0)
+            if rank == 0:
+                frame.as_tensor().fill_(0x5A)
+            frame.sync()
+            bands.run_band_into_frame(plan, d_src.data_ptr(), pitch, frame, bpp, fixca.bpc_of(img.dtype), P, flags,
+                                      torch.cuda.current_stream().cuda_stream)
+            frame.sync()
+            if rank == 0:
+                got = frame.as_tensor()[:, :row_bytes].cpu().numpy().copy().view(img.dtype).reshape(h, w, ch)
+                want = chk.region(img, orc.Params(interpolation=interp, **kw))
+                if tol == 0:
+                    same = got.tobytes() == want.tobytes()
+                else:
+                    same = int(np.abs(got.astype(np.int64) - want.astype(np.int64)).max()) <= tol
+                ok = ok and same
+                if not same:
+                    out_q.put(("mismatch", n))
+            frame.close()
+        if rank == 0:
+            out_q.put(("ok", ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_bands_stored_into_a_peer_frame_world2_nccl():
+    """Needs two GPUs of one box (skipped on a single-GPU box): compute + gather in one kernel over NVLink."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    results = []
+    while not q.empty():
+        results.append(q.get())
+    assert ("ok", True) in results, results
