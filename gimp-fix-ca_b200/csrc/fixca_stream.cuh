@@ -393,7 +393,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			tap_weights<INTERP>((float)td, w[k]);
 #pragma unroll
 			for (int j = 0; j < 4; ++j)
-				w[k][j] += 0.f;		// -0 -> +0: the sign of an all-zero sum must not depend on the fold
+				w[k][j] = w[k][j] * Codec::kHScale + 0.f;	// power of two (integer samples are read as subnormals); -0 -> +0: the sign of an all-zero sum must not depend on the fold
 			// ... with zero weights, so that they do not bend a warp of the last strip
 			if (x0 + lt * P + k > xl)
 				w[k][0] = w[k][1] = w[k][2] = w[k][3] = 0.f;

@@ -58,30 +58,34 @@ __device__ __forceinline__ void tap_weights(float t, float (&w)[4])
 	}
 }
 
-// Sample codecs.  The integer <-> float conversions are kept off the XU pipe (I2F.U16 / F2I run
-// there at 16 lanes/clk/SM and were the top pipe of the first strip kernel, profiles/r01_*_d.md):
-//   load   ld.shared.u8/u16 zero-extends into a 32-bit register; cvt.rn.f32.u32 -> I2FP (ALU pipe)
+// Sample codecs.  The integer <-> float conversions cost no instruction at all:
+//   load   ld.shared.u8/u16 zero-extends into a 32-bit register, and that register IS the operand: the bit
+//          pattern of the integer v read as a float is the subnormal v * 2^-149, exact, and FMUL / FFMA take
+//          subnormal operands at full rate.  The horizontal weights carry 2^100 (kHScale) and the vertical
+//          weights 2^49 (inside kInvMax), so every intermediate is the value an I2FP-converted sample would
+//          give times a power of two: the same mantissa after every rounding (no intermediate that matters
+//          comes near the subnormal range: 2^-49 * 1e-30 is still normal).  (First version: cvt.rn.f32.u32 ->
+//          I2FP on the ALU pipe, 8 of the 60 instructions per row of an RGB8 Cubic thread; before that I2F
+//          on the XU pipe, profiles/r01_*_d.md.)
 //   store  the vertical weights are pre-scaled by 1/max so the last FMA saturates to [0,1] (FFMA.SAT
 //          = clip_d, fix-ca.c:873-880); one more FMA with 1.5 * 2^23 rounds max * r to nearest-even in
 //          the low mantissa bits, which st.shared.u8/u16 then stores.
+constexpr float kIntHScale = 0x1p100f, kIntVScale = 0x1p49f;	// 100 + 49 = 149
 template <class S> struct StripCodec;
 template <> struct StripCodec<uint8_t> {
-	static constexpr float kInvMax = (float)(1.0 / 255.0);
+	static constexpr float kHScale = kIntHScale;
+	static constexpr float kInvMax = (float)(1.0 / 255.0) * kIntVScale;
 	__device__ __forceinline__ static float load(const unsigned char *p)
 	{
 		unsigned v;
-		float f;
 		asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)));
-		asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
-		return f;
+		return __uint_as_float(v);
 	}
 	__device__ __forceinline__ static float load_at(uint32_t saddr)	// 32-bit shared-window address
 	{
 		unsigned v;
-		float f;
 		asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
-		asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
-		return f;
+		return __uint_as_float(v);
 	}
 	__device__ __forceinline__ static void store(unsigned char *p, float sat01)
 	{
@@ -89,22 +93,19 @@ template <> struct StripCodec<uint8_t> {
 	}
 };
 template <> struct StripCodec<uint16_t> {
-	static constexpr float kInvMax = (float)(1.0 / 65535.0);
+	static constexpr float kHScale = kIntHScale;
+	static constexpr float kInvMax = (float)(1.0 / 65535.0) * kIntVScale;
 	__device__ __forceinline__ static float load(const unsigned char *p)
 	{
 		unsigned v;
-		float f;
 		asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)));
-		asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
-		return f;
+		return __uint_as_float(v);
 	}
 	__device__ __forceinline__ static float load_at(uint32_t saddr)
 	{
 		unsigned v;
-		float f;
 		asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
-		asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
-		return f;
+		return __uint_as_float(v);
 	}
 	__device__ __forceinline__ static void store(unsigned char *p, float sat01)
 	{
@@ -112,6 +113,7 @@ template <> struct StripCodec<uint16_t> {
 	}
 };
 template <> struct StripCodec<float> {
+	static constexpr float kHScale = 1.0f;
 	static constexpr float kInvMax = 1.0f;
 	__device__ __forceinline__ static float load(const unsigned char *p) { return *reinterpret_cast<const float *>(p); }
 	__device__ __forceinline__ static float load_at(uint32_t saddr)
@@ -124,6 +126,7 @@ template <> struct StripCodec<float> {
 };
 
 template <> struct StripCodec<__half> {	// bpc = -2: computed like float images, stored with one rounding to half
+	static constexpr float kHScale = 1.0f;
 	static constexpr float kInvMax = 1.0f;
 	__device__ __forceinline__ static float load(const unsigned char *p) { return __half2float(*reinterpret_cast<const __half *>(p)); }
 	__device__ __forceinline__ static float load_at(uint32_t saddr)
@@ -309,6 +312,9 @@ __global__ void __launch_bounds__(2 * TW / P) strip_kernel(const __grid_constant
 			double td;
 			cidx[k] = base_index(a.g.x[c], x, td);
 			tap_weights<INTERP>((float)td, w[k]);
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				w[k][j] *= Codec::kHScale;	// exact: a power of two (integer samples are read as subnormals)
 			idx0[k] = cidx[k] - OFF - k;		// first tap minus k (unclamped)
 			bmin = min(bmin, idx0[k]);
 		}
