@@ -998,7 +998,7 @@ static int copy_threads()
 // the kernel of chunk i and D2H of chunk i-1 overlap (PCIe is full duplex).
 static int region_host_band(int dev, const unsigned char *src, unsigned char *dst, int width, int height,
 			    const Format &f, const fixca_params *params, const Geometry &g,
-			    int y1, int y2, unsigned flags, bool progress)
+			    int x1, int x2, int y1, int y2, unsigned flags, bool progress)
 {
 	if (dev < 0 || dev >= 16)
 		return fail(FIXCA_ERR_NO_DEVICE, "device ordinal %d out of range", dev);
@@ -1010,6 +1010,9 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 
 	const size_t row_bytes = (size_t)width * f.bpp;
 	const size_t pitch = align_up(row_bytes, 128);
+	// FIXCA_COLUMN_SELECTION: the rows are computed full width on the device (a pixel's arithmetic does not
+	// depend on x1 / x2, fix-ca.c:1105-1320) and only columns [x1,x2) come back
+	const size_t sel_off = (size_t)x1 * f.bpp, sel_bytes = (size_t)(x2 - x1) * f.bpp;
 	int band_lo, band_hi;
 	source_rows(g, y1, y2, band_lo, band_hi);
 	const int src_rows = band_hi - band_lo + 1;
@@ -1020,7 +1023,7 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 	// streaming kernel's chunk height, so every launch of the band shares one chunk grid), at most 256 chunks.
 	// look at the first rows actually touched: callers may pass a whole-image base pointer of
 	// which only this band's rows are backed by memory
-	const bool src_pinned = is_pinned(src + (size_t)band_lo * row_bytes), dst_pinned = is_pinned(dst + (size_t)y1 * row_bytes);
+	const bool src_pinned = is_pinned(src + (size_t)band_lo * row_bytes), dst_pinned = is_pinned(dst + (size_t)y1 * row_bytes + sel_off);
 	// (pageable callers: smaller chunks, the staging copies of a chunk are not overlapped with its own transfers;
 	// measured on 100 MP RGB16: 16 MB 27.3 ms, 32 MB 28.7 ms, 64 MB 41.9 ms)
 	const size_t chunk_bytes = (size_t)std::max(1, env_int("FIXCA_CHUNK_MB", (src_pinned && dst_pinned) ? 32 : 16)) << 20;
@@ -1048,7 +1051,7 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 		if ((rc = cx.reserve_pinned(cx.h_in, cx.h_in_cap, in_slot * ring))) return rc;
 	}
 	if (!dst_pinned) {
-		out_slot = (size_t)chunk_rows * row_bytes;
+		out_slot = (size_t)chunk_rows * sel_bytes;
 		if ((rc = cx.reserve_pinned(cx.h_out, cx.h_out_cap, out_slot * ring))) return rc;
 	}
 
@@ -1069,7 +1072,11 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 		CUDA_TRY(cudaEventSynchronize(e_down));
 		if (!dst_pinned) {
 			const unsigned char *slot = cx.h_out + (size_t)(i % ring) * out_slot;
-			pool.copy(dst + (size_t)chunk_y1[i] * row_bytes, slot, (size_t)(chunk_y2[i] - chunk_y1[i]) * row_bytes);
+			if (sel_bytes == row_bytes)
+				pool.copy(dst + (size_t)chunk_y1[i] * row_bytes, slot, (size_t)(chunk_y2[i] - chunk_y1[i]) * row_bytes);
+			else
+				for (int y = chunk_y1[i]; y < chunk_y2[i]; ++y)
+					memcpy(dst + (size_t)y * row_bytes + sel_off, slot + (size_t)(y - chunk_y1[i]) * sel_bytes, sel_bytes);
 		}
 		if (progress && g_progress)
 			for (int y = chunk_y1[i]; y < chunk_y2[i]; ++y)
@@ -1115,9 +1122,9 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 		}
 		CUDA_TRY(cudaEventRecord(e_run, cx.s_run));
 		CUDA_TRY(cudaStreamWaitEvent(cx.s_down, e_run, 0));
-		unsigned char *to = dst_pinned ? dst + (size_t)c1 * row_bytes : cx.h_out + (size_t)(i % ring) * out_slot;
-		CUDA_TRY(cudaMemcpy2DAsync(to, row_bytes, cx.d_dst + (size_t)(c1 - y1) * pitch, pitch,
-					   row_bytes, c2 - c1, cudaMemcpyDeviceToHost, cx.s_down));
+		unsigned char *to = dst_pinned ? dst + (size_t)c1 * row_bytes + sel_off : cx.h_out + (size_t)(i % ring) * out_slot;
+		CUDA_TRY(cudaMemcpy2DAsync(to, dst_pinned ? row_bytes : sel_bytes, cx.d_dst + (size_t)(c1 - y1) * pitch + sel_off, pitch,
+					   sel_bytes, c2 - c1, cudaMemcpyDeviceToHost, cx.s_down));
 		CUDA_TRY(cudaEventRecord(e_down, cx.s_down));
 	}
 	for (int i = std::max(0, nchunks - ring); i < nchunks; ++i)
@@ -1130,13 +1137,15 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 }
 
 static int host_prologue(const unsigned char *src, unsigned char *dst, int width, int height, int bytes, int bpc,
-			 const fixca_params *params, int x1, int x2, int y1, int y2, Format &f, Geometry &g)
+			 const fixca_params *params, int x1, int x2, int y1, int y2, Format &f, Geometry &g, unsigned flags = 0)
 {
 	int rc = check_common(src, dst, width, height, params, y1, y2);
 	if (rc) return rc;
 	if ((rc = parse_format(bytes, bpc, f))) return rc;
-	if (x1 != 0 || x2 != width)
-		return fail(FIXCA_ERR_REGION, "columns [%d,%d) of %d: only full-width row bands are defined (the reference's own x1 != 0 path is broken)", x1, x2, width);
+	if ((x1 != 0 || x2 != width) && !(flags & FIXCA_COLUMN_SELECTION))
+		return fail(FIXCA_ERR_REGION, "columns [%d,%d) of %d: only full-width row bands are defined (the reference's own x1 != 0 path is broken); FIXCA_COLUMN_SELECTION opts in to the repaired form", x1, x2, width);
+	if (x1 < 0 || x2 > width || x1 >= x2)
+		return fail(FIXCA_ERR_REGION, "columns [%d,%d) outside 0..%d", x1, x2, width);
 	if (f.kind == SK_U64 && params->interpolation != 0)
 		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples with Linear/Cubic need 80-bit long double arithmetic (fix-ca.c:728-733)");
 	return make_geometry(width, height, params, g);
@@ -1148,7 +1157,7 @@ extern "C" int fixca_cuda_region_ex(const unsigned char *src, unsigned char *dst
 {
 	Format f;
 	Geometry g;
-	int rc = host_prologue(src, dst, width, height, bytes, bpc, params, x1, x2, y1, y2, f, g);
+	int rc = host_prologue(src, dst, width, height, bytes, bpc, params, x1, x2, y1, y2, f, g, flags);
 	if (rc) return rc;
 	int dev;
 	if ((rc = current_device_or(device, dev))) return rc;
@@ -1160,7 +1169,7 @@ extern "C" int fixca_cuda_region_ex(const unsigned char *src, unsigned char *dst
 		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples: the preview's saturation boost needs 80-bit long double arithmetic (fix-ca.c:728-733)");
 	int prev = -1;
 	cudaGetDevice(&prev);
-	rc = region_host_band(dev, src, dst, width, height, f, params, g, y1, y2, flags, show_progress != 0);
+	rc = region_host_band(dev, src, dst, width, height, f, params, g, x1, x2, y1, y2, flags, show_progress != 0);
 	if (prev >= 0)
 		cudaSetDevice(prev);
 	return rc;
@@ -1216,7 +1225,7 @@ extern "C" int fixca_cuda_region_multi(const unsigned char *src, unsigned char *
 		if (b1[i] == b2[i])
 			continue;
 		workers.emplace_back([&, i]() {
-			rcs[i] = region_host_band(dv[i], src, dst, width, height, f, params, g, b1[i], b2[i], flags, false);
+			rcs[i] = region_host_band(dv[i], src, dst, width, height, f, params, g, 0, width, b1[i], b2[i], flags, false);
 			if (rcs[i])
 				errs[i] = tl_error;
 		});

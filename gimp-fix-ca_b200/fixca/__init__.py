@@ -28,6 +28,7 @@ INTERP_NONE, INTERP_LINEAR, INTERP_CUBIC = 0, 1, 2
 PRECISION_EXACT, PRECISION_FAST = 0x0, 0x1
 FORCE_DIRECT, FORCE_TILED = 0x10, 0x20
 PREVIEW_OVERLAY = 0x40      # saturate() + centerline() on the rows written (the show_progress=False call)
+COLUMN_SELECTION = 0x80     # accept x1 != 0 / x2 != width: columns [x1, x2) of the full-width result (extension)
 INPUT_MAX = 30.0
 
 OK = 0

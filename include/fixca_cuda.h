@@ -103,6 +103,15 @@ typedef struct fixca_params {
  * lens cross and diagonals, fix-ca.c:945-996) are applied to every row written.  Set automatically by
  * fixca_cuda_region*() when show_progress == 0; pass it to fixca_cuda_region_dev() to get the same. */
 #define FIXCA_PREVIEW_OVERLAY  0x40u
+/* Extension ("correct selection handling"): accept x1 != 0 / x2 != width in
+ * fixca_cuda_region_ex().  The reference's arithmetic for a pixel never depends on x1 / x2 (every index in
+ * fix-ca.c:1105-1320 is an absolute column), but three buffer-indexing bugs break its own x1 != 0 path
+ * (band_adj multiplied by `bytes` twice :1084/:856, the green copy offset in pixels instead of bytes :1098,
+ * and fix_ca() handing GEGL a selection-strided rectangle :369-370), so without this flag such calls return
+ * FIXCA_ERR_REGION.  With it, columns [x1,x2) of rows [y1,y2) of dst receive exactly what the full-width
+ * pass computes for them, and nothing else in dst is written (src and dst stay whole-image buffers,
+ * width * height * bytes, as set_data() addresses them, :864-871). */
+#define FIXCA_COLUMN_SELECTION 0x80u
 
 /* ------------------------------------------------------------------------- */
 /* The pass, host buffers: replaces fix_ca_region()                           */

@@ -56,6 +56,9 @@ def test_argument_errors_before_any_gpu_work(fx):
 
     assert rc(img, out, 8, 8, 3, 1, P(), 1, 8, 0, 8) == fx.ERR_REGION           # x1 != 0
     assert rc(img, out, 8, 8, 3, 1, P(), 0, 7, 0, 8) == fx.ERR_REGION
+    # ... and with the opt-in (FIXCA_COLUMN_SELECTION) only sane column ranges pass the argument check
+    assert rc(img, out, 8, 8, 3, 1, P(), 3, 3, 0, 8, True, fx.COLUMN_SELECTION) == fx.ERR_REGION
+    assert rc(img, out, 8, 8, 3, 1, P(), 0, 9, 0, 8, True, fx.COLUMN_SELECTION) == fx.ERR_REGION
     assert rc(img, out, 8, 8, 3, -2, P(), 0, 8, 0, 8) == fx.ERR_FORMAT          # half
     assert rc(img, out, 8, 8, 3, -99, P(), 0, 8, 0, 8) == fx.ERR_FORMAT
     assert rc(img, out, 8, 8, 5, 1, P(), 0, 8, 0, 8) == fx.ERR_FORMAT

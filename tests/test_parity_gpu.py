@@ -250,6 +250,42 @@ def test_band_call_writes_only_its_rows(fx, checker):
         assert (d2[y] == full[y]).all()
 
 
+def test_column_selection_is_the_crop_of_the_full_width_pass(fx, checker):
+    """FIXCA_COLUMN_SELECTION (extension): columns [x1,x2) of rows [y1,y2) get what the
+    full-width pass computes for them -- the reference's per-pixel arithmetic (fix-ca.c:1105-1320 never uses
+    x1 / x2 in an index), checked against the reference run full width -- and nothing else is written.
+    Without the flag the call is refused like before (the reference's own x1 != 0 path is broken)."""
+    import torch
+
+    for (h, w, ch, dt, interp, flags) in ((333, 411, 4, "u2", 2, fx.PRECISION_EXACT), (257, 300, 3, "u1", 1, fx.PRECISION_EXACT),
+                                          (129, 200, 3, "f4", 0, fx.PRECISION_EXACT), (1400, 2100, 3, "u1", 2, fx.PRECISION_EXACT)):
+        img = orc.synth_image(h, w, ch, dt, 77)
+        kw = dict(KW, lens_x=w // 2 - 7, lens_y=h // 3, interpolation=interp)
+        full = checker.region(img, orc.Params(**kw))
+        bpp = ch * img.dtype.itemsize
+        for (x1, x2, y1, y2) in ((5, w - 9, 10, h - 20), (0, 17, 0, h), (w - 1, w, 3, 4), (100, 101, 0, h), (0, w, 7, 90)):
+            # pageable caller (numpy; the 8.8 MB case goes through the staging rings) and pinned caller
+            for pinned in (False, True):
+                if pinned:
+                    t = torch.empty(img.nbytes, dtype=torch.uint8, pin_memory=True)
+                    dst = t.numpy().view(img.dtype).reshape(img.shape)
+                else:
+                    dst = np.empty_like(img)
+                dst.view(np.uint8)[:] = 0xA5
+                before = dst.copy()
+                fx.fix_ca_region(img, dst, w, h, bpp, fx.bpc_of(img.dtype), fx.FixCaParams(**kw), x1, x2, y1, y2, True,
+                                 flags | fx.COLUMN_SELECTION)
+                assert dst[y1:y2, x1:x2].tobytes() == full[y1:y2, x1:x2].tobytes(), (h, w, x1, x2, y1, y2, pinned)
+                dst[y1:y2, x1:x2] = before[y1:y2, x1:x2]
+                assert dst.tobytes() == before.tobytes(), "bytes outside the selection were written"
+    img = orc.synth_image(16, 16, 3, "u1", 1)
+    for (x1, x2, flags) in ((1, 16, fx.PRECISION_EXACT), (4, 4, fx.COLUMN_SELECTION), (-1, 8, fx.COLUMN_SELECTION),
+                            (0, 17, fx.COLUMN_SELECTION)):
+        with pytest.raises(fx.FixCaError) as e:
+            fx.fix_ca_region(img, np.zeros_like(img), 16, 16, 3, 1, fx.FixCaParams(), x1, x2, 0, 16, True, flags)
+        assert e.value.code == fx.ERR_REGION
+
+
 def test_progress_protocol_matches_reference(fx):
     # fix-ca.c:1022-1023, 1331-1332, 1335-1336
     img = orc.synth_image(50, 64, 3, "u1", 2)
