@@ -77,12 +77,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Wait with a suspend-time hint: the helper warps are far ahead of the data and must not burn
-// issue slots polling.
-__device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity, uint32_t hint_ns)
+// Wait of a helper warp: these are far ahead of the data and should not poll on the schedulers.  The
+// suspend-time hint of try_wait alone does not keep them off: ncu's per-instruction counts (r01 Z, 32 x 4K RGB8,
+// profiles/r01_ncu_stream_u8x3_cubic_batch_Z.md) showed the two helper loops coming back after ~11 ns and
+// executing 26 % of ALL warp instructions of the kernel (90-150 polls per wait).  A real nanosleep between
+// the polls removes those instructions; the kernel time did not move (1.446 ms per 128 frames either way: the
+// compute warps are bound by their own dependency chains at 16 warps per SM, not by issue slots), so this is
+// hygiene -- fewer wasted issue slots and less power -- not a speed-up.
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity, uint32_t hint_ns, bool sleep = true)
 {
 	uint32_t done;
-	do {
+	for (;;) {
 		asm volatile(
 			"{\n\t.reg .pred p;\n\t"
 			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -90,7 +95,11 @@ __device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity,
 			: "=r"(done)
 			: "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
 			: "memory");
-	} while (!done);
+		if (done)
+			break;
+		if (sleep)
+			__nanosleep(hint_ns);
+	}
 }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read()
@@ -221,7 +230,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		int inf = 0, ipar = 0;	// i % NF, (i / NF) & 1
 		for (int i = 0; i < nchunks; ++i) {
 			if (i >= NF)	// the slot's previous tenant (chunk i - NF) must be finished
-				mbar_wait_sleepy(&done[inf], (uint32_t)(ipar ^ 1), 2000u);
+				mbar_wait_sleepy(&done[inf], (uint32_t)(ipar ^ 1), 1000u, !(a.debug & 4));
 			const int y_first = ya + i * CH;
 			const int nr = min(CH, yb - y_first);
 			StreamMeta &m = meta[inf];
@@ -313,7 +322,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				request_window(j + D);
 			if (j + 1 < nchunks)
 				request_tile(j + 1);
-			mbar_wait_sleepy(&done[jnf], (uint32_t)jpar, 500u);
+			mbar_wait_sleepy(&done[jnf], (uint32_t)jpar, 100u, !(a.debug & 4));
 			tma_store_3d(&tm_out, c0_tile, ya + j * CH - a.dst_row0, frame, stage + jstg * STAGE_BYTES);
 			bulk_commit();
 			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
