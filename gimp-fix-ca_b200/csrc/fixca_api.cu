@@ -452,10 +452,16 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 			depth = std::min(forced_d, STREAM_MAX_D);
 	} else {
 		// Most CTAs per SM that still leave a pipeline depth of 2 (the HBM latency needs ~2 chunks in
-		// flight per CTA); then the deepest pipeline that fits beside them.
+		// flight per CTA).  Deeper is not better: with 2+ CTAs per SM a third chunk in flight per CTA costs
+		// bandwidth for the 1536-byte strips (100 MP RGB16 None: depth 2 0.199 ms, depth 3-6 0.211 ms, depth 8
+		// 0.219 ms; 8K RGBA16 None 0.093 -> 0.089 ms, Linear 0.090 -> 0.087 ms: the strips of a row drift further
+		// apart and their requests lose the DRAM pages they share), a lone CTA per SM wants 4 (0.212 against
+		// 0.247 / 0.258 ms at depth 3 / 2).  The narrower strips (RGBA f32: 64 pixels = 1024 bytes, 8 compute
+		// warps per SM) keep the deepest pipeline that fits: capped at 2 they lose 8-10 %.
+		const bool wide_strip = k->tw * f.bpp >= 1536;
 		for (int want = want_ctas; want >= 1 && !depth; --want) {
 			const size_t budget = std::min<size_t>(limit, (227 * 1024) / want - 1024);
-			for (int d = STREAM_MAX_D; d >= (want > 1 ? 2 : 1); --d) {
+			for (int d = !wide_strip ? STREAM_MAX_D : want > 1 ? 2 : 4; d >= (want > 1 ? 2 : 1); --d) {
 				layout(d);
 				if (total <= budget) {
 					depth = d;

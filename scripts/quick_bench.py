@@ -167,6 +167,20 @@ if __name__ == "__main__":
                         run("cubic ctas%s D%s dbg%s" % (ctas, d, dbg), 8192, 12288, 3, torch.int16, 2, 2, F, reps=5)
                     except fixca.FixCaError as e:
                         print("ctas", ctas, "D", d, str(e)[:80])
+    if which == "nonepipe":
+        os.environ["FIXCA_VERBOSE"] = "1"
+        run("100MP rgb16 none   default", 8192, 12288, 3, torch.int16, 2, 0, E, reps=5)
+        run("100MP rgb16 linear default", 8192, 12288, 3, torch.int16, 2, 1, F, reps=5)
+        run("100MP rgb16 cubic  default", 8192, 12288, 3, torch.int16, 2, 2, F, reps=5)
+        os.environ["FIXCA_VERBOSE"] = "0"
+        for ctas in ("1", "2", "3", "4"):
+            for d in ("2", "3", "4", "6", "8"):
+                os.environ["FIXCA_STREAM_CTAS"] = ctas
+                os.environ["FIXCA_STREAM_DEPTH"] = d
+                try:
+                    run("none ctas%s D%s" % (ctas, d), 8192, 12288, 3, torch.int16, 2, 0, E, reps=5)
+                except fixca.FixCaError as e:
+                    print("ctas", ctas, "D", d, str(e)[:80])
     if which == "strip":
         for tw in ("256", "128"):
             os.environ["FIXCA_STRIP_TW"] = tw
