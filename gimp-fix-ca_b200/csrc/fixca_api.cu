@@ -1344,6 +1344,59 @@ extern "C" int fixca_cuda_frames(const unsigned char *const *src_frames, unsigne
 	return rc;
 }
 
+// Frames sharded by index over several GPUs of the box from one process (BASELINE configs[4]: "batch stream of
+// frames sharded across 8xB200"): device d of ndev takes frames d, d + ndev, ... through its own ring, stream
+// set and PCIe link, on its own worker thread.  Frames are independent (fix-ca.c:373-374 per frame): no
+// exchange between devices.
+extern "C" int fixca_cuda_frames_multi(const unsigned char *const *src_frames, unsigned char *const *dst_frames, int nframes,
+				       int width, int height, int bytes, int bpc, const fixca_params *params,
+				       unsigned flags, const int *devices, int ndev)
+{
+	if (nframes < 0 || (nframes > 0 && (!src_frames || !dst_frames)))
+		return fail(FIXCA_ERR_ARG, "bad frame list");
+	if (ndev <= 0 || ndev > 16)
+		return fail(FIXCA_ERR_ARG, "ndev %d outside 1..16", ndev);
+	if (nframes == 0)
+		return FIXCA_OK;
+	int have = 0;
+	if (cudaGetDeviceCount(&have) != cudaSuccess || have <= 0) {
+		cudaGetLastError();
+		return fail(FIXCA_ERR_NO_DEVICE, "no CUDA device; this library has no CPU path");
+	}
+	std::vector<int> dv(ndev), rcs(ndev, 0);
+	std::vector<std::string> errs(ndev), kern(ndev);
+	for (int i = 0; i < ndev; ++i) {
+		dv[i] = devices ? devices[i] : i;
+		if (dv[i] < 0 || dv[i] >= have)
+			return fail(FIXCA_ERR_NO_DEVICE, "device %d requested, %d present", dv[i], have);
+	}
+	std::vector<std::vector<const unsigned char *>> srcs(ndev);
+	std::vector<std::vector<unsigned char *>> dsts(ndev);
+	for (int i = 0; i < nframes; ++i) {
+		srcs[i % ndev].push_back(src_frames[i]);
+		dsts[i % ndev].push_back(dst_frames[i]);
+	}
+	std::vector<std::thread> workers;
+	for (int d = 0; d < ndev; ++d) {
+		if (srcs[d].empty())
+			continue;
+		workers.emplace_back([&, d]() {
+			rcs[d] = fixca_cuda_frames(srcs[d].data(), dsts[d].data(), (int)srcs[d].size(), width, height, bytes, bpc,
+						   params, flags, dv[d]);
+			if (rcs[d])
+				errs[d] = tl_error;
+			kern[d] = tl_kernel;
+		});
+	}
+	for (std::thread &t : workers)
+		t.join();
+	for (int d = 0; d < ndev; ++d)
+		if (rcs[d])
+			return fail(rcs[d], "frames of device %d: %s", dv[d], errs[d].c_str());
+	snprintf(tl_kernel, sizeof tl_kernel, "%s", kern[0].c_str());
+	return FIXCA_OK;
+}
+
 // ---------------------------------------------------------------------------
 // host-side logic
 // ---------------------------------------------------------------------------

@@ -42,7 +42,7 @@ EXPORTS = (
     "fixca_check_params", "fixca_color_size", "fixca_color_size_half", "fixca_params_default", "fixca_cuda_set_progress",
     "fixca_cuda_last_error", "fixca_strerror", "fixca_cuda_device_count", "fixca_cuda_last_kernel",
     "fixca_cuda_launch_count", "fixca_cuda_release", "fixca_version",
-    "fixca_cuda_frame_alloc", "fixca_cuda_frame_open", "fixca_cuda_frame_close", "fixca_cuda_frame_free",
+    "fixca_cuda_frames_multi", "fixca_cuda_frame_alloc", "fixca_cuda_frame_open", "fixca_cuda_frame_close", "fixca_cuda_frame_free",
 )
 IPC_HANDLE_BYTES = 64
 
@@ -98,6 +98,8 @@ def load() -> ctypes.CDLL:
     L.fixca_cuda_region_dev.argtypes = [vp, ctypes.c_size_t, i, i, vp, ctypes.c_size_t, i, i, i, i, i, pp, i, i,
                                         ctypes.c_uint, vp]
     L.fixca_cuda_frames.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), i, i, i, i, i, pp, ctypes.c_uint, i]
+    L.fixca_cuda_frames_multi.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), i, i, i, i, i, pp, ctypes.c_uint,
+                                          ctypes.POINTER(i), i]
     L.fixca_cuda_frames_dev.argtypes = [vp, ctypes.c_size_t, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.c_size_t, i,
                                         i, i, i, i, pp, ctypes.c_uint, vp]
     L.fixca_cuda_frame_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
@@ -195,17 +197,24 @@ def fix_ca_frames_dev(d_src: int, src_pitch: int, src_frame_stride: int, d_dst: 
                                         width, height, bytes, bpc, ctypes.byref(params), flags, stream))
 
 
-def correct_frames(frames, params: FixCaParams, flags=PRECISION_EXACT, device=-1):
-    """A stream of equal-shaped host frames through the pinned H2D / kernel / D2H ring."""
+def correct_frames(frames, params: FixCaParams, flags=PRECISION_EXACT, device=-1, devices=None, outs=None):
+    """A stream of equal-shaped host frames through the pinned H2D / kernel / D2H ring of one device, or
+    (``devices``) sharded by index over several GPUs from this process."""
     if not frames:
         return []
     h, w, ch = frames[0].shape
-    outs = [np.zeros_like(f) for f in frames]
+    if outs is None:
+        outs = [np.zeros_like(f) for f in frames]
     n = len(frames)
     src = (ctypes.c_void_p * n)(*[f.ctypes.data for f in frames])
     dst = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
-    _check(load().fixca_cuda_frames(src, dst, n, w, h, ch * frames[0].dtype.itemsize, bpc_of(frames[0].dtype),
-                                    ctypes.byref(params), flags, device))
+    if devices is not None:
+        arr = (ctypes.c_int * len(devices))(*devices)
+        _check(load().fixca_cuda_frames_multi(src, dst, n, w, h, ch * frames[0].dtype.itemsize, bpc_of(frames[0].dtype),
+                                              ctypes.byref(params), flags, arr, len(devices)))
+    else:
+        _check(load().fixca_cuda_frames(src, dst, n, w, h, ch * frames[0].dtype.itemsize, bpc_of(frames[0].dtype),
+                                        ctypes.byref(params), flags, device))
     return outs
 
 

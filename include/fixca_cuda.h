@@ -222,6 +222,16 @@ FIXCA_API int fixca_cuda_frames(const unsigned char *const *src_frames, unsigned
 				int nframes, int width, int height, int bytes, int bpc,
 				const fixca_params *params, unsigned flags, int device);
 
+/*
+ * The same stream of host frames sharded by index over `ndev` GPUs of the box from one process (BASELINE
+ * "batch stream of frames sharded across 8xB200"): device i of ndev takes frames i, i + ndev, ... through its own
+ * ring and PCIe link on its own worker thread.  Frames are independent, so there is no exchange between
+ * devices.  devices == NULL means 0..ndev-1.
+ */
+FIXCA_API int fixca_cuda_frames_multi(const unsigned char *const *src_frames, unsigned char *const *dst_frames,
+				      int nframes, int width, int height, int bytes, int bpc,
+				      const fixca_params *params, unsigned flags, const int *devices, int ndev);
+
 /* ------------------------------------------------------------------------- */
 /* Host-side logic (no GPU needed)                                            */
 /* ------------------------------------------------------------------------- */

@@ -314,6 +314,11 @@ def test_multi_device_bands_and_frames(fx, checker):
     outs = fx.correct_frames(frames, fx.FixCaParams(**kw), flags=fx.PRECISION_EXACT)
     for f, o in zip(frames, outs):
         assert o.tobytes() == checker.region(f, orc.Params(**kw)).tobytes()
+    # the same stream sharded by index over devices from one process (a device may serve several shards)
+    for nd in (1, 2, 3):
+        outs = fx.correct_frames(frames, fx.FixCaParams(**kw), flags=fx.PRECISION_EXACT, devices=[i % ndev for i in range(nd)])
+        for f, o in zip(frames, outs):
+            assert o.tobytes() == checker.region(f, orc.Params(**kw)).tobytes(), nd
 
 
 def test_device_resident_entry_with_torch_buffers(fx, checker):
