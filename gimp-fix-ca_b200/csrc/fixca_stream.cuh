@@ -77,17 +77,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Wait of a helper warp: these are far ahead of the data and should not poll on the schedulers.  The
-// suspend-time hint of try_wait alone does not keep them off: ncu's per-instruction counts (r01 Z, 32 x 4K RGB8,
-// profiles/r01_ncu_stream_u8x3_cubic_batch_Z.md) showed the two helper loops coming back after ~11 ns and
-// executing 26 % of ALL warp instructions of the kernel (90-150 polls per wait).  A real nanosleep between
-// the polls removes those instructions; the kernel time did not move (1.446 ms per 128 frames either way: the
-// compute warps are bound by their own dependency chains at 16 warps per SM, not by issue slots), so this is
-// hygiene -- fewer wasted issue slots and less power -- not a speed-up.
-__device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity, uint32_t hint_ns, bool sleep = true)
+// Wait of a helper warp, with a suspend-time hint.  The hint does not park the warp for long: ncu's
+// per-instruction counts (r01 Z / b, 32 x 4K RGB8 frames) show these two loops coming back every ~11-25 ns and
+// executing a quarter of all warp instructions of the kernel (60-150 polls per wait), and an explicit
+// nanosleep.u32 of 100 / 1000 ns between the polls returns just as early (half the polls, twice the instructions
+// per poll).  It does not cost time either -- kernel times with and without the nanosleep were identical on one
+// box for every format -- the polls only fill issue slots the compute warps leave empty; it does mean that
+// "issue slots busy" in the ncu summaries overstates the compute warps' own issue pressure by that quarter.
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity, uint32_t hint_ns)
 {
 	uint32_t done;
-	for (;;) {
+	do {
 		asm volatile(
 			"{\n\t.reg .pred p;\n\t"
 			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -95,11 +95,18 @@ __device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity,
 			: "=r"(done)
 			: "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
 			: "memory");
-		if (done)
-			break;
-		if (sleep)
-			__nanosleep(hint_ns);
-	}
+	} while (!done);
+}
+// A compute warp hands its part of a chunk over: every lane's staging writes are made visible to the async proxy
+// (the TMA store the producer issues next), the warp converges, one lane arrives.  One arrival per warp instead of
+// one per thread: the helper warps sleep in NANOSLEEP.SYNCS between polls and every arrival on a barrier of the
+// CTA wakes them (their ~130 polls per wait were the ~128 thread arrivals of a chunk).
+__device__ __forceinline__ void warp_arrive(uint64_t *bar)
+{
+	fence_proxy_async_smem();
+	__syncwarp();
+	if ((threadIdx.x & 31) == 0)
+		mbar_arrive(bar);
 }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read()
@@ -182,7 +189,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	if (tid == 0) {
 		for (int i = 0; i < NF; ++i) {
 			mbar_init(reinterpret_cast<uint64_t *>(&hdr->full[i]), 3);	// window rows, pass-through tile, row coefficients
-			mbar_init(reinterpret_cast<uint64_t *>(&hdr->done[i]), NTC);
+			mbar_init(reinterpret_cast<uint64_t *>(&hdr->done[i]), NTC / 32);	// one arrival per compute warp (warp_arrive)
 		}
 		fence_mbar_init();
 	}
@@ -230,7 +237,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		int inf = 0, ipar = 0;	// i % NF, (i / NF) & 1
 		for (int i = 0; i < nchunks; ++i) {
 			if (i >= NF)	// the slot's previous tenant (chunk i - NF) must be finished
-				mbar_wait_sleepy(&done[inf], (uint32_t)(ipar ^ 1), 1000u, !(a.debug & 4));
+				mbar_wait_sleepy(&done[inf], (uint32_t)(ipar ^ 1), 2000u);
 			const int y_first = ya + i * CH;
 			const int nr = min(CH, yb - y_first);
 			StreamMeta &m = meta[inf];
@@ -322,7 +329,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				request_window(j + D);
 			if (j + 1 < nchunks)
 				request_tile(j + 1);
-			mbar_wait_sleepy(&done[jnf], (uint32_t)jpar, 100u, !(a.debug & 4));
+			mbar_wait_sleepy(&done[jnf], (uint32_t)jpar, 500u);
 			tma_store_3d(&tm_out, c0_tile, ya + j * CH - a.dst_row0, frame, stage + jstg * STAGE_BYTES);
 			bulk_commit();
 			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
@@ -373,8 +380,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 					for (int k = 0; k < P; ++k)
 						*reinterpret_cast<S *>(q + r * OUT_PITCH + k * BPP) = v[r][k];
 			}
-			fence_proxy_async_smem();
-			mbar_arrive(done_bar);
+			warp_arrive(done_bar);
 		}
 	} else {
 	typedef StripCodec<S> Codec;
@@ -519,8 +525,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			if (a.debug & 1) {	// timing experiment: memory pipeline only (results are wrong)
 				s_done = s_end;
 				prow = win_c + (uint32_t)(((s_done + 1) % NR) * wpitch);
-				fence_proxy_async_smem();
-				mbar_arrive(done_bar);
+				warp_arrive(done_bar);
 				continue;
 			}
 
@@ -672,8 +677,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				walk(s_end);
 			}
 			// staging writes -> visible to the TMA store the producer issues after this barrier
-			fence_proxy_async_smem();
-			mbar_arrive(done_bar);
+			warp_arrive(done_bar);
 		}
 	};
 	// (measured: 100 MP RGB16 Cubic 0.212 -> 0.208 ms, RGBA8 0.068 -> 0.066 ms; four-column groups (RGB8)
