@@ -72,6 +72,30 @@ def test_argument_errors_before_any_gpu_work(fx):
     assert rc(big, np.zeros_like(big), 8, 8, 24, 8, P(interpolation=2), 0, 8, 0, 8) == fx.ERR_UNSUPPORTED
 
 
+def test_multi_gpu_entries_check_their_arguments_first(fx):
+    """fixca_cuda_frames_multi / fixca_cuda_frame_*: argument errors come before any device work; without a GPU the
+    allocation fails loudly (no CPU path)."""
+    import ctypes
+
+    L = fx.load()
+    img = np.zeros((8, 8, 3), np.uint8)
+    out = np.zeros_like(img)
+    vp = ctypes.c_void_p
+    srcs, dsts = (vp * 1)(img.ctypes.data), (vp * 1)(out.ctypes.data)
+    P = fx.FixCaParams()
+    assert L.fixca_cuda_frames_multi(srcs, dsts, 1, 8, 8, 3, 1, ctypes.byref(P), 0, None, 0) == fx.ERR_ARG      # ndev 0
+    assert L.fixca_cuda_frames_multi(srcs, dsts, 1, 8, 8, 3, 1, ctypes.byref(P), 0, None, 17) == fx.ERR_ARG
+    assert L.fixca_cuda_frames_multi(None, dsts, 1, 8, 8, 3, 1, ctypes.byref(P), 0, None, 1) == fx.ERR_ARG
+    assert L.fixca_cuda_frames_multi(srcs, dsts, 0, 8, 8, 3, 1, ctypes.byref(P), 0, None, 1) == fx.OK          # empty stream
+    ptr = vp()
+    assert L.fixca_cuda_frame_open(None, ctypes.byref(ptr)) == fx.ERR_ARG
+    assert L.fixca_cuda_frame_alloc(0, ctypes.byref(ptr), ctypes.create_string_buffer(64)) == fx.ERR_ARG
+    assert L.fixca_cuda_frame_close(None) == fx.OK and L.fixca_cuda_frame_free(None) == fx.OK
+    if fx.device_count() == 0:
+        assert L.fixca_cuda_frame_alloc(1 << 20, ctypes.byref(ptr), ctypes.create_string_buffer(64)) == fx.ERR_NO_DEVICE
+        assert L.fixca_cuda_frames_multi(srcs, dsts, 1, 8, 8, 3, 1, ctypes.byref(P), 0, None, 1) == fx.ERR_NO_DEVICE
+
+
 def test_band_source_rows_match_oracle_tables(fx, restatement):
     rng = np.random.default_rng(5)
     for n in range(200):
