@@ -121,6 +121,12 @@ if __name__ == "__main__":
         for w in (6144, 6000, 5888, 6100):
             run("rgb8 cubic w=%d" % w, 4000, w, 3, torch.uint8, 1, 2, F)
             run("rgb8 linear w=%d" % w, 4000, w, 3, torch.uint8, 1, 1, F)
+    if which == "none16":
+        run("100MP rgb16 none", 8192, 12288, 3, torch.int16, 2, 0, E)
+        run("24MP rgb16 none", 4000, 6000, 3, torch.int16, 2, 0, E)
+        run("8MP rgb16 none", 2160, 3840, 3, torch.int16, 2, 0, E)
+        run("8K rgba16 none", 4320, 7680, 4, torch.int16, 2, 0, E, lens=(658, 1280))
+        run("24MP rgba16 none", 4000, 6000, 4, torch.int16, 2, 0, E)
     if which == "none":
         run("100MP rgb16 none", 8192, 12288, 3, torch.int16, 2, 0, E)
         run("24MP rgb8 none", 4000, 6000, 3, torch.uint8, 1, 0, E)
