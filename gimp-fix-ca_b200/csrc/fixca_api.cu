@@ -49,8 +49,66 @@ static int fail(int code, const char *fmt, ...)
 				    "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
 	} while (0)
 
-static fixca_progress_fn g_progress = nullptr;
-static void *g_progress_user = nullptr;
+// Progress callback: per calling thread (the plug-in installs it on, and calls from, its only thread,
+// fix-ca.c:1022-1023; concurrent callers on other threads neither see nor race on it).
+static thread_local fixca_progress_fn g_progress = nullptr;
+static thread_local void *g_progress_user = nullptr;
+
+// ---------------------------------------------------------------------------
+// tuning switches: read from the environment once
+// ---------------------------------------------------------------------------
+static std::mutex g_tuning_mu;
+static Tuning g_tuning;
+static std::atomic<int> g_tuning_gen{0};	// 0 = not read yet
+
+static int env_int(const char *name, int dflt)
+{
+	const char *s = getenv(name);
+	return (s && *s) ? atoi(s) : dflt;
+}
+
+static void read_tuning_locked()
+{
+	Tuning t;
+	const char *e = getenv("FIXCA_FAST_KERNEL");
+	t.fast_kernel = (e && !strcmp(e, "strip")) ? 2 : 3;
+	e = getenv("FIXCA_NONE_KERNEL");
+	t.none_tiled = e && !strcmp(e, "tiled");
+	t.strip_tw128 = env_int("FIXCA_STRIP_TW", 0) == 128;
+	t.stream_noalt = env_int("FIXCA_STREAM_NOALT", 0) != 0;
+	t.tile_h = env_int("FIXCA_TILE_H", 0);
+	t.tile_ctas = env_int("FIXCA_TILE_CTAS", 3);
+	t.stream_ctas = env_int("FIXCA_STREAM_CTAS", 0);
+	t.stream_depth = env_int("FIXCA_STREAM_DEPTH", 0);
+	t.stream_segs = env_int("FIXCA_STREAM_SEGS", 0);
+	t.stream_waves = env_int("FIXCA_STREAM_WAVES", 0);
+	t.stream_debug = env_int("FIXCA_STREAM_DEBUG", 0);
+	t.no_pdl = env_int("FIXCA_NO_PDL", 0);
+	t.verbose = env_int("FIXCA_VERBOSE", 0);
+	t.chunk_mb = env_int("FIXCA_CHUNK_MB", 0);
+	t.copy_threads = env_int("FIXCA_COPY_THREADS", 0);
+	e = getenv("FIXCA_PRECISION");
+	t.precision_fast = e && (e[0] == 'f' || e[0] == 'F');
+	t.generation = g_tuning_gen.load() + 1;
+	g_tuning = t;
+	g_tuning_gen.store(t.generation);
+}
+
+const Tuning &fixca::tuning()
+{
+	if (!g_tuning_gen.load()) {
+		std::lock_guard<std::mutex> lock(g_tuning_mu);
+		if (!g_tuning_gen.load())
+			read_tuning_locked();
+	}
+	return g_tuning;
+}
+
+extern "C" void fixca_cuda_reload_tuning(void)
+{
+	std::lock_guard<std::mutex> lock(g_tuning_mu);
+	read_tuning_locked();
+}
 
 // ---------------------------------------------------------------------------
 // format and geometry
@@ -70,8 +128,9 @@ static int parse_format(int bytes, int bpc, Format &f)
 	case -4: f.kind = SK_F32; f.sample_bytes = 4; break;
 	case -8: f.kind = SK_F64; f.sample_bytes = 8; break;
 	case -2: f.kind = SK_F16; f.sample_bytes = 2; break;	// extension: the reference's commented-out half branch
+	case FIXCA_BPC_U15: f.kind = SK_U15; f.sample_bytes = 2; break;	// extension: 15-bit unsigned in 16-bit storage
 	default:
-		return fail(FIXCA_ERR_FORMAT, "unsupported bpc %d (the reference handles 1,2,4,8,-4,-8, and -2 in commented-out code; fix-ca.c:688-707)", bpc);
+		return fail(FIXCA_ERR_FORMAT, "unsupported bpc %d (the reference handles 1,2,4,8,-4,-8, and -2 in commented-out code; 15 = u15 is this library's extension; fix-ca.c:688-707)", bpc);
 	}
 	if (bytes == 3 * f.sample_bytes)
 		f.nch = 3;
@@ -88,6 +147,15 @@ static int make_geometry(int width, int height, const fixca_params *p, Geometry 
 {
 	if (p->interpolation < 0 || p->interpolation > 2)
 		return fail(FIXCA_ERR_INTERP, "interpolation %d outside 0..2", p->interpolation);
+	// NaN / infinite amounts, shifts or lens, and lens coordinates whose (int) cast or width - xc would
+	// overflow, are undefined behaviour in the reference (fix-ca.c:1033-1045, :801): rejected here
+	const double all[8] = {p->blue, p->red, p->lens_x, p->lens_y, p->x_blue, p->x_red, p->y_blue, p->y_red};
+	for (double v : all)
+		if (!(v == v) || v > 1.0e300 || v < -1.0e300)
+			return fail(FIXCA_ERR_ARG, "non-finite parameter (blue %g red %g lens %g,%g shifts %g %g %g %g)",
+				    p->blue, p->red, p->lens_x, p->lens_y, p->x_blue, p->x_red, p->y_blue, p->y_red);
+	if (p->lens_x > 1073741824.0 || p->lens_x < -1073741824.0 || p->lens_y > 1073741824.0 || p->lens_y < -1073741824.0)
+		return fail(FIXCA_ERR_ARG, "lens centre %g,%g outside +-2^30", p->lens_x, p->lens_y);
 	const int xc = (int)p->lens_x, yc = (int)p->lens_y;
 	int m = xc >= yc ? xc : yc;
 	if (width - xc > m) m = width - xc;
@@ -217,12 +285,6 @@ static void window_extent_stream(const Geometry &g, int bpp, int tw, int slack, 
 	}
 }
 
-static int env_int(const char *name, int dflt)
-{
-	const char *s = getenv(name);
-	return (s && *s) ? atoi(s) : dflt;
-}
-
 static int g_sm_count[64];	// per device, 0 = not queried
 
 static int sm_count(int dev)
@@ -266,7 +328,10 @@ static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_
 	a.g = g;
 	pl.src_rows_avail = src_rows;
 
-	const bool tma_ok = g.monotone && (src_pitch % 16 == 0) && (dst_pitch % 16 == 0) &&
+	// FIXCA_TIGHT_ROWS: the TMA kernels store whole 16-byte units, i.e. up to 15 bytes past width * bpp of every
+	// destination row; a caller whose rows are views into a wider buffer forbids that
+	const bool tight_ok = !(flags & FIXCA_TIGHT_ROWS) || ((size_t)g.width * f.bpp) % 16 == 0;
+	const bool tma_ok = tight_ok && g.monotone && (src_pitch % 16 == 0) && (dst_pitch % 16 == 0) &&
 			    ((uintptr_t)d_src % 16 == 0) && ((uintptr_t)d_dst % 16 == 0) &&
 			    (batch.nframes <= 1 || (batch.src_stride % 16 == 0 && batch.dst_stride % 16 == 0));
 	bool want_tiled = tma_ok && !(flags & FIXCA_FORCE_DIRECT);
@@ -295,8 +360,8 @@ static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_
 			k = lookup_fast_variant(f.kind, f.nch, g.interp, 2);
 		}
 		// Prefer the tallest tile that still leaves room for `want` CTAs per SM.
-		const int target_ctas = env_int("FIXCA_TILE_CTAS", 3);
-		const int forced_th = env_int("FIXCA_TILE_H", 0);
+		const int target_ctas = std::max(1, tuning().tile_ctas);
+		const int forced_th = tuning().tile_h;
 		static const int th_choices[] = {64, 48, 32, 24, 16, 12, 8, 4};
 		const size_t sm_total = 227 * 1024;
 		int best_th = 0;
@@ -356,7 +421,7 @@ static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_
 	}
 	if (flags & FIXCA_FORCE_TILED)
 		return fail(FIXCA_ERR_ARG, "FIXCA_FORCE_TILED: the tiled kernel cannot take this call (%s)",
-			    tma_ok ? "source window exceeds shared memory" : "non-monotone map, or pitch/pointer not 16-byte aligned");
+			    tma_ok ? "source window exceeds shared memory" : "non-monotone map, pitch/pointer not 16-byte aligned, or FIXCA_TIGHT_ROWS with rows that are not whole 16-byte units");
 
 	pl.k = pick_kernel(f, g.interp, flags, false);
 	if (!pl.k)
@@ -422,8 +487,8 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	// instruction-bound and have small CTAs (measured: RGB8 0.086 -> 0.062 ms, RGBA16 0.155 -> 0.131 ms
 	// going from 2 to 4 CTAs per SM); the 3-channel 16-bit / float strips fit 2 per SM at depth 2.
 	const int compute_warps = 2 * k->tw / k->strip_p / 32;
-	const int want_ctas = std::max(1, env_int("FIXCA_STREAM_CTAS", std::max(2, 32 / compute_warps)));
-	const int forced_d = env_int("FIXCA_STREAM_DEPTH", 0);
+	const int want_ctas = tuning().stream_ctas > 0 ? tuning().stream_ctas : std::max(2, 32 / compute_warps);
+	const int forced_d = tuning().stream_depth;
 	size_t total = 0, off_meta = 0, off_win = 0, off_out = 0, ring_rows = 0;
 	int depth = 0;
 	// first / last source row each chunk touches (one scan; the map is monotone, so a chunk's extremes
@@ -482,7 +547,8 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	// half-height segments copy 5-7 % faster (100 MP RGB16 0.199 -> 0.187 ms = the measured copy peak, 8K RGBA16
 	// 0.089 -> 0.085 ms); Linear / Cubic and the other sample sizes are level or lose (RGB8 None 81 -> 75 %).
 	int waves = (g.interp == 0 && f.bpp / f.nch == 2 && rows / segs >= 512) ? 2 : 1;
-	waves = std::max(1, env_int("FIXCA_STREAM_WAVES", waves));
+	if (tuning().stream_waves > 0)
+		waves = tuning().stream_waves;
 	segs *= waves;
 	if (pl.nframes > 1) {
 		// a batch fills the GPU with frames x strips x segments CTAs: long segments (>= 256 rows) so that
@@ -490,7 +556,7 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 		const int fill = (sm_count(dev) * per_sm + strips * pl.nframes - 1) / (strips * pl.nframes);
 		segs = std::max(fill, (rows + 255) / 256);
 	}
-	const int forced = env_int("FIXCA_STREAM_SEGS", 0);
+	const int forced = tuning().stream_segs;
 	if (forced > 0)
 		segs = forced;
 	int seg_rows = (int)align_up((size_t)(rows + segs - 1) / segs, CH);
@@ -506,7 +572,7 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	a.ring_rows = (int)ring_rows;
 	a.seg_rows = seg_rows;
 	a.depth = depth;
-	a.debug = env_int("FIXCA_STREAM_DEBUG", 0);
+	a.debug = tuning().stream_debug;	// honoured by -DFIXCA_TUNING builds only
 	a.off_ytab = (int)off_meta;
 	a.off_win = (int)off_win;
 	a.off_out = (int)off_out;
@@ -515,7 +581,7 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	pl.grid = dim3(strips, segs, pl.nframes);
 	if (pl.nframes > 65535)
 		return false;
-	if (env_int("FIXCA_VERBOSE", 0))
+	if (tuning().verbose)
 		fprintf(stderr, "fixca: %s grid %d x %d, %d threads, smem %zu B (ring %zu rows x %d B, depth %d), seg %d rows, %d CTA/SM\n",
 			k->name, strips, segs, threads, total, ring_rows, wb, depth, seg_rows, per_sm);
 	// rows as the kernels see them: align16(width * bpp) bytes (they may touch the padding bytes)
@@ -533,8 +599,9 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 
 // Planning costs tens of microseconds (window scans in FP64, three tensor-map encodes), a third of
 // the kernel itself; callers that repeat a call (frame streams, benchmarks, the chunks of a band) hit
-// a small per-thread cache instead.  The key holds every input of make_plan_uncached, including the
-// tuning environment.
+// a per-thread cache instead, sized for the chunk plans of a few host calls in flight (one 100 MP call
+// makes ~19 distinct chunk plans).  The key holds every input of make_plan_uncached, including the
+// generation of the tuning switches.
 struct PlanKey {
 	int kind, nch, bpp, interp, width, height, monotone;
 	int axis_center[4], axis_size[4];
@@ -547,22 +614,6 @@ struct PlanKey {
 	int nframes;
 	size_t src_frame_stride, dst_frame_stride;
 };
-
-static unsigned env_signature()
-{
-	static const char *const names[] = {"FIXCA_FAST_KERNEL", "FIXCA_STRIP_TW", "FIXCA_TILE_H", "FIXCA_TILE_CTAS",
-					    "FIXCA_STREAM_CTAS", "FIXCA_STREAM_DEPTH", "FIXCA_STREAM_SEGS", "FIXCA_STREAM_WAVES",
-					    "FIXCA_STREAM_DEBUG", "FIXCA_VERBOSE", "FIXCA_NONE_KERNEL", "FIXCA_STREAM_NOALT",
-					    "FIXCA_NO_PDL"};
-	unsigned h = 2166136261u;
-	for (const char *n : names) {
-		const char *v = getenv(n);
-		for (; v && *v; ++v)
-			h = (h ^ (unsigned char)*v) * 16777619u;
-		h = (h ^ 0xffu) * 16777619u;
-	}
-	return h;
-}
 
 static int make_plan(const Format &f, const Geometry &g, const void *d_src, size_t src_pitch, int src_row0, int src_rows,
 		     void *d_dst, size_t dst_pitch, int dst_row0, int y1, int y2, unsigned flags, int dev, Plan &pl,
@@ -580,15 +631,19 @@ static int make_plan(const Format &f, const Geometry &g, const void *d_src, size
 	k.src = d_src; k.dst = d_dst; k.src_pitch = src_pitch; k.dst_pitch = dst_pitch;
 	k.src_row0 = src_row0; k.src_rows = src_rows; k.dst_row0 = dst_row0; k.y1 = y1; k.y2 = y2; k.dev = dev;
 	k.flags = flags;
-	k.env = env_signature();
+	k.env = (unsigned)tuning().generation;
 	k.nframes = batch.nframes; k.src_frame_stride = batch.src_stride; k.dst_frame_stride = batch.dst_stride;
-	constexpr int SLOTS = 8;
+	constexpr int SLOTS = 96;
 	static thread_local PlanKey keys[SLOTS];
 	static thread_local Plan plans[SLOTS];
-	static thread_local bool used[SLOTS];
+	static thread_local unsigned long long hashes[SLOTS];	// 0 = empty slot
 	static thread_local int next = 0;
+	unsigned long long h = 1469598103934665603ull;
+	for (size_t i = 0; i < sizeof k; ++i)
+		h = (h ^ reinterpret_cast<const unsigned char *>(&k)[i]) * 1099511628211ull;
+	h |= 1ull;
 	for (int i = 0; i < SLOTS; ++i)
-		if (used[i] && !memcmp(&keys[i], &k, sizeof k)) {
+		if (hashes[i] == h && !memcmp(&keys[i], &k, sizeof k)) {
 			pl = plans[i];
 			return FIXCA_OK;
 		}
@@ -596,7 +651,7 @@ static int make_plan(const Format &f, const Geometry &g, const void *d_src, size
 	if (rc == FIXCA_OK) {
 		keys[next] = k;
 		plans[next] = pl;
-		used[next] = true;
+		hashes[next] = h;
 		next = (next + 1) % SLOTS;
 	}
 	return rc;
@@ -627,7 +682,7 @@ static int launch_plan(const Plan &pl, cudaStream_t stream)
 	KernelArgs a = pl.args;
 	CUtensorMap tm[3] = {pl.tm_win, pl.tm_tile, pl.tm_out};
 	void *params[] = {&a, &tm[0], &tm[1], &tm[2]};	// the tensor maps are only declared by stream kernels
-	if (pl.k->stream && !env_int("FIXCA_NO_PDL", 0)) {
+	if (pl.k->stream && !tuning().no_pdl) {
 		// programmatic dependent launch (see griddep_wait() in fixca_stream.cuh): back-to-back launches in one
 		// stream overlap the next grid's set-up with this grid's tail; memory ordering is unchanged
 		cudaLaunchConfig_t cfg = {};
@@ -646,6 +701,27 @@ static int launch_plan(const Plan &pl, cudaStream_t stream)
 	}
 	g_launches.fetch_add(1);
 	snprintf(tl_kernel, sizeof tl_kernel, "%s", pl.k->name);
+	return FIXCA_OK;
+}
+
+// What each entry point accepts beyond the precision / kernel-selection bits.
+enum { ALLOW_PREVIEW = 1, ALLOW_COLUMNS = 2 };
+static int check_flags(unsigned flags, int allow, const Format &f, const fixca_params *p, const char *entry)
+{
+	const unsigned known = FIXCA_PRECISION_MASK | FIXCA_FORCE_DIRECT | FIXCA_FORCE_TILED | FIXCA_PREVIEW_OVERLAY |
+			       FIXCA_COLUMN_SELECTION | FIXCA_TIGHT_ROWS;
+	if (flags & ~known)
+		return fail(FIXCA_ERR_ARG, "%s: unknown flag bits %#x", entry, flags & ~known);
+	if ((flags & FIXCA_PRECISION_MASK) > FIXCA_PRECISION_FAST)
+		return fail(FIXCA_ERR_ARG, "%s: unknown precision %#x", entry, flags & FIXCA_PRECISION_MASK);
+	if ((flags & FIXCA_PREVIEW_OVERLAY) && !(allow & ALLOW_PREVIEW))
+		return fail(FIXCA_ERR_UNSUPPORTED, "%s: the preview overlay is a single-image call (fixca_cuda_region*, fixca_cuda_region_dev)", entry);
+	if ((flags & FIXCA_COLUMN_SELECTION) && !(allow & ALLOW_COLUMNS))
+		return fail(FIXCA_ERR_UNSUPPORTED, "%s: FIXCA_COLUMN_SELECTION is an option of fixca_cuda_region_ex only", entry);
+	if (f.kind == SK_U64 && p->interpolation != 0)
+		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples with Linear/Cubic need 80-bit long double arithmetic (fix-ca.c:728-733)");
+	if ((flags & FIXCA_PREVIEW_OVERLAY) && f.kind == SK_U64 && p->saturation != 0.0)
+		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples: the preview's saturation boost needs 80-bit long double arithmetic (fix-ca.c:728-733)");
 	return FIXCA_OK;
 }
 
@@ -690,8 +766,7 @@ extern "C" int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int sr
 	if (rc) return rc;
 	Format f;
 	if ((rc = parse_format(bytes, bpc, f))) return rc;
-	if (f.kind == SK_U64 && params->interpolation != 0)
-		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples with Linear/Cubic need 80-bit long double arithmetic (fix-ca.c:728-733)");
+	if ((rc = check_flags(flags, ALLOW_PREVIEW, f, params, "fixca_cuda_region_dev"))) return rc;
 	Geometry g;
 	if ((rc = make_geometry(width, height, params, g))) return rc;
 	if (src_pitch < (size_t)width * bytes || dst_pitch < (size_t)width * bytes)
@@ -707,8 +782,6 @@ extern "C" int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int sr
 		return fail(FIXCA_ERR_ARG, "dst_row0 %d is past the first output row %d", dst_row0, y1);
 	int dev;
 	if ((rc = current_device_or(-1, dev))) return rc;
-	if ((flags & FIXCA_PREVIEW_OVERLAY) && f.kind == SK_U64 && params->saturation != 0.0)
-		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples: the preview's saturation boost needs 80-bit long double arithmetic (fix-ca.c:728-733)");
 	Plan pl;
 	if ((rc = make_plan(f, g, d_src, src_pitch, src_row0, src_rows, d_dst, dst_pitch, dst_row0, y1, y2, flags, dev, pl))) return rc;
 	if ((rc = launch_plan(pl, (cudaStream_t)stream))) return rc;
@@ -791,10 +864,7 @@ extern "C" int fixca_cuda_frames_dev(const void *d_src, size_t src_pitch, size_t
 	if (rc) return rc;
 	Format f;
 	if ((rc = parse_format(bytes, bpc, f))) return rc;
-	if (f.kind == SK_U64 && params->interpolation != 0)
-		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples with Linear/Cubic need 80-bit long double arithmetic (fix-ca.c:728-733)");
-	if (flags & FIXCA_PREVIEW_OVERLAY)
-		return fail(FIXCA_ERR_UNSUPPORTED, "the preview overlay is a single-frame call (fixca_cuda_region_dev)");
+	if ((rc = check_flags(flags, 0, f, params, "fixca_cuda_frames_dev"))) return rc;
 	Geometry g;
 	if ((rc = make_geometry(width, height, params, g))) return rc;
 	const size_t row = (size_t)width * bytes;
@@ -1002,12 +1072,16 @@ private:
 static int copy_threads()
 {
 	const int hw = (int)std::thread::hardware_concurrency();
-	return std::max(1, env_int("FIXCA_COPY_THREADS", std::min(8, std::max(1, hw / 2))));
+	return tuning().copy_threads > 0 ? tuning().copy_threads : std::min(8, std::max(1, hw / 2));
 }
 
 // One band [y1,y2) of a host image on one device: upload the source rows the
 // band reads, run, download.  Rows move in chunks so that H2D of chunk i+1,
 // the kernel of chunk i and D2H of chunk i-1 overlap (PCIe is full duplex).
+static int region_host_band_locked(DeviceCtx &cx, int dev, const unsigned char *src, unsigned char *dst, int width, int height,
+				   const Format &f, const fixca_params *params, const Geometry &g,
+				   int x1, int x2, int y1, int y2, unsigned flags, bool progress);
+
 static int region_host_band(int dev, const unsigned char *src, unsigned char *dst, int width, int height,
 			    const Format &f, const fixca_params *params, const Geometry &g,
 			    int x1, int x2, int y1, int y2, unsigned flags, bool progress)
@@ -1019,6 +1093,26 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 	int rc;
 	if ((rc = cx.init(dev))) return rc;
 	CUDA_TRY(cudaSetDevice(dev));
+	rc = region_host_band_locked(cx, dev, src, dst, width, height, f, params, g, x1, x2, y1, y2, flags, progress);
+	if (rc) {
+		// leave no copy in flight behind an error: H2D may still read the pinned ring, D2H may still write the
+		// caller's dst, and both outlive this call's lock (the error text of the failure is kept)
+		char keep[sizeof tl_error];
+		memcpy(keep, tl_error, sizeof keep);
+		cudaStreamSynchronize(cx.s_up);
+		cudaStreamSynchronize(cx.s_run);
+		cudaStreamSynchronize(cx.s_down);
+		cudaGetLastError();
+		memcpy(tl_error, keep, sizeof keep);
+	}
+	return rc;
+}
+
+static int region_host_band_locked(DeviceCtx &cx, int dev, const unsigned char *src, unsigned char *dst, int width, int height,
+				   const Format &f, const fixca_params *params, const Geometry &g,
+				   int x1, int x2, int y1, int y2, unsigned flags, bool progress)
+{
+	int rc;
 
 	const size_t row_bytes = (size_t)width * f.bpp;
 	const size_t pitch = align_up(row_bytes, 128);
@@ -1038,7 +1132,7 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 	const bool src_pinned = is_pinned(src + (size_t)band_lo * row_bytes), dst_pinned = is_pinned(dst + (size_t)y1 * row_bytes + sel_off);
 	// (pageable callers: smaller chunks, the staging copies of a chunk are not overlapped with its own transfers;
 	// measured on 100 MP RGB16: 16 MB 27.3 ms, 32 MB 28.7 ms, 64 MB 41.9 ms)
-	const size_t chunk_bytes = (size_t)std::max(1, env_int("FIXCA_CHUNK_MB", (src_pinned && dst_pinned) ? 32 : 16)) << 20;
+	const size_t chunk_bytes = (size_t)(tuning().chunk_mb > 0 ? tuning().chunk_mb : (src_pinned && dst_pinned) ? 32 : 16) << 20;
 	int chunk_rows = (int)std::max<size_t>(64, chunk_bytes / std::max<size_t>(row_bytes, 1));
 	chunk_rows = std::max(chunk_rows, (y2 - y1 + 255) / 256);
 	chunk_rows = (chunk_rows + 7) & ~7;
@@ -1149,17 +1243,17 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 }
 
 static int host_prologue(const unsigned char *src, unsigned char *dst, int width, int height, int bytes, int bpc,
-			 const fixca_params *params, int x1, int x2, int y1, int y2, Format &f, Geometry &g, unsigned flags = 0)
+			 const fixca_params *params, int x1, int x2, int y1, int y2, Format &f, Geometry &g, unsigned flags,
+			 int allow, const char *entry)
 {
 	int rc = check_common(src, dst, width, height, params, y1, y2);
 	if (rc) return rc;
 	if ((rc = parse_format(bytes, bpc, f))) return rc;
+	if ((rc = check_flags(flags, allow, f, params, entry))) return rc;
 	if ((x1 != 0 || x2 != width) && !(flags & FIXCA_COLUMN_SELECTION))
 		return fail(FIXCA_ERR_REGION, "columns [%d,%d) of %d: only full-width row bands are defined (the reference's own x1 != 0 path is broken); FIXCA_COLUMN_SELECTION opts in to the repaired form", x1, x2, width);
 	if (x1 < 0 || x2 > width || x1 >= x2)
 		return fail(FIXCA_ERR_REGION, "columns [%d,%d) outside 0..%d", x1, x2, width);
-	if (f.kind == SK_U64 && params->interpolation != 0)
-		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples with Linear/Cubic need 80-bit long double arithmetic (fix-ca.c:728-733)");
 	return make_geometry(width, height, params, g);
 }
 
@@ -1169,16 +1263,15 @@ extern "C" int fixca_cuda_region_ex(const unsigned char *src, unsigned char *dst
 {
 	Format f;
 	Geometry g;
-	int rc = host_prologue(src, dst, width, height, bytes, bpc, params, x1, x2, y1, y2, f, g, flags);
+	if (!show_progress)	// the preview call (fix-ca.c:656-657): saturation boost + centre lines on top
+		flags |= FIXCA_PREVIEW_OVERLAY;
+	int rc = host_prologue(src, dst, width, height, bytes, bpc, params, x1, x2, y1, y2, f, g, flags,
+			       ALLOW_PREVIEW | ALLOW_COLUMNS, "fixca_cuda_region_ex");
 	if (rc) return rc;
 	int dev;
 	if ((rc = current_device_or(device, dev))) return rc;
 	if (y1 == y2)
 		return FIXCA_OK;
-	if (!show_progress)	// the preview call (fix-ca.c:656-657): saturation boost + centre lines on top
-		flags |= FIXCA_PREVIEW_OVERLAY;
-	if ((flags & FIXCA_PREVIEW_OVERLAY) && f.kind == SK_U64 && params->saturation != 0.0)
-		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples: the preview's saturation boost needs 80-bit long double arithmetic (fix-ca.c:728-733)");
 	int prev = -1;
 	cudaGetDevice(&prev);
 	rc = region_host_band(dev, src, dst, width, height, f, params, g, x1, x2, y1, y2, flags, show_progress != 0);
@@ -1191,10 +1284,7 @@ extern "C" int fixca_cuda_region(const unsigned char *src, unsigned char *dst, i
 				 int bytes, int bpc, const fixca_params *params,
 				 int x1, int x2, int y1, int y2, int show_progress)
 {
-	unsigned flags = FIXCA_PRECISION_EXACT;
-	const char *e = getenv("FIXCA_PRECISION");
-	if (e && (e[0] == 'f' || e[0] == 'F'))
-		flags = FIXCA_PRECISION_FAST;
+	const unsigned flags = tuning().precision_fast ? FIXCA_PRECISION_FAST : FIXCA_PRECISION_EXACT;
 	return fixca_cuda_region_ex(src, dst, width, height, bytes, bpc, params, x1, x2, y1, y2, show_progress, flags, -1);
 }
 
@@ -1215,7 +1305,8 @@ extern "C" int fixca_cuda_region_multi(const unsigned char *src, unsigned char *
 {
 	Format f;
 	Geometry g;
-	int rc = host_prologue(src, dst, width, height, bytes, bpc, params, 0, width, y1, y2, f, g);
+	int rc = host_prologue(src, dst, width, height, bytes, bpc, params, 0, width, y1, y2, f, g, flags,
+			       ALLOW_PREVIEW, "fixca_cuda_region_multi");
 	if (rc) return rc;
 	int have = 0;
 	if (cudaGetDeviceCount(&have) != cudaSuccess || have <= 0) {
@@ -1261,7 +1352,8 @@ extern "C" int fixca_cuda_frames(const unsigned char *const *src_frames, unsigne
 		return FIXCA_OK;
 	Format f;
 	Geometry g;
-	int rc = host_prologue(src_frames[0], dst_frames[0], width, height, bytes, bpc, params, 0, width, 0, height, f, g);
+	int rc = host_prologue(src_frames[0], dst_frames[0], width, height, bytes, bpc, params, 0, width, 0, height, f, g, flags,
+			       0, "fixca_cuda_frames");
 	if (rc) return rc;
 	int dev;
 	if ((rc = current_device_or(device, dev))) return rc;
@@ -1467,6 +1559,15 @@ extern "C" int fixca_color_size_half(const char *name, int bpp)
 	return fixca_color_size(name, bpp);
 }
 
+extern "C" int fixca_color_size_ext(const char *name, int bpp)
+{
+	// color_size() with both "TODO for another day" rows answered: half as in fixca_color_size_half(), and
+	// "u15" (fix-ca.c:694-695) -> FIXCA_BPC_U15 for RGB / RGBA of 16-bit storage
+	if (name && !strstr(name, "double") && !strstr(name, "float") && !strstr(name, "half") && strstr(name, "u15"))
+		return (bpp == 6 || bpp == 8) ? FIXCA_BPC_U15 : FIXCA_BPC_UNSUPPORTED;
+	return fixca_color_size_half(name, bpp);
+}
+
 extern "C" void fixca_params_default(fixca_params *p)
 {
 	if (!p) return;
@@ -1482,6 +1583,30 @@ extern "C" void fixca_cuda_set_progress(fixca_progress_fn fn, void *user)
 {
 	g_progress = fn;
 	g_progress_user = user;
+}
+
+// Pinned (page-locked, portable) host memory for the caller's image buffers: what fix_ca() allocates with
+// g_new at fix-ca.c:366-367 / :648-649.  A buffer from here is recognised by fixca_cuda_region*() and moved
+// by DMA directly, without the staging copies pageable memory needs.  NULL when no GPU is usable or the
+// allocation fails: the caller then falls back to its own allocator (and to its CPU path).
+extern "C" void *fixca_cuda_host_alloc(size_t bytes)
+{
+	int dev;
+	if (!bytes || current_device_or(-1, dev))
+		return nullptr;
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+		cudaGetLastError();
+		fail(FIXCA_ERR_NOMEM, "cudaHostAlloc of %zu bytes failed", bytes);
+		return nullptr;
+	}
+	return p;
+}
+
+extern "C" void fixca_cuda_host_free(void *p)
+{
+	if (p && cudaFreeHost(p) != cudaSuccess)
+		cudaGetLastError();
 }
 
 extern "C" const char *fixca_cuda_last_error(void) { return tl_error; }

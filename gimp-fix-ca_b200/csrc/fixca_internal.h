@@ -10,7 +10,8 @@
 namespace fixca {
 
 // SK_F16 (bpc = -2) is the extension of SURVEY.md 8(f) #4: the reference carries it as commented-out code
-enum SampleKind { SK_U8 = 0, SK_U16, SK_U32, SK_U64, SK_F32, SK_F64, SK_F16, SK_COUNT };
+// SK_U15 (bpc = 15) is the other half of that row: 15-bit unsigned samples, which the reference only rejects
+enum SampleKind { SK_U8 = 0, SK_U16, SK_U32, SK_U64, SK_F32, SK_F64, SK_F16, SK_U15, SK_COUNT };
 enum ArithKind  { AR_COPY = 0, AR_EXACT = 1, AR_FAST = 2 };
 
 // Every kernel has the signature  __global__ void k(const KernelArgs).
@@ -28,15 +29,33 @@ struct KernelEntry {
 
 constexpr int TILE_W = 128;
 
+// Tuning switches, read from the environment ONCE per process (and again only when a
+// caller asks through fixca_cuda_reload_tuning(): tests and A/B probes that change the environment
+// mid-process).  `generation` is part of the plan-cache key.
+struct Tuning {
+	int generation = 0;
+	int fast_kernel = 3;	// lookup_fast_variant(): 2 strip, 3 stream (FIXCA_FAST_KERNEL=strip|stream)
+	int none_tiled = 0;	// FIXCA_NONE_KERNEL=tiled
+	int strip_tw128 = 0;	// FIXCA_STRIP_TW=128
+	int stream_noalt = 0;	// FIXCA_STREAM_NOALT=1
+	int tile_h = 0, tile_ctas = 3;
+	int stream_ctas = 0, stream_depth = 0, stream_segs = 0, stream_waves = 0;
+	int stream_debug = 0;	// honoured by -DFIXCA_TUNING builds only
+	int no_pdl = 0, verbose = 0;
+	int chunk_mb = 0, copy_threads = 0;
+	int precision_fast = 0;	// FIXCA_PRECISION=fast: what the flag-less fixca_cuda_region() computes in
+};
+const Tuning &tuning();
+
 // sample_bytes in {1,2,4,8}; nch in {3,4}
 const KernelEntry *lookup_none(int sample_bytes, int nch, bool tiled);
 // the streaming None kernel for this format, or nullptr (8-byte samples, FIXCA_NONE_KERNEL=tiled)
 const KernelEntry *lookup_none_stream(int sample_bytes, int nch);
-// kind in {SK_U8,SK_U16,SK_U32,SK_F32,SK_F64,SK_F16}; interp in {1,2}
+// kind in {SK_U8,SK_U16,SK_U32,SK_F32,SK_F64,SK_F16,SK_U15}; interp in {1,2}
 const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled);
-// kind in {SK_U8,SK_U16,SK_F32,SK_F16}; interp in {1,2}
+// kind in {SK_U8,SK_U16,SK_F32,SK_F16,SK_U15}; interp in {1,2}
 const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled);
-// variant: 0 direct, 1 first-round tiled, 2 strip, 3 stream, 4 narrower stream (may be nullptr)
+// variant: 0 direct, 2 strip, 3 stream, 4 narrower stream (may be nullptr)
 const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int variant);
 
 // kernels_preview.cu: saturate() + centerline() on destination rows [y1, y2) (fix-ca.c:1322-1327)

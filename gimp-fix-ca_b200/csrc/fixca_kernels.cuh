@@ -65,6 +65,13 @@ struct KernelArgs {
 	int  debug;			// bit 0: skip the arithmetic (timing experiments only)
 };
 
+// 15-bit unsigned samples in 16-bit storage (babl's "u15": 0 .. 32768 <-> [0.0, 1.0]).  The reference rejects
+// them ("TODO for another day", fix-ca.c:694-695); the extension (bpc code 15) gives them the
+// arithmetic of the reference's other unsigned types with max = 32768: get_pixel v / 32768 (exact: a power
+// of two), set_pixel round(d * 32768) after clip_d.  Stored values above 32768 decode to > 1.0 and are
+// clipped like float samples.  A distinct type so that templates tell it from uint16_t.
+struct u15_t { uint16_t v; };
+
 // ---------------------------------------------------------------------------
 // Arithmetic policies
 // ---------------------------------------------------------------------------
@@ -102,6 +109,7 @@ struct ExactF64 {
 	__device__ __forceinline__ static double decode(uint8_t v)  { return div_by_max<255>(v); }
 	__device__ __forceinline__ static double decode(uint16_t v) { return div_by_max<65535>(v); }
 	__device__ __forceinline__ static double decode(uint32_t v) { return __ddiv_rn((double)v, 4294967295.0); }
+	__device__ __forceinline__ static double decode(u15_t v)    { return __dmul_rn((double)v.v, 0x1p-15); }	// v / 32768, exact
 	__device__ __forceinline__ static double decode(float v)    { return (double)v; }
 	__device__ __forceinline__ static double decode(double v)   { return v; }
 	// half: the reference's commented-out branch `ret += *p` (fix-ca.c:740-742): an exact widening
@@ -116,6 +124,7 @@ struct ExactF64 {
 	__device__ __forceinline__ static void encode(uint8_t &o, double d)  { o = (uint8_t)__double2uint_rz(round(__dmul_rn(clip(d), 255.0))); }
 	__device__ __forceinline__ static void encode(uint16_t &o, double d) { o = (uint16_t)__double2uint_rz(round(__dmul_rn(clip(d), 65535.0))); }
 	__device__ __forceinline__ static void encode(uint32_t &o, double d) { o = __double2uint_rz(round(__dmul_rn(clip(d), 4294967295.0))); }
+	__device__ __forceinline__ static void encode(u15_t &o, double d)    { o.v = (uint16_t)__double2uint_rz(round(__dmul_rn(clip(d), 32768.0))); }
 	__device__ __forceinline__ static void encode(float &o, double d)    { o = __double2float_rn(clip(d)); }
 	__device__ __forceinline__ static void encode(double &o, double d)   { o = clip(d); }
 	// `*p = d` (fix-ca.c:768-770, commented out there): one rounding, double -> half, nearest-even
@@ -180,12 +189,14 @@ struct FastF32 {
 
 	__device__ __forceinline__ static float decode(uint8_t v)  { return (float)v; }
 	__device__ __forceinline__ static float decode(uint16_t v) { return (float)v; }
+	__device__ __forceinline__ static float decode(u15_t v)    { return (float)v.v; }
 	__device__ __forceinline__ static float decode(float v)    { return v; }
 	__device__ __forceinline__ static float decode(__half v)   { return __half2float(v); }
 
 	// clip_d's order: <= 0 first, then >= max; NaN passes (float images only).
 	__device__ __forceinline__ static void encode(uint8_t &o, float d)  { o = (uint8_t)__float2uint_rn(fminf(fmaxf(d, 0.f), 255.f)); }
 	__device__ __forceinline__ static void encode(uint16_t &o, float d) { o = (uint16_t)__float2uint_rn(fminf(fmaxf(d, 0.f), 65535.f)); }
+	__device__ __forceinline__ static void encode(u15_t &o, float d)    { o.v = (uint16_t)__float2uint_rn(fminf(fmaxf(d, 0.f), 32768.f)); }
 	__device__ __forceinline__ static void encode(float &o, float d)    { o = (d <= 0.f) ? 0.f : ((d >= 1.f) ? 1.f : d); }
 	__device__ __forceinline__ static void encode(__half &o, float d)   { o = __float2half_rn((d <= 0.f) ? 0.f : ((d >= 1.f) ? 1.f : d)); }
 

@@ -49,6 +49,14 @@
 
 namespace fixca {
 
+// Timing experiments (FIXCA_STREAM_DEBUG: bit 0 skips the arithmetic -- wrong pixels --, bit 1 disables the narrow
+// form) exist in -DFIXCA_TUNING builds only (make TUNING=1); the release library ignores KernelArgs::debug.
+#ifdef FIXCA_TUNING
+#define STREAM_DEBUG_BIT(a, bit) ((a).debug & (bit))
+#else
+#define STREAM_DEBUG_BIT(a, bit) 0
+#endif
+
 constexpr int STREAM_CH = 8;	// output rows per chunk
 // Pipeline depth D (KernelArgs::depth, chosen by the host from the shared memory left): chunks whose
 // window rows are requested ahead of the compute warps -- these come from HBM and carry the
@@ -364,7 +372,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			unsigned char *q = stage + jstg * STAGE_BYTES + qoff;
 			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
 			jstg = jstg + 1 == NSTG ? 0 : jstg + 1;
-			if (!(a.debug & 1)) {
+			if (!STREAM_DEBUG_BIT(a, 1)) {
 				// rows past the band's end (last chunk) repeat valid offsets and are clipped by the store
 				S v[CH][P];
 #pragma unroll
@@ -522,7 +530,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			const int *lastp = m.last[c];
 			int next_last = lastp[0];
 
-			if (a.debug & 1) {	// timing experiment: memory pipeline only (results are wrong)
+			if (STREAM_DEBUG_BIT(a, 1)) {	// timing experiment: memory pipeline only (results are wrong)
 				s_done = s_end;
 				prow = win_c + (uint32_t)(((s_done + 1) % NR) * wpitch);
 				warp_arrive(done_bar);
@@ -683,7 +691,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	// (measured: 100 MP RGB16 Cubic 0.212 -> 0.208 ms, RGBA8 0.068 -> 0.066 ms; four-column groups (RGB8)
 	// did not gain -- Linear lost 10 % -- so they keep the one regular form)
 	constexpr bool HAS_NARROW = P == 2 || P == 3;
-	bool narrow = regular && HAS_NARROW && !(a.debug & 2);	// debug bit 1: A/B runs without the narrow form
+	bool narrow = regular && HAS_NARROW && !STREAM_DEBUG_BIT(a, 2);	// debug bit 1: A/B runs without the narrow form
 #pragma unroll
 	for (int k = 0; k < P; ++k)
 		narrow = narrow && wt[k][NW - 1] == 0.f;

@@ -112,6 +112,16 @@ template <> struct StripCodec<uint16_t> {
 		*reinterpret_cast<uint16_t *>(p) = (uint16_t)__float_as_uint(fmaf(sat01, 65535.0f, 12582912.0f));
 	}
 };
+template <> struct StripCodec<u15_t> {	// bpc = 15: the loads of u16, max = 32768
+	static constexpr float kHScale = kIntHScale;
+	static constexpr float kInvMax = (float)(1.0 / 32768.0) * kIntVScale;
+	__device__ __forceinline__ static float load(const unsigned char *p) { return StripCodec<uint16_t>::load(p); }
+	__device__ __forceinline__ static float load_at(uint32_t saddr) { return StripCodec<uint16_t>::load_at(saddr); }
+	__device__ __forceinline__ static void store(unsigned char *p, float sat01)
+	{
+		*reinterpret_cast<uint16_t *>(p) = (uint16_t)__float_as_uint(fmaf(sat01, 32768.0f, 12582912.0f));
+	}
+};
 template <> struct StripCodec<float> {
 	static constexpr float kHScale = 1.0f;
 	static constexpr float kInvMax = 1.0f;

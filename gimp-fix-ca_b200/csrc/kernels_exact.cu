@@ -21,6 +21,7 @@ static const KernelEntry exact_table[] = {
 	EXACT_ENTRIES(float, "f32"),
 	EXACT_ENTRIES(double, "f64"),
 	EXACT_ENTRIES(__half, "f16"),
+	EXACT_ENTRIES(u15_t, "u15"),
 };
 
 const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled)
@@ -33,6 +34,7 @@ const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled
 	case SK_F32: s = 3; break;
 	case SK_F64: s = 4; break;
 	case SK_F16: s = 5; break;
+	case SK_U15: s = 6; break;
 	default: return nullptr;
 	}
 	if ((nch != 3 && nch != 4) || (interp != 1 && interp != 2))

@@ -1,8 +1,8 @@
 // kernels_fast.cu -- Linear / Cubic in FP32 on raw sample values: within +-1 LSB
 // of the reference for u8 / u16, ~2 ulp(1.0) for float.
 //
-//   strip_kernel  (fixca_strip.cuh)  the fast path: P columns per thread, ring-buffered rows
-//   tiled_kernel  (FastF32)          the first-round one-column-per-thread kernel, kept for A/B
+//   stream_kernel (fixca_stream.cuh) the measured path: persistent column strips, TMA ring
+//   strip_kernel  (fixca_strip.cuh)  per-tile fallback when the ring does not fit (same bytes)
 //   direct_kernel (FastF32)          per-pixel gather, any geometry
 #include <cstdlib>
 #include <cstring>
@@ -10,21 +10,18 @@
 
 namespace fixca {
 
-#define FAST_ENTRIES(S, TAG)                                                                                  \
-	{ (kernel_fn)tiled_kernel<S, 3, 1, FastF32, TILE_W>, "tiled/linear/f32/" TAG "x3", TILE_W, (int)sizeof(FastF32::YCoef), (int)sizeof(S), 0 }, \
-	{ (kernel_fn)tiled_kernel<S, 4, 1, FastF32, TILE_W>, "tiled/linear/f32/" TAG "x4", TILE_W, (int)sizeof(FastF32::YCoef), (int)sizeof(S), 0 }, \
-	{ (kernel_fn)tiled_kernel<S, 3, 2, FastF32, TILE_W>, "tiled/cubic/f32/" TAG "x3", TILE_W, (int)sizeof(FastF32::YCoef), (int)sizeof(S), 0 },  \
-	{ (kernel_fn)tiled_kernel<S, 4, 2, FastF32, TILE_W>, "tiled/cubic/f32/" TAG "x4", TILE_W, (int)sizeof(FastF32::YCoef), (int)sizeof(S), 0 },  \
+#define DIRECT_ENTRIES(S, TAG)                                                                                \
 	{ (kernel_fn)direct_kernel<S, 3, 1, FastF32>, "direct/linear/f32/" TAG "x3", 0, 0, (int)sizeof(S), 0 },  \
 	{ (kernel_fn)direct_kernel<S, 4, 1, FastF32>, "direct/linear/f32/" TAG "x4", 0, 0, (int)sizeof(S), 0 },  \
 	{ (kernel_fn)direct_kernel<S, 3, 2, FastF32>, "direct/cubic/f32/" TAG "x3", 0, 0, (int)sizeof(S), 0 },   \
 	{ (kernel_fn)direct_kernel<S, 4, 2, FastF32>, "direct/cubic/f32/" TAG "x4", 0, 0, (int)sizeof(S), 0 }
 
-static const KernelEntry fast_table[] = {
-	FAST_ENTRIES(uint8_t, "u8"),
-	FAST_ENTRIES(uint16_t, "u16"),
-	FAST_ENTRIES(float, "f32"),
-	FAST_ENTRIES(__half, "f16"),
+static const KernelEntry direct_table[] = {
+	DIRECT_ENTRIES(uint8_t, "u8"),
+	DIRECT_ENTRIES(uint16_t, "u16"),
+	DIRECT_ENTRIES(float, "f32"),
+	DIRECT_ENTRIES(__half, "f16"),
+	DIRECT_ENTRIES(u15_t, "u15"),
 };
 
 // Columns per thread are picked so that the lane stride in shared memory, P * bytes-per-pixel,
@@ -40,6 +37,7 @@ static const KernelEntry strip_table[] = {
 	STRIP_ENTRIES(uint16_t, "u16", 2, 256, 1, 128),
 	STRIP_ENTRIES(float, "f32", 1, 128, 1, 128),
 	STRIP_ENTRIES(__half, "f16", 2, 256, 1, 128),
+	STRIP_ENTRIES(u15_t, "u15", 2, 256, 1, 128),
 };
 
 // ALT4: 4-channel strips put red and blue of one pixel on neighbouring lanes (half the row span
@@ -55,6 +53,7 @@ static const KernelEntry stream_table[] = {
 	STREAM_ENTRIES(uint16_t, "u16", 2, 256, 3, 192, true),	// 8-byte pixels, lanes alternate channels: 3 columns = conflict-free, 7 loads per 3 outputs
 	STREAM_ENTRIES(float, "f32", 1, 128, 1, 64, true),	// 16-byte pixels: 64 + halo columns fit one 2 KB TMA box
 	STREAM_ENTRIES(__half, "f16", 2, 256, 3, 192, true),	// 16-bit floats: the layouts of u16
+	STREAM_ENTRIES(u15_t, "u15", 2, 256, 3, 192, true),	// 15-bit unsigned in 16-bit storage: the layouts of u16
 };
 
 // Narrower 16-bit RGBA strips for the calls whose window (strip + shift + slack columns) would not fit one
@@ -85,7 +84,7 @@ static const KernelEntry strip_u16x3_tw128[] = {
 	{ (kernel_fn)strip_kernel<uint16_t, 3, 2, 2, 128>, "strip/cubic/f32/u16x3/tw128", 128, 16, 2, 2 },
 };
 
-// variant: 0 direct, 1 first-round tiled, 2 strip, 3 stream, 4 narrower stream (nullptr when there is none)
+// variant: 0 direct, 2 strip, 3 stream, 4 narrower stream (nullptr when there is none)
 const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int variant)
 {
 	if (variant == 4)
@@ -97,22 +96,18 @@ const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int
 	case SK_U16: s = 1; break;
 	case SK_F32: s = 2; break;
 	case SK_F16: s = 3; break;
+	case SK_U15: s = 4; break;
 	default: return nullptr;
 	}
 	if ((nch != 3 && nch != 4) || (interp != 1 && interp != 2))
 		return nullptr;
-	const char *tw = getenv("FIXCA_STRIP_TW");	// tuning: narrower tiles for the headline format
-	const bool tw128 = kind == SK_U16 && nch == 3 && tw && atoi(tw) == 128;
-	if (variant == 3 && nch == 4 && (kind == SK_U16 || kind == SK_F32)) {
-		const char *na = getenv("FIXCA_STREAM_NOALT");
-		if (na && atoi(na))
-			return &stream_x4_noalt[(kind == SK_F32 ? 2 : 0) + interp - 1];
-	}
+	const bool tw128 = kind == SK_U16 && nch == 3 && tuning().strip_tw128;	// tuning: narrower tiles for the headline format
+	if (variant == 3 && nch == 4 && (kind == SK_U16 || kind == SK_F32) && tuning().stream_noalt)
+		return &stream_x4_noalt[(kind == SK_F32 ? 2 : 0) + interp - 1];
 	switch (variant) {
 	case 3: return tw128 ? &stream_u16x3_tw128[interp - 1] : &stream_table[s * 4 + (interp - 1) * 2 + (nch - 3)];
 	case 2: return tw128 ? &strip_u16x3_tw128[interp - 1] : &strip_table[s * 4 + (interp - 1) * 2 + (nch - 3)];
-	case 1: return &fast_table[s * 8 + (interp - 1) * 2 + (nch - 3)];
-	default: return &fast_table[s * 8 + 4 + (interp - 1) * 2 + (nch - 3)];
+	default: return &direct_table[s * 4 + (interp - 1) * 2 + (nch - 3)];
 	}
 }
 
@@ -120,12 +115,7 @@ const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled)
 {
 	if (!tiled)
 		return lookup_fast_variant(kind, nch, interp, 0);
-	const char *e = getenv("FIXCA_FAST_KERNEL");	// "tiled" | "strip" | "stream" (default), for A/B runs
-	if (e && !strcmp(e, "tiled"))
-		return lookup_fast_variant(kind, nch, interp, 1);
-	if (e && !strcmp(e, "strip"))
-		return lookup_fast_variant(kind, nch, interp, 2);
-	return lookup_fast_variant(kind, nch, interp, 3);
+	return lookup_fast_variant(kind, nch, interp, tuning().fast_kernel);	// FIXCA_FAST_KERNEL = strip | stream (default), for A/B runs
 }
 
 } // namespace fixca

@@ -35,8 +35,7 @@ static const KernelEntry none_stream_table[] = {
 
 const KernelEntry *lookup_none_stream(int sample_bytes, int nch)
 {
-	const char *e = getenv("FIXCA_NONE_KERNEL");	// "tiled" | "stream" (default), for A/B runs
-	if (e && !strcmp(e, "tiled"))
+	if (tuning().none_tiled)	// FIXCA_NONE_KERNEL = tiled | stream (default), for A/B runs
 		return nullptr;
 	if (nch != 3 && nch != 4)
 		return nullptr;

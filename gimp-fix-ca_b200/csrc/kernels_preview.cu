@@ -31,6 +31,10 @@ template <> struct Norm<uint16_t> {
 	__device__ static double get(uint16_t v) { return (double)v / 65535.0; }
 	__device__ static uint16_t put(double d) { return (uint16_t)(uint32_t)__double2int_rz(round(d * 65535.0)); }
 };
+template <> struct Norm<u15_t> {	// extension, bpc = 15: the pattern of the unsigned types with max = 32768
+	__device__ static double get(u15_t v) { return (double)v.v / 32768.0; }
+	__device__ static u15_t put(double d) { u15_t o; o.v = (uint16_t)(uint32_t)__double2int_rz(round(d * 32768.0)); return o; }
+};
 template <> struct Norm<uint32_t> {
 	__device__ static double get(uint32_t v) { return (double)v / 4294967295.0; }
 	__device__ static uint32_t put(double d) { return (uint32_t)__double2ll_rz(round(d * 4294967295.0)); }
@@ -195,6 +199,7 @@ cudaError_t launch_preview(int kind, int nch, unsigned char *dst, long long pitc
 	case SK_F32: return launch_s<float>(nch, a, st);
 	case SK_F64: return launch_s<double>(nch, a, st);
 	case SK_F16: return launch_s<__half>(nch, a, st);
+	case SK_U15: return launch_s<u15_t>(nch, a, st);
 	default: return cudaErrorInvalidValue;
 	}
 }

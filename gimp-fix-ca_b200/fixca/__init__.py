@@ -29,6 +29,7 @@ PRECISION_EXACT, PRECISION_FAST = 0x0, 0x1
 FORCE_DIRECT, FORCE_TILED = 0x10, 0x20
 PREVIEW_OVERLAY = 0x40      # saturate() + centerline() on the rows written (the show_progress=False call)
 COLUMN_SELECTION = 0x80     # accept x1 != 0 / x2 != width: columns [x1, x2) of the full-width result (extension)
+TIGHT_ROWS = 0x100          # device entries: never write past width * bytes of a destination row
 INPUT_MAX = 30.0
 
 OK = 0
@@ -43,7 +44,9 @@ EXPORTS = (
     "fixca_cuda_last_error", "fixca_strerror", "fixca_cuda_device_count", "fixca_cuda_last_kernel",
     "fixca_cuda_launch_count", "fixca_cuda_release", "fixca_version",
     "fixca_cuda_frames_multi", "fixca_cuda_frame_alloc", "fixca_cuda_frame_open", "fixca_cuda_frame_close", "fixca_cuda_frame_free",
+    "fixca_cuda_host_alloc", "fixca_cuda_host_free", "fixca_cuda_reload_tuning", "fixca_color_size_ext",
 )
+BPC_HALF, BPC_U15 = -2, 15
 IPC_HANDLE_BYTES = 64
 
 
@@ -112,6 +115,8 @@ def load() -> ctypes.CDLL:
     L.fixca_resolve_lens.restype = None
     L.fixca_check_params.argtypes = [pp]
     L.fixca_color_size.argtypes = [ctypes.c_char_p, i]
+    L.fixca_color_size_half.argtypes = [ctypes.c_char_p, i]
+    L.fixca_color_size_ext.argtypes = [ctypes.c_char_p, i]
     L.fixca_params_default.argtypes = [pp]
     L.fixca_params_default.restype = None
     L.fixca_cuda_set_progress.argtypes = [PROGRESS_FN, vp]
@@ -123,6 +128,11 @@ def load() -> ctypes.CDLL:
     L.fixca_cuda_launch_count.restype = ctypes.c_long
     L.fixca_cuda_release.restype = None
     L.fixca_version.restype = ctypes.c_char_p
+    L.fixca_cuda_host_alloc.argtypes = [ctypes.c_size_t]
+    L.fixca_cuda_host_alloc.restype = vp
+    L.fixca_cuda_host_free.argtypes = [vp]
+    L.fixca_cuda_host_free.restype = None
+    L.fixca_cuda_reload_tuning.restype = None
     _lib = L
     return L
 
@@ -162,8 +172,9 @@ def fix_ca_region(src, dst, orig_width, orig_height, bytes, bpc, params, x1, x2,
 
 
 def correct(image: np.ndarray, params: FixCaParams, y1=None, y2=None, out=None, flags=PRECISION_EXACT,
-            device=-1, devices=None) -> np.ndarray:
-    """Array-level convenience: (H, W, C) uint8/16/32/64/float32/float64 image in, corrected image out."""
+            device=-1, devices=None, bpc=None) -> np.ndarray:
+    """Array-level convenience: (H, W, C) uint8/16/32/64/float16/32/64 image in, corrected image out.
+    ``bpc`` overrides the code derived from the dtype (BPC_U15 for 15-bit samples held in uint16)."""
     assert image.ndim == 3 and image.flags["C_CONTIGUOUS"]
     h, w, ch = image.shape
     y1 = 0 if y1 is None else y1
@@ -171,12 +182,13 @@ def correct(image: np.ndarray, params: FixCaParams, y1=None, y2=None, out=None, 
     if out is None:
         out = np.zeros_like(image)
     bytes_ = ch * image.dtype.itemsize
+    bpc = bpc_of(image.dtype) if bpc is None else bpc
     if devices is not None:
         arr = (ctypes.c_int * len(devices))(*devices)
-        _check(load().fixca_cuda_region_multi(image.ctypes.data, out.ctypes.data, w, h, bytes_, bpc_of(image.dtype),
+        _check(load().fixca_cuda_region_multi(image.ctypes.data, out.ctypes.data, w, h, bytes_, bpc,
                                               ctypes.byref(params), y1, y2, flags, arr, len(devices)))
     else:
-        fix_ca_region(image, out, w, h, bytes_, bpc_of(image.dtype), params, 0, w, y1, y2, True, flags, device)
+        fix_ca_region(image, out, w, h, bytes_, bpc, params, 0, w, y1, y2, True, flags, device)
     return out
 
 
@@ -273,6 +285,11 @@ def color_size_half(format_name: str, bytes_per_pixel: int) -> int:
     return load().fixca_color_size_half(format_name.encode(), bytes_per_pixel)
 
 
+def color_size_ext(format_name: str, bytes_per_pixel: int) -> int:
+    """color_size() with both of the reference's "TODO for another day" formats answered (half -2, u15 15)."""
+    return load().fixca_color_size_ext(format_name.encode(), bytes_per_pixel)
+
+
 def device_count() -> int:
     return load().fixca_cuda_device_count()
 
@@ -283,6 +300,32 @@ def last_kernel() -> str:
 
 def launch_count() -> int:
     return load().fixca_cuda_launch_count()
+
+
+def reload_tuning() -> None:
+    """Re-read the FIXCA_* tuning variables (they are read once per process)."""
+    load().fixca_cuda_reload_tuning()
+
+
+class PinnedBuffer:
+    """Pinned host memory from fixca_cuda_host_alloc (what the patched plug-in uses in place of g_new,
+    fix-ca.c:366-367): ``array(dtype, shape)`` views it as numpy; ``free()`` releases it."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        self.ptr = load().fixca_cuda_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise FixCaError(ERR_NOMEM, load().fixca_cuda_last_error().decode() or "fixca_cuda_host_alloc failed")
+
+    def array(self, dtype=np.uint8, shape=None) -> np.ndarray:
+        buf = (ctypes.c_ubyte * self.nbytes).from_address(self.ptr)
+        a = np.frombuffer(buf, dtype=dtype)
+        return a if shape is None else a.reshape(shape)
+
+    def free(self) -> None:
+        if self.ptr:
+            load().fixca_cuda_host_free(self.ptr)
+            self.ptr = None
 
 
 _progress_keepalive = None

@@ -62,6 +62,13 @@ typedef struct fixca_params {
  *   -4, -8      float, double
  *   -99         unsupported (half, u15, ...)                                  */
 #define FIXCA_BPC_UNSUPPORTED (-99)
+/* Extensions, the two formats color_size() marks "TODO for another day":
+ *   -2   IEEE half (fix-ca.c:692-693, the reference's own commented-out branches)
+ *   15   babl "u15": 15-bit unsigned in 16-bit storage, 0..32768 <-> [0,1] (fix-ca.c:694-695 rejects it; here
+ *        it gets the arithmetic of the other unsigned types with max = 32768: get_pixel v / 32768, set_pixel
+ *        round(d * 32768) after clip_d; None copies the 16-bit storage untouched)               */
+#define FIXCA_BPC_HALF (-2)
+#define FIXCA_BPC_U15  15
 
 /* ------------------------------------------------------------------------- */
 /* Status codes (0 = success; the reference's region returns void, its driver */
@@ -112,6 +119,11 @@ typedef struct fixca_params {
  * pass computes for them, and nothing else in dst is written (src and dst stay whole-image buffers,
  * width * height * bytes, as set_data() addresses them, :864-871). */
 #define FIXCA_COLUMN_SELECTION 0x80u
+/* Device-resident entries only: the destination rows are views into a wider buffer, so nothing past
+ * width * bytes of a row may be written.  The TMA kernels store whole 16-byte units (up to 15 bytes into the
+ * row's pitch padding); with this flag they are used only when width * bytes is a multiple of 16 and the
+ * per-pixel direct kernel takes the call otherwise. */
+#define FIXCA_TIGHT_ROWS       0x100u
 
 /* ------------------------------------------------------------------------- */
 /* The pass, host buffers: replaces fix_ca_region()                           */
@@ -263,6 +275,9 @@ FIXCA_API int fixca_color_size(const char *babl_format_name, int bytes_per_pixel
  * with one rounding (`*p = d`, :768-770).  Everything else answers like fixca_color_size(). */
 FIXCA_API int fixca_color_size_half(const char *babl_format_name, int bytes_per_pixel);
 
+/* fixca_color_size_half() plus "u15" names (fix-ca.c:694-695) -> FIXCA_BPC_U15 (bytes per pixel 6 or 8). */
+FIXCA_API int fixca_color_size_ext(const char *babl_format_name, int bytes_per_pixel);
+
 /* Defaults of fix_ca_params_default (fix-ca.c:85-97). */
 FIXCA_API void fixca_params_default(fixca_params *params);
 
@@ -273,7 +288,23 @@ FIXCA_API void fixca_params_default(fixca_params *params);
  * init once, update((y-y1)/(y2-y1)) for every row with (y-y1) % 8 == 0, then
  * update(0.0).  kind: 0 = init, 1 = update. */
 typedef void (*fixca_progress_fn)(int kind, double fraction, void *user);
+/* The callback belongs to the calling thread: install it on the thread that makes the fixca_cuda_region*()
+ * call (the plug-in has one). */
 FIXCA_API void fixca_cuda_set_progress(fixca_progress_fn fn, void *user);
+
+/*
+ * Pinned host memory for the image buffers fix_ca() allocates with g_new (fix-ca.c:366-367; the preview's at
+ * :648-649).  Buffers from here are moved by DMA without staging copies (100 MP RGB16: 13 ms per call instead
+ * of 32 ms from pageable memory).  fixca_cuda_host_alloc returns NULL when no GPU is usable or the allocation
+ * fails -- the caller keeps its own allocator as the fallback; free with fixca_cuda_host_free only.
+ */
+FIXCA_API void *fixca_cuda_host_alloc(size_t bytes);
+FIXCA_API void  fixca_cuda_host_free(void *p);
+
+/* Re-read the FIXCA_* tuning variables.  They are read once per process; tests and A/B
+ * probes that change the environment afterwards call this.  Not for use while other threads are inside
+ * the library. */
+FIXCA_API void fixca_cuda_reload_tuning(void);
 
 FIXCA_API const char *fixca_cuda_last_error(void);	/* thread-local text of the last failure */
 FIXCA_API const char *fixca_strerror(int code);

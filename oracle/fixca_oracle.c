@@ -105,6 +105,9 @@ static double decode (const unsigned char *p, int bpc)
 	case -4: { float v; memcpy (&v, p, 4); r += v; break; }
 	/* half precision: the branch the reference keeps commented out (fix-ca.c:740-742), see patch_half.py */
 	case -2: { _Float16 v; memcpy (&v, p, 2); r += v; break; }
+	/* u15 (0 .. 32768 <-> [0,1]): the reference answers "TODO for another day" (fix-ca.c:694-695); the pattern
+	 * of its other unsigned types with max = 32768, see patch_u15.py */
+	case 15: { uint16_t v; memcpy (&v, p, 2); r += v; r /= 32768; break; }
 	default: break;
 	}
 	return r;
@@ -123,6 +126,7 @@ static void encode (unsigned char *p, double d, int bpc)
 	case -8: memcpy (p, &d, 8); break;
 	case -4: { float v = (float) d; memcpy (p, &v, 4); break; }
 	case -2: { _Float16 v = (_Float16) d; memcpy (p, &v, 2); break; }	/* fix-ca.c:768-770, commented out there */
+	case 15: { uint16_t v = round (d * 32768); memcpy (p, &v, 2); break; }	/* extension, see decode() */
 	default: break;
 	}
 }
@@ -217,9 +221,9 @@ static int setup (job *j, const unsigned char *src, unsigned char *dst, int W, i
 	int xc, yc, m, b, interp;
 	double s_blue, s_red;
 
-	b = bpc < 0 ? -bpc : bpc;
+	b = bpc == 15 ? 2 : bpc < 0 ? -bpc : bpc;
 	interp = (int) p[P_INTERP];
-	if (!(bpc == 1 || bpc == 2 || bpc == 4 || bpc == 8 || bpc == -4 || bpc == -8 || bpc == -2))
+	if (!(bpc == 1 || bpc == 2 || bpc == 4 || bpc == 8 || bpc == -4 || bpc == -8 || bpc == -2 || bpc == 15))
 		return -2;
 	if (bytes != 3 * b && bytes != 4 * b)
 		return -2;
@@ -346,6 +350,7 @@ static void put_sample (unsigned char *p, double d, int bpc)
 	case -8: memcpy (p, &d, 8); break;
 	case -4: { float v = (float) d; memcpy (p, &v, 4); break; }
 	case -2: { _Float16 v = (_Float16) d; memcpy (p, &v, 2); break; }	/* fix-ca.c:768-770, commented out there */
+	case 15: { uint16_t v = round (d * 32768); memcpy (p, &v, 2); break; }	/* extension, see decode() */
 	default: break;
 	}
 }
@@ -406,7 +411,7 @@ static void hsv_to_rgb (double h, double s, double v, double *r, double *g, doub
 /* saturate(), fix-ca.c:922-943, on one row */
 static void saturate_row (unsigned char *row, int width, int bytes, int bpc, double s_scale)
 {
-	int b = bpc < 0 ? -bpc : bpc, x;
+	int b = bpc == 15 ? 2 : bpc < 0 ? -bpc : bpc, x;
 	for (x = 0; x < width; ++x) {
 		unsigned char *px = row + (size_t) x * bytes;
 		double r = decode (px, bpc), g = decode (px + b, bpc), bl = decode (px + 2 * b, bpc);
@@ -433,7 +438,7 @@ static void put_rgb (unsigned char *px, double c, int b, int bpc)
  * dashed vertical line and the two diagonals elsewhere */
 static void centerline_row (unsigned char *row, int width, int bytes, int bpc, int y, int xc, int yc)
 {
-	int b = bpc < 0 ? -bpc : bpc, i, x;
+	int b = bpc == 15 ? 2 : bpc < 0 ? -bpc : bpc, i, x;
 	double c = 1.0;
 	if (y == yc) {
 		i = (xc < 0 ? -xc : xc) % 16;

@@ -25,6 +25,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 RESTATEMENT_SO = os.path.join(HERE, "libfixca_oracle.so")
 REFERENCE_SO = os.path.join(HERE, "_ref", "libfixca_ref.so")
 REFERENCE_HALF_SO = os.path.join(HERE, "_ref", "libfixca_ref_half.so")
+REFERENCE_U15_SO = os.path.join(HERE, "_ref", "libfixca_ref_u15.so")
+BPC_U15 = 15    # 15-bit unsigned samples held in uint16 (extension; include/fixca_cuda.h FIXCA_BPC_U15)
 
 _c_int = ctypes.c_int
 _c_dp = ctypes.POINTER(ctypes.c_double)
@@ -56,7 +58,7 @@ def build(force: bool = False) -> None:
     """Run oracle/Makefile (restatement always; _ref only where the reference is mounted)."""
     if force or not os.path.exists(RESTATEMENT_SO) or (
             os.path.exists("/root/reference/fix-ca.c") and not (os.path.exists(REFERENCE_SO) and os.path.exists(
-                REFERENCE_HALF_SO) and os.path.exists(os.path.join(HERE, "_ref", "libfixca_plugin_cuda.so")) and
+                REFERENCE_HALF_SO) and os.path.exists(REFERENCE_U15_SO) and os.path.exists(os.path.join(HERE, "_ref", "libfixca_plugin_cuda.so")) and
                 os.path.exists(os.path.join(HERE, "_ref", "libfixca_plugin_cuda_half.so")))):
         subprocess.run(["make", "-C", HERE, "-s"], check=True,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -89,9 +91,12 @@ class Restatement:
 
     kind = "port"
 
-    def region(self, src: np.ndarray, p: Params, y1=None, y2=None, dst=None, threads: int = 1, preview: bool = False):
-        """preview=True is the call with show_progress == FALSE: saturation boost + centre lines on top."""
-        h, w, bytes_, bpc = _img_args(src)
+    def region(self, src: np.ndarray, p: Params, y1=None, y2=None, dst=None, threads: int = 1, preview: bool = False,
+               bpc=None):
+        """preview=True is the call with show_progress == FALSE: saturation boost + centre lines on top.
+        ``bpc`` overrides the code derived from the dtype (BPC_U15 for 15-bit samples held in uint16)."""
+        h, w, bytes_, bpc0 = _img_args(src)
+        bpc = bpc0 if bpc is None else bpc
         y1 = 0 if y1 is None else y1
         y2 = h if y2 is None else y2
         if dst is None:
@@ -160,8 +165,10 @@ class Reference:
         L.ref_preview_update.argtypes = [_c_int] * 4 + [_c_dp, _c_vp]
         L.ref_preview_update.restype = _c_int
 
-    def region(self, src: np.ndarray, p: Params, y1=None, y2=None, dst=None, threads: int = 1, preview: bool = False):
-        h, w, bytes_, bpc = _img_args(src)
+    def region(self, src: np.ndarray, p: Params, y1=None, y2=None, dst=None, threads: int = 1, preview: bool = False,
+               bpc=None):
+        h, w, bytes_, bpc0 = _img_args(src)
+        bpc = bpc0 if bpc is None else bpc
         y1 = 0 if y1 is None else y1
         y2 = h if y2 is None else y2
         if dst is None:
@@ -260,6 +267,28 @@ class ReferenceHalf(Reference):
             globals()["REFERENCE_SO"] = so
 
 
+class ReferenceU15(Reference):
+    """The reference with u15 samples written into color_size() / get_pixel() / set_pixel() in the pattern of
+    its other unsigned types (oracle/patch_u15.py; fix-ca.c:694-695 only rejects them): the checker for
+    bpc = 15.  For every other format it computes what ``Reference`` computes."""
+
+    kind = "reference+u15"
+
+    @staticmethod
+    def available() -> bool:
+        build()
+        return os.path.exists(REFERENCE_U15_SO)
+
+    def __init__(self):
+        build()
+        so = REFERENCE_SO
+        try:
+            globals()["REFERENCE_SO"] = REFERENCE_U15_SO
+            Reference.__init__(self)
+        finally:
+            globals()["REFERENCE_SO"] = so
+
+
 PLUGIN_CUDA_HALF_SO = os.path.join(HERE, "_ref", "libfixca_plugin_cuda_half.so")
 
 
@@ -292,6 +321,18 @@ def best_checker():
 def half_checker():
     """Checker for float16 images: the reference with its half lines enabled, else the restatement."""
     return ReferenceHalf() if ReferenceHalf.available() else Restatement()
+
+
+def u15_checker():
+    """Checker for u15 images (bpc = 15): the reference with the u15 rows written in, else the restatement."""
+    return ReferenceU15() if ReferenceU15.available() else Restatement()
+
+
+def synth_u15(h: int, w: int, ch: int, seed: int, wide: bool = False) -> np.ndarray:
+    """Seeded u15 image in uint16 storage: values 0 .. 32768; ``wide`` also draws the out-of-range codes
+    32769 .. 65535 (they decode to > 1.0 and are clipped by Linear / Cubic, copied by None)."""
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 65535 if wide else 32768, size=(h, w, ch), dtype=np.uint16, endpoint=True)
 
 
 def synth_image(h: int, w: int, ch: int, dtype: str, seed: int, wide: bool = False) -> np.ndarray:

@@ -44,3 +44,16 @@ def fx():
 
     fixca.load()
     return fixca
+
+
+@pytest.fixture
+def tuning(fx, monkeypatch):
+    """Set a FIXCA_* tuning variable for one test.  The library reads them once per process, so the change
+    (and its undo) is followed by fixca_cuda_reload_tuning()."""
+    def set_var(name, value):
+        monkeypatch.setenv(name, value)
+        fx.reload_tuning()
+
+    yield set_var
+    monkeypatch.undo()
+    fx.reload_tuning()

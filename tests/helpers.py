@@ -12,8 +12,19 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "golden.json")
 FIXTURE_RAW = os.path.join(ROOT, "oracle", "_ref", "full-branches.rgb")
 
 GOLDEN_HALF = os.path.join(ROOT, "tests", "golden", "golden_half.json")
+GOLDEN_U15 = os.path.join(ROOT, "tests", "golden", "golden_u15.json")
 _golden = None
 _golden_half = None
+_golden_u15 = None
+
+
+def golden_u15():
+    """Digests of the u15 extension (tests/golden/make_golden_u15.py)."""
+    global _golden_u15
+    if _golden_u15 is None:
+        with open(GOLDEN_U15) as f:
+            _golden_u15 = json.load(f)
+    return _golden_u15
 
 
 def golden_half():
@@ -45,6 +56,8 @@ def fx_params(fx, c):
 
 
 def case_image(c) -> np.ndarray:
+    if c["dtype"] == "u15":     # 15-bit samples in uint16 storage (bpc = 15)
+        return orc.synth_u15(c["h"], c["w"], c["ch"], c["seed"], c.get("wide", False))
     return orc.synth_image(c["h"], c["w"], c["ch"], c["dtype"], c["seed"], c.get("wide", False))
 
 

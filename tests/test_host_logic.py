@@ -183,6 +183,66 @@ def test_exact_decode_division_is_correctly_rounded_for_every_8_and_16_bit_sampl
             assert float(Fr(q0) + Fr(e) * Fr(r)) == v / float(m), (m, v)
 
 
+def test_color_size_ext_u15(fx):
+    """fixca_color_size_ext: color_size() with both "TODO for another day" rows answered (fix-ca.c:692-695)."""
+    assert fx.color_size("R'G'B' u15", 6) == -99 and fx.color_size_half("R'G'B' u15", 6) == -99
+    assert fx.color_size_ext("R'G'B' u15", 6) == fx.BPC_U15 == 15 and fx.color_size_ext("R'G'B'A u15", 8) == 15
+    assert fx.color_size_ext("Y u15", 2) == -99                     # neither RGB nor RGBA of 16-bit storage
+    assert fx.color_size_ext("R'G'B' half", 6) == -2
+    for name, bpp in (("R'G'B' u8", 3), ("RGBA u16", 8), ("RGB float", 12), ("RGBA double", 32), ("CMYK u8", 4)):
+        assert fx.color_size_ext(name, bpp) == fx.color_size(name, bpp)
+
+
+def test_host_alloc_without_gpu_returns_null(fx):
+    """fixca_cuda_host_alloc: NULL (the caller keeps its own allocator) when no GPU is usable; freeing NULL is a no-op."""
+    L = fx.load()
+    L.fixca_cuda_host_free(None)
+    if fx.device_count() > 0:
+        pytest.skip("a GPU is present; the pinned path is covered by the gpu tests")
+    assert not L.fixca_cuda_host_alloc(4096)
+    with pytest.raises(fx.FixCaError):
+        fx.PinnedBuffer(4096)
+
+
+def test_non_finite_parameters_are_rejected(fx):
+    """NaN / infinite amounts, shifts and lens coordinates (undefined behaviour in the reference: (int) NaN,
+    floor(NaN) as a row index) and lens coordinates beyond +-2^30 fail with ERR_ARG before any planning."""
+    P = fx.FixCaParams
+    nan, inf = float("nan"), float("inf")
+    for kw in (dict(y_red=nan), dict(x_blue=inf), dict(blue=nan), dict(red=-inf), dict(lens_x=nan), dict(lens_y=inf),
+               dict(lens_x=3.0e9), dict(lens_y=-2.0e9)):
+        p = P(interpolation=1, **{"lens_x": 50, "lens_y": 40, **kw})
+        with pytest.raises(fx.FixCaError) as e:
+            fx.band_source_rows(100, 80, p, 10, 20)
+        assert e.value.code == fx.ERR_ARG, kw
+    # the lens value the PDB quirk produces (SURVEY App. D #1) stays legal
+    assert fx.band_source_rows(100, 80, P(lens_x=-858993459.0, lens_y=0.0, interpolation=2), 10, 20)[0] >= 0
+
+
+def test_flags_are_validated_by_every_entry(fx):
+    """Unknown flag bits, the preview overlay on the frame entries and column selections outside region_ex are
+    argument errors everywhere (checked before any device work)."""
+    import ctypes
+
+    L = fx.load()
+    img = np.zeros((8, 8, 3), np.uint8)
+    out = np.zeros_like(img)
+    p = fx.FixCaParams(lens_x=4, lens_y=4)
+    vp = ctypes.c_void_p
+    srcs, dsts = (vp * 1)(img.ctypes.data), (vp * 1)(out.ctypes.data)
+    assert L.fixca_cuda_region_ex(img.ctypes.data, out.ctypes.data, 8, 8, 3, 1, ctypes.byref(p), 0, 8, 0, 8, 1, 0x4000, -1) == fx.ERR_ARG
+    assert L.fixca_cuda_region_ex(img.ctypes.data, out.ctypes.data, 8, 8, 3, 1, ctypes.byref(p), 0, 8, 0, 8, 1, 0x2, -1) == fx.ERR_ARG
+    assert L.fixca_cuda_frames(srcs, dsts, 1, 8, 8, 3, 1, ctypes.byref(p), fx.PREVIEW_OVERLAY, 0) == fx.ERR_UNSUPPORTED
+    assert L.fixca_cuda_frames_dev(img.ctypes.data, 24, 192, out.ctypes.data, 24, 192, 1, 8, 8, 3, 1, ctypes.byref(p),
+                                   fx.PREVIEW_OVERLAY, None) == fx.ERR_UNSUPPORTED
+    assert L.fixca_cuda_region_multi(img.ctypes.data, out.ctypes.data, 8, 8, 3, 1, ctypes.byref(p), 0, 8,
+                                     fx.COLUMN_SELECTION, None, 1) == fx.ERR_UNSUPPORTED
+    big = np.zeros((8, 8, 3), np.uint64)
+    ps = fx.FixCaParams(lens_x=4, lens_y=4, interpolation=0, saturation=20.0)
+    assert L.fixca_cuda_region_multi(big.ctypes.data, big.ctypes.data, 8, 8, 24, 8, ctypes.byref(ps), 0, 8,
+                                     fx.PREVIEW_OVERLAY, None, 1) == fx.ERR_UNSUPPORTED
+
+
 def test_color_size_half_extension(fx):
     """fixca_color_size_half: the reference's color_size() with its commented-out half line enabled
     (fix-ca.c:692-693); fixca_color_size keeps answering like the shipped reference."""

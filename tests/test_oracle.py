@@ -10,7 +10,7 @@ import pytest
 
 import oracle as orc
 from fixture_io import encode_gimp_bmp24
-from helpers import case_image, fixture_image, golden, golden_half, max_dim, md5, oracle_params
+from helpers import case_image, fixture_image, golden, golden_half, golden_u15, max_dim, md5, oracle_params
 
 
 def test_restatement_matches_golden_suite(restatement):
@@ -179,3 +179,42 @@ def test_half_reference_build_matches_golden_and_leaves_other_formats_alone(refe
     assert half.color_size("R'G'B' half", 6) == -2 and half.color_size("R'G'B'A half", 8) == -2
     assert reference.color_size("R'G'B' half", 6) == -99
     assert half.color_size("R'G'B' u16", 6) == 2 and half.color_size("R'G'B' float", 12) == -4
+
+
+# ---------------------------------------------------------------------------------------------
+# u15 (bpc = 15): the rows the reference leaves "TODO for another day", written in by oracle/patch_u15.py
+# ---------------------------------------------------------------------------------------------
+def test_u15_restatement_matches_golden(restatement):
+    g = golden_u15()
+    bad = [c["name"] for c in g["suite"]
+           if md5(restatement.region(case_image(c), oracle_params(c), bpc=orc.BPC_U15)) != c["md5"]]
+    bad += [c["name"] for c in g["preview"]
+            if md5(restatement.region(case_image(c), oracle_params(c), preview=True, bpc=orc.BPC_U15)) != c["md5"]]
+    assert not bad, "%d u15 cases differ, first: %s" % (len(bad), bad[:5])
+
+
+def test_u15_reference_build_matches_golden_and_leaves_other_formats_alone(reference):
+    if not orc.ReferenceU15.available():
+        pytest.skip("oracle/_ref/libfixca_ref_u15.so not built (needs /root/reference at build time)")
+    u15 = orc.ReferenceU15()
+    sample = golden_u15()["suite"][::5]
+    bad = [c["name"] for c in sample if md5(u15.region(case_image(c), oracle_params(c), bpc=orc.BPC_U15)) != c["md5"]]
+    assert not bad, bad[:5]
+    # the written-in rows are the only difference: every other format computes what the unpatched build does
+    for c in golden()["suite"][::97]:
+        assert md5(u15.region(case_image(c), oracle_params(c))) == c["md5"], c["name"]
+    assert u15.color_size("R'G'B' u15", 6) == 15 and reference.color_size("R'G'B' u15", 6) == -99
+    assert u15.color_size("R'G'B' u16", 6) == 2 and u15.color_size("R'G'B' float", 12) == -4
+
+
+def test_u15_is_the_u16_pass_at_another_scale(restatement):
+    """The spec of the extension in one property: decode v / 32768 and encode round(d * 32768) are the u16
+    branches with another maximum, so interpolation None moves the same 16-bit codes u16 does, and a constant
+    image stays constant under Linear / Cubic (weights sum to one; 12345 / 32768 is exact)."""
+    img = orc.synth_u15(40, 61, 3, seed=5, wide=True)
+    p = orc.Params(blue=3.0, red=-2.0, lens_x=30, lens_y=20, interpolation=0, x_blue=0.7, y_red=-0.9)
+    assert restatement.region(img, p, bpc=orc.BPC_U15).tobytes() == restatement.region(img, p).tobytes()
+    flat = np.full((33, 47, 4), 12345, dtype=np.uint16)
+    for interp in (1, 2):
+        p.interpolation = interp
+        assert (restatement.region(flat, p, bpc=orc.BPC_U15) == 12345).all()

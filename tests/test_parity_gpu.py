@@ -12,7 +12,7 @@ import pytest
 
 import oracle as orc
 from fixture_io import encode_gimp_bmp24
-from helpers import golden_half, case_image, fixture_image, fx_params, golden, lsb_diff, max_dim, md5, oracle_params
+from helpers import golden_half, golden_u15, case_image, fixture_image, fx_params, golden, lsb_diff, max_dim, md5, oracle_params
 
 pytestmark = pytest.mark.gpu
 
@@ -145,11 +145,11 @@ def test_matrix_none_stream(fx, checker, dtype, ch):
 
 @pytest.mark.parametrize("variant", ["stream", "strip"])
 @pytest.mark.parametrize("dtype,ch", [("u1", 3), ("u1", 4), ("u2", 3), ("u2", 4), ("f4", 3), ("f4", 4)])
-def test_matrix_fast(fx, checker, dtype, ch, variant, monkeypatch):
+def test_matrix_fast(fx, checker, dtype, ch, variant, tuning):
     """FAST (FP32) arithmetic, streaming kernel and its per-tile fallback (strip): every format x Linear/Cubic x awkward shapes
     (tiles narrower than a warp's column group, widths that are not a multiple of the tile) x
     lens positions x scales on both sides of 1, against the checker within the stated tolerance."""
-    monkeypatch.setenv("FIXCA_FAST_KERNEL", variant)
+    tuning("FIXCA_FAST_KERNEL", variant)
     tol = FLOAT_ABS_TOL if dtype == "f4" else FAST_LSB_TOL
     n, kernels = 0, set()
     for (h, w), interp, lens, amounts in itertools.product(
@@ -174,8 +174,8 @@ def test_matrix_fast(fx, checker, dtype, ch, variant, monkeypatch):
 
 
 @pytest.mark.parametrize("variant", ["stream", "tiled"])
-def test_none_is_bit_exact_for_every_sample_size_including_nan_payloads(fx, checker, variant, monkeypatch):
-    monkeypatch.setenv("FIXCA_NONE_KERNEL", variant)
+def test_none_is_bit_exact_for_every_sample_size_including_nan_payloads(fx, checker, variant, tuning):
+    tuning("FIXCA_NONE_KERNEL", variant)
     rng = np.random.default_rng(3)
     for dt, ch in itertools.product(("u1", "u2", "u4", "u8"), (3, 4)):
         img = rng.integers(0, np.iinfo(dt).max, size=(131, 259, ch), dtype=dt, endpoint=True)
@@ -505,6 +505,49 @@ def test_float_pitch_padding_is_never_sampled(fx, checker):
 
 
 # ---------------------------------------------------------------------------------------------
+# u15 (bpc = 15), SURVEY.md 8(f) #4: checker = the reference with the u15 rows written in (oracle/patch_u15.py)
+# ---------------------------------------------------------------------------------------------
+def test_u15_golden_suite_bit_exact(fx):
+    """None and EXACT Linear / Cubic on u15 images: identical bytes (266 digests + 36 preview digests)."""
+    g = golden_u15()
+    bad, kernels = [], set()
+    for c in g["suite"]:
+        got = fx.correct(case_image(c), fx_params(fx, c), flags=fx.PRECISION_EXACT, bpc=fx.BPC_U15)
+        kernels.add(fx.last_kernel().rsplit("/", 1)[0])
+        if md5(got) != c["md5"]:
+            bad.append(c["name"])
+    for c in g["preview"]:
+        got = fx.correct(case_image(c), fx_params(fx, c), flags=fx.PRECISION_EXACT | fx.PREVIEW_OVERLAY, bpc=fx.BPC_U15)
+        if md5(got) != c["md5"]:
+            bad.append(c["name"])
+    assert not bad, "%d u15 cases differ, first: %s" % (len(bad), bad[:8])
+    assert {"stream/none/copy", "tiled/cubic/f64", "tiled/linear/f64"} <= kernels, kernels
+
+
+@pytest.mark.parametrize("variant", ["stream", "strip"])
+def test_u15_fast_within_one_lsb(fx, variant, tuning):
+    """FAST (FP32) Linear / Cubic on u15 (streaming kernel and its per-tile fallback): within one code of the checker,
+    in-range and out-of-range (> 32768, clipped) inputs; pass-through channels are copies."""
+    tuning("FIXCA_FAST_KERNEL", variant)
+    chk = orc.u15_checker()
+    worst, n, nbad, kernels = 0, 0, 0, set()
+    for (h, w), ch, interp, wide in itertools.product(((65, 257), (301, 517), (40, 2051), (7, 129)), (3, 4), (1, 2), (False, True)):
+        kw = dict(KW, lens_x=w // 2, lens_y=h // 2, interpolation=interp)
+        img = orc.synth_u15(h, w, ch, seed=h + w + ch + interp, wide=wide)
+        want = chk.region(img, orc.Params(**kw), bpc=orc.BPC_U15)
+        got = fx.correct(img, fx.FixCaParams(**kw), flags=fx.PRECISION_FAST, bpc=fx.BPC_U15)
+        kernels.add(fx.last_kernel().split("/")[0])
+        d = np.abs(got.astype(np.int64) - want.astype(np.int64))
+        worst = max(worst, int(d.max()))
+        n += d.size
+        nbad += int((d != 0).sum())
+        assert np.array_equal(got[..., 1], img[..., 1])
+    assert worst <= FAST_LSB_TOL, worst
+    assert nbad / n < 5e-3, nbad / n
+    assert kernels == {variant}, kernels
+
+
+# ---------------------------------------------------------------------------------------------
 # BASELINE.json's full sizes: size-independent properties + oracle on sampled bands
 # ---------------------------------------------------------------------------------------------
 FULL = [  # (name, h, w, ch, dtype, params)  -- SURVEY.md 8(d)
@@ -545,7 +588,7 @@ def test_full_size_properties(fx, checker, name, h, w, ch, dtype, kw):
 
 
 @pytest.mark.parametrize("name,h,w,ch,dtype,kw", FULL, ids=[f[0] for f in FULL])
-def test_full_size_fast_within_one_lsb(fx, checker, name, h, w, ch, dtype, kw, monkeypatch):
+def test_full_size_fast_within_one_lsb(fx, checker, name, h, w, ch, dtype, kw, tuning):
     """The bench configuration itself (FAST arithmetic, strip kernel) at BASELINE.json's sizes:
     +-1 LSB on sampled bands, pass-through channels identical, and band-split invariance."""
     rng = np.random.default_rng(5)
@@ -570,7 +613,7 @@ def test_full_size_fast_within_one_lsb(fx, checker, name, h, w, ch, dtype, kw, m
     fx.correct(img, p, y1=y1, y2=y2, out=band, flags=fx.PRECISION_FAST)
     assert (band[y1:y2] == full[y1:y2]).all()
     # the per-tile fallback kernel shares the arithmetic (same weights, same FMA order): same bytes
-    monkeypatch.setenv("FIXCA_FAST_KERNEL", "strip")
+    tuning("FIXCA_FAST_KERNEL", "strip")
     fx.correct(img, p, y1=y1, y2=y2, out=band, flags=fx.PRECISION_FAST)
     assert fx.last_kernel().startswith("strip") and (band[y1:y2] == full[y1:y2]).all()
 
