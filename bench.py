@@ -23,8 +23,18 @@ scaling, bands are independent: no data-path collective).
   cpu_baseline  the reference's own fix-ca.c (oracle/_ref, compiled unmodified) on this host's
              cores, rank 0, N=1 only, on a bounded row sample of the same image.
 
-The oracle is used here only for cpu_baseline / --impl reference and for a spot parity
-check of the e2e output; the measured CUDA path never touches it.
+  parity     every rank checks three row bands (top, middle, bottom) of its own e2e output against the
+             reference's own code; the worst difference over all ranks is reported.
+  workloads  (N = 1) one sub-record per BASELINE config (cfg2..cfg5, the frame batch, the EXACT headline):
+             kernel time over rotating buffer sets larger than L2, roofline fraction, oracle parity.
+  gather / strong_scaling  (N > 1) the bands stored straight into rank 0's frame over NVLink by the kernels
+             themselves (peer stores; compared with the NCCL gather and with the oracle on rows that came from
+             remote ranks), and BASELINE configs[3] as written: ONE 8192x6144 RGB f32 image split over N ranks.
+
+  python bench.py --gpus N --scaling strong [--workload W]   # the strong-scaling form as the main line
+
+The oracle is used here only for cpu_baseline / --impl reference and for the parity checks of
+outputs the CUDA path has already produced; the measured CUDA path never touches it.
 """
 from __future__ import annotations
 
@@ -196,7 +206,7 @@ def run_reference(args):
     W, Hr, ch, dts, interp, kw, lens = WORKLOADS[args.workload]
     dt = np.dtype(dts)
     n = max(1, args.gpus)
-    H = Hr * n
+    H = Hr * (1 if args.scaling == "strong" else n)
     lx, ly = (W // 2, H // 2) if lens == "centre" else lens
     p = orc.Params(interpolation=interp, lens_x=float(lx), lens_y=float(ly), **kw)
     cores = os.cpu_count() or 1
@@ -218,7 +228,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "megapixels/sec (cubic, lateral+directional)" if interp == 2 else "megapixels/sec",
         "value": round(mps, 3), "unit": "MP/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(per_step * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(per_step * 1e3, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.workload, n, "host cores; %s" % sample),
         "cpu_baseline": {"value": round(mps, 3), "unit": "MP/s", "cores": cores, "kind": chk.kind, "sample": sample},
@@ -244,6 +254,165 @@ def workload_config(name, n, extra=None):
 # ---------------------------------------------------------------------------------------------
 # the CUDA path
 # ---------------------------------------------------------------------------------------------
+L2_BYTES = 126e6
+
+
+def rotating_sets(src_bytes, pair_bytes):
+    """Buffer sets a device-resident timing loop rotates through so that no launch finds its input in the 126 MB L2:
+    one set when the input alone is > 3x L2 (the launch evicts its own head before it ends), otherwise enough sets
+    that two L2 capacities of other traffic pass between two uses of a set."""
+    if src_bytes >= 3 * L2_BYTES:
+        return 1
+    return min(8, 1 + int(-(-2 * L2_BYTES // pair_bytes)))
+
+
+def device_rows(t, row_bytes, dt, W, ch):
+    """getter(lo, hi) -> numpy rows [lo, hi] of a (rows, pitch) uint8 device tensor whose row 0 is image row `base`."""
+    def make(base):
+        def get(lo, hi):
+            return t[lo - base:hi + 1 - base, :row_bytes].contiguous().cpu().numpy().view(dt).reshape(hi + 1 - lo, W, ch)
+        return get
+    return make
+
+
+def check_bands(exact, get_src, get_out, y1, y2, W, H, ch, dt, interp, kw, lx, ly, rows=6):
+    """Three sample bands of output rows [y1, y2): get_out(ya, yb - 1) / get_src(lo, hi) fetch rows (inclusive) from
+    wherever they live; the reference's own code recomputes them from the same source rows."""
+    try:
+        import fixca
+        fp = fixca.FixCaParams(interpolation=interp, lens_x=float(lx), lens_y=float(ly), **kw)
+        worst, nbad, ntot, nrows, res = 0, 0, 0, 0, None
+        for ya, yb in sample_bands(y1, y2, rows):
+            lo, hi = fixca.band_source_rows(W, H, fp, ya, yb)
+            res = oracle_check(exact, get_src(lo, hi), lo, get_out(ya, yb - 1), ya, W, H, ch, dt, interp, kw, lx, ly, rows=yb - ya)
+            if "error" in res:
+                return res
+            worst = max(worst, res["max_abs_diff"])
+            nbad += res["mismatch_fraction"] * res["checked_rows"]
+            nrows += res["checked_rows"]
+        res = dict(res)
+        res.pop("bands", None)
+        res.update({"checked_rows": nrows, "max_abs_diff": worst, "mismatch_fraction": round(nbad / max(1, nrows), 7)})
+        res["ok"] = bool(worst <= res["tolerance"])
+        return res
+    except Exception as e:
+        return {"error": repr(e)}
+
+
+def device_workload(name, torch, fixca, dev, rank=0, world=1, exact=False, steps=50, check=True, seed=11,
+                    barrier=None, max_over_ranks=None, rows_override=None):
+    """One BASELINE workload, device-resident, timed over rotating buffer sets (no L2-resident inputs): the whole
+    image on this GPU (world = 1) or this rank's band of ONE image split over `world` ranks (strong scaling)."""
+    from fixca import bands
+    W, H, ch, dts, interp, kw, lens = WORKLOADS[name]
+    dt = np.dtype(dts)
+    bpp, bpc = ch * dt.itemsize, bpc_of(dt)
+    lx, ly = (W // 2, H // 2) if lens == "centre" else lens
+    p = fixca.FixCaParams(interpolation=interp, lens_x=float(lx), lens_y=float(ly), **kw)
+    flags = fixca.PRECISION_EXACT if exact else fixca.PRECISION_FAST
+    F = WORKLOAD_FRAMES.get(name, 0)
+    row_bytes = W * bpp
+    pitch = (row_bytes + 127) // 128 * 128
+    stream = torch.cuda.current_stream()
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    if F:
+        src_rows, y1, y2, lo = F * H, 0, H, 0
+    else:
+        plan = bands.plan_band(W, H, p, rank, world, 0, rows_override if rows_override else None)
+        y1, y2, lo, src_rows = plan.y1, plan.y2, plan.src_lo, plan.src_rows
+    out_rows = F * H if F else y2 - y1
+    nsets = rotating_sets(src_rows * pitch, (src_rows + out_rows) * pitch)
+    if dt.kind == "f":
+        first = torch.rand((src_rows, pitch // 4), dtype=torch.float32, device=dev, generator=g).view(torch.uint8)
+    else:
+        first = torch.randint(0, 256, (src_rows, pitch), dtype=torch.uint8, device=dev, generator=g)
+    srcs = [first] + [first.clone() for _ in range(nsets - 1)]
+    dsts = [torch.empty((out_rows, pitch), dtype=torch.uint8, device=dev) for _ in range(nsets)]
+
+    def call(i):
+        if F:
+            fixca.fix_ca_frames_dev(srcs[i].data_ptr(), pitch, pitch * H, dsts[i].data_ptr(), pitch, pitch * H, F, W, H, bpp, bpc,
+                                    p, flags, stream.cuda_stream)
+        else:
+            bands.run_band_device(plan, srcs[i].data_ptr(), pitch, dsts[i].data_ptr(), pitch, bpp, bpc, p, flags, stream.cuda_stream)
+
+    for k in range(max(3, nsets)):
+        call(k % nsets)
+    if barrier:
+        barrier()
+    else:
+        torch.cuda.synchronize()
+    n0 = fixca.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(steps):
+        call(k % nsets)
+    e1.record(stream)
+    if barrier:
+        barrier()
+    else:
+        torch.cuda.synchronize()
+    launches = fixca.launch_count() - n0
+    kernel = fixca.last_kernel()
+    local_ms = e0.elapsed_time(e1) / steps
+    ms = max_over_ranks(local_ms) if max_over_ranks else local_ms
+    mp = W * (H * F if F else (H if world > 1 else y2 - y1)) / 1e6        # whole job (all ranks' bands)
+    alg = 2.0 * bpp * W * out_rows                                       # this rank's launch
+    peak, _ = measured_peak()
+    rec = {"workload": name, "value": round(mp / (ms * 1e-3), 1), "unit": "MP/s", "ms_per_step": round(ms, 5), "steps": steps,
+           "dtype": "f64" if exact else "f32", "kernel": kernel, "launches_per_step": launches // max(1, steps),
+           "buffer_sets": nsets,
+           "cache": ("%d rotating buffer sets of %.0f MB (no launch finds its input in the 126 MB L2)" % (nsets, (src_rows + out_rows) * pitch / 1e6))
+                    if nsets > 1 else "input %.0f MB > 3x L2" % (src_rows * pitch / 1e6),
+           "roofline": {"bound": "hbm", "achieved": round(alg / (local_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(alg / (local_ms * 1e-3) / 1e9 / peak, 4), "traffic": ncu_traffic(name, kernel),
+                        "algorithmic_bytes_per_launch": int(alg), "launch_ms": round(local_ms, 5)}}
+    if check:
+        mk_s, mk_d = device_rows(srcs[0], row_bytes, dt, W, ch), device_rows(dsts[0], row_bytes, dt, W, ch)
+        if F:
+            res = []
+            for f in (0, F - 1):
+                res.append(check_bands(exact, mk_s(-f * H), mk_d(-f * H), 0, H, W, H, ch, dt, interp, kw, lx, ly))
+            par = res[0] if "error" in res[0] else res[1] if "error" in res[1] else dict(
+                res[0], max_abs_diff=max(res[0]["max_abs_diff"], res[1]["max_abs_diff"]),
+                checked_rows=res[0]["checked_rows"] + res[1]["checked_rows"], ok=res[0]["ok"] and res[1]["ok"], frames=[0, F - 1])
+        else:
+            par = check_bands(exact, mk_s(lo), mk_d(y1), y1, y2, W, H, ch, dt, interp, kw, lx, ly)
+        rec["parity"] = par
+    del srcs, dsts, first
+    torch.cuda.empty_cache()
+    return rec
+
+
+def strong_scaling_record(name, torch, dist, fixca, dev, rank, world, barrier, max_over_ranks, steps):
+    """BASELINE configs[3] as written: ONE image row-banded over the N ranks (plus the same image on one GPU in the
+    same run, and the fixed cost of a launch), so that the line carries its own efficiency."""
+    W, H = WORKLOADS[name][0], WORKLOADS[name][1]
+    split = device_workload(name, torch, fixca, dev, rank, world, steps=steps, barrier=barrier, max_over_ranks=max_over_ranks)
+    one = tiny = None
+    if rank == 0:
+        one = device_workload(name, torch, fixca, dev, 0, 1, steps=max(10, steps // 2), check=False)
+        tiny = device_workload(name, torch, fixca, dev, 0, 1, steps=steps, check=False, rows_override=8)
+    barrier()
+    par = split.get("parity")
+    split["parity"] = merge_parity(par, world, dist, dev)
+    if rank != 0:
+        return None
+    t1, tn, tf = one["ms_per_step"], split["ms_per_step"], tiny["ms_per_step"]
+    eff = t1 / (world * tn)
+    band_rows = -(-H // world)
+    return {"workload": name, "scaling": "strong", "image": "%dx%d" % (W, H), "n_gpus": world, "rows_per_gpu": band_rows,
+            "ms_per_step": tn, "value": split["value"], "unit": "MP/s", "one_gpu_ms_per_step_same_run": t1,
+            "efficiency_vs_one_gpu": round(eff, 4), "fixed_cost_ms": tf, "fixed_cost_share": round(tf / tn, 4),
+            "buffer_sets": split["buffer_sets"], "cache": split["cache"], "roofline_frac_per_gpu": split["roofline"]["frac"],
+            "kernel": split["kernel"], "parity": split["parity"],
+            "limiter": "per-launch fixed cost (CTA set-up, ring priming, pipeline fill and drain; measured as an 8-row launch: "
+                       "%.1f us of the %.1f us step) -- a %d-row band is %.0f us of streaming at one GPU's rate"
+                       % (tf * 1e3, tn * 1e3, band_rows, t1 / world * 1e3),
+            "how": "every rank computes its band (+halo rows) of the one image, rotating buffer sets, CUDA events, max over ranks"}
+
+
 def run_cuda_batch(args, torch, dist, fixca, rank, world, local, dev, barrier, max_over_ranks):
     """Frame batches (BASELINE configs[4]): every rank holds `frames` device-resident frames; a step is one launch
     over all of them.  e2e: the host-frame stream API (pinned H2D / kernel / D2H ring) on a few frames."""
@@ -289,7 +458,19 @@ def run_cuda_batch(args, torch, dist, fixca, rank, world, local, dev, barrier, m
     achieved = alg_bytes / (local_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
 
-    e2e = parity = None
+    # every rank: three bands of its first and last frame against the reference's own code
+    parity = None
+    if not args.no_check:
+        flat_s, flat_d = d_src.view(F * H, pitch), d_dst.view(F * H, pitch)
+        mk_s, mk_d = device_rows(flat_s, row_bytes, dt, W, ch), device_rows(flat_d, row_bytes, dt, W, ch)
+        res = [check_bands(args.exact, mk_s(-f * H), mk_d(-f * H), 0, H, W, H, ch, dt, interp, kw, lx, ly) for f in (0, F - 1)]
+        bad = [r for r in res if "error" in r]
+        parity = bad[0] if bad else dict(res[0], max_abs_diff=max(r["max_abs_diff"] for r in res),
+                                         checked_rows=sum(r["checked_rows"] for r in res))
+        parity = merge_parity(parity, world, dist, dev)
+        parity["what"] = "three row bands of the first and the last device-resident frame of every rank"
+
+    e2e = None
     if not args.no_e2e:
         nf = 16
         h_src = torch.empty((nf, H, row_bytes), dtype=torch.uint8, pin_memory=True)
@@ -318,8 +499,10 @@ def run_cuda_batch(args, torch, dist, fixca, rank, world, local, dev, barrier, m
                "h2d_bytes_per_step": int(nf * H * row_bytes) * world, "d2h_bytes_per_step": int(nf * H * row_bytes) * world,
                "steps": e2e_steps, "ms_per_step": round(dt_e2e / e2e_steps * 1e3, 3),
                "api": "fixca_cuda_frames (%d pinned host frames per step, H2D / kernel / D2H ring), synchronous" % nf}
-        if rank == 0 and not args.no_check:
-            parity = spot_check(args, h_src[0], h_dst[0], W, H, ch, dt, p, 0, 0, kw, interp, lx, ly)
+        if not args.no_check:
+            # the host-frame API's output must be the device batch's bytes (same kernels, same arithmetic)
+            same = bool(torch.equal(h_dst[nf - 1], d_dst[nf - 1, :, :row_bytes].cpu()))
+            e2e["identical_to_device_batch"] = same
     if rank == 0:
         cfg = workload_config(args.workload, 1, "arithmetic %s; kernel %s" % (
             "exact FP64 (bit-identical)" if args.exact else "fast FP32 (+-1 LSB of the reference)", kernel))
@@ -346,6 +529,40 @@ def run_cuda_batch(args, torch, dist, fixca, rank, world, local, dev, barrier, m
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def plugin_run_record(torch, fixca, W, H, ch, dts, interp, kw):
+    """The reference plug-in's own run() with INTEGRATION.md's patch (oracle/_ref/libfixca_plugin_cuda.so, built where
+    the reference is mounted): fix_ca() takes its two whole-image buffers from fixca_cuda_host_alloc and calls
+    fixca_cuda_region() at fix-ca.c:373-374.  Reported: the wall time inside that call (fixca_cuda_last_call_ms) and
+    of run() as a whole (which includes the fake GIMP's GEGL copies)."""
+    try:
+        import oracle as orc
+        if not orc.PatchedPlugin.available():
+            return {"unavailable": "oracle/_ref/libfixca_plugin_cuda.so not built"}
+        plug = orc.PatchedPlugin()
+        fmt = {"u1": "R'G'B' u8", "u2": "R'G'B' u16", "f4": "RGB float"}[dts] if ch == 3 else \
+              {"u1": "R'G'B'A u8", "u2": "R'G'B'A u16", "f4": "RGBA float"}[dts]
+        img = host_image(orc, H, W, ch, dts, seed=4)
+        calls, runs = [], []
+        for rep in range(3):
+            px = img.copy()
+            n0 = fixca.launch_count()
+            t0 = time.perf_counter()
+            st = plug.run(px, fmt, 1, 12, interpolation=interp, lens_x=float(W // 2), lens_y=float(H // 2), **kw)
+            runs.append((time.perf_counter() - t0) * 1e3)
+            calls.append(fixca.last_call_ms())
+            if st != 3 or fixca.launch_count() == n0:
+                return {"error": "run() status %d, launches %d" % (st, fixca.launch_count() - n0)}
+        del px, img
+        return {"region_call_ms": round(min(calls[1:]), 3), "region_call_ms_first": round(calls[0], 3),
+                "run_ms": round(min(runs[1:]), 1), "run_ms_first": round(runs[0], 1), "kernel": fixca.last_kernel(),
+                "arithmetic": "exact FP64 (the plug-in's default)",
+                "how": "oracle.PatchedPlugin.run(): the reference's run() -> fix_ca() with pinned buffers "
+                       "(fixca_cuda_host_alloc, pooled after the first call) -> fixca_cuda_region(); run_ms includes the "
+                       "fake GIMP's two whole-image GEGL copies"}
+    except Exception as e:
+        return {"error": repr(e)}
 
 
 def run_cuda(args):
@@ -382,11 +599,12 @@ def run_cuda(args):
 
     if args.workload in WORKLOAD_FRAMES:
         return run_cuda_batch(args, torch, dist, fixca, rank, world, local, dev, barrier, max_over_ranks)
+    strong = args.scaling == "strong"
     W, Hr, ch, dts, interp, kw, lens = WORKLOADS[args.workload]
     dt = np.dtype(dts)
     bpp = ch * dt.itemsize
     bpc = bpc_of(dt)
-    H = Hr * world
+    H = Hr if strong else Hr * world
     lx, ly = (W // 2, H // 2) if lens == "centre" else lens
     p = fixca.FixCaParams(interpolation=interp, lens_x=float(lx), lens_y=float(ly), **kw)
     flags = fixca.PRECISION_EXACT if args.exact else fixca.PRECISION_FAST
@@ -396,7 +614,7 @@ def run_cuda(args):
     row_bytes = W * bpp
     pitch = (row_bytes + 127) // 128 * 128
 
-    # ---- device-resident band (+halo), synthetic noise ----
+    # ---- device-resident band (+halo), synthetic noise; rotating buffer sets when a band would sit in L2 ----
     g = torch.Generator(device=dev)
     g.manual_seed(4 + rank)
     if dt.kind == "f":
@@ -404,13 +622,19 @@ def run_cuda(args):
     else:
         d_src = torch.randint(0, 256, (src_rows, pitch), dtype=torch.uint8, device=dev, generator=g)
     d_dst = torch.empty((y2 - y1, pitch), dtype=torch.uint8, device=dev)
+    nsets = rotating_sets(src_rows * pitch, (src_rows + y2 - y1) * pitch)
+    set_src = [d_src] + [d_src.clone() for _ in range(nsets - 1)]
+    set_dst = [d_dst] + [torch.empty_like(d_dst) for _ in range(nsets - 1)]
     stream = torch.cuda.current_stream()
+    turn = [0]
 
     def step():
-        bands.run_band_device(plan, d_src.data_ptr(), pitch, d_dst.data_ptr(), pitch, bpp, bpc, p, flags, stream.cuda_stream)
+        i = turn[0] % nsets
+        turn[0] += 1
+        bands.run_band_device(plan, set_src[i].data_ptr(), pitch, set_dst[i].data_ptr(), pitch, bpp, bpc, p, flags, stream.cuda_stream)
 
     sampler = ClockSampler(_nvml_index(local))
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, args.warmup, nsets)):
         step()
     barrier()
     n0 = fixca.launch_count()
@@ -426,7 +650,6 @@ def run_cuda(args):
     kernel = fixca.last_kernel()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
-    mp_step = W * (y2 - y1) / 1e6                     # this rank's pixels (equal bands)
     total_mp_step = W * H / 1e6
     value = total_mp_step / (ms_step * 1e-3)
     # roofline of the (single) kernel each step launches: local mean launch time
@@ -434,14 +657,18 @@ def run_cuda(args):
     alg_bytes = 2.0 * bpp * W * (y2 - y1)
     achieved = alg_bytes / (local_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
+    turn[0] = 0
+    step()      # set 0 holds this rank's output again (the gather and parity legs read d_dst)
+    torch.cuda.synchronize()
+    mk_src, mk_dst = device_rows(d_src, row_bytes, dt, W, ch), device_rows(d_dst, row_bytes, dt, W, ch)
 
-    # ---- optional: reassembly of the bands on rank 0 (NCCL send/recv over NVLink), outside the timed steps.
-    # Bands are independent, so this is the only inter-GPU traffic the pass can have; it is
-    # reported beside the step time to show why it is kept off the measured path.
+    # ---- N > 1: reassembly of the bands on rank 0.  Bands are independent, so this is the only inter-GPU traffic the
+    # pass can have; timed beside the steps.  Two forms: the kernels' own stores into rank 0's frame
+    # (peer mapping over NVLink: compute + gather in ONE kernel) and NCCL send/recv of finished bands.
     gather = None
-    if args.gather and world > 1:
+    if world > 1 and not args.no_gather and not strong:
         times = []
-        for rep in range(4):
+        for rep in range(3):
             barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record(stream)
@@ -450,12 +677,10 @@ def run_cuda(args):
             barrier()
             if rep:
                 times.append(max_over_ranks(g0.elapsed_time(g1)))
-            del full
-        gather = {"ms": round(min(times), 3), "bytes_into_rank0": int((world - 1) * (y2 - y1) * pitch),
-                  "how": "fixca.bands.gather_bands: one NCCL send/recv per band to rank 0, best of 3"}
-        # The same reassembly folded into the pass: rank 0 owns the whole frame, every rank's kernel stores its
-        # finished chunks straight into it (TMA stores through the CUDA IPC peer mapping, NVLink): compute + gather
-        # in one kernel, timed like a step (barrier both sides, max over ranks).
+            if rep < 2:
+                del full
+        gather = {"nccl_ms": round(min(times), 3), "bytes_into_rank0": int((world - 1) * (y2 - y1) * pitch),
+                  "nccl_how": "fixca.bands.gather_bands: one NCCL send/recv per finished band to rank 0 (after the step), best of 2"}
         frame = bands.PeerFrame(H, pitch, owner=0)
 
         def peer_step():
@@ -473,18 +698,56 @@ def run_cuda(args):
             barrier()
             ptimes.append(max_over_ranks(g0.elapsed_time(g1)))
         peer_kernel = fixca.last_kernel()
-        step()
-        full = bands.gather_bands(d_dst, plan, dst_rank=0)
         frame.sync()
         same = None
+        remote = None
+        ft = frame.as_tensor() if rank == 0 else None
         if rank == 0:
-            same = bool(torch.equal(frame.as_tensor()[:, :row_bytes], full[:, :row_bytes]))
+            same = bool(torch.equal(ft[:, :row_bytes], full[:, :row_bytes]))
         del full
+        if not args.no_check:
+            # rows that crossed NVLink, against the reference's own code: rank 0 hands every remote rank the three
+            # sample bands of that rank's rows as they sit in the gathered frame; the rank checks them with its own
+            # source rows
+            all_plans = [bands.plan_band(W, H, p, r, world) for r in range(world)]
+            mine = None
+            if rank == 0:
+                for r in range(1, world):
+                    sb = sample_bands(all_plans[r].y1, all_plans[r].y2)
+                    pack = torch.cat([ft[a:b, :row_bytes] for a, b in sb], dim=0).contiguous()
+                    dist.send(pack, dst=r)
+            else:
+                sb = sample_bands(y1, y2)
+                mine = torch.empty((sum(b - a for a, b in sb), row_bytes), dtype=torch.uint8, device=dev)
+                dist.recv(mine, src=0)
+                got = mine.cpu().numpy().view(dt).reshape(-1, W, ch)
+                offs = np.cumsum([0] + [b - a for a, b in sb])
+
+                def get_out(ya, yb_incl):
+                    k = [a for a, _ in sb].index(ya)
+                    return got[offs[k]:offs[k] + (yb_incl + 1 - ya)]
+
+                remote = check_bands(args.exact, mk_src(lo), get_out, y1, y2, W, H, ch, dt, interp, kw, lx, ly)
+            if rank == 0:
+                remote = {"max_abs_diff": 0, "checked_rows": 0, "tolerance": 0 if args.exact else 1, "checker": "-"}
+            remote = merge_parity(remote, world, dist, dev)
+            remote["what"] = "three row bands of every REMOTE rank's rows, read back from rank 0's gathered frame"
+            remote["ranks_checked"] -= 1      # rank 0 contributes no remote rows
+            remote["ranks"] = world - 1
+            remote["ok"] = bool(remote["ranks_checked"] == world - 1 and remote["max_abs_diff"] <= remote["tolerance"])
+        del ft
         frame.close()
-        gather["peer_store"] = {"ms": round(min(ptimes), 3), "median_ms": round(sorted(ptimes)[len(ptimes) // 2], 3),
-                                "identical_to_nccl_gather": same, "kernel": peer_kernel,
-                                "how": "fixca.bands.PeerFrame + run_band_into_frame: every rank's kernel writes its band "
-                                       "into rank 0's frame over NVLink (compute + gather, one kernel); max over ranks"}
+        remote_bytes = (world - 1) * (y2 - y1) * pitch
+        gather.update({"peer_store_ms": round(min(ptimes), 3), "peer_store_median_ms": round(sorted(ptimes)[len(ptimes) // 2], 3),
+                       "peer_store_gbs_into_rank0": round(remote_bytes / (min(ptimes) * 1e-3) / 1e9, 1),
+                       "identical_to_nccl_gather": same, "kernel": peer_kernel, "remote_rows_parity": remote,
+                       "peer_store_how": "fixca.bands.PeerFrame + run_band_into_frame: every rank's kernel TMA-stores its band "
+                                         "into rank 0's frame over NVLink (compute + gather, one kernel); barrier both sides, max over ranks"})
+
+    strong_rec = None
+    if world > 1 and not strong and not args.no_strong:
+        strong_rec = strong_scaling_record("cfg4_50mp_rgbf32_cubic", torch, dist, fixca, dev, rank, world, barrier,
+                                           max_over_ranks, steps=max(20, min(100, args.steps)))
 
     # ---- end to end through the host C ABI: pinned host band, H2D + kernels + D2H timed ----
     e2e = None
@@ -535,8 +798,8 @@ def run_cuda(args):
         h_dst.copy_(dst_keep)
         del d_in, d_out, dst_keep
         barrier()
-        # the call exactly as the plug-in makes it: pageable buffers (g_new, fix-ca.c:366-367), staged through
-        # the library's pinned rings by its copy threads (rank 0 of a single-GPU run only; reported, not the e2e value)
+        # the call exactly as the UNPATCHED plug-in would make it: pageable buffers (g_new, fix-ca.c:366-367), staged
+        # through the library's pinned rings by its copy threads (single-GPU run only; reported, not the e2e value)
         pageable_ms = None
         if world == 1:
             p_src = np.empty((src_rows, row_bytes), dtype=np.uint8)
@@ -555,24 +818,53 @@ def run_cuda(args):
                "h2d_bytes_per_step": int(src_rows * row_bytes) * world, "d2h_bytes_per_step": int((y2 - y1) * row_bytes) * world,
                "steps": e2e_steps, "ms_per_step": round(dt_e2e / e2e_steps * 1e3, 3),
                "api": "fixca_cuda_region_ex (host pointers, pinned), synchronous"}
-        if rank == 0 and not args.no_check:
-            parity = spot_check(args, h_src, h_dst, W, H, ch, dt, p, lo, y1, kw, interp, lx, ly)
+        if not args.no_check:
+            hs = h_src.numpy().view(dt).reshape(src_rows, W, ch)
+            hd = h_dst.numpy().view(dt).reshape(y2 - y1, W, ch)
+            parity = check_bands(args.exact, lambda a, b: hs[a - lo:b + 1 - lo], lambda a, b: hd[a - y1:b + 1 - y1],
+                                 y1, y2, W, H, ch, dt, interp, kw, lx, ly)
+    elif not args.no_check:
+        parity = check_bands(args.exact, mk_src(lo), mk_dst(y1), y1, y2, W, H, ch, dt, interp, kw, lx, ly)
+    if not args.no_check:
+        parity = merge_parity(parity, world, dist, dev)
+        if args.no_e2e:
+            parity["what"] = "three row bands (top / middle / bottom) of every rank's device-resident band"
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args)
 
+    workloads = plugin = None
+    if world == 1 and not args.no_workloads and args.workload == DEFAULT_WORKLOAD and not args.exact:
+        del set_src, set_dst
+        workloads = []
+        for name, ex, st in (("cfg2_24mp_rgb8_linear", False, 100), ("cfg3_8k_rgba16_cubic", False, 60),
+                             ("cfg4_50mp_rgbf32_cubic", False, 40), ("cfg5_4k_rgb8_cubic", False, 200),
+                             ("cfg5_batch_4k_rgb8_cubic", False, 10), ("target_100mp_rgb16_cubic", True, 10)):
+            try:
+                workloads.append(device_workload(name, torch, fixca, dev, exact=ex, steps=st, check=not args.no_check))
+            except Exception as e:
+                workloads.append({"workload": name, "error": repr(e)})
+        if e2e is not None:
+            plugin = plugin_run_record(torch, fixca, W, Hr, ch, dts, interp, kw)
+
     if rank == 0:
+        cfg = workload_config(args.workload, world, "arithmetic %s; kernel %s" % (
+            "exact FP64 (bit-identical)" if args.exact else "fast FP32 (+-1 LSB of the reference)", kernel))
+        if strong:
+            cfg.update({"image": "%dx%d" % (W, H), "rows_per_gpu": -(-H // world),
+                        "parallelism": "ONE image row-banded over %d GPU(s) (+halo rows), no collective" % world})
+        if nsets > 1:
+            cfg["cache"] = "%d rotating buffer sets of %.0f MB per GPU (no launch finds its input in the 126 MB L2)" % (
+                nsets, (src_rows + y2 - y1) * pitch / 1e6)
         line = {
             "metric": "megapixels/sec (cubic, lateral+directional)" if interp == 2 else "megapixels/sec",
             "value": round(value, 1), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 5), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f64" if args.exact or dts not in ("u1", "u2", "f4") else "f32",
             "data": "synthetic",
-            "config": workload_config(args.workload, world,
-                                      "arithmetic %s; kernel %s" % ("exact FP64 (bit-identical)" if args.exact else
-                                                                    "fast FP32 (+-1 LSB of the reference)", kernel)),
+            "config": cfg,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload, kernel),
                          "peak_source": peak_src, "kernel": kernel,
@@ -584,6 +876,12 @@ def run_cuda(args):
             line["parity"] = parity
         if gather is not None:
             line["gather"] = gather
+        if strong_rec is not None:
+            line["strong_scaling"] = strong_rec
+        if workloads is not None:
+            line["workloads"] = workloads
+        if plugin is not None and e2e is not None:
+            e2e["plugin_run"] = plugin
         print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -609,35 +907,77 @@ def _nvml_index(local: int) -> int:
     return local
 
 
-def spot_check(args, h_src, h_dst, W, H, ch, dt, p, lo, y1, kw, interp, lx, ly):
-    """The first rows of rank 0's e2e output against the reference's own code (oracle = checker).
-    Rank 0 holds the top band, so its host buffer starts at image row 0; the checker is given an
-    H-row view of it and only ever reads the rows output rows [0, rows) need (band independence,
-    SURVEY.md 8(e))."""
+def whole_image_view(rows, row0, H):
+    """(H, W, ch) view of a whole image of which only rows [row0, row0 + n) exist, backed by `rows` (n, W, ch):
+    what the reference-facing ABI takes (a whole-image pointer; only the rows a band needs are ever read, SURVEY.md
+    8(e)).  Nothing outside the backed rows may be touched through it."""
+    import ctypes
+    rb = rows.strides[0]
+    one = np.frombuffer((ctypes.c_ubyte * rows.dtype.itemsize).from_address(rows.ctypes.data - row0 * rb), dtype=rows.dtype)
+    v = np.lib.stride_tricks.as_strided(one, shape=(H,) + rows.shape[1:], strides=rows.strides)
+    return v
+
+
+def sample_bands(y1, y2, rows=6):
+    """Top, middle and bottom `rows`-row bands of [y1, y2) (the middle one straddles a chunk border)."""
+    n = y2 - y1
+    if n <= 3 * rows:
+        return [(y1, y2)]
+    mid = y1 + (n // 2 // 8) * 8 - rows // 2
+    return [(y1, y1 + rows), (mid, mid + rows), (y2 - rows, y2)]
+
+
+def oracle_check(exact, src_rows, lo, got_rows, y1, W, H, ch, dt, interp, kw, lx, ly, rows=6):
+    """Rows of an output band the CUDA path produced (got_rows = image rows [y1, y1 + n)) against the reference's
+    own code run on the same source rows (src_rows = image rows [lo, lo + m)): three sample bands."""
     try:
         import fixca
         chk, orc = cpu_checker()
-        rows = 6
-        if lo != 0 or y1 != 0:
-            return None
-        need_lo, need_hi = fixca.band_source_rows(W, H, p, 0, rows)
-        src = h_src.numpy().view(dt).reshape(h_src.shape[0], W, ch)
-        got = h_dst.numpy().view(dt).reshape(h_dst.shape[0], W, ch)[:rows]
-        if need_hi >= src.shape[0]:
-            return None
-        want = np.zeros((rows, W, ch), dtype=dt)
-        as_strided = np.lib.stride_tricks.as_strided
         P = orc.Params(interpolation=interp, lens_x=float(lx), lens_y=float(ly), **kw)
-        chk.region(as_strided(src, shape=(H, W, ch), strides=src.strides), P, 0, rows,
-                   dst=as_strided(want, shape=(H, W, ch), strides=want.strides))
-        if dt.kind == "f":
-            d = float(np.abs(want.astype(np.float64) - got.astype(np.float64)).max())
-        else:
-            d = int(np.abs(want.astype(np.int64) - got.astype(np.int64)).max())
-        return {"checked_rows": rows, "max_abs_diff": d, "checker": chk.kind,
-                "tolerance": 0 if args.exact or interp == 0 else (1 if dt.kind != "f" else 1e-6)}
+        fp = fixca.FixCaParams(interpolation=interp, lens_x=float(lx), lens_y=float(ly), **kw)
+        src_v = whole_image_view(src_rows, lo, H)
+        worst, nbad, ntot, bands = 0, 0, 0, []
+        for ya, yb in sample_bands(y1, y1 + got_rows.shape[0], rows):
+            need_lo, need_hi = fixca.band_source_rows(W, H, fp, ya, yb)
+            if need_lo < lo or need_hi >= lo + src_rows.shape[0]:
+                return {"error": "sample band [%d,%d) needs source rows [%d,%d] outside [%d,%d)" % (ya, yb, need_lo, need_hi, lo, lo + src_rows.shape[0])}
+            want = np.zeros((yb - ya, W, ch), dtype=dt)
+            chk.region(src_v, P, ya, yb, dst=whole_image_view(want, ya, H))
+            got = got_rows[ya - y1:yb - y1]
+            if dt.kind == "f":
+                d = np.abs(want.astype(np.float64) - got.astype(np.float64))
+            else:
+                d = np.abs(want.astype(np.int64) - got.astype(np.int64))
+            worst = max(worst, float(d.max()) if dt.kind == "f" else int(d.max()))
+            nbad += int((d != 0).sum())
+            ntot += d.size
+            bands.append([ya, yb])
+        return {"checked_rows": int(sum(b - a for a, b in bands)), "bands": bands, "max_abs_diff": worst,
+                "mismatch_fraction": round(nbad / max(1, ntot), 7), "checker": chk.kind,
+                "tolerance": 0 if exact or interp == 0 else (1 if dt.kind != "f" else 1e-6)}
     except Exception as e:  # the check is advisory; never hide the bench line
         return {"error": repr(e)}
+
+
+def merge_parity(parity, world, dist, dev):
+    """Worst difference over all ranks (every rank checked its own band)."""
+    import torch
+    bad = 1.0 if (parity is None or "error" in parity) else 0.0
+    t = torch.tensor([0.0 if bad else float(parity["max_abs_diff"]), bad,
+                      0.0 if bad else float(parity["checked_rows"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        t = torch.stack([mx[0], sm[1], sm[2]])
+    out = dict(parity or {})
+    out.pop("bands", None)
+    out.update({"max_abs_diff": (int(t[0].item()) if float(t[0].item()).is_integer() else float(t[0].item())),
+                "ranks_checked": int(world - t[1].item()), "ranks": world, "checked_rows": int(t[2].item()),
+                "what": "three row bands (top / middle / bottom) of every rank's own band of the e2e output"})
+    out["ok"] = bool(out["ranks_checked"] == world and out["max_abs_diff"] <= out.get("tolerance", 0))
+    return out
 
 
 def cpu_baseline(args):
@@ -678,7 +1018,13 @@ def main():
     ap.add_argument("--exact", action="store_true", help="FP64 bit-exact arithmetic instead of fast FP32")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", action="store_true", help="also time the reassembly of the bands on rank 0 (N > 1)")
+    ap.add_argument("--scaling", choices=("weak", "strong"), default="weak",
+                    help="weak: every rank owns a full-size band of an N-times taller image (default); strong: ONE image "
+                         "of the workload's size split over the N ranks")
+    ap.add_argument("--gather", action="store_true", help="(default for N > 1; kept for older command lines)")
+    ap.add_argument("--no-gather", action="store_true", help="skip the reassembly of the bands on rank 0 (N > 1)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (N > 1)")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the per-config sub-records (N = 1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--quick-cpu", action="store_true")

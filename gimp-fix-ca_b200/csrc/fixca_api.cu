@@ -8,6 +8,7 @@
 // point returns FIXCA_ERR_NO_DEVICE / FIXCA_ERR_CUDA.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -109,6 +110,9 @@ extern "C" void fixca_cuda_reload_tuning(void)
 	std::lock_guard<std::mutex> lock(g_tuning_mu);
 	read_tuning_locked();
 }
+
+static void pinned_pool_release();
+static thread_local double tl_last_call_ms;
 
 // ---------------------------------------------------------------------------
 // format and geometry
@@ -1274,7 +1278,9 @@ extern "C" int fixca_cuda_region_ex(const unsigned char *src, unsigned char *dst
 		return FIXCA_OK;
 	int prev = -1;
 	cudaGetDevice(&prev);
+	const auto t0 = std::chrono::steady_clock::now();
 	rc = region_host_band(dev, src, dst, width, height, f, params, g, x1, x2, y1, y2, flags, show_progress != 0);
+	tl_last_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	if (prev >= 0)
 		cudaSetDevice(prev);
 	return rc;
@@ -1589,25 +1595,93 @@ extern "C" void fixca_cuda_set_progress(fixca_progress_fn fn, void *user)
 // g_new at fix-ca.c:366-367 / :648-649.  A buffer from here is recognised by fixca_cuda_region*() and moved
 // by DMA directly, without the staging copies pageable memory needs.  NULL when no GPU is usable or the
 // allocation fails: the caller then falls back to its own allocator (and to its CPU path).
+//
+// Page-locking costs ~0.2 ms per MB, far more than the pass itself, and the plug-in allocates two whole-image
+// buffers per run() and per preview refresh (:648-649, every slider move): freed buffers are kept in a small
+// pool (at most 4 buffers / 4 GiB) and handed out again to requests they fit (within 2x); fixca_cuda_release()
+// returns the pool to the system.
+namespace {
+struct PinnedPool {
+	struct Buf { void *p; size_t cap; bool used; };
+	std::mutex mu;
+	std::vector<Buf> bufs;
+};
+PinnedPool g_pinned;
+}
+
 extern "C" void *fixca_cuda_host_alloc(size_t bytes)
 {
 	int dev;
 	if (!bytes || current_device_or(-1, dev))
 		return nullptr;
+	{
+		std::lock_guard<std::mutex> lock(g_pinned.mu);
+		PinnedPool::Buf *best = nullptr;
+		for (PinnedPool::Buf &b : g_pinned.bufs)
+			if (!b.used && b.cap >= bytes && b.cap / 2 <= bytes && (!best || b.cap < best->cap))
+				best = &b;
+		if (best) {
+			best->used = true;
+			return best->p;
+		}
+	}
 	void *p = nullptr;
 	if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
 		cudaGetLastError();
 		fail(FIXCA_ERR_NOMEM, "cudaHostAlloc of %zu bytes failed", bytes);
 		return nullptr;
 	}
+	std::lock_guard<std::mutex> lock(g_pinned.mu);
+	g_pinned.bufs.push_back({p, bytes, true});
 	return p;
 }
 
 extern "C" void fixca_cuda_host_free(void *p)
 {
-	if (p && cudaFreeHost(p) != cudaSuccess)
+	if (!p)
+		return;
+	void *drop = nullptr;
+	{
+		std::lock_guard<std::mutex> lock(g_pinned.mu);
+		size_t idle_bytes = 0, idle = 0;
+		for (PinnedPool::Buf &b : g_pinned.bufs)
+			if (!b.used) { idle_bytes += b.cap; ++idle; }
+		for (size_t i = 0; i < g_pinned.bufs.size(); ++i) {
+			PinnedPool::Buf &b = g_pinned.bufs[i];
+			if (b.p != p)
+				continue;
+			if (idle < 4 && idle_bytes + b.cap <= ((size_t)4 << 30)) {
+				b.used = false;		// kept for the next request
+				return;
+			}
+			drop = b.p;
+			g_pinned.bufs.erase(g_pinned.bufs.begin() + (long)i);
+			break;
+		}
+		if (!drop)
+			drop = p;	// not ours to pool (allocated before a release): still pinned memory
+	}
+	if (cudaFreeHost(drop) != cudaSuccess)
 		cudaGetLastError();
 }
+
+static void pinned_pool_release()
+{
+	std::lock_guard<std::mutex> lock(g_pinned.mu);
+	for (size_t i = 0; i < g_pinned.bufs.size();) {
+		if (!g_pinned.bufs[i].used) {
+			if (cudaFreeHost(g_pinned.bufs[i].p) != cudaSuccess)
+				cudaGetLastError();
+			g_pinned.bufs.erase(g_pinned.bufs.begin() + (long)i);
+		} else {
+			++i;
+		}
+	}
+}
+
+// wall-clock duration of the last fixca_cuda_region*() host call on this thread (what a plug-in spends inside
+// the call that replaces its row loop)
+extern "C" double fixca_cuda_last_call_ms(void) { return tl_last_call_ms; }
 
 extern "C" const char *fixca_cuda_last_error(void) { return tl_error; }
 extern "C" const char *fixca_cuda_last_kernel(void) { return tl_kernel; }
@@ -1643,6 +1717,7 @@ extern "C" int fixca_cuda_device_count(void)
 
 extern "C" void fixca_cuda_release(void)
 {
+	pinned_pool_release();
 	for (DeviceCtx &c : g_ctx) {
 		std::lock_guard<std::mutex> lock(c.mu);
 		c.release();

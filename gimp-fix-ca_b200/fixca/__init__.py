@@ -44,7 +44,7 @@ EXPORTS = (
     "fixca_cuda_last_error", "fixca_strerror", "fixca_cuda_device_count", "fixca_cuda_last_kernel",
     "fixca_cuda_launch_count", "fixca_cuda_release", "fixca_version",
     "fixca_cuda_frames_multi", "fixca_cuda_frame_alloc", "fixca_cuda_frame_open", "fixca_cuda_frame_close", "fixca_cuda_frame_free",
-    "fixca_cuda_host_alloc", "fixca_cuda_host_free", "fixca_cuda_reload_tuning", "fixca_color_size_ext",
+    "fixca_cuda_host_alloc", "fixca_cuda_host_free", "fixca_cuda_reload_tuning", "fixca_color_size_ext", "fixca_cuda_last_call_ms",
 )
 BPC_HALF, BPC_U15 = -2, 15
 IPC_HANDLE_BYTES = 64
@@ -133,6 +133,7 @@ def load() -> ctypes.CDLL:
     L.fixca_cuda_host_free.argtypes = [vp]
     L.fixca_cuda_host_free.restype = None
     L.fixca_cuda_reload_tuning.restype = None
+    L.fixca_cuda_last_call_ms.restype = ctypes.c_double
     _lib = L
     return L
 
@@ -296,6 +297,11 @@ def device_count() -> int:
 
 def last_kernel() -> str:
     return load().fixca_cuda_last_kernel().decode()
+
+
+def last_call_ms() -> float:
+    """Wall-clock milliseconds of the last fixca_cuda_region*() host call on this thread."""
+    return float(load().fixca_cuda_last_call_ms())
 
 
 def launch_count() -> int:

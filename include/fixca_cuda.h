@@ -296,7 +296,9 @@ FIXCA_API void fixca_cuda_set_progress(fixca_progress_fn fn, void *user);
  * Pinned host memory for the image buffers fix_ca() allocates with g_new (fix-ca.c:366-367; the preview's at
  * :648-649).  Buffers from here are moved by DMA without staging copies (100 MP RGB16: 13 ms per call instead
  * of 32 ms from pageable memory).  fixca_cuda_host_alloc returns NULL when no GPU is usable or the allocation
- * fails -- the caller keeps its own allocator as the fallback; free with fixca_cuda_host_free only.
+ * fails -- the caller keeps its own allocator as the fallback; free with fixca_cuda_host_free only.  Freed
+ * buffers are pooled (page-locking costs more than the pass: <= 4 buffers, <= 4 GiB) and handed out again, which
+ * is what the dialog's preview needs (two whole-image buffers per refresh); fixca_cuda_release() empties the pool.
  */
 FIXCA_API void *fixca_cuda_host_alloc(size_t bytes);
 FIXCA_API void  fixca_cuda_host_free(void *p);
@@ -313,6 +315,9 @@ FIXCA_API int  fixca_cuda_device_count(void);		/* 0 when no driver / no GPU */
  * ("tiled/cubic/f32/u16x3", "direct/...", "none/..."), and how many kernels it launched. */
 FIXCA_API const char *fixca_cuda_last_kernel(void);
 FIXCA_API long fixca_cuda_launch_count(void);		/* kernels launched by this library so far */
+/* Wall-clock milliseconds the last fixca_cuda_region() / _ex() call on this thread took (uploads, kernels,
+ * downloads): what a plug-in spends inside the call that replaces its row loop. */
+FIXCA_API double fixca_cuda_last_call_ms(void);
 FIXCA_API void fixca_cuda_release(void);		/* free cached device / pinned buffers */
 FIXCA_API const char *fixca_version(void);
 

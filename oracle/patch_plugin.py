@@ -23,24 +23,50 @@ static void fixca_progress (int kind, double fraction, void *user)
 	else
 		gimp_progress_update (fraction);
 }
+/* The two whole-image buffers (fix-ca.c:366-367, :648-649) come from pinned memory when a GPU is present, so
+ * that the library moves them by DMA without staging copies; g_new stays the fallback. */
+static void *fixca_pinned[4];
+static guchar *fixca_img_new (gsize n)
+{
+	void *p = fixca_cuda_device_count () > 0 ? fixca_cuda_host_alloc (n) : NULL;
+	int i;
+	for (i = 0; p && i < 4; i++)
+		if (!fixca_pinned[i]) {
+			fixca_pinned[i] = p;
+			return p;
+		}
+	if (p)
+		fixca_cuda_host_free (p);
+	return g_new (guchar, n);
+}
+static void fixca_img_free (void *p)
+{
+	int i;
+	for (i = 0; p && i < 4; i++)
+		if (fixca_pinned[i] == p) {
+			fixca_pinned[i] = NULL;
+			fixca_cuda_host_free (p);
+			return;
+		}
+	g_free (p);
+}
+#define FIXCA_IMG_NEW(n) fixca_img_new (n)
+#define FIXCA_IMG_FREE(p) fixca_img_free (p)
+#else
+#define FIXCA_IMG_NEW(n) g_new (guchar, n)
+#define FIXCA_IMG_FREE(p) g_free (p)
 #endif
 '''
 
 CALL_BLOCK = r'''
 #ifdef HAVE_FIXCA_CUDA
 	fixca_cuda_set_progress (fixca_progress, NULL);
-	if (x == 0 && width == xImg && fixca_cuda_device_count () > 0) {
-		if (fixca_cuda_region (srcImg, destImg, xImg, yImg, bppImg, bpcImg,
-				       (const fixca_params *) params,
-				       x, x + width, y, y + height, TRUE) != 0) {
-			g_message ("%s", fixca_cuda_last_error ());
-			g_free (destImg);
-			g_free (srcImg);
-			g_object_unref (destBuf);
-			g_object_unref (srcBuf);
-			return -1;
-		}
-	} else
+	/* any failure of the library (no usable GPU, out of memory, a format it declines) falls back to the CPU loop */
+	if (x == 0 && width == xImg && fixca_cuda_device_count () > 0 &&
+	    fixca_cuda_region (srcImg, destImg, xImg, yImg, bppImg, bpcImg, (const fixca_params *) params,
+			       x, x + width, y, y + height, TRUE) == 0)
+		;
+	else
 #endif
 '''
 
@@ -75,6 +101,11 @@ def patch(text: str) -> str:
         raise SystemExit("patch_plugin: expected exactly one preview call, found %d" % len(calls))
     c = calls[0]
     text = text[:c.start()] + "\n" + PREVIEW_BLOCK.strip("\n") + text[c.start():]
+    # (4) the whole-image buffers of fix_ca() and preview_update() (fix-ca.c:366-367, :648-649 and their g_free's)
+    text, n_new = re.subn(r'\b(srcImg|destImg)(\s*)= g_new \(guchar, ([^;]*)\);', r'\1\2= FIXCA_IMG_NEW (\3);', text)
+    text, n_free = re.subn(r'\bg_free ?\((srcImg|destImg)\);', r'FIXCA_IMG_FREE (\1);', text)
+    if n_new != 4 or n_free != 4:
+        raise SystemExit("patch_plugin: expected 4 buffer allocations and 4 frees, found %d / %d" % (n_new, n_free))
     return text
 
 

@@ -121,9 +121,11 @@ def test_band_plans_cover_the_image_without_overlap():
             assert pl.halo_rows <= 2 * 64                      # halo <= ~64 rows per side
 
 
-def _peer_worker(rank, world, port, out_q):
+def _peer_worker(rank, world, port, out_q, one_gpu=False):
     """One process per GPU (NCCL): every rank's kernel stores its band into rank 0's frame (PeerFrame, CUDA IPC
-    peer mapping over NVLink); rank 0 compares the frame with the oracle's full image."""
+    peer mapping over NVLink); rank 0 compares the frame with the oracle's full image.  one_gpu: the same
+    processes on ONE device (gloo for the rendezvous; the frame is still another process's allocation, mapped
+    through the same fixca_cuda_frame_open) -- what a single-GPU box can check of this path."""
     for p in (os.path.join(ROOT, "gimp-fix-ca_b200"), os.path.join(ROOT, "oracle"), ROOT):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -133,9 +135,12 @@ def _peer_worker(rank, world, port, out_q):
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    torch.cuda.set_device(0 if one_gpu else rank)
+    dev = torch.device("cuda", 0 if one_gpu else rank)
+    if one_gpu:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         chk = orc.best_checker()
         ok = True
@@ -177,6 +182,30 @@ def _peer_worker(rank, world, port, out_q):
             out_q.put(("ok", ok))
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_bands_stored_into_another_process_frame_one_gpu():
+    """The peer-frame path on a single-GPU box: two processes on device 0, rank 1's kernel stores its band into the frame
+    rank 0 allocated (CUDA IPC mapping), rank 0 checks the assembled frame against the oracle.  (The kernels of the two
+    processes do not wait on one another.)"""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    results = []
+    while not q.empty():
+        results.append(q.get())
+    assert ("ok", True) in results, results
 
 
 @pytest.mark.gpu
