@@ -230,7 +230,7 @@ static const KernelEntry *pick_kernel(const Format &f, int interp, unsigned flag
 	if (interp == 0)
 		return lookup_none(f.sample_bytes, f.nch, tiled);
 	const bool fast = (flags & FIXCA_PRECISION_MASK) == FIXCA_PRECISION_FAST &&
-			  (f.kind == SK_U8 || f.kind == SK_U16 || f.kind == SK_F32 || f.kind == SK_F16);
+			  (f.kind == SK_U8 || f.kind == SK_U16 || f.kind == SK_F32 || f.kind == SK_F16 || f.kind == SK_U15);
 	return fast ? lookup_fast(f.kind, f.nch, interp, tiled) : lookup_exact(f.kind, f.nch, interp, tiled);
 }
 

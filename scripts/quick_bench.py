@@ -18,13 +18,21 @@ def run(name, h, w, ch, tdtype, bpc, interp, flags, reps=10, lens=None):
     es = torch.empty((), dtype=tdtype).element_size()
     bpp = ch * es
     pitch = (w * bpp + 127) // 128 * 128
-    src = torch.randint(0, 255, (h, pitch), dtype=torch.uint8, device="cuda")
-    dst = torch.empty_like(src)
+    fixca.reload_tuning()       # callers change FIXCA_* between runs; the library reads them once
+    # rotating buffer sets (bench.py's rule): no launch finds its input in the 126 MB L2
+    nsets = 1 if h * pitch >= 3 * 126e6 else min(8, 1 + int(-(-2 * 126e6 // (2 * h * pitch))))
+    srcs = [torch.randint(0, 255, (h, pitch), dtype=torch.uint8, device="cuda") for _ in range(nsets)]
+    dsts = [torch.empty_like(srcs[0]) for _ in range(nsets)]
     lx, ly = lens if lens else (w // 2, h // 2)
     p = fixca.FixCaParams(interpolation=interp, lens_x=lx, lens_y=ly, **KW)
     st = torch.cuda.current_stream().cuda_stream
-    call = lambda: fixca.fix_ca_region_dev(src.data_ptr(), pitch, 0, h, dst.data_ptr(), pitch, 0, w, h, bpp, bpc, p, 0, h, flags, st)
-    for _ in range(3):
+    turn = [0]
+
+    def call():
+        i = turn[0] % nsets
+        turn[0] += 1
+        fixca.fix_ca_region_dev(srcs[i].data_ptr(), pitch, 0, h, dsts[i].data_ptr(), pitch, 0, w, h, bpp, bpc, p, 0, h, flags, st)
+    for _ in range(3 + nsets):
         call()
     torch.cuda.synchronize()
     ts = []
@@ -50,6 +58,7 @@ def run_batch(name, nf, h, w, ch, tdtype, bpc, interp, flags, reps=5):
     pitch = (w * bpp + 127) // 128 * 128
     src = torch.randint(0, 255, (nf, h, pitch), dtype=torch.uint8, device="cuda")
     dst = torch.empty_like(src)
+    fixca.reload_tuning()
     p = fixca.FixCaParams(interpolation=interp, lens_x=w // 2, lens_y=h // 2, **KW)
     st = torch.cuda.current_stream().cuda_stream
     batch = lambda: fixca.fix_ca_frames_dev(src.data_ptr(), pitch, pitch * h, dst.data_ptr(), pitch, pitch * h, nf, w, h, bpp, bpc, p, flags, st)
@@ -110,6 +119,19 @@ if __name__ == "__main__":
         run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
         run("8K rgba16 linear fast", 4320, 7680, 4, torch.int16, 2, 1, F, lens=(658, 1280))
         run("33MP rgba8 cubic fast", 4320, 7680, 4, torch.uint8, 1, 2, F)
+        run("50MP rgb f32 cubic fast", 6144, 8192, 3, torch.float32, -4, 2, F)
+        run("50MP rgba f32 cubic fast", 6144, 8192, 4, torch.float32, -4, 2, F)
+    if which == "ab":       # the A/B set of the r02 kernel work: RGB8 first, then one of every other layout
+        run_batch("4K rgb8 cubic", 64, 2160, 3840, 3, torch.uint8, 1, 2, F)
+        run("4K rgb8 cubic fast", 2160, 3840, 3, torch.uint8, 1, 2, F)
+        run("24MP rgb8 cubic fast", 4000, 6000, 3, torch.uint8, 1, 2, F)
+        run("24MP rgb8 linear fast", 4000, 6000, 3, torch.uint8, 1, 1, F)
+        run("24MP rgb8 none", 4000, 6000, 3, torch.uint8, 1, 0, E)
+        run("33MP rgba8 cubic fast", 4320, 7680, 4, torch.uint8, 1, 2, F)
+        run("100MP rgb16 cubic fast", 8192, 12288, 3, torch.int16, 2, 2, F)
+        run("100MP rgb16 linear fast", 8192, 12288, 3, torch.int16, 2, 1, F)
+        run("100MP rgb16 none", 8192, 12288, 3, torch.int16, 2, 0, E)
+        run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
         run("50MP rgb f32 cubic fast", 6144, 8192, 3, torch.float32, -4, 2, F)
         run("50MP rgba f32 cubic fast", 6144, 8192, 4, torch.float32, -4, 2, F)
     if which == "rgb8":

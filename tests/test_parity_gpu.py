@@ -640,10 +640,16 @@ def test_full_size_fast_within_one_lsb(fx, checker, name, h, w, ch, dtype, kw, t
     band = np.zeros_like(img)
     fx.correct(img, p, y1=y1, y2=y2, out=band, flags=fx.PRECISION_FAST)
     assert (band[y1:y2] == full[y1:y2]).all()
-    # the per-tile fallback kernel shares the arithmetic (same weights, same FMA order): same bytes
+    # the per-tile fallback kernel shares the arithmetic (same weights, same FMA order): same bytes for integer
+    # samples; float samples agree within the tolerance (columns whose taps are clamped to an image edge add the
+    # merged weights in a different order)
     tuning("FIXCA_FAST_KERNEL", "strip")
     fx.correct(img, p, y1=y1, y2=y2, out=band, flags=fx.PRECISION_FAST)
-    assert fx.last_kernel().startswith("strip") and (band[y1:y2] == full[y1:y2]).all()
+    assert fx.last_kernel().startswith("strip")
+    if dtype == "f4":
+        assert _absdiff(band[y1:y2], full[y1:y2]).max() <= FLOAT_ABS_TOL
+    else:
+        assert (band[y1:y2] == full[y1:y2]).all()
 
 
 def test_cfg5_frame_batch_full_size(fx, checker):
