@@ -904,8 +904,8 @@ struct DeviceCtx {
 	int dev = -1;
 	bool ready = false;
 	cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
-	unsigned char *d_src = nullptr, *d_dst = nullptr;
-	size_t d_src_cap = 0, d_dst_cap = 0;
+	unsigned char *d_src = nullptr, *d_dst = nullptr, *d_aux = nullptr;	// d_aux: the preview's 8-bit window
+	size_t d_src_cap = 0, d_dst_cap = 0, d_aux_cap = 0;
 	unsigned char *h_in = nullptr, *h_out = nullptr;	// pinned staging rings
 	size_t h_in_cap = 0, h_out_cap = 0;
 	std::vector<cudaEvent_t> events;
@@ -955,10 +955,11 @@ struct DeviceCtx {
 		events.clear();
 		if (d_src) cudaFree(d_src);
 		if (d_dst) cudaFree(d_dst);
+		if (d_aux) cudaFree(d_aux);
 		if (h_in) cudaFreeHost(h_in);
 		if (h_out) cudaFreeHost(h_out);
-		d_src = d_dst = h_in = h_out = nullptr;
-		d_src_cap = d_dst_cap = h_in_cap = h_out_cap = 0;
+		d_src = d_dst = d_aux = h_in = h_out = nullptr;
+		d_src_cap = d_dst_cap = d_aux_cap = h_in_cap = h_out_cap = 0;
 		cudaStreamDestroy(s_up); cudaStreamDestroy(s_run); cudaStreamDestroy(s_down);
 		ready = false;
 	}
@@ -1082,13 +1083,17 @@ static int copy_threads()
 // One band [y1,y2) of a host image on one device: upload the source rows the
 // band reads, run, download.  Rows move in chunks so that H2D of chunk i+1,
 // the kernel of chunk i and D2H of chunk i-1 overlap (PCIe is full duplex).
+// preview_update()'s 8-bit window (fix-ca.c:659-671): when given, `dst` of the band call is the tight 8-bit buffer of
+// window columns [x, x + pw) (row y1 first) instead of the full-precision image
+struct Window8 { int x, pw; };
+
 static int region_host_band_locked(DeviceCtx &cx, int dev, const unsigned char *src, unsigned char *dst, int width, int height,
 				   const Format &f, const fixca_params *params, const Geometry &g,
-				   int x1, int x2, int y1, int y2, unsigned flags, bool progress);
+				   int x1, int x2, int y1, int y2, unsigned flags, bool progress, const Window8 *w8);
 
 static int region_host_band(int dev, const unsigned char *src, unsigned char *dst, int width, int height,
 			    const Format &f, const fixca_params *params, const Geometry &g,
-			    int x1, int x2, int y1, int y2, unsigned flags, bool progress)
+			    int x1, int x2, int y1, int y2, unsigned flags, bool progress, const Window8 *w8 = nullptr)
 {
 	if (dev < 0 || dev >= 16)
 		return fail(FIXCA_ERR_NO_DEVICE, "device ordinal %d out of range", dev);
@@ -1097,7 +1102,7 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 	int rc;
 	if ((rc = cx.init(dev))) return rc;
 	CUDA_TRY(cudaSetDevice(dev));
-	rc = region_host_band_locked(cx, dev, src, dst, width, height, f, params, g, x1, x2, y1, y2, flags, progress);
+	rc = region_host_band_locked(cx, dev, src, dst, width, height, f, params, g, x1, x2, y1, y2, flags, progress, w8);
 	if (rc) {
 		// leave no copy in flight behind an error: H2D may still read the pinned ring, D2H may still write the
 		// caller's dst, and both outlive this call's lock (the error text of the failure is kept)
@@ -1114,7 +1119,7 @@ static int region_host_band(int dev, const unsigned char *src, unsigned char *ds
 
 static int region_host_band_locked(DeviceCtx &cx, int dev, const unsigned char *src, unsigned char *dst, int width, int height,
 				   const Format &f, const fixca_params *params, const Geometry &g,
-				   int x1, int x2, int y1, int y2, unsigned flags, bool progress)
+				   int x1, int x2, int y1, int y2, unsigned flags, bool progress, const Window8 *w8)
 {
 	int rc;
 
@@ -1123,17 +1128,24 @@ static int region_host_band_locked(DeviceCtx &cx, int dev, const unsigned char *
 	// FIXCA_COLUMN_SELECTION: the rows are computed full width on the device (a pixel's arithmetic does not
 	// depend on x1 / x2, fix-ca.c:1105-1320) and only columns [x1,x2) come back
 	const size_t sel_off = (size_t)x1 * f.bpp, sel_bytes = (size_t)(x2 - x1) * f.bpp;
+	// what comes back, and where it goes in the caller's buffer: the full-precision rows at their place in the image,
+	// or (w8) the tight 8-bit window whose first row is image row y1
+	const size_t o_row = w8 ? (size_t)w8->pw * f.nch : row_bytes;	// host row stride of dst
+	const size_t o_off = w8 ? 0 : sel_off;
+	const size_t o_bytes = w8 ? o_row : sel_bytes;			// bytes per row that come back
+	const int o_y0 = w8 ? y1 : 0;					// dst row 0 is image row o_y0
 	int band_lo, band_hi;
 	source_rows(g, y1, y2, band_lo, band_hi);
 	const int src_rows = band_hi - band_lo + 1;
 	if ((rc = cx.reserve_dev(cx.d_src, cx.d_src_cap, pitch * src_rows))) return rc;
 	if ((rc = cx.reserve_dev(cx.d_dst, cx.d_dst_cap, pitch * (size_t)(y2 - y1)))) return rc;
+	if (w8 && (rc = cx.reserve_dev(cx.d_aux, cx.d_aux_cap, o_row * (size_t)(y2 - y1)))) return rc;
 
 	// Chunking: ~32 MB (pinned caller) / ~16 MB (pageable caller) of rows per chunk (FIXCA_CHUNK_MB), at least 64 rows, a multiple of 8 rows (the
 	// streaming kernel's chunk height, so every launch of the band shares one chunk grid), at most 256 chunks.
 	// look at the first rows actually touched: callers may pass a whole-image base pointer of
 	// which only this band's rows are backed by memory
-	const bool src_pinned = is_pinned(src + (size_t)band_lo * row_bytes), dst_pinned = is_pinned(dst + (size_t)y1 * row_bytes + sel_off);
+	const bool src_pinned = is_pinned(src + (size_t)band_lo * row_bytes), dst_pinned = is_pinned(dst + (size_t)(y1 - o_y0) * o_row + o_off);
 	// (pageable callers: smaller chunks, the staging copies of a chunk are not overlapped with its own transfers;
 	// measured on 100 MP RGB16: 16 MB 27.3 ms, 32 MB 28.7 ms, 64 MB 41.9 ms)
 	const size_t chunk_bytes = (size_t)(tuning().chunk_mb > 0 ? tuning().chunk_mb : (src_pinned && dst_pinned) ? 32 : 16) << 20;
@@ -1161,7 +1173,7 @@ static int region_host_band_locked(DeviceCtx &cx, int dev, const unsigned char *
 		if ((rc = cx.reserve_pinned(cx.h_in, cx.h_in_cap, in_slot * ring))) return rc;
 	}
 	if (!dst_pinned) {
-		out_slot = (size_t)chunk_rows * sel_bytes;
+		out_slot = (size_t)chunk_rows * o_bytes;
 		if ((rc = cx.reserve_pinned(cx.h_out, cx.h_out_cap, out_slot * ring))) return rc;
 	}
 
@@ -1182,11 +1194,11 @@ static int region_host_band_locked(DeviceCtx &cx, int dev, const unsigned char *
 		CUDA_TRY(cudaEventSynchronize(e_down));
 		if (!dst_pinned) {
 			const unsigned char *slot = cx.h_out + (size_t)(i % ring) * out_slot;
-			if (sel_bytes == row_bytes)
-				pool.copy(dst + (size_t)chunk_y1[i] * row_bytes, slot, (size_t)(chunk_y2[i] - chunk_y1[i]) * row_bytes);
+			if (o_bytes == o_row)
+				pool.copy(dst + (size_t)(chunk_y1[i] - o_y0) * o_row, slot, (size_t)(chunk_y2[i] - chunk_y1[i]) * o_row);
 			else
 				for (int y = chunk_y1[i]; y < chunk_y2[i]; ++y)
-					memcpy(dst + (size_t)y * row_bytes + sel_off, slot + (size_t)(y - chunk_y1[i]) * sel_bytes, sel_bytes);
+					memcpy(dst + (size_t)(y - o_y0) * o_row + o_off, slot + (size_t)(y - chunk_y1[i]) * o_bytes, o_bytes);
 		}
 		if (progress && g_progress)
 			for (int y = chunk_y1[i]; y < chunk_y2[i]; ++y)
@@ -1230,11 +1242,17 @@ static int region_host_band_locked(DeviceCtx &cx, int dev, const unsigned char *
 						(int)params->lens_x, (int)params->lens_y, params->saturation, cx.s_run));
 			g_launches.fetch_add(1);
 		}
+		if (w8) {	// fix-ca.c:659-671: the window's samples as 8-bit
+			CUDA_TRY(launch_to8(f.kind, f.nch, cx.d_dst, (long long)pitch, y1, c1, c2, w8->x, w8->pw, f.bpp,
+					    cx.d_aux + (size_t)(c1 - y1) * o_row, cx.s_run));
+			g_launches.fetch_add(1);
+		}
 		CUDA_TRY(cudaEventRecord(e_run, cx.s_run));
 		CUDA_TRY(cudaStreamWaitEvent(cx.s_down, e_run, 0));
-		unsigned char *to = dst_pinned ? dst + (size_t)c1 * row_bytes + sel_off : cx.h_out + (size_t)(i % ring) * out_slot;
-		CUDA_TRY(cudaMemcpy2DAsync(to, dst_pinned ? row_bytes : sel_bytes, cx.d_dst + (size_t)(c1 - y1) * pitch + sel_off, pitch,
-					   sel_bytes, c2 - c1, cudaMemcpyDeviceToHost, cx.s_down));
+		unsigned char *to = dst_pinned ? dst + (size_t)(c1 - o_y0) * o_row + o_off : cx.h_out + (size_t)(i % ring) * out_slot;
+		const unsigned char *from_dev = w8 ? cx.d_aux + (size_t)(c1 - y1) * o_row : cx.d_dst + (size_t)(c1 - y1) * pitch + sel_off;
+		CUDA_TRY(cudaMemcpy2DAsync(to, dst_pinned ? o_row : o_bytes, from_dev, w8 ? o_row : pitch,
+					   o_bytes, c2 - c1, cudaMemcpyDeviceToHost, cx.s_down));
 		CUDA_TRY(cudaEventRecord(e_down, cx.s_down));
 	}
 	for (int i = std::max(0, nchunks - ring); i < nchunks; ++i)
@@ -1283,6 +1301,36 @@ extern "C" int fixca_cuda_region_ex(const unsigned char *src, unsigned char *dst
 	tl_last_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	if (prev >= 0)
 		cudaSetDevice(prev);
+	return rc;
+}
+
+// preview_update()'s middle in one call (fix-ca.c:656-671): the pass over rows [y, y + ph) with the preview overlay,
+// then the 8-bit down-conversion of window columns [x, x + pw); only the window's bytes come back.
+extern "C" int fixca_cuda_preview(const unsigned char *src, unsigned char *prev, int width, int height,
+				  int bytes, int bpc, const fixca_params *params, int x, int y, int pw, int ph)
+{
+	Format f;
+	Geometry g;
+	if (x < 0 || pw <= 0 || x + pw > width || ph < 0)
+		return fail(FIXCA_ERR_ARG, "preview window %d+%d x %d+%d outside the %dx%d image", x, pw, y, ph, width, height);
+	const unsigned flags = (tuning().precision_fast ? FIXCA_PRECISION_FAST : FIXCA_PRECISION_EXACT) | FIXCA_PREVIEW_OVERLAY;
+	int rc = host_prologue(src, prev, width, height, bytes, bpc, params, 0, width, y, y + ph, f, g, flags,
+			       ALLOW_PREVIEW, "fixca_cuda_preview");
+	if (rc) return rc;
+	if (f.kind == SK_U64)
+		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples: the 8-bit preview needs 80-bit long double arithmetic (fix-ca.c:728-733)");
+	int dev;
+	if ((rc = current_device_or(-1, dev))) return rc;
+	if (ph == 0)
+		return FIXCA_OK;
+	int prevdev = -1;
+	cudaGetDevice(&prevdev);
+	const Window8 w8 = {x, pw};
+	const auto t0 = std::chrono::steady_clock::now();
+	rc = region_host_band(dev, src, prev, width, height, f, params, g, 0, width, y, y + ph, flags, false, &w8);
+	tl_last_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	if (prevdev >= 0)
+		cudaSetDevice(prevdev);
 	return rc;
 }
 

@@ -62,4 +62,8 @@ const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int
 cudaError_t launch_preview(int kind, int nch, unsigned char *dst, long long pitch, int dst_row0, int y1, int y2, int width,
 			   int xc, int yc, double saturation, cudaStream_t st);
 
+// kernels_preview.cu: the 8-bit preview buffer (fix-ca.c:659-671) of window columns [x, x + pw) of corrected rows [y1, y2)
+cudaError_t launch_to8(int kind, int nch, const unsigned char *src, long long pitch, int src_row0, int y1, int y2, int x, int pw,
+		       int bpp, unsigned char *out, cudaStream_t st);
+
 } // namespace fixca

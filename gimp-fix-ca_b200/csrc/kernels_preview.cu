@@ -180,7 +180,73 @@ cudaError_t launch_s(int nch, const PreviewArgs &a, cudaStream_t st)
 	return cudaGetLastError();
 }
 
+// preview_update()'s down-conversion (fix-ca.c:659-671): every sample of the preview window goes through
+// get_pixel() and set_pixel(..., 1), i.e. round(v / max * 255) stored into a guchar (no clip_d: pass-through
+// samples of float images may lie outside [0,1], and None copies anything).  The store is C's double -> unsigned
+// char conversion as x86-64 compiles it: truncate to a 32-bit int (out of range / NaN -> INT_MIN), keep the low byte.
+struct To8Args {
+	const unsigned char *src;	// row src_row0 of the corrected rows
+	long long pitch;
+	int src_row0, y1, y2;		// rows [y1, y2)
+	int x, samples;			// first column of the window, samples (pixels * channels) per window row
+	unsigned char *out;		// row y1 of the window, tight rows of `samples` bytes
+	int bpp;
+};
+
+template <class S>
+__global__ void __launch_bounds__(256) to8_kernel(const To8Args a)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = a.y1 + blockIdx.y;
+	if (j >= a.samples || y >= a.y2)
+		return;
+	const S *row = reinterpret_cast<const S *>(a.src + (long long)(y - a.src_row0) * a.pitch + (long long)a.x * a.bpp);
+	const double v = round(Norm<S>::get(row[j]) * 255.0);
+	const int iv = (v >= -2147483648.0 && v < 2147483648.0) ? (int)v : (int)0x80000000;
+	a.out[(long long)(y - a.y1) * a.samples + j] = (unsigned char)iv;
+}
+template <>
+__global__ void __launch_bounds__(256) to8_kernel<uint8_t>(const To8Args a)	// b == 1: a memcpy in the reference (:661-664)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = a.y1 + blockIdx.y;
+	if (j >= a.samples || y >= a.y2)
+		return;
+	a.out[(long long)(y - a.y1) * a.samples + j] = a.src[(long long)(y - a.src_row0) * a.pitch + (long long)a.x * a.bpp + j];
+}
+
+template <class S>
+cudaError_t launch_to8_s(To8Args a, cudaStream_t st)
+{
+	for (int y = a.y1; y < a.y2; y += 32768) {
+		To8Args b = a;
+		b.y1 = y;
+		b.y2 = y + 32768 < a.y2 ? y + 32768 : a.y2;
+		b.out = a.out + (long long)(y - a.y1) * a.samples;
+		to8_kernel<S><<<dim3((a.samples + 255) / 256, b.y2 - b.y1), 256, 0, st>>>(b);
+	}
+	return cudaGetLastError();
+}
+
 } // namespace
+
+// The 8-bit preview buffer of window columns [x, x + pw) of corrected rows [y1, y2) (fix-ca.c:659-671).
+cudaError_t launch_to8(int kind, int nch, const unsigned char *src, long long pitch, int src_row0, int y1, int y2, int x, int pw,
+		       int bpp, unsigned char *out, cudaStream_t st)
+{
+	To8Args a;
+	a.src = src; a.pitch = pitch; a.src_row0 = src_row0; a.y1 = y1; a.y2 = y2; a.x = x; a.samples = pw * nch; a.out = out; a.bpp = bpp;
+	switch (kind) {
+	case SK_U8:  return launch_to8_s<uint8_t>(a, st);
+	case SK_U16: return launch_to8_s<uint16_t>(a, st);
+	case SK_U32: return launch_to8_s<uint32_t>(a, st);
+	case SK_F32: return launch_to8_s<float>(a, st);
+	case SK_F64: return launch_to8_s<double>(a, st);
+	case SK_F16: return launch_to8_s<__half>(a, st);
+	case SK_U15: return launch_to8_s<u15_t>(a, st);
+	default: return cudaErrorInvalidValue;	// u64: 80-bit long double in the reference
+	}
+}
 
 // Applies the preview epilogue to destination rows [y1, y2) in place.  kind: SampleKind.
 cudaError_t launch_preview(int kind, int nch, unsigned char *dst, long long pitch, int dst_row0, int y1, int y2, int width,

@@ -44,7 +44,7 @@ EXPORTS = (
     "fixca_cuda_last_error", "fixca_strerror", "fixca_cuda_device_count", "fixca_cuda_last_kernel",
     "fixca_cuda_launch_count", "fixca_cuda_release", "fixca_version",
     "fixca_cuda_frames_multi", "fixca_cuda_frame_alloc", "fixca_cuda_frame_open", "fixca_cuda_frame_close", "fixca_cuda_frame_free",
-    "fixca_cuda_host_alloc", "fixca_cuda_host_free", "fixca_cuda_reload_tuning", "fixca_color_size_ext", "fixca_cuda_last_call_ms",
+    "fixca_cuda_host_alloc", "fixca_cuda_host_free", "fixca_cuda_reload_tuning", "fixca_color_size_ext", "fixca_cuda_last_call_ms", "fixca_cuda_preview",
 )
 BPC_HALF, BPC_U15 = -2, 15
 IPC_HANDLE_BYTES = 64
@@ -96,6 +96,7 @@ def load() -> ctypes.CDLL:
     L = ctypes.CDLL(LIB_PATH)
     i, vp, pp = ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(FixCaParams)
     L.fixca_cuda_region.argtypes = [vp, vp, i, i, i, i, pp, i, i, i, i, i]
+    L.fixca_cuda_preview.argtypes = [vp, vp, i, i, i, i, pp, i, i, i, i]
     L.fixca_cuda_region_ex.argtypes = [vp, vp, i, i, i, i, pp, i, i, i, i, i, ctypes.c_uint, i]
     L.fixca_cuda_region_multi.argtypes = [vp, vp, i, i, i, i, pp, i, i, ctypes.c_uint, ctypes.POINTER(i), i]
     L.fixca_cuda_region_dev.argtypes = [vp, ctypes.c_size_t, i, i, vp, ctypes.c_size_t, i, i, i, i, i, pp, i, i,
@@ -170,6 +171,16 @@ def fix_ca_region(src, dst, orig_width, orig_height, bytes, bpc, params, x1, x2,
         rc = L.fixca_cuda_region_ex(s, d, orig_width, orig_height, bytes, bpc, ctypes.byref(params),
                                     x1, x2, y1, y2, 1 if show_progress else 0, flags, device)
     _check(rc)
+
+
+def preview(image: np.ndarray, params: FixCaParams, x: int, y: int, pw: int, ph: int, bpc=None) -> np.ndarray:
+    """preview_update()'s middle (fix-ca.c:656-671): the 8-bit preview buffer of window (x, y, pw, ph), shape
+    (ph, pw, channels): correction + saturation boost + centre lines + get_pixel / set_pixel(.., 1)."""
+    h, w, ch = image.shape
+    out = np.zeros((ph, pw, ch), dtype=np.uint8)
+    _check(load().fixca_cuda_preview(image.ctypes.data, out.ctypes.data, w, h, ch * image.dtype.itemsize,
+                                     bpc_of(image.dtype) if bpc is None else bpc, ctypes.byref(params), x, y, pw, ph))
+    return out
 
 
 def correct(image: np.ndarray, params: FixCaParams, y1=None, y2=None, out=None, flags=PRECISION_EXACT,

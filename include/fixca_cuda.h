@@ -151,6 +151,16 @@ FIXCA_API int fixca_cuda_region(const unsigned char *src, unsigned char *dst,
 				const fixca_params *params,
 				int x1, int x2, int y1, int y2, int show_progress);
 
+/*
+ * The middle of preview_update() in one call (fix-ca.c:656-671): fix_ca_region(src, dest, ..., 0, width, y, y + ph,
+ * FALSE) -- the pass over the preview's rows with the saturation boost and the centre lines -- followed by the
+ * down-conversion of window columns [x, x + pw) to the 8-bit buffer the plug-in hands to
+ * gimp_preview_draw_buffer(): every sample through get_pixel() and set_pixel(..., 1) (8-bit drawables: a copy).
+ * `prev` is pw * ph * channels bytes, tight rows; only those bytes come back from the GPU (no destImg at all).
+ */
+FIXCA_API int fixca_cuda_preview(const unsigned char *src, unsigned char *prev, int width, int height,
+				 int bytes, int bpc, const fixca_params *params, int x, int y, int pw, int ph);
+
 /* As above with FIXCA_* flags and an explicit CUDA device ordinal (-1 = current). */
 FIXCA_API int fixca_cuda_region_ex(const unsigned char *src, unsigned char *dst,
 				   int width, int height, int bytes, int bpc,

@@ -73,12 +73,20 @@ CALL_BLOCK = r'''
 
 PREVIEW_BLOCK = r'''
 #ifdef HAVE_FIXCA_CUDA
-	/* show_progress = FALSE: the library draws the saturation boost and the centre lines as well */
+	/* the pass with show_progress = FALSE (saturation boost and centre lines included) and the 8-bit
+	 * down-conversion of the window, on the GPU; only the window's bytes come back */
+	b = bpcImg < 0 ? -bpcImg : bpcImg;
 	if (fixca_cuda_device_count () > 0 &&
-	    fixca_cuda_region (srcImg, destImg, xImg, yImg, bppImg, bpcImg, (const fixca_params *) params,
-			       0, xImg, y, y + height, FALSE) == 0)
+	    fixca_cuda_preview (srcImg, prevImg, xImg, yImg, bppImg, bpcImg, (const fixca_params *) params,
+				x, y, width, height) == 0)
 		;
-	else
+	else {
+#endif
+'''
+
+PREVIEW_END = r'''
+#ifdef HAVE_FIXCA_CUDA
+	}
 #endif
 '''
 
@@ -100,7 +108,9 @@ def patch(text: str) -> str:
     if len(calls) != 1:
         raise SystemExit("patch_plugin: expected exactly one preview call, found %d" % len(calls))
     c = calls[0]
-    text = text[:c.start()] + "\n" + PREVIEW_BLOCK.strip("\n") + text[c.start():]
+    end = text.index("\n\tgimp_preview_draw_buffer (ptr, prevImg", c.end())     # after the conversion loop (:659-671)
+    text = (text[:c.start()] + "\n" + PREVIEW_BLOCK.strip("\n") + text[c.start():end] + "\n" + PREVIEW_END.strip("\n") +
+            text[end:])
     # (4) the whole-image buffers of fix_ca() and preview_update() (fix-ca.c:366-367, :648-649 and their g_free's)
     text, n_new = re.subn(r'\b(srcImg|destImg)(\s*)= g_new \(guchar, ([^;]*)\);', r'\1\2= FIXCA_IMG_NEW (\3);', text)
     text, n_free = re.subn(r'\bg_free ?\((srcImg|destImg)\);', r'FIXCA_IMG_FREE (\1);', text)

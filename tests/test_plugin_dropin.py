@@ -83,12 +83,15 @@ def _compare_previews(plugins, expect_gpu):
 
     ref, patched = plugins
     n = 0
-    for (shape, dt, fmt), (win, sat, interp, lens) in [(d, c) for d in DRAWABLES[:3] for c in PREVIEWS]:
+    for (shape, dt, fmt), (win, sat, interp, lens) in [(d, c) for d in DRAWABLES for c in PREVIEWS]:
         n += 1
         h, w = shape[0], shape[1]
         x, y, ww, hh = win
         ww, hh = min(ww, w - x), min(hh, h - y)
-        img = orc.synth_image(h, w, shape[2], dt, seed=8000 + n)
+        if ww <= 0 or hh <= 0:
+            continue        # the window lies outside this (small) drawable
+        # float drawables: also samples outside [0,1] (pass-through channels are not clipped; set_pixel(.., 1) wraps them)
+        img = orc.synth_image(h, w, shape[2], dt, seed=8000 + n, wide=bool(n % 2))
         P = orc.Params(blue=3.0, red=-2.0, lens_x=lens[0], lens_y=lens[1], interpolation=interp, saturation=sat,
                        x_blue=0.7, y_red=-0.9)
         want = ref.preview_update(img.copy(), fmt, x, y, ww, hh, P)
