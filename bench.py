@@ -397,6 +397,7 @@ def strong_scaling_record(name, torch, dist, fixca, dev, rank, world, barrier, m
     barrier()
     par = split.get("parity")
     split["parity"] = merge_parity(par, world, dist, dev)
+    split["parity"]["what"] = "three row bands (top / middle / bottom) of every rank's device-resident band of the one image"
     if rank != 0:
         return None
     t1, tn, tf = one["ms_per_step"], split["ms_per_step"], tiny["ms_per_step"]
@@ -737,12 +738,101 @@ def run_cuda(args):
             remote["ok"] = bool(remote["ranks_checked"] == world - 1 and remote["max_abs_diff"] <= remote["tolerance"])
         del ft
         frame.close()
+
+        # two roots: the frame's upper half lives on rank 0, its lower half on rank world/2 -- each rank's kernel
+        # stores into the root that owns its rows, so the bytes enter through two GPUs' NVLink ports instead of one
+        two = None
+        if world >= 4 and world % 2 == 0:
+            half_rows = (y2 - y1) * (world // 2)
+            roots = (0, world // 2)
+            fr = [bands.PeerFrame(half_rows, pitch, owner=roots[k], row0=k * half_rows) for k in range(2)]
+            mine_fr = fr[0] if rank < world // 2 else fr[1]
+
+            def two_step():
+                bands.run_band_into_frame(plan, d_src.data_ptr(), pitch, mine_fr, bpp, bpc, p, flags, stream.cuda_stream)
+
+            for _ in range(3):
+                two_step()
+            ttimes = []
+            for rep in range(6):
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
+                two_step()
+                g1.record(stream)
+                barrier()
+                ttimes.append(max_over_ranks(g0.elapsed_time(g1)))
+            fr[0].sync()
+            ok2 = 1.0
+            if rank in roots:       # each root compares its own band as it sits in its half frame with its d_dst
+                t = mine_fr.as_tensor()
+                ok2 = 1.0 if torch.equal(t[y1 - mine_fr.row0:y2 - mine_fr.row0, :row_bytes], d_dst[:, :row_bytes]) else 0.0
+            okt = torch.tensor([ok2], dtype=torch.float64, device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            for f2 in fr:
+                f2.close()
+            in_per_root = (world // 2 - 1) * (y2 - y1) * pitch
+            two = {"ms": round(min(ttimes), 3), "roots": list(roots), "gbs_into_each_root": round(in_per_root / (min(ttimes) * 1e-3) / 1e9, 1),
+                   "gbs_total": round(2 * in_per_root / (min(ttimes) * 1e-3) / 1e9, 1), "roots_own_rows_intact": bool(okt.item() == 1.0)}
+
+        # all-gather form: every rank owns a whole frame; every kernel stores each finished chunk into all of them
+        # (its own through HBM, the others over NVLink) in the same launch.  Checked against NCCL's all_gather.
+        allf = bands.AllFrames(H, pitch)
+
+        def all_step():
+            bands.run_band_into_all(plan, d_src.data_ptr(), pitch, allf, bpp, bpc, p, flags, stream.cuda_stream)
+
+        for _ in range(2):
+            all_step()
+        atimes = []
+        for rep in range(5):
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            all_step()
+            g1.record(stream)
+            barrier()
+            atimes.append(max_over_ranks(g0.elapsed_time(g1)))
+        all_kernel = fixca.last_kernel()
+        allf.sync()
+        parts = [torch.empty_like(d_dst) for _ in range(world)]
+        ntimes = []
+        for rep in range(3):
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            dist.all_gather(parts, d_dst)
+            g1.record(stream)
+            barrier()
+            if rep:
+                ntimes.append(max_over_ranks(g0.elapsed_time(g1)))
+        mine_ok = 1.0
+        at = allf.as_tensor()
+        for r in range(world):
+            if not torch.equal(at[r * (y2 - y1):(r + 1) * (y2 - y1), :row_bytes], parts[r][:, :row_bytes]):
+                mine_ok = 0.0
+        okt = torch.tensor([mine_ok], dtype=torch.float64, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        del parts, at
+        allf.close()
+        in_per_gpu = (world - 1) * (y2 - y1) * pitch
+        allgather = {"ms": round(min(atimes), 3), "median_ms": round(sorted(atimes)[len(atimes) // 2], 3),
+                     "nccl_all_gather_ms": round(min(ntimes), 3),
+                     "gbs_into_each_gpu": round(in_per_gpu / (min(atimes) * 1e-3) / 1e9, 1),
+                     "nvlink_peer_copy_reference_gbs": 770.0, "nvlink_nominal_gbs": 900.0,
+                     "identical_to_nccl_all_gather_on_every_rank": bool(okt.item() == 1.0), "kernel": all_kernel,
+                     "how": "fixca.bands.AllFrames + run_band_into_all (fixca_cuda_region_dev_fanout): every rank's kernel "
+                            "TMA-stores each finished chunk into all %d frames in one launch; NCCL: dist.all_gather of the "
+                            "finished bands after the step" % world}
         remote_bytes = (world - 1) * (y2 - y1) * pitch
         gather.update({"peer_store_ms": round(min(ptimes), 3), "peer_store_median_ms": round(sorted(ptimes)[len(ptimes) // 2], 3),
                        "peer_store_gbs_into_rank0": round(remote_bytes / (min(ptimes) * 1e-3) / 1e9, 1),
                        "identical_to_nccl_gather": same, "kernel": peer_kernel, "remote_rows_parity": remote,
                        "peer_store_how": "fixca.bands.PeerFrame + run_band_into_frame: every rank's kernel TMA-stores its band "
-                                         "into rank 0's frame over NVLink (compute + gather, one kernel); barrier both sides, max over ranks"})
+                                         "into rank 0's frame over NVLink (compute + gather, one kernel); barrier both sides, max over ranks",
+                       "all_gather": allgather})
+        if two is not None:
+            gather["two_roots"] = two
 
     strong_rec = None
     if world > 1 and not strong and not args.no_strong:

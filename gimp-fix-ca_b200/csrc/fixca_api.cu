@@ -211,16 +211,21 @@ struct Plan {
 	size_t smem = 0;
 	// stream kernel: TMA tensor maps of the source (window groups, pass-through tiles) and destination
 	CUtensorMap tm_win, tm_tile, tm_out;
+	StreamFanout fan;	// further destinations of a fan-out launch (fan.n = 0 otherwise)
+	void *fan_dst[STREAM_MAX_FAN];	// their base pointers (row dst_row0), as requested
 	int src_rows_avail = 0;	// rows of the source band present at args.src
 	// a batch of equal frames in one launch (stream kernels: grid.z = frame, 3-D tensor maps)
 	int nframes = 1;
 	size_t src_frame_stride = 0, dst_frame_stride = 0;
 };
 
-// frames of a batch: frame i starts src_stride / dst_stride bytes after frame i - 1
+// frames of a batch: frame i starts src_stride / dst_stride bytes after frame i - 1; fan-out: further destination
+// frames (same pitch and first row as d_dst) every finished chunk is stored into as well
 struct Batch {
 	int nframes = 1;
 	size_t src_stride = 0, dst_stride = 0;
+	int nfan = 0;
+	void *fan[STREAM_MAX_FAN] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -316,6 +321,10 @@ static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_
 			      const Batch &batch)
 {
 	pl = Plan();
+	memset(&pl.fan, 0, sizeof pl.fan);
+	pl.fan.n = batch.nfan;	// taken by the streaming kernels only; the caller loops over destinations otherwise
+	for (int i = 0; i < STREAM_MAX_FAN; ++i)
+		pl.fan_dst[i] = i < batch.nfan ? batch.fan[i] : nullptr;
 	pl.nframes = batch.nframes;
 	pl.src_frame_stride = batch.src_stride;
 	pl.dst_frame_stride = batch.dst_stride;
@@ -341,7 +350,7 @@ static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_
 	bool want_tiled = tma_ok && !(flags & FIXCA_FORCE_DIRECT);
 	// only the streaming kernels take a batch in one launch; every other plan is for one frame and the
 	// caller loops (pl.nframes tells which)
-	struct OneFrame { Plan &p; ~OneFrame() { if (!p.k || !p.k->stream) { p.nframes = 1; p.src_frame_stride = p.dst_frame_stride = 0; } } } one_frame{pl};
+	struct OneFrame { Plan &p; ~OneFrame() { if (!p.k || !p.k->stream) { p.nframes = 1; p.src_frame_stride = p.dst_frame_stride = 0; p.fan.n = 0; } } } one_frame{pl};
 
 	if (want_tiled) {
 		const KernelEntry *k = pick_kernel(f, g.interp, flags, true);
@@ -598,6 +607,10 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	    !make_tensor_map(pl.tm_tile, a.src, (size_t)a.src_pitch, row_bytes, src_rows, nf, sfs, (unsigned)(k->tw * f.bpp), CH) ||
 	    !make_tensor_map(pl.tm_out, a.dst, (size_t)a.dst_pitch, row_bytes, dst_rows, nf, dfs, (unsigned)(k->tw * f.bpp), CH))
 		return false;
+	for (int i = 0; i < pl.fan.n; ++i) {
+		if (!make_tensor_map(pl.fan.tm[i], pl.fan_dst[i], (size_t)a.dst_pitch, row_bytes, dst_rows, nf, dfs, (unsigned)(k->tw * f.bpp), CH))
+			return false;
+	}
 	return true;
 }
 
@@ -617,6 +630,8 @@ struct PlanKey {
 	unsigned env;
 	int nframes;
 	size_t src_frame_stride, dst_frame_stride;
+	int nfan;
+	const void *fan[STREAM_MAX_FAN];
 };
 
 static int make_plan(const Format &f, const Geometry &g, const void *d_src, size_t src_pitch, int src_row0, int src_rows,
@@ -637,6 +652,9 @@ static int make_plan(const Format &f, const Geometry &g, const void *d_src, size
 	k.flags = flags;
 	k.env = (unsigned)tuning().generation;
 	k.nframes = batch.nframes; k.src_frame_stride = batch.src_stride; k.dst_frame_stride = batch.dst_stride;
+	k.nfan = batch.nfan;
+	for (int i = 0; i < batch.nfan; ++i)
+		k.fan[i] = batch.fan[i];
 	constexpr int SLOTS = 96;
 	static thread_local PlanKey keys[SLOTS];
 	static thread_local Plan plans[SLOTS];
@@ -685,7 +703,8 @@ static int launch_plan(const Plan &pl, cudaStream_t stream)
 	}
 	KernelArgs a = pl.args;
 	CUtensorMap tm[3] = {pl.tm_win, pl.tm_tile, pl.tm_out};
-	void *params[] = {&a, &tm[0], &tm[1], &tm[2]};	// the tensor maps are only declared by stream kernels
+	StreamFanout fan = pl.fan;
+	void *params[] = {&a, &tm[0], &tm[1], &tm[2], &fan};	// the tensor maps are only declared by stream kernels
 	if (pl.k->stream && !tuning().no_pdl) {
 		// programmatic dependent launch (see griddep_wait() in fixca_stream.cuh): back-to-back launches in one
 		// stream overlap the next grid's set-up with this grid's tail; memory ordering is unchanged
@@ -794,6 +813,55 @@ extern "C" int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int sr
 		CUDA_TRY(launch_preview(f.kind, f.nch, (unsigned char *)d_dst, (long long)dst_pitch, dst_row0, y1, y2, width,
 					(int)params->lens_x, (int)params->lens_y, params->saturation, (cudaStream_t)stream));
 		g_launches.fetch_add(1);
+	}
+	return FIXCA_OK;
+}
+
+// The band stored into several destination frames at once (the all-gather form of the reassembly): the streaming
+// kernels fan every finished chunk out from shared memory to all frames in one launch; any other kernel is
+// launched once per destination.
+extern "C" int fixca_cuda_region_dev_fanout(const void *d_src, size_t src_pitch, int src_row0, int src_rows,
+					    void *const *d_dsts, int ndst, size_t dst_pitch, int dst_row0,
+					    int width, int height, int bytes, int bpc,
+					    const fixca_params *params, int y1, int y2, unsigned flags, void *stream)
+{
+	if (!d_dsts || ndst < 1 || ndst > STREAM_MAX_FAN + 1)
+		return fail(FIXCA_ERR_ARG, "fan-out over %d destinations (1..%d)", ndst, STREAM_MAX_FAN + 1);
+	for (int i = 0; i < ndst; ++i)
+		if (!d_dsts[i])
+			return fail(FIXCA_ERR_ARG, "fan-out destination %d is NULL", i);
+	int rc = check_common(d_src, d_dsts[0], width, height, params, y1, y2);
+	if (rc) return rc;
+	Format f;
+	if ((rc = parse_format(bytes, bpc, f))) return rc;
+	if ((rc = check_flags(flags, 0, f, params, "fixca_cuda_region_dev_fanout"))) return rc;
+	Geometry g;
+	if ((rc = make_geometry(width, height, params, g))) return rc;
+	if (src_pitch < (size_t)width * bytes || dst_pitch < (size_t)width * bytes)
+		return fail(FIXCA_ERR_ARG, "pitch smaller than a row (%zu / %zu < %zu)", src_pitch, dst_pitch, (size_t)width * bytes);
+	if (y1 == y2)
+		return FIXCA_OK;
+	int lo, hi;
+	source_rows(g, y1, y2, lo, hi);
+	if (src_row0 < 0 || lo < src_row0 || hi >= src_row0 + src_rows || src_row0 + src_rows > height)
+		return fail(FIXCA_ERR_ARG, "source rows [%d,%d) do not cover the rows [%d,%d] that output rows [%d,%d) read",
+			    src_row0, src_row0 + src_rows, lo, hi, y1, y2);
+	if (dst_row0 < 0 || dst_row0 > y1)
+		return fail(FIXCA_ERR_ARG, "dst_row0 %d is past the first output row %d", dst_row0, y1);
+	int dev;
+	if ((rc = current_device_or(-1, dev))) return rc;
+	Batch b;
+	b.nfan = ndst - 1;
+	for (int i = 1; i < ndst; ++i)
+		b.fan[i - 1] = d_dsts[i];
+	Plan pl;
+	if ((rc = make_plan(f, g, d_src, src_pitch, src_row0, src_rows, d_dsts[0], dst_pitch, dst_row0, y1, y2, flags, dev, pl, b))) return rc;
+	if ((rc = launch_plan(pl, (cudaStream_t)stream))) return rc;
+	if (pl.fan.n != ndst - 1) {	// not a streaming kernel: one launch per remaining destination
+		for (int i = 1; i < ndst; ++i) {
+			if ((rc = make_plan(f, g, d_src, src_pitch, src_row0, src_rows, d_dsts[i], dst_pitch, dst_row0, y1, y2, flags, dev, pl))) return rc;
+			if ((rc = launch_plan(pl, (cudaStream_t)stream))) return rc;
+		}
 	}
 	return FIXCA_OK;
 }

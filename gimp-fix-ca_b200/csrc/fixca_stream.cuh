@@ -68,6 +68,15 @@ constexpr int STREAM_MAX_NF = STREAM_MAX_D + 1;
 constexpr int STREAM_NSTG = 3;
 #define STREAM_COL_SLACK(P) ((P) + 4)	// >= NS = P + taps: pixels of window slack per side (host and device)
 
+// Fan-out (the all-gather form of the reassembly): besides tm_out, every finished chunk is stored
+// into up to STREAM_MAX_FAN further destination frames -- other GPUs' copies of the frame, mapped over NVLink -- by
+// the same TMA lane, from the same staging buffer.  n = 0 for every ordinary launch.
+constexpr int STREAM_MAX_FAN = 7;
+struct alignas(64) StreamFanout {
+	CUtensorMap tm[STREAM_MAX_FAN];
+	int n;
+};
+
 struct StreamMeta {
 	float4 wy[STREAM_CH][2];	// vertical weights per output row and channel, by tap position (position_weights)
 	int    last[2][STREAM_CH + 1];	// highest tap row of each output row (INT_MAX after the chunk's last row)
@@ -155,12 +164,14 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *tm)
 // tm_win   source image, box = win_pitch bytes x 4 rows     (window ring groups)
 // tm_tile  source image, box = TW * BPP bytes x CH rows      (pass-through pixels of a chunk)
 // tm_out   destination rows [dst_row0, y2), same box         (finished chunks; clipped at y2 and at the row end)
+// fan      further destinations of the same geometry (fan-out / all-gather form), usually none
 // All three are 3-D maps (8-byte elements x rows x frames of a batch, blockIdx.z = frame) over rows of
 // align16(width * BPP) bytes; row coordinates are relative to src_row0 / dst_row0.
 template <class S, int NCH, int INTERP, int P, int TW, bool ALT = false>
 __global__ void __launch_bounds__(2 * TW / P + 64, (2 * TW / P + 64) <= 192 ? 4 : 2)	// register budget: 4 (2) resident CTAs
 stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUtensorMap tm_win,
-	      const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ CUtensorMap tm_out)
+	      const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ CUtensorMap tm_out,
+	      const __grid_constant__ StreamFanout fan)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	constexpr int BPP = NCH * (int)sizeof(S);
@@ -298,6 +309,8 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		prefetch_tensormap(&tm_win);
 		prefetch_tensormap(&tm_tile);
 		prefetch_tensormap(&tm_out);
+		for (int e = 0; e < fan.n; ++e)
+			prefetch_tensormap(&fan.tm[e]);
 		const int NRG = NR >> 2;		// ring capacity in 4-row groups
 		const int group_bytes = 4 * wpitch;
 		const int c0_win = wb0 >> 3, c0_tile = (x0 * BPP) >> 3;
@@ -339,6 +352,8 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				request_tile(j + 1);
 			mbar_wait_sleepy(&done[jnf], (uint32_t)jpar, 500u);
 			tma_store_3d(&tm_out, c0_tile, ya + j * CH - a.dst_row0, frame, stage + jstg * STAGE_BYTES);
+			for (int e = 0; e < fan.n; ++e)		// the same chunk into the other frames (peer GPUs, over NVLink)
+				tma_store_3d(&fan.tm[e], c0_tile, ya + j * CH - a.dst_row0, frame, stage + jstg * STAGE_BYTES);
 			bulk_commit();
 			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
 			jstg = jstg + 1 == NSTG ? 0 : jstg + 1;

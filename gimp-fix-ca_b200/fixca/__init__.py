@@ -44,7 +44,7 @@ EXPORTS = (
     "fixca_cuda_last_error", "fixca_strerror", "fixca_cuda_device_count", "fixca_cuda_last_kernel",
     "fixca_cuda_launch_count", "fixca_cuda_release", "fixca_version",
     "fixca_cuda_frames_multi", "fixca_cuda_frame_alloc", "fixca_cuda_frame_open", "fixca_cuda_frame_close", "fixca_cuda_frame_free",
-    "fixca_cuda_host_alloc", "fixca_cuda_host_free", "fixca_cuda_reload_tuning", "fixca_color_size_ext", "fixca_cuda_last_call_ms", "fixca_cuda_preview",
+    "fixca_cuda_host_alloc", "fixca_cuda_host_free", "fixca_cuda_reload_tuning", "fixca_color_size_ext", "fixca_cuda_last_call_ms", "fixca_cuda_preview", "fixca_cuda_region_dev_fanout",
 )
 BPC_HALF, BPC_U15 = -2, 15
 IPC_HANDLE_BYTES = 64
@@ -101,6 +101,8 @@ def load() -> ctypes.CDLL:
     L.fixca_cuda_region_multi.argtypes = [vp, vp, i, i, i, i, pp, i, i, ctypes.c_uint, ctypes.POINTER(i), i]
     L.fixca_cuda_region_dev.argtypes = [vp, ctypes.c_size_t, i, i, vp, ctypes.c_size_t, i, i, i, i, i, pp, i, i,
                                         ctypes.c_uint, vp]
+    L.fixca_cuda_region_dev_fanout.argtypes = [vp, ctypes.c_size_t, i, i, ctypes.POINTER(vp), i, ctypes.c_size_t, i, i, i, i, i, pp,
+                                               i, i, ctypes.c_uint, vp]
     L.fixca_cuda_frames.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), i, i, i, i, i, pp, ctypes.c_uint, i]
     L.fixca_cuda_frames_multi.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), i, i, i, i, i, pp, ctypes.c_uint,
                                           ctypes.POINTER(i), i]
@@ -210,6 +212,16 @@ def fix_ca_region_dev(d_src: int, src_pitch: int, src_row0: int, src_rows: int, 
     """Device-resident pass (raw CUDA pointers, asynchronous on ``stream``)."""
     _check(load().fixca_cuda_region_dev(d_src, src_pitch, src_row0, src_rows, d_dst, dst_pitch, dst_row0,
                                         width, height, bytes, bpc, ctypes.byref(params), y1, y2, flags, stream))
+
+
+def fix_ca_region_dev_fanout(d_src: int, src_pitch: int, src_row0: int, src_rows: int, d_dsts, dst_pitch: int,
+                             dst_row0: int, width: int, height: int, bytes: int, bpc: int, params: FixCaParams,
+                             y1: int, y2: int, flags: int = PRECISION_EXACT, stream: int = 0) -> None:
+    """The device-resident pass with several destination frames (raw CUDA pointers, same pitch and first row): every
+    finished chunk is stored into each of them by the same launch (all-gather form of the reassembly)."""
+    arr = (ctypes.c_void_p * len(d_dsts))(*d_dsts)
+    _check(load().fixca_cuda_region_dev_fanout(d_src, src_pitch, src_row0, src_rows, arr, len(d_dsts), dst_pitch, dst_row0,
+                                               width, height, bytes, bpc, ctypes.byref(params), y1, y2, flags, stream))
 
 
 def fix_ca_frames_dev(d_src: int, src_pitch: int, src_frame_stride: int, d_dst: int, dst_pitch: int,

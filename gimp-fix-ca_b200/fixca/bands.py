@@ -17,8 +17,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from . import (FixCaParams, band_source_rows, bpc_of, fix_ca_region_dev, split_bands, PRECISION_EXACT,
-               frame_alloc, frame_open, frame_close, frame_free)
+from . import (FixCaParams, band_source_rows, bpc_of, fix_ca_region_dev, fix_ca_region_dev_fanout, split_bands,
+               PRECISION_EXACT, frame_alloc, frame_open, frame_close, frame_free)
 
 
 @dataclass
@@ -67,10 +67,11 @@ class PeerFrame:
     the kernel's TMA stores land in the owner's memory, so computing a band and gathering it are one kernel.
     Collective over `group`: every rank constructs it, `sync()`s before the owner reads, and `close()`s it."""
 
-    def __init__(self, rows: int, pitch: int, owner: int = 0, group=None):
+    def __init__(self, rows: int, pitch: int, owner: int = 0, group=None, row0: int = 0):
         import torch.distributed as dist
 
-        self.rows, self.pitch, self.owner, self.group = rows, pitch, owner, group
+        # row0: the image row the frame's first row holds (a frame may cover a part of the image: several owners)
+        self.rows, self.pitch, self.owner, self.group, self.row0 = rows, pitch, owner, group, row0
         self.rank = dist.get_rank(group)
         box = [None]
         if self.rank == owner:
@@ -123,8 +124,68 @@ def run_band_into_frame(plan: BandPlan, d_src_ptr: int, src_pitch: int, frame: P
     place in the whole frame (dst_row0 = 0), over NVLink when the frame lives on another GPU."""
     if plan.y1 == plan.y2:
         return
-    fix_ca_region_dev(d_src_ptr, src_pitch, plan.src_lo, plan.src_rows, frame.ptr, frame.pitch, 0,
+    fix_ca_region_dev(d_src_ptr, src_pitch, plan.src_lo, plan.src_rows, frame.ptr, frame.pitch, frame.row0,
                       plan.width, plan.height, bytes_per_pixel, bpc, params, plan.y1, plan.y2, flags, stream)
+
+
+class AllFrames:
+    """All-gather form: every rank owns a whole destination frame and maps everybody else's (CUDA IPC; peer access
+    over NVLink / NVSwitch).  `run_band_into_all()` makes this rank's kernel store each finished chunk of its band
+    into all of them in one launch, so after `sync()` every GPU holds the whole corrected frame.  Collective."""
+
+    def __init__(self, rows: int, pitch: int, group=None):
+        import torch.distributed as dist
+
+        self.rows, self.pitch, self.group = rows, pitch, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.own, handle = frame_alloc(rows * pitch)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        self.ptrs = [self.own if r == self.rank else frame_open(handles[r]) for r in range(self.world)]
+        self._open = True
+
+    def sync(self) -> None:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def as_tensor(self):
+        """This rank's own frame as a (rows, pitch) uint8 torch tensor (a view, no copy)."""
+        import torch
+
+        class _Mem:
+            pass
+
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (self.rows, self.pitch), "typestr": "|u1", "data": (self.own, False),
+                                      "version": 3}
+        self._keep = m
+        return torch.as_tensor(m, device="cuda")
+
+    def close(self) -> None:
+        import torch.distributed as dist
+
+        if not self._open:
+            return
+        self._open = False
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                frame_close(p)
+        dist.barrier(group=self.group)
+        frame_free(self.own)
+
+
+def run_band_into_all(plan: BandPlan, d_src_ptr: int, src_pitch: int, frames: AllFrames, bytes_per_pixel: int,
+                      bpc: int, params: FixCaParams, flags: int = PRECISION_EXACT, stream: int = 0) -> None:
+    """Launch this rank's band with every rank's frame as a destination (own frame first): rows [y1, y2) land at
+    their place in all `world` copies of the frame."""
+    if plan.y1 == plan.y2:
+        return
+    order = [frames.own] + [p for r, p in enumerate(frames.ptrs) if r != frames.rank]
+    fix_ca_region_dev_fanout(d_src_ptr, src_pitch, plan.src_lo, plan.src_rows, order, frames.pitch, 0,
+                             plan.width, plan.height, bytes_per_pixel, bpc, params, plan.y1, plan.y2, flags, stream)
 
 
 def gather_bands(band, plan: BandPlan, dst_rank: int = 0, group=None):

@@ -228,7 +228,17 @@ FIXCA_API int fixca_cuda_frames_dev(const void *d_src, size_t src_pitch, size_t 
  * fixca_cuda_frame_alloc: cudaMalloc on the current device + cudaIpcGetMemHandle.
  * fixca_cuda_frame_open:  cudaIpcOpenMemHandle in ANOTHER process (CUDA refuses the exporting process).
  * fixca_cuda_frame_close / _free: undo them (after the ranks have met).
+ *
+ * All-gather form (every GPU ends up with the whole frame): each rank allocates a frame, opens everybody else's and
+ * calls fixca_cuda_region_dev_fanout() with all of them: the streaming kernels store every finished chunk from
+ * shared memory into each frame (its own through HBM, the others through NVLink) in the same launch.
  */
+#define FIXCA_MAX_FANOUT 8
+FIXCA_API int fixca_cuda_region_dev_fanout(const void *d_src, size_t src_pitch, int src_row0, int src_rows,
+					   void *const *d_dsts, int ndst, size_t dst_pitch, int dst_row0,
+					   int width, int height, int bytes, int bpc,
+					   const fixca_params *params, int y1, int y2,
+					   unsigned flags, void *stream);
 #define FIXCA_IPC_HANDLE_BYTES 64
 FIXCA_API int fixca_cuda_frame_alloc(size_t bytes, void **d_frame, unsigned char handle[FIXCA_IPC_HANDLE_BYTES]);
 FIXCA_API int fixca_cuda_frame_open(const unsigned char handle[FIXCA_IPC_HANDLE_BYTES], void **d_frame);

@@ -167,17 +167,36 @@ def _peer_worker(rank, world, port, out_q, one_gpu=False):
             bands.run_band_into_frame(plan, d_src.data_ptr(), pitch, frame, bpp, fixca.bpc_of(img.dtype), P, flags,
                                       torch.cuda.current_stream().cuda_stream)
             frame.sync()
-            if rank == 0:
-                got = frame.as_tensor()[:, :row_bytes].cpu().numpy().copy().view(img.dtype).reshape(h, w, ch)
-                want = chk.region(img, orc.Params(interpolation=interp, **kw))
+            want = chk.region(img, orc.Params(interpolation=interp, **kw))
+
+            def matches(t):
+                got = t[:, :row_bytes].cpu().numpy().copy().view(img.dtype).reshape(h, w, ch)
                 if tol == 0:
-                    same = got.tobytes() == want.tobytes()
-                else:
-                    same = int(np.abs(got.astype(np.int64) - want.astype(np.int64)).max()) <= tol
+                    return got.tobytes() == want.tobytes()
+                return int(np.abs(got.astype(np.int64) - want.astype(np.int64)).max()) <= tol
+
+            if rank == 0:
+                same = matches(frame.as_tensor())
                 ok = ok and same
                 if not same:
                     out_q.put(("mismatch", n))
             frame.close()
+            # all-gather form: every rank owns a frame, every rank's kernel stores its band into all of them
+            allf = bands.AllFrames(h, pitch)
+            allf.as_tensor().fill_(0x5A)
+            allf.sync()
+            bands.run_band_into_all(plan, d_src.data_ptr(), pitch, allf, bpp, fixca.bpc_of(img.dtype), P, flags,
+                                    torch.cuda.current_stream().cuda_stream)
+            allf.sync()
+            same = matches(allf.as_tensor())
+            if not same:
+                out_q.put(("all-gather mismatch", n, rank))
+            flag = torch.tensor([1 if same else 0])
+            if not one_gpu:
+                flag = flag.to(dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = ok and bool(flag.item())
+            allf.close()
         if rank == 0:
             out_q.put(("ok", ok))
     finally:

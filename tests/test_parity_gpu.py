@@ -321,6 +321,40 @@ def test_multi_device_bands_and_frames(fx, checker):
             assert o.tobytes() == checker.region(f, orc.Params(**kw)).tobytes(), nd
 
 
+def test_fanout_stores_every_destination(fx, checker):
+    """fixca_cuda_region_dev_fanout: one launch stores the band into several frames (the all-gather form; here all
+    frames live on this GPU).  Streaming kernels (FAST, None) fan out in ONE launch; EXACT goes launch by launch.
+    Every frame holds the single-destination result, and nothing outside the band's rows is written."""
+    import torch
+
+    h, w, ch = 403, 640, 3
+    st = torch.cuda.current_stream().cuda_stream
+    for dt, interp, flags, streaming in (("u2", 2, fx.PRECISION_FAST, True), ("u1", 0, fx.PRECISION_EXACT, True),
+                                         ("f4", 1, fx.PRECISION_FAST, True), ("u2", 2, fx.PRECISION_EXACT, False)):
+        img = orc.synth_image(h, w, ch, dt, 91)
+        kw = dict(KW, lens_x=300, lens_y=128, interpolation=interp)
+        p = fx.FixCaParams(**kw)
+        want = fx.correct(img, p, flags=flags)
+        bpp = ch * img.dtype.itemsize
+        pitch = (w * bpp + 127) // 128 * 128
+        src = torch.zeros((h, pitch), dtype=torch.uint8, device="cuda")
+        src[:, :w * bpp] = torch.from_numpy(img.view(np.uint8).reshape(h, w * bpp)).cuda()
+        y1, y2 = 96, 301
+        for ndst in (1, 3, 8):
+            frames = [torch.full((h, pitch), 0x5A, dtype=torch.uint8, device="cuda") for _ in range(ndst)]
+            n0 = fx.launch_count()
+            fx.fix_ca_region_dev_fanout(src.data_ptr(), pitch, 0, h, [f.data_ptr() for f in frames], pitch, 0, w, h, bpp,
+                                        fx.bpc_of(img.dtype), p, y1, y2, flags, st)
+            torch.cuda.synchronize()
+            assert fx.launch_count() - n0 == (1 if streaming else ndst), (dt, interp, ndst, fx.last_kernel())
+            for f in frames:
+                got = f[:, :w * bpp].cpu().numpy()
+                assert got[y1:y2].tobytes() == want[y1:y2].tobytes(), (dt, interp, ndst)
+                assert (got[:y1] == 0x5A).all() and (got[y2:] == 0x5A).all()
+    with pytest.raises(fx.FixCaError):
+        fx.fix_ca_region_dev_fanout(src.data_ptr(), pitch, 0, h, [src.data_ptr()] * 9, pitch, 0, w, h, bpp, -4, p, 0, h, flags, st)
+
+
 def test_device_resident_entry_with_torch_buffers(fx, checker):
     import torch
 
