@@ -156,8 +156,19 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # the reference on host cores (cpu_baseline and --impl reference)
 # ---------------------------------------------------------------------------------------------
-def cpu_checker():
+_restatement = None
+
+
+def cpu_checker(image_bytes=0):
+    """The reference's own code; for images beyond 2 GiB (the N-times taller images of the weak-scaling runs) its
+    plain-C restatement, which is pinned byte-for-byte against it: fix-ca.c computes buffer offsets in `gint`
+    ((orig_width * y + x) * bytes, fix-ca.c:855/:868), which overflows there."""
+    global _restatement
     import oracle as orc
+    if image_bytes >= 2 ** 31:
+        if _restatement is None:
+            _restatement = orc.Restatement()
+        return _restatement, orc
     return orc.best_checker(), orc
 
 
@@ -1022,7 +1033,7 @@ def oracle_check(exact, src_rows, lo, got_rows, y1, W, H, ch, dt, interp, kw, lx
     own code run on the same source rows (src_rows = image rows [lo, lo + m)): three sample bands."""
     try:
         import fixca
-        chk, orc = cpu_checker()
+        chk, orc = cpu_checker(W * H * ch * dt.itemsize)
         P = orc.Params(interpolation=interp, lens_x=float(lx), lens_y=float(ly), **kw)
         fp = fixca.FixCaParams(interpolation=interp, lens_x=float(lx), lens_y=float(ly), **kw)
         src_v = whole_image_view(src_rows, lo, H)
@@ -1043,7 +1054,8 @@ def oracle_check(exact, src_rows, lo, got_rows, y1, W, H, ch, dt, interp, kw, lx
             ntot += d.size
             bands.append([ya, yb])
         return {"checked_rows": int(sum(b - a for a, b in bands)), "bands": bands, "max_abs_diff": worst,
-                "mismatch_fraction": round(nbad / max(1, ntot), 7), "checker": chk.kind,
+                "mismatch_fraction": round(nbad / max(1, ntot), 7),
+                "checker": chk.kind if W * H * ch * dt.itemsize < 2 ** 31 else "port (restatement pinned against the reference; fix-ca.c's gint offsets overflow past 2 GiB)",
                 "tolerance": 0 if exact or interp == 0 else (1 if dt.kind != "f" else 1e-6)}
     except Exception as e:  # the check is advisory; never hide the bench line
         return {"error": repr(e)}

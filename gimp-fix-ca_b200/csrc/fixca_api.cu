@@ -341,9 +341,11 @@ static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_
 	a.g = g;
 	pl.src_rows_avail = src_rows;
 
-	// FIXCA_TIGHT_ROWS: the TMA kernels store whole 16-byte units, i.e. up to 15 bytes past width * bpp of every
-	// destination row; a caller whose rows are views into a wider buffer forbids that
-	const bool tight_ok = !(flags & FIXCA_TIGHT_ROWS) || ((size_t)g.width * f.bpp) % 16 == 0;
+	// The TMA kernels store whole 16-byte units, i.e. up to 15 bytes past width * bpp of every destination row.
+	// Harmless in row padding, fatal when the rows are views into a wider buffer: taken only when the rows are whole
+	// 16-byte units or the caller declares the padding scratch (FIXCA_PADDING_SCRATCH; the host drivers' own pitched
+	// staging buffers always are)
+	const bool tight_ok = (flags & FIXCA_PADDING_SCRATCH) || ((size_t)g.width * f.bpp) % 16 == 0;
 	const bool tma_ok = tight_ok && g.monotone && (src_pitch % 16 == 0) && (dst_pitch % 16 == 0) &&
 			    ((uintptr_t)d_src % 16 == 0) && ((uintptr_t)d_dst % 16 == 0) &&
 			    (batch.nframes <= 1 || (batch.src_stride % 16 == 0 && batch.dst_stride % 16 == 0));
@@ -434,7 +436,7 @@ static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_
 	}
 	if (flags & FIXCA_FORCE_TILED)
 		return fail(FIXCA_ERR_ARG, "FIXCA_FORCE_TILED: the tiled kernel cannot take this call (%s)",
-			    tma_ok ? "source window exceeds shared memory" : "non-monotone map, pitch/pointer not 16-byte aligned, or FIXCA_TIGHT_ROWS with rows that are not whole 16-byte units");
+			    tma_ok ? "source window exceeds shared memory" : "non-monotone map, pitch/pointer not 16-byte aligned, or rows that are not whole 16-byte units without FIXCA_PADDING_SCRATCH");
 
 	pl.k = pick_kernel(f, g.interp, flags, false);
 	if (!pl.k)
@@ -732,7 +734,7 @@ enum { ALLOW_PREVIEW = 1, ALLOW_COLUMNS = 2 };
 static int check_flags(unsigned flags, int allow, const Format &f, const fixca_params *p, const char *entry)
 {
 	const unsigned known = FIXCA_PRECISION_MASK | FIXCA_FORCE_DIRECT | FIXCA_FORCE_TILED | FIXCA_PREVIEW_OVERLAY |
-			       FIXCA_COLUMN_SELECTION | FIXCA_TIGHT_ROWS;
+			       FIXCA_COLUMN_SELECTION | FIXCA_PADDING_SCRATCH;
 	if (flags & ~known)
 		return fail(FIXCA_ERR_ARG, "%s: unknown flag bits %#x", entry, flags & ~known);
 	if ((flags & FIXCA_PRECISION_MASK) > FIXCA_PRECISION_FAST)
@@ -1303,7 +1305,7 @@ static int region_host_band_locked(DeviceCtx &cx, int dev, const unsigned char *
 		CUDA_TRY(cudaEventRecord(e_up, cx.s_up));
 		CUDA_TRY(cudaStreamWaitEvent(cx.s_run, e_up, 0));
 		Plan pl;
-		if ((rc = make_plan(f, g, cx.d_src, pitch, band_lo, src_rows, cx.d_dst, pitch, y1, c1, c2, flags, dev, pl))) return rc;
+		if ((rc = make_plan(f, g, cx.d_src, pitch, band_lo, src_rows, cx.d_dst, pitch, y1, c1, c2, flags | FIXCA_PADDING_SCRATCH, dev, pl))) return rc;
 		if ((rc = launch_plan(pl, cx.s_run))) return rc;
 		if (flags & FIXCA_PREVIEW_OVERLAY) {
 			CUDA_TRY(launch_preview(f.kind, f.nch, cx.d_dst, (long long)pitch, y1, c1, c2, width,
@@ -1545,7 +1547,7 @@ extern "C" int fixca_cuda_frames(const unsigned char *const *src_frames, unsigne
 			unsigned char *to = s.staged_out ? s.h_out : dst_frames[i];
 			CUDA_TRY(cudaMemcpy2DAsync(s.d_src, pitch, from, row_bytes, row_bytes, height, cudaMemcpyHostToDevice, s.s));
 			Plan pl;
-			if ((r = make_plan(f, g, s.d_src, pitch, 0, height, s.d_dst, pitch, 0, 0, height, flags, dev, pl))) return r;
+			if ((r = make_plan(f, g, s.d_src, pitch, 0, height, s.d_dst, pitch, 0, 0, height, flags | FIXCA_PADDING_SCRATCH, dev, pl))) return r;
 			if ((r = launch_plan(pl, s.s))) return r;
 			CUDA_TRY(cudaMemcpy2DAsync(to, row_bytes, s.d_dst, pitch, row_bytes, height, cudaMemcpyDeviceToHost, s.s));
 			s.frame = i;

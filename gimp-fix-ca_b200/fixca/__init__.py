@@ -29,7 +29,7 @@ PRECISION_EXACT, PRECISION_FAST = 0x0, 0x1
 FORCE_DIRECT, FORCE_TILED = 0x10, 0x20
 PREVIEW_OVERLAY = 0x40      # saturate() + centerline() on the rows written (the show_progress=False call)
 COLUMN_SELECTION = 0x80     # accept x1 != 0 / x2 != width: columns [x1, x2) of the full-width result (extension)
-TIGHT_ROWS = 0x100          # device entries: never write past width * bytes of a destination row
+PADDING_SCRATCH = 0x100     # device entries: the bytes up to the next 16-byte boundary of each dst row are scratch
 INPUT_MAX = 30.0
 
 OK = 0

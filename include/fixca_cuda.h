@@ -119,11 +119,12 @@ typedef struct fixca_params {
  * pass computes for them, and nothing else in dst is written (src and dst stay whole-image buffers,
  * width * height * bytes, as set_data() addresses them, :864-871). */
 #define FIXCA_COLUMN_SELECTION 0x80u
-/* Device-resident entries only: the destination rows are views into a wider buffer, so nothing past
- * width * bytes of a row may be written.  The TMA kernels store whole 16-byte units (up to 15 bytes into the
- * row's pitch padding); with this flag they are used only when width * bytes is a multiple of 16 and the
- * per-pixel direct kernel takes the call otherwise. */
-#define FIXCA_TIGHT_ROWS       0x100u
+/* Device-resident entries only.  The TMA kernels store whole 16-byte units: when width * bytes is not a multiple of
+ * 16 they write up to 15 bytes past the end of every destination row.  In the padding of pitched rows that is
+ * harmless, in a sub-rectangle view of a wider buffer it would overwrite live pixels -- so without this flag such
+ * calls take the per-pixel direct kernel (exact row ends, several times slower).  Pass it when the bytes between
+ * width * bytes and the next 16-byte boundary of each destination row are scratch. */
+#define FIXCA_PADDING_SCRATCH  0x100u
 
 /* ------------------------------------------------------------------------- */
 /* The pass, host buffers: replaces fix_ca_region()                           */
@@ -190,10 +191,10 @@ FIXCA_API int fixca_cuda_region_multi(const unsigned char *src, unsigned char *d
  * d_dst + (y - dst_row0) * dst_pitch.  For a whole resident image pass
  * src_row0 = dst_row0 = 0, src_rows = height.  The source rows present must
  * cover fixca_band_source_rows(y1,y2) or FIXCA_ERR_ARG is returned.
- * Asynchronous on `stream` (a cudaStream_t, NULL = default stream).  The tiled
- * kernels need both pitches to be multiples of 16 bytes and both pointers
- * 16-byte aligned; they may write the padding bytes [width*bytes, pitch) of
- * the destination rows.  Otherwise the direct kernel is used.
+ * Asynchronous on `stream` (a cudaStream_t, NULL = default stream).  The TMA
+ * kernels need both pitches to be multiples of 16 bytes, both pointers 16-byte
+ * aligned, and rows that are whole 16-byte units (or FIXCA_PADDING_SCRATCH);
+ * otherwise the direct kernel is used.
  */
 FIXCA_API int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int src_row0, int src_rows,
 				    void *d_dst, size_t dst_pitch, int dst_row0,

@@ -150,6 +150,7 @@ def _peer_worker(rank, world, port, out_q, one_gpu=False):
             (1200, 900, 3, "f4", 0, fixca.PRECISION_EXACT, 0, dict(blue=30.0, red=-30.0, lens_x=450, lens_y=600, y_blue=30.0, y_red=-30.0)),
         ]
         for n, (h, w, ch, dt, interp, flags, tol, kw) in enumerate(cases):
+            flags |= fixca.PADDING_SCRATCH          # the frames are pitched: the bytes after a row's end are scratch
             img = orc.synth_image(h, w, ch, dt, seed=700 + n)
             P = fixca.FixCaParams(interpolation=interp, **kw)
             plan = bands.plan_band(w, h, P, rank, world)

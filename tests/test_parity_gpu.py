@@ -394,6 +394,32 @@ def test_device_resident_entry_with_torch_buffers(fx, checker):
     assert fx.last_kernel().startswith("direct") and d2.cpu().numpy().tobytes() == want2.tobytes()
 
 
+def test_rows_that_are_views_into_a_wider_buffer_are_not_overrun(fx, checker):
+    """Device-resident destination rows that are a sub-rectangle of a wider buffer (pitch > row, width * bytes not a
+    multiple of 16): by default nothing past width * bytes of a row is written (the per-pixel kernel takes the call);
+    with FIXCA_PADDING_SCRATCH the TMA kernels run and may use the bytes up to the next 16-byte boundary."""
+    import torch
+    stream = torch.cuda.current_stream().cuda_stream
+    h, w, ch = 90, 333, 3                  # 999 bytes per row
+    img = orc.synth_image(h, w, ch, "u1", 61)
+    kw = dict(KW, lens_x=160, lens_y=40, interpolation=2)
+    want = checker.region(img, orc.Params(**kw))
+    pitch = 1024 + 512                     # the image sits inside a wider buffer
+    src = torch.zeros((h, pitch), dtype=torch.uint8, device="cuda")
+    src[:, :w * ch] = torch.from_numpy(img.reshape(h, w * ch)).cuda()
+    for flags, kernel in ((fx.PRECISION_FAST, "direct"), (fx.PRECISION_FAST | fx.PADDING_SCRATCH, "stream"),
+                          (fx.PRECISION_EXACT, "direct"), (fx.PRECISION_EXACT | fx.PADDING_SCRATCH, "tiled")):
+        dst = torch.full((h, pitch), 0x5A, dtype=torch.uint8, device="cuda")
+        fx.fix_ca_region_dev(src.data_ptr(), pitch, 0, h, dst.data_ptr(), pitch, 0, w, h, ch, 1, fx.FixCaParams(**kw), 0, h, flags, stream)
+        torch.cuda.synchronize()
+        assert fx.last_kernel().startswith(kernel), (flags, fx.last_kernel())
+        got = dst.cpu().numpy()
+        d = np.abs(got[:, :w * ch].reshape(h, w, ch).astype(np.int64) - want.astype(np.int64)).max()
+        assert d <= (FAST_LSB_TOL if flags & fx.PRECISION_FAST else 0)
+        keep = w * ch if kernel == "direct" else (w * ch + 15) // 16 * 16
+        assert (got[:, keep:] == 0x5A).all(), (flags, kernel)
+
+
 def test_device_batch_of_frames_matches_single_frames(fx, checker):
     """fixca_cuda_frames_dev: a batch in one launch (grid layer per frame, long segments) gives every frame the
     bytes of its own single-frame call; formats without a streaming kernel are looped per frame."""
@@ -416,7 +442,8 @@ def test_device_batch_of_frames_matches_single_frames(fx, checker):
             v = src[k * fstride:k * fstride + pitch * h].view(h, pitch)
             v[:, :w * bpp] = torch.from_numpy(fr.view(np.uint8).reshape(h, w * bpp)).cuda()
         n0 = launches()
-        fx.fix_ca_frames_dev(src.data_ptr(), pitch, fstride, dst.data_ptr(), pitch, fstride, nf, w, h, bpp, bpc, p, flags, stream)
+        fx.fix_ca_frames_dev(src.data_ptr(), pitch, fstride, dst.data_ptr(), pitch, fstride, nf, w, h, bpp, bpc, p,
+                             flags | fx.PADDING_SCRATCH, stream)     # rows are pitched: their padding is scratch
         torch.cuda.synchronize()
         streaming = fx.last_kernel().startswith("stream")
         assert launches() - n0 == (1 if streaming else nf), (fx.last_kernel(), launches() - n0)
@@ -530,7 +557,7 @@ def test_float_pitch_padding_is_never_sampled(fx, checker):
         src[:, :w * bpp] = torch.from_numpy(img.view(np.uint8).reshape(h, w * bpp)).cuda()
         dst = torch.zeros_like(src)
         fx.fix_ca_region_dev(src.data_ptr(), pitch, 0, h, dst.data_ptr(), pitch, 0, w, h, bpp, -4,
-                             fx.FixCaParams(**kw), 0, h, fx.PRECISION_FAST, stream)
+                             fx.FixCaParams(**kw), 0, h, fx.PRECISION_FAST | fx.PADDING_SCRATCH, stream)
         torch.cuda.synchronize()
         got = dst[:, :w * bpp].cpu().numpy().view(np.float32).reshape(h, w, ch)
         assert fx.last_kernel().startswith("stream")
