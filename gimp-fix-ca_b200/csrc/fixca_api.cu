@@ -75,6 +75,8 @@ static void read_tuning_locked()
 	t.fast_kernel = (e && !strcmp(e, "strip")) ? 2 : 3;
 	e = getenv("FIXCA_NONE_KERNEL");
 	t.none_tiled = e && !strcmp(e, "tiled");
+	e = getenv("FIXCA_EXACT_KERNEL");
+	t.exact_tiled = e && !strcmp(e, "tiled");
 	t.strip_tw128 = env_int("FIXCA_STRIP_TW", 0) == 128;
 	t.stream_noalt = env_int("FIXCA_STREAM_NOALT", 0) != 0;
 	t.tile_h = env_int("FIXCA_TILE_H", 0);
@@ -230,13 +232,18 @@ struct Batch {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// FAST arithmetic is taken for the formats that have it; every other Linear / Cubic call computes EXACT
+static bool wants_fast(const Format &f, unsigned flags)
+{
+	return (flags & FIXCA_PRECISION_MASK) == FIXCA_PRECISION_FAST &&
+	       (f.kind == SK_U8 || f.kind == SK_U16 || f.kind == SK_F32 || f.kind == SK_F16 || f.kind == SK_U15);
+}
+
 static const KernelEntry *pick_kernel(const Format &f, int interp, unsigned flags, bool tiled)
 {
 	if (interp == 0)
 		return lookup_none(f.sample_bytes, f.nch, tiled);
-	const bool fast = (flags & FIXCA_PRECISION_MASK) == FIXCA_PRECISION_FAST &&
-			  (f.kind == SK_U8 || f.kind == SK_U16 || f.kind == SK_F32 || f.kind == SK_F16 || f.kind == SK_U15);
-	return fast ? lookup_fast(f.kind, f.nch, interp, tiled) : lookup_exact(f.kind, f.nch, interp, tiled);
+	return wants_fast(f, flags) ? lookup_fast(f.kind, f.nch, interp, tiled) : lookup_exact(f.kind, f.nch, interp, tiled);
 }
 
 static int g_smem_optin[64];	// per device, 0 = not queried
@@ -362,6 +369,12 @@ static int make_plan_uncached(const Format &f, const Geometry &g, const void *d_
 		if (g.interp == 0) {
 			const KernelEntry *ks = lookup_none_stream(f.sample_bytes, f.nch);
 			if (ks && plan_stream(ks, f, g, y1, y2, dev, limit, pl))
+				return FIXCA_OK;
+		}
+		if (g.interp != 0 && !wants_fast(f, flags)) {
+			// EXACT on integer samples: the streaming kernel with exact repair of near-tie samples, when it fits
+			const KernelEntry *kr = lookup_exact_stream(f.kind, f.nch, g.interp);
+			if (kr && plan_stream(kr, f, g, y1, y2, dev, limit, pl))
 				return FIXCA_OK;
 		}
 		if (k->stream) {
@@ -504,7 +517,7 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	const int compute_warps = 2 * k->tw / k->strip_p / 32;
 	const int want_ctas = tuning().stream_ctas > 0 ? tuning().stream_ctas : std::max(2, 32 / compute_warps);
 	const int forced_d = tuning().stream_depth;
-	size_t total = 0, off_meta = 0, off_win = 0, off_out = 0, ring_rows = 0;
+	size_t total = 0, off_meta = 0, off_win = 0, off_out = 0, off_rq = 0, ring_rows = 0;
 	int depth = 0;
 	// first / last source row each chunk touches (one scan; the map is monotone, so a chunk's extremes
 	// sit at its first and last output row)
@@ -525,6 +538,10 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 		off_win = align_up(off_meta + (size_t)(d + 1) * sizeof(StreamMeta), 128);
 		off_out = align_up(off_win + ring_rows * (size_t)wb, 128);
 		total = off_out + (size_t)STREAM_NSTG * CH * k->tw * f.bpp;
+		if (k->repair) {	// per-warp queues of near-tie samples, u16 entries
+			off_rq = align_up(total, 16);
+			total = off_rq + (size_t)(2 * k->tw / k->strip_p / 32) * (32 + 32 * k->strip_p) * 2;
+		}
 	};
 	if (forced_d > 0) {
 		layout(std::min(forced_d, STREAM_MAX_D));
@@ -591,6 +608,7 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	a.off_ytab = (int)off_meta;
 	a.off_win = (int)off_win;
 	a.off_out = (int)off_out;
+	a.off_rq = (int)off_rq;
 	pl.smem = total;
 	pl.block = dim3(threads);
 	pl.grid = dim3(strips, segs, pl.nframes);

@@ -24,7 +24,8 @@ struct KernelEntry {
 	int         ycoef_bytes;// per-row table entry size (tiled)
 	int         sample_bytes;
 	int         strip_p;	// > 0: strip_kernel with this many columns per thread (blockDim = 2 * tw / strip_p)
-	int         stream;	// != 0: stream_kernel (blockDim = 2 * tw / strip_p + 32, grid = strips x segments)
+	int         stream;	// != 0: stream_kernel (blockDim = 2 * tw / strip_p + 64, grid = strips x segments)
+	int         repair;	// != 0: the exact-repair form of stream_kernel (per-warp queues in shared memory)
 };
 
 constexpr int TILE_W = 128;
@@ -36,6 +37,7 @@ struct Tuning {
 	int generation = 0;
 	int fast_kernel = 3;	// lookup_fast_variant(): 2 strip, 3 stream (FIXCA_FAST_KERNEL=strip|stream)
 	int none_tiled = 0;	// FIXCA_NONE_KERNEL=tiled
+	int exact_tiled = 0;	// FIXCA_EXACT_KERNEL=tiled: EXACT Linear / Cubic on tiled_kernel<ExactF64> for every format
 	int strip_tw128 = 0;	// FIXCA_STRIP_TW=128
 	int stream_noalt = 0;	// FIXCA_STREAM_NOALT=1
 	int tile_h = 0, tile_ctas = 3;
@@ -53,6 +55,8 @@ const KernelEntry *lookup_none(int sample_bytes, int nch, bool tiled);
 const KernelEntry *lookup_none_stream(int sample_bytes, int nch);
 // kind in {SK_U8,SK_U16,SK_U32,SK_F32,SK_F64,SK_F16,SK_U15}; interp in {1,2}
 const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled);
+// the exact-repair streaming kernel for this format, or nullptr (floats, u32, FIXCA_EXACT_KERNEL=tiled)
+const KernelEntry *lookup_exact_stream(SampleKind kind, int nch, int interp);
 // kind in {SK_U8,SK_U16,SK_F32,SK_F16,SK_U15}; interp in {1,2}
 const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled);
 // variant: 0 direct, 2 strip, 3 stream, 4 narrower stream (may be nullptr)

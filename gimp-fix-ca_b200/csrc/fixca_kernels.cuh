@@ -63,6 +63,7 @@ struct KernelArgs {
 	int  ring_rows;			// window ring capacity in rows (multiple of 4)
 	int  depth;			// chunks prefetched ahead (pipeline depth D)
 	int  debug;			// bit 0: skip the arithmetic (timing experiments only)
+	int  off_rq;			// exact-repair stream kernels: per-warp queues of near-tie samples (u16 entries)
 };
 
 // 15-bit unsigned samples in 16-bit storage (babl's "u15": 0 .. 32768 <-> [0.0, 1.0]).  The reference rejects
@@ -243,6 +244,42 @@ __global__ void __launch_bounds__(256) direct_none_kernel(const __grid_constant_
 	}
 }
 
+// One output sample of channel c at (x, y) in the reference's own (non-shared) form, fix-ca.c:1135-1186 (Linear) /
+// :1204-1320 (Cubic): coordinates, clamp-to-edge taps, horizontal pass per tap row, vertical pass, clip + encode.
+// fetch(row, col) returns sample c of the source pixel at absolute (row, col).  Used by direct_kernel (global
+// memory) and by the streaming kernel's exact repair of near-tie samples (window ring in shared memory).
+template <class S, int INTERP, class A, class Fetch>
+__device__ __forceinline__ S interp_sample(const Geometry &g, int c, int x, int y, Fetch fetch)
+{
+	const int W = g.width, H = g.height;
+	double tx, ty;
+	const int cx = base_index(g.x[c], x, tx);
+	const int cy = base_index(g.y[c], y, ty);
+	const typename A::XCoef kx = A::make_x(tx, INTERP);
+	const typename A::YCoef ky = A::make_y(cy, ty, INTERP);
+	typename A::acc_t r;
+	if (INTERP == 1) {
+		const int c1 = cx + 1 < W ? cx + 1 : W - 1;
+		const int r1 = cy + 1 < H ? cy + 1 : H - 1;
+		const typename A::acc_t h0 = A::hlin(A::decode(fetch(cy, cx)), A::decode(fetch(cy, c1)), kx);
+		const typename A::acc_t h1 = A::hlin(A::decode(fetch(r1, cx)), A::decode(fetch(r1, c1)), kx);
+		r = A::vlin(h0, h1, ky);
+	} else {
+		const int q0 = cx > 0 ? cx - 1 : 0, q2 = cx + 1 < W ? cx + 1 : W - 1, q3 = cx + 2 < W ? cx + 2 : W - 1;
+		typename A::acc_t h[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const int row = clampi(cy - 1 + k, 0, H - 1);
+			h[k] = A::hcub(A::decode(fetch(row, q0)), A::decode(fetch(row, cx)), A::decode(fetch(row, q2)),
+				       A::decode(fetch(row, q3)), kx);
+		}
+		r = A::vcub(h[0], h[1], h[2], h[3], ky);
+	}
+	S out;
+	A::encode(out, r);
+	return out;
+}
+
 // Linear / Cubic, per-pixel evaluation in the reference's own (non-shared) form.
 template <class S, int NCH, int INTERP, class A>
 __global__ void __launch_bounds__(256) direct_kernel(const __grid_constant__ KernelArgs a)
@@ -251,43 +288,16 @@ __global__ void __launch_bounds__(256) direct_kernel(const __grid_constant__ Ker
 	const int y = a.y1 + blockIdx.y * blockDim.y + threadIdx.y;
 	if (x >= a.g.width || y >= a.y2)
 		return;
-	const int W = a.g.width, H = a.g.height;
 	const S *own = src_row_ptr<S>(a, y) + (size_t)x * NCH;
 	S *out = reinterpret_cast<S *>(a.dst + (long long)(y - a.dst_row0) * a.dst_pitch) + (size_t)x * NCH;
 	out[1] = own[1];
 	if (NCH == 4)
 		out[3] = own[3];
 #pragma unroll
-	for (int c = 0; c < 2; ++c) {
-		double tx, ty;
-		const int cx = base_index(a.g.x[c], x, tx);
-		const int cy = base_index(a.g.y[c], y, ty);
-		const typename A::XCoef kx = A::make_x(tx, INTERP);
-		const typename A::YCoef ky = A::make_y(cy, ty, INTERP);
-		typename A::acc_t r;
-		if (INTERP == 1) {
-			const int c1 = cx + 1 < W ? cx + 1 : W - 1;
-			const int r1 = cy + 1 < H ? cy + 1 : H - 1;
-			const S *row0 = src_row_ptr<S>(a, cy) + 2 * c;
-			const S *row1 = src_row_ptr<S>(a, r1) + 2 * c;
-			const typename A::acc_t h0 = A::hlin(A::decode(row0[(size_t)cx * NCH]), A::decode(row0[(size_t)c1 * NCH]), kx);
-			const typename A::acc_t h1 = A::hlin(A::decode(row1[(size_t)cx * NCH]), A::decode(row1[(size_t)c1 * NCH]), kx);
-			r = A::vlin(h0, h1, ky);
-		} else {
-			const size_t o0 = (size_t)(cx > 0 ? cx - 1 : 0) * NCH;
-			const size_t o1 = (size_t)cx * NCH;
-			const size_t o2 = (size_t)(cx + 1 < W ? cx + 1 : W - 1) * NCH;
-			const size_t o3 = (size_t)(cx + 2 < W ? cx + 2 : W - 1) * NCH;
-			typename A::acc_t h[4];
-#pragma unroll
-			for (int k = 0; k < 4; ++k) {
-				const S *row = src_row_ptr<S>(a, clampi(cy - 1 + k, 0, H - 1)) + 2 * c;
-				h[k] = A::hcub(A::decode(row[o0]), A::decode(row[o1]), A::decode(row[o2]), A::decode(row[o3]), kx);
-			}
-			r = A::vcub(h[0], h[1], h[2], h[3], ky);
-		}
-		A::encode(out[2 * c], r);
-	}
+	for (int c = 0; c < 2; ++c)
+		out[2 * c] = interp_sample<S, INTERP, A>(a.g, c, x, y, [&](int row, int col) {
+			return src_row_ptr<S>(a, row)[(size_t)col * NCH + 2 * c];
+		});
 }
 
 // ---------------------------------------------------------------------------

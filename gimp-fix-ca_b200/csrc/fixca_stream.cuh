@@ -167,7 +167,12 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *tm)
 // fan      further destinations of the same geometry (fan-out / all-gather form), usually none
 // All three are 3-D maps (8-byte elements x rows x frames of a batch, blockIdx.z = frame) over rows of
 // align16(width * BPP) bytes; row coordinates are relative to src_row0 / dst_row0.
-template <class S, int NCH, int INTERP, int P, int TW, bool ALT = false>
+// REPAIR (8-bit samples, Linear / Cubic): the bit-exact form.  The FP32 pipeline runs as in FAST mode (weights
+// rounded once from FP64); every output whose FP32 value lies within Codec::kEps -- a proven bound on |FP32 value -
+// reference value| -- of a rounding boundary is queued per warp and recomputed with the reference's own FP64
+// arithmetic (interp_sample<ExactF64>, taps read from the window ring), 32 queued samples at a time so that the
+// FP64 work runs on full warps.  Everything else rounds to the same integer in both arithmetics.
+template <class S, int NCH, int INTERP, int P, int TW, bool ALT = false, bool REPAIR = false>
 __global__ void __launch_bounds__(2 * TW / P + 64, (2 * TW / P + 64) <= 192 ? 4 : 2)	// register budget: 4 (2) resident CTAs
 stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUtensorMap tm_win,
 	      const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ CUtensorMap tm_out,
@@ -275,7 +280,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				if constexpr (INTERP == 0)
 					last = nearest_index(a.g.y[ch], y_first + r);
 				else
-					m.wy[r][ch] = position_weights<INTERP>(a.g.y[ch], y_first + r, H, StripCodec<S>::kInvMax, last);
+					m.wy[r][ch] = position_weights<INTERP, REPAIR>(a.g.y[ch], y_first + r, H, StripCodec<S>::kInvMax, last);
 				m.last[ch][r] = last;
 				if (r == nr - 1) {
 					m.last[ch][nr] = INT_MAX;
@@ -428,7 +433,15 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			// clipped by the TMA store); past the image the coordinate clamps to W - 1 ...
 			double td;
 			const int i0 = base_index(a.g.x[c], x0 + lt * P + k, td);
-			tap_weights<INTERP>((float)td, w[k]);
+			if (REPAIR) {	// FP64 weights, rounded once (the error bound counts one rounding per weight)
+				double wd[4];
+				tap_weights_d<INTERP>(td, wd);
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+					w[k][j] = (float)wd[j];
+			} else {
+				tap_weights<INTERP>((float)td, w[k]);
+			}
 #pragma unroll
 			for (int j = 0; j < 4; ++j)
 				w[k][j] = w[k][j] * Codec::kHScale + 0.f;	// power of two (integer samples are read as subnormals); -0 -> +0: the sign of an all-zero sum must not depend on the fold
@@ -524,6 +537,44 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	const uint32_t win_end = win_c + (uint32_t)(NR * wpitch);
 	uint32_t prow = win_c + (uint32_t)(((s_done + 1) % NR) * wpitch);	// shared sample 0 of row s_done + 1
 
+	// ---- REPAIR: this warp's queue of near-tie samples (entry = chunk row << 8 | column in group << 5 | lane) ----
+	// (channel-per-warp layouts only: every lane of a warp runs the same code, so the queue state is warp-uniform)
+	static_assert(!(REPAIR && ALT), "the exact-repair form needs warp-uniform control flow");
+	constexpr int RQ_CAP = 32 + 32 * P;		// < 32 pending + what one output row can add
+	const int lane = tid & 31;
+	uint16_t *const rq = reinterpret_cast<uint16_t *>(smem + a.off_rq) + (REPAIR ? (tid >> 5) * RQ_CAP : 0);
+	int rq_n = 0;				// warp-uniform
+	// n <= 32 queued samples, one per lane, through the reference's own arithmetic (fix-ca.c:1135-1186, :1204-1320):
+	// coordinates, clamp-to-edge taps read from the window ring, FP64 in the reference's operation order
+	auto repair = [&](const int n, const int y_first, unsigned char *const stg) {
+		__syncwarp();
+		if (lane < n) {
+			const unsigned e = rq[rq_n - n + lane];
+			const int elt = (tid & ~31) + (int)(e & 31u) - c * HALF, ek = (int)(e >> 5) & 7, er = (int)(e >> 8);
+			const S v = interp_sample<S, INTERP, ExactF64>(a.g, c, x0 + elt * P + ek, y_first + er, [&](int row, int col) {
+				return *reinterpret_cast<const S *>(win + (row % NR) * wpitch + col * BPP + 2 * c * (int)sizeof(S) - wb0);
+			});
+			*reinterpret_cast<S *>(stg + er * OUT_PITCH + (elt * P + ek) * BPP + 2 * c * (int)sizeof(S)) = v;
+		}
+		rq_n -= n;
+		__syncwarp();
+	};
+	// the columns `flags` marks in chunk row r join the queue; a full warp's worth is repaired at once
+	auto enqueue = [&](const unsigned flags, const int r, const int y_first, unsigned char *const stg) {
+#pragma unroll
+		for (int k = 0; k < P; ++k) {
+			const bool f = (flags >> k) & 1u;
+			const unsigned m = __ballot_sync(0xffffffffu, f);
+			if (m) {
+				if (f)
+					rq[rq_n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((r << 8) | (k << 5) | lane);
+				rq_n += __popc(m);
+			}
+		}
+		if (rq_n >= 32)
+			repair(32, y_first, stg);
+	};
+
 	// form 0: bent; 1: regular, NW weights per column; 2: regular and no column group of the warp
 	// straddles a drift of the tap window (the usual case: the map drifts one sample every
 	// 1 / |scale - 1| columns), so the extra weight is 0 everywhere and T weights / P + T - 1 samples do
@@ -537,7 +588,10 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			mbar_wait(&full[jnf], (uint32_t)jpar);
 			const StreamMeta &m = meta[jnf];
 			uint64_t *const done_bar = &done[jnf];
-			unsigned char *q = stage + jstg * STAGE_BYTES + qoff;
+			unsigned char *const stg = stage + jstg * STAGE_BYTES;	// this chunk's staging buffer
+			unsigned char *q = stg + qoff;
+			const int y_first = ya + j * CH;
+			int er = 0;		// REPAIR: chunk row the next emit writes
 			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
 			jstg = jstg + 1 == NSTG ? 0 : jstg + 1;
 			const int s_end = m.s_end[c];
@@ -592,7 +646,9 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				constexpr int U = decltype(slot)::value;
 #pragma unroll 1
 				while (next_last <= s_done) {
-					vertical_emit<INTERP, U, P, BPP, Codec>(hr, *wy, q);
+					const unsigned fl = vertical_emit<INTERP, U, P, BPP, Codec, REPAIR>(hr, *wy, q);
+					if (REPAIR)
+						enqueue(fl, er++, y_first, stg);
 					wy += 2;
 					q += OUT_PITCH;
 					next_last = *++lastp;
@@ -675,12 +731,15 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 						else
 							load_row(prow, smp[0]);
 						hfilter(smp[REG ? u & 1 : 0], hr[u & 3]);
+						unsigned fl;
 						switch (u & 3) {
-						case 0: vertical_emit<INTERP, 0, P, BPP, Codec>(hr, wy[2 * u], q + u * OUT_PITCH); break;
-						case 1: vertical_emit<INTERP, 1, P, BPP, Codec>(hr, wy[2 * u], q + u * OUT_PITCH); break;
-						case 2: vertical_emit<INTERP, 2, P, BPP, Codec>(hr, wy[2 * u], q + u * OUT_PITCH); break;
-						default: vertical_emit<INTERP, 3, P, BPP, Codec>(hr, wy[2 * u], q + u * OUT_PITCH); break;
+						case 0: fl = vertical_emit<INTERP, 0, P, BPP, Codec, REPAIR>(hr, wy[2 * u], q + u * OUT_PITCH); break;
+						case 1: fl = vertical_emit<INTERP, 1, P, BPP, Codec, REPAIR>(hr, wy[2 * u], q + u * OUT_PITCH); break;
+						case 2: fl = vertical_emit<INTERP, 2, P, BPP, Codec, REPAIR>(hr, wy[2 * u], q + u * OUT_PITCH); break;
+						default: fl = vertical_emit<INTERP, 3, P, BPP, Codec, REPAIR>(hr, wy[2 * u], q + u * OUT_PITCH); break;
 						}
+						if (REPAIR)
+							enqueue(fl, er++, y_first, stg);
 						prow = pnext;
 					}
 					wy += 2 * UNR;
@@ -699,6 +758,9 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				}
 				walk(s_end);
 			}
+			if (REPAIR)	// what is left of the queue (its rows and taps belong to this chunk)
+				while (rq_n > 0)
+					repair(min(rq_n, 32), y_first, stg);
 			// staging writes -> visible to the TMA store the producer issues after this barrier
 			warp_arrive(done_bar);
 		}

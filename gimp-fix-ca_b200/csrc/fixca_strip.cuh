@@ -58,6 +58,21 @@ __device__ __forceinline__ void tap_weights(float t, float (&w)[4])
 	}
 }
 
+// The same weights evaluated in FP64 (the caller rounds them to FP32 once): the exact-repair kernels' error bound
+//  counts one rounding per weight.
+template <int INTERP>
+__device__ __forceinline__ void tap_weights_d(double t, double (&w)[4])
+{
+	if (INTERP == 1) {
+		w[0] = 1.0 - t; w[1] = t; w[2] = 0.0; w[3] = 0.0;
+	} else {
+		w[0] = ((2.0 - t) * t - 1.0) * t * 0.5;
+		w[1] = ((3.0 * t - 5.0) * t * t + 2.0) * 0.5;
+		w[2] = ((4.0 - 3.0 * t) * t + 1.0) * t * 0.5;
+		w[3] = (t - 1.0) * t * t * 0.5;
+	}
+}
+
 // Sample codecs.  The integer <-> float conversions cost no instruction at all:
 //   load   ld.shared.u8/u16 zero-extends into a 32-bit register, and that register IS the operand: the bit
 //          pattern of the integer v read as a float is the subnormal v * 2^-149, exact, and FMUL / FFMA take
@@ -91,6 +106,15 @@ template <> struct StripCodec<uint8_t> {
 	{
 		*p = (unsigned char)__float_as_uint(fmaf(sat01, 255.0f, 12582912.0f));
 	}
+	// exact-repair kernels: store, and report whether the FP32 value lies within kEps of a rounding boundary
+	// (kEps bounds |FP32 value - reference value| in LSB for raw samples <= kRawMax)
+	static constexpr float kMax = 255.0f, kEps = 0.07f * 255.0f / 65535.0f;
+	__device__ __forceinline__ static bool store_flag(unsigned char *p, float sat01)
+	{
+		const float r = fmaf(sat01, kMax, 12582912.0f);
+		*p = (unsigned char)__float_as_uint(r);
+		return fabsf(fmaf(sat01, kMax, 12582912.0f - r)) >= 0.5f - kEps;
+	}
 };
 template <> struct StripCodec<uint16_t> {
 	static constexpr float kHScale = kIntHScale;
@@ -111,6 +135,13 @@ template <> struct StripCodec<uint16_t> {
 	{
 		*reinterpret_cast<uint16_t *>(p) = (uint16_t)__float_as_uint(fmaf(sat01, 65535.0f, 12582912.0f));
 	}
+	static constexpr float kMax = 65535.0f, kEps = 0.07f;
+	__device__ __forceinline__ static bool store_flag(unsigned char *p, float sat01)
+	{
+		const float r = fmaf(sat01, kMax, 12582912.0f);
+		*reinterpret_cast<uint16_t *>(p) = (uint16_t)__float_as_uint(r);
+		return fabsf(fmaf(sat01, kMax, 12582912.0f - r)) >= 0.5f - kEps;
+	}
 };
 template <> struct StripCodec<u15_t> {	// bpc = 15: the loads of u16, max = 32768
 	static constexpr float kHScale = kIntHScale;
@@ -120,6 +151,13 @@ template <> struct StripCodec<u15_t> {	// bpc = 15: the loads of u16, max = 3276
 	__device__ __forceinline__ static void store(unsigned char *p, float sat01)
 	{
 		*reinterpret_cast<uint16_t *>(p) = (uint16_t)__float_as_uint(fmaf(sat01, 32768.0f, 12582912.0f));
+	}
+	static constexpr float kMax = 32768.0f, kEps = 0.07f;	// raw codes run to 65535 (out-of-range inputs): the bound of u16
+	__device__ __forceinline__ static bool store_flag(unsigned char *p, float sat01)
+	{
+		const float r = fmaf(sat01, kMax, 12582912.0f);
+		*reinterpret_cast<uint16_t *>(p) = (uint16_t)__float_as_uint(r);
+		return fabsf(fmaf(sat01, kMax, 12582912.0f - r)) >= 0.5f - kEps;
 	}
 };
 template <> struct StripCodec<float> {
@@ -133,6 +171,7 @@ template <> struct StripCodec<float> {
 		return f;
 	}
 	__device__ __forceinline__ static void store(unsigned char *p, float sat01) { *reinterpret_cast<float *>(p) = sat01; }
+	__device__ __forceinline__ static bool store_flag(unsigned char *p, float sat01) { store(p, sat01); return false; }
 };
 
 template <> struct StripCodec<__half> {	// bpc = -2: computed like float images, stored with one rounding to half
@@ -146,6 +185,7 @@ template <> struct StripCodec<__half> {	// bpc = -2: computed like float images,
 		return __half2float(__ushort_as_half(v));
 	}
 	__device__ __forceinline__ static void store(unsigned char *p, float sat01) { *reinterpret_cast<__half *>(p) = __float2half_rn(sat01); }
+	__device__ __forceinline__ static bool store_flag(unsigned char *p, float sat01) { store(p, sat01); return false; }
 };
 
 // Samples whose bit patterns include NaN / Inf (a zero weight does not silence them)
@@ -158,16 +198,29 @@ template <> struct is_float_sample<__half> { static constexpr bool value = true;
 // last - 3.  Clamp-to-edge taps (fix-ca.c:1219-1256, :1149-1158) land on the same row and their
 // weights add up; positions that hold no tap get weight 0.  Pre-scaled by inv_max so that the
 // vertical pass lands in [0,1] units.
-template <int INTERP>
+// PRECISE (exact-repair kernels): tap weights and the merge of clamped taps in FP64, one rounding to FP32 at the end.
+template <int INTERP, bool PRECISE = false>
 __device__ __forceinline__ float4 position_weights(const Axis &ay, int y, int H, float inv_max, int &last)
 {
 	constexpr int T = INTERP == 1 ? 2 : 4;
 	constexpr int OFF = INTERP == 1 ? 0 : 1;
 	double td;
 	const int i0 = base_index(ay, y, td);
+	last = clampi(i0 - OFF + T - 1, 0, H - 1);
+	if (PRECISE) {
+		double wd[4], posd[4] = {0.0, 0.0, 0.0, 0.0};
+		tap_weights_d<INTERP>(td, wd);
+#pragma unroll
+		for (int j = 0; j < T; ++j) {
+			const int p = last - clampi(i0 - OFF + j, 0, H - 1);
+#pragma unroll
+			for (int m = 0; m < 4; ++m)
+				posd[m] += (p == m) ? wd[j] * (double)inv_max : 0.0;
+		}
+		return make_float4((float)posd[3], (float)posd[2], (float)posd[1], (float)posd[0]);
+	}
 	float w[4];
 	tap_weights<INTERP>((float)td, w);
-	last = clampi(i0 - OFF + T - 1, 0, H - 1);
 	float pos[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
 	for (int j = 0; j < T; ++j) {
@@ -182,9 +235,11 @@ __device__ __forceinline__ float4 position_weights(const Axis &ay, int y, int H,
 // One output row of P columns from the ring of horizontal rows; U = ring slot of the newest row.
 // Chain order oldest -> newest; the last FMA saturates (clip_d, fix-ca.c:873-880).  Linear has taps
 // at the two newest positions only.
-template <int INTERP, int U, int P, int BPP, class Codec>
-__device__ __forceinline__ void vertical_emit(const float (&hr)[4][P], const float4 w, unsigned char *q)
+// REPAIR: returns a mask of the columns whose FP32 value lies within Codec::kEps of a rounding boundary.
+template <int INTERP, int U, int P, int BPP, class Codec, bool REPAIR = false>
+__device__ __forceinline__ unsigned vertical_emit(const float (&hr)[4][P], const float4 w, unsigned char *q)
 {
+	unsigned flags = 0;
 #pragma unroll
 	for (int k = 0; k < P; ++k) {
 		float v;
@@ -196,8 +251,12 @@ __device__ __forceinline__ void vertical_emit(const float (&hr)[4][P], const flo
 			v = fmaf(w.z, hr[(U + 3) & 3][k], v);
 		}
 		v = __saturatef(fmaf(w.w, hr[U][k], v));
-		Codec::store(q + k * BPP, v);
+		if (REPAIR)
+			flags |= Codec::store_flag(q + k * BPP, v) ? 1u << k : 0u;
+		else
+			Codec::store(q + k * BPP, v);
 	}
+	return flags;
 }
 
 // S      sample type (uint8_t, uint16_t, float)

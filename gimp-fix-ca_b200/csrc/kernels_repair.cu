@@ -1,0 +1,32 @@
+// kernels_repair.cu -- Linear / Cubic, bit-identical to the reference (fix-ca.c:1122-1320), for 8-bit samples:
+// stream_kernel<..., REPAIR = true> runs the FP32 streaming pipeline and recomputes, in the reference's own FP64
+// arithmetic, exactly the samples whose FP32 value lies within a proven error bound of a rounding boundary
+// (DESIGN.md 4.6).  Every other format, and geometries the streaming kernel cannot take, stay on
+// tiled_kernel<ExactF64> (kernels_exact.cu).
+#include "fixca_internal.h"
+
+namespace fixca {
+
+// Only 8-bit samples: there the bound (|FP32 - reference| <= 2.7e-4 LSB) sends 0.05 % of the samples to the FP64
+// repair and EXACT runs 2.1x (Cubic) / 1.7x (Linear) faster than the FP64 tile kernel.  For 16-bit samples the same bound
+// is 0.07 LSB, 14 % of the samples need the repair, and the kernel measured 2.34 ms against 1.19 ms (100 MP RGB16
+// Cubic): they stay on tiled_kernel<ExactF64>.
+// layouts as in kernels_fast.cu (columns per thread, strip width)
+#define REPAIR_ENTRIES(S, TAG, P3, TW3, P4, TW4)                                                              \
+	{ (kernel_fn)stream_kernel<S, 3, 1, P3, TW3, false, true>, "stream/linear/f32+f64/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1, 1 }, \
+	{ (kernel_fn)stream_kernel<S, 4, 1, P4, TW4, false, true>, "stream/linear/f32+f64/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1, 1 }, \
+	{ (kernel_fn)stream_kernel<S, 3, 2, P3, TW3, false, true>, "stream/cubic/f32+f64/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1, 1 },  \
+	{ (kernel_fn)stream_kernel<S, 4, 2, P4, TW4, false, true>, "stream/cubic/f32+f64/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1, 1 }
+
+static const KernelEntry repair_table[] = {
+	REPAIR_ENTRIES(uint8_t, "u8", 4, 256, 3, 192),
+};
+
+const KernelEntry *lookup_exact_stream(SampleKind kind, int nch, int interp)
+{
+	if (kind != SK_U8 || (nch != 3 && nch != 4) || (interp != 1 && interp != 2) || tuning().exact_tiled)
+		return nullptr;
+	return &repair_table[(interp - 1) * 2 + (nch - 3)];
+}
+
+} // namespace fixca

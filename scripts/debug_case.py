@@ -1,32 +1,38 @@
 #!/usr/bin/env python
-"""Developer probe: one FAST case against the oracle, printing where the mismatches sit."""
-import os, sys
+"""Developer probe: run named golden cases through two kernel choices and print where they differ.
+    python scripts/debug_case.py <case name> [<case name> ...]"""
+import json
+import os
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "gimp-fix-ca_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import numpy as np
-import fixca, oracle as orc
-h, w, ch, dtype, interp = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], int(sys.argv[5])
-amounts = (float(sys.argv[6]), float(sys.argv[7])) if len(sys.argv) > 7 else (3.0, -2.0)
-KW = dict(blue=3.0, red=-2.0, x_blue=0.7, x_red=-0.4, y_blue=0.3, y_red=-0.9)
-kw = dict(KW, blue=amounts[0], red=amounts[1], lens_x=w // 2, lens_y=h // 2, interpolation=interp)
-if os.environ.get("PLANT"):
-    # fill shared memory with NaN / Inf bit patterns first (a u32 None pass over all-ones samples)
-    junk = np.full((h, w, ch), 0xFFFFFFFF, dtype="u4")
-    for _ in range(3):
-        fixca.correct(junk, fixca.FixCaParams(**dict(kw, interpolation=0)))
+for p in ("gimp-fix-ca_b200", "oracle", "tests"):
+    sys.path.insert(0, os.path.join(ROOT, p))
+import numpy as np  # noqa: E402
+
+import fixca  # noqa: E402
+import oracle as orc  # noqa: E402
+from helpers import case_image, fx_params, oracle_params  # noqa: E402
+
+cases = {c["name"]: c for c in json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["suite"]}
 chk = orc.best_checker()
-img = orc.synth_image(h, w, ch, dtype, seed=5000)
-want = chk.region(img, orc.Params(**kw))
-got = fixca.correct(img, fixca.FixCaParams(**kw), flags=fixca.PRECISION_FAST)
-print(fixca.last_kernel())
-d = np.abs(got.astype(np.float64) - want.astype(np.float64))
-tol = 1e-6 if dtype.startswith("f") else 1
-bad = np.argwhere(d > tol)
-print("bad samples", len(bad), "max", d.max())
-if len(bad):
-    ys, xs, cs = bad[:, 0], bad[:, 1], bad[:, 2]
-    print("rows", np.unique(ys)[:40], "...", "n rows", len(np.unique(ys)))
-    print("cols", np.unique(xs)[:40], "...", "n cols", len(np.unique(xs)))
-    print("channels", np.unique(cs))
-    for y, x, c in bad[:10]:
-        print(y, x, c, got[y, x, c], want[y, x, c])
+for name in sys.argv[1:]:
+    c = cases[name]
+    img = case_image(c)
+    want = chk.region(img, oracle_params(c))
+    os.environ.pop("FIXCA_EXACT_KERNEL", None)
+    fixca.reload_tuning()
+    a = fixca.correct(img, fx_params(fixca, c))
+    ka = fixca.last_kernel()
+    os.environ["FIXCA_EXACT_KERNEL"] = "tiled"
+    fixca.reload_tuning()
+    b = fixca.correct(img, fx_params(fixca, c))
+    kb = fixca.last_kernel()
+    print(name, {k: c[k] for k in c if k not in ("name", "md5")})
+    for lab, got, k in (("auto", a, ka), ("tiled", b, kb)):
+        d = np.argwhere(got != want)
+        print("  %-5s %-28s mismatches %d" % (lab, k, len(d)))
+        for y, x, ch in d[:12]:
+            print("     y=%d x=%d ch=%d got=%d want=%d" % (y, x, ch, got[y, x, ch], want[y, x, ch]))
+        if len(d):
+            print("     rows", sorted(set(d[:, 0]))[:20], "cols", sorted(set(d[:, 1]))[:20])

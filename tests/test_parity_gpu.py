@@ -30,17 +30,28 @@ def _need_gpu(fx):
 # ---------------------------------------------------------------------------------------------
 # golden digests (produced by the reference's own code, tests/golden/make_golden.py)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("force", ["auto", "direct"])
-def test_golden_suite_bit_exact(fx, force):
+@pytest.mark.parametrize("force", ["auto", "direct", "tiled"])
+def test_golden_suite_bit_exact(fx, force, tuning):
+    """EXACT arithmetic through each of its kernel families: auto = the streaming kernel with exact repair of
+    near-tie samples for 8/16-bit integers (f32+f64) and tiled_kernel<ExactF64> for the rest; tiled = the FP64 tile
+    kernel for every format (FIXCA_EXACT_KERNEL=tiled); direct = the per-pixel kernel."""
+    if force == "tiled":
+        tuning("FIXCA_EXACT_KERNEL", "tiled")
     flags = fx.PRECISION_EXACT | (fx.FORCE_DIRECT if force == "direct" else 0)
     bad, kernels = [], set()
     for c in golden()["suite"]:
         got = fx.correct(case_image(c), fx_params(fx, c), flags=flags)
-        kernels.add(fx.last_kernel().split("/")[0])
+        k = fx.last_kernel().split("/")
+        kernels.add(k[0] + ("/" + k[2] if k[1] != "none" else "/none"))
         if md5(got) != c["md5"]:
             bad.append(c["name"])
     assert not bad, "%d of %d golden cases differ (%s), first: %s" % (len(bad), len(golden()["suite"]), force, bad[:8])
-    assert ("tiled" in kernels) if force == "auto" else (kernels == {"direct"})
+    if force == "auto":
+        assert {"stream/f32+f64", "tiled/f64"} <= kernels, kernels
+    elif force == "tiled":
+        assert "tiled/f64" in kernels and "stream/f32+f64" not in kernels, kernels
+    else:
+        assert {k.split("/")[0] for k in kernels} == {"direct"}, kernels
 
 
 def test_golden_suite_fast_within_tolerance(fx, checker):
@@ -67,7 +78,7 @@ def test_known_answer_test1_md5(fx):
         pytest.skip("oracle/_ref/full-branches.rgb missing (generated where /root/reference is mounted)")
     g = golden()["fixture"]
     out = fx.correct(img, fx.FixCaParams(blue=6.0, red=-2.4, lens_x=0, lens_y=0, interpolation=1))
-    assert "tiled/linear/f64" in fx.last_kernel()
+    assert "stream/linear/f32+f64" in fx.last_kernel()
     assert md5(out) == g["test1_raw_md5"]
     assert hashlib.md5(encode_gimp_bmp24(out)).hexdigest() == "c472550cda23c8cb717853ac0dd93e2b"
 
@@ -330,7 +341,8 @@ def test_fanout_stores_every_destination(fx, checker):
     h, w, ch = 403, 640, 3
     st = torch.cuda.current_stream().cuda_stream
     for dt, interp, flags, streaming in (("u2", 2, fx.PRECISION_FAST, True), ("u1", 0, fx.PRECISION_EXACT, True),
-                                         ("f4", 1, fx.PRECISION_FAST, True), ("u2", 2, fx.PRECISION_EXACT, False)):
+                                         ("f4", 1, fx.PRECISION_FAST, True), ("u2", 2, fx.PRECISION_EXACT, False),
+                                         ("u1", 2, fx.PRECISION_EXACT, True)):
         img = orc.synth_image(h, w, ch, dt, 91)
         kw = dict(KW, lens_x=300, lens_y=128, interpolation=interp)
         p = fx.FixCaParams(**kw)
@@ -408,7 +420,7 @@ def test_rows_that_are_views_into_a_wider_buffer_are_not_overrun(fx, checker):
     src = torch.zeros((h, pitch), dtype=torch.uint8, device="cuda")
     src[:, :w * ch] = torch.from_numpy(img.reshape(h, w * ch)).cuda()
     for flags, kernel in ((fx.PRECISION_FAST, "direct"), (fx.PRECISION_FAST | fx.PADDING_SCRATCH, "stream"),
-                          (fx.PRECISION_EXACT, "direct"), (fx.PRECISION_EXACT | fx.PADDING_SCRATCH, "tiled")):
+                          (fx.PRECISION_EXACT, "direct"), (fx.PRECISION_EXACT | fx.PADDING_SCRATCH, "stream/cubic/f32+f64")):
         dst = torch.full((h, pitch), 0x5A, dtype=torch.uint8, device="cuda")
         fx.fix_ca_region_dev(src.data_ptr(), pitch, 0, h, dst.data_ptr(), pitch, 0, w, h, ch, 1, fx.FixCaParams(**kw), 0, h, flags, stream)
         torch.cuda.synchronize()
@@ -636,12 +648,12 @@ def _absdiff(a, b):
 
 
 @pytest.mark.parametrize("name,h,w,ch,dtype,kw", FULL, ids=[f[0] for f in FULL])
-def test_full_size_properties(fx, checker, name, h, w, ch, dtype, kw):
+def test_full_size_properties(fx, checker, name, h, w, ch, dtype, kw, tuning):
     img = _full_image(4, h, w, ch, dtype)
     tol = FLOAT_ABS_TOL if dtype == "f4" else FAST_LSB_TOL
     p = fx.FixCaParams(**kw)
     full = fx.correct(img, p)
-    assert fx.last_kernel().startswith("tiled")
+    assert fx.last_kernel().startswith("stream/%s/f32+f64" % ("linear" if kw["interpolation"] == 1 else "cubic") if dtype == "u1" else "tiled")
     # green / alpha untouched everywhere
     assert (full[..., 1] == img[..., 1]).all() and (ch == 3 or (full[..., 3] == img[..., 3]).all())
     # oracle on sampled bands (top edge, an interior band straddling chunk borders, bottom edge)
@@ -655,6 +667,12 @@ def test_full_size_properties(fx, checker, name, h, w, ch, dtype, kw):
     fx.correct(img, p, y1=h // 3, y2=h, out=halves)
     assert md5(halves) == md5(full)
     del halves
+    # the FP64 tile kernel (the exact path of the float formats) computes the same bytes as the repair kernel
+    if dtype == "u1":
+        tuning("FIXCA_EXACT_KERNEL", "tiled")
+        other = fx.correct(img, p)
+        assert fx.last_kernel().startswith("tiled") and md5(other) == md5(full)
+        del other
     # fast arithmetic: within tolerance of the exact result on the whole image
     fast = fx.correct(img, p, flags=fx.PRECISION_FAST)
     bad = 0
