@@ -102,6 +102,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 // pressure by that quarter), and the prompt wake-up is worth having: with the hand-over on named barriers
 // (bar.arrive / bar.sync: the waiting warps parked by the hardware, no polling at all) the Cubic kernels were
 // 3-9 % slower (headline 0.198 -> 0.204 ms, 128 x 4K RGB8 68 -> 65 %), only None gained (100 MP RGB16 94.5 -> 97.5 %).
+// A/B (FIXCA_TUNING builds, FIXCA_STREAM_DEBUG >> 8 = nanoseconds): a helper warp that tests the barrier and then
+// really sleeps (nanosleep.u32, no wake-up on barrier traffic) instead of the try_wait loop below
+__device__ __forceinline__ void mbar_wait_naps(uint64_t *bar, uint32_t parity, uint32_t nap_ns)
+{
+	for (;;) {
+		uint32_t done;
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			"selp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(done)
+			: "r"(smem_u32(bar)), "r"(parity)
+			: "memory");
+		if (done)
+			return;
+		asm volatile("nanosleep.u32 %0;" ::"r"(nap_ns) : "memory");
+	}
+}
 __device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity, uint32_t hint_ns)
 {
 	uint32_t done;
@@ -261,6 +279,11 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		int inf = 0, ipar = 0;	// i % NF, (i / NF) & 1
 		for (int i = 0; i < nchunks; ++i) {
 			if (i >= NF)	// the slot's previous tenant (chunk i - NF) must be finished
+#ifdef FIXCA_TUNING
+				if (a.debug >> 8)
+					mbar_wait_naps(&done[inf], (uint32_t)(ipar ^ 1), (uint32_t)(a.debug >> 8));
+				else
+#endif
 				mbar_wait_sleepy(&done[inf], (uint32_t)(ipar ^ 1), 2000u);
 			const int y_first = ya + i * CH;
 			const int nr = min(CH, yb - y_first);
@@ -355,6 +378,11 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				request_window(j + D);
 			if (j + 1 < nchunks)
 				request_tile(j + 1);
+#ifdef FIXCA_TUNING
+			if (a.debug >> 8)
+				mbar_wait_naps(&done[jnf], (uint32_t)jpar, (uint32_t)(a.debug >> 8));
+			else
+#endif
 			mbar_wait_sleepy(&done[jnf], (uint32_t)jpar, 500u);
 			tma_store_3d(&tm_out, c0_tile, ya + j * CH - a.dst_row0, frame, stage + jstg * STAGE_BYTES);
 			for (int e = 0; e < fan.n; ++e)		// the same chunk into the other frames (peer GPUs, over NVLink)
