@@ -4,7 +4,7 @@
  *
  * This is the drop-in boundary: plain C, plain pointers and sizes.  Each entry
  * point names the piece of the reference plug-in (JoesCat/gimp-fix-ca,
- * fix-ca.c) it replaces or restates.  INTEGRATION.md shows the ~15-line patch
+ * fix-ca.c) it replaces or restates.  INTEGRATION.md shows the patch (~50 lines)
  * that makes fix-ca.c call fixca_cuda_region() instead of its CPU row loop.
  *
  * There is no CPU fallback: every compute entry point fails with
