@@ -134,6 +134,14 @@ if __name__ == "__main__":
         run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
         run("50MP rgb f32 cubic fast", 6144, 8192, 3, torch.float32, -4, 2, F)
         run("50MP rgba f32 cubic fast", 6144, 8192, 4, torch.float32, -4, 2, F)
+    if which == "small":    # launches dominated by the fixed cost
+        run("4K rgb8 cubic fast", 2160, 3840, 3, torch.uint8, 1, 2, F)
+        run("4K rgb8 linear fast", 2160, 3840, 3, torch.uint8, 1, 1, F)
+        run("24MP rgb8 linear fast", 4000, 6000, 3, torch.uint8, 1, 1, F)
+        run("768-row rgb f32 cubic band", 768, 8192, 3, torch.float32, -4, 2, F)
+        run("1536-row rgb f32 cubic band", 1536, 8192, 3, torch.float32, -4, 2, F)
+        run("1080p rgba8 cubic", 1080, 1920, 4, torch.uint8, 1, 2, F)
+        run("100MP rgb16 cubic fast", 8192, 12288, 3, torch.int16, 2, 2, F)
     if which == "naps":     # FIXCA_LIB = the TUNING build: helper warps that nap between barrier tests (debug >> 8 = ns)
         for ns in (0, 64, 128, 256, 512, 1024):
             os.environ["FIXCA_STREAM_DEBUG"] = str(ns << 8)
