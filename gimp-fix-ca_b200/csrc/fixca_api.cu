@@ -502,6 +502,30 @@ static bool make_tensor_map(CUtensorMap &tm, const void *base, size_t pitch, siz
 		   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// CTAs of kernel k the hardware keeps resident per SM at this block size and dynamic shared memory (the grid of a
+// streaming launch is sized to be resident all at once); asked once per (kernel, threads, shared memory, device)
+static int resident_ctas(const KernelEntry *k, int threads, size_t smem, int dev)	// (smem: the caller's own limit; part of the key only)
+{
+	struct Key { const void *fn; int threads; size_t smem; int dev; int n; };
+	static thread_local Key cache[16];
+	static thread_local int next = 0;
+	for (const Key &c : cache)
+		if (c.fn == (const void *)k->fn && c.threads == threads && c.smem == smem && c.dev == dev)
+			return c.n;
+	int n = 64;		// unknown: no extra limit
+	cudaFuncAttributes fa;
+	if (cudaFuncGetAttributes(&fa, (const void *)k->fn) == cudaSuccess && fa.numRegs > 0) {
+		// registers are allocated per warp in units of 256; 64 K registers per SM
+		const int per_warp = (fa.numRegs * 32 + 255) / 256 * 256;
+		n = std::max(1, 65536 / (per_warp * ((threads + 31) / 32)));
+	} else {
+		cudaGetLastError();
+	}
+	cache[next] = Key{(const void *)k->fn, threads, smem, dev, n};
+	next = (next + 1) % 16;
+	return n;
+}
+
 static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g, int y1, int y2, int dev, int limit, Plan &pl)
 {
 	const int CH = STREAM_CH;
@@ -535,10 +559,10 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 			max_rows = std::max(max_rows, c_hi[std::min(j + d, nchunks_all - 1)] - c_lo[j] + 1);
 		ring_rows = align_up((size_t)max_rows, 4) + 8;	// whole 4-row groups at both ends
 		off_meta = align_up(sizeof(StreamHeader), 16);
-		off_win = align_up(off_meta + (size_t)(d + 1) * sizeof(StreamMeta), 128);
+		off_win = align_up(off_meta + (size_t)(d + 1) * (k->repair == 2 ? sizeof(StreamMetaWide) : sizeof(StreamMeta)), 128);
 		off_out = align_up(off_win + ring_rows * (size_t)wb, 128);
 		total = off_out + (size_t)STREAM_NSTG * CH * k->tw * f.bpp;
-		if (k->repair) {	// per-warp queues of near-tie samples, u16 entries
+		if (k->repair == 1) {	// per-warp queues of near-tie samples, u16 entries
 			off_rq = align_up(total, 16);
 			total = off_rq + (size_t)(2 * k->tw / k->strip_p / 32) * (32 + 32 * k->strip_p) * 2;
 		}
@@ -572,6 +596,7 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	int per_sm = (int)((227 * 1024) / (total + 1024));
 	per_sm = std::max(1, std::min(per_sm, 2048 / threads));
 	per_sm = std::min(per_sm, want_ctas);
+	per_sm = std::min(per_sm, resident_ctas(k, threads, total, dev));	// registers (the FP64 pipelines: 2 per SM)
 	const int strips = (g.width + k->tw - 1) / k->tw;
 	const int rows = y2 - y1;
 	int segs = std::max(1, sm_count(dev) * per_sm / strips);

@@ -25,7 +25,7 @@ struct KernelEntry {
 	int         sample_bytes;
 	int         strip_p;	// > 0: strip_kernel with this many columns per thread (blockDim = 2 * tw / strip_p)
 	int         stream;	// != 0: stream_kernel (blockDim = 2 * tw / strip_p + 64, grid = strips x segments)
-	int         repair;	// != 0: the exact-repair form of stream_kernel (per-warp queues in shared memory)
+	int         repair;	// 1: the exact-repair form of stream_kernel (FP32 pipeline, per-warp queues in shared memory); 2: WIDE (FP64 pipeline)
 };
 
 constexpr int TILE_W = 128;

@@ -77,12 +77,14 @@ struct alignas(64) StreamFanout {
 	int n;
 };
 
-struct StreamMeta {
-	float4 wy[STREAM_CH][2];	// vertical weights per output row and channel, by tap position (position_weights)
+template <class V4> struct StreamMetaT {
+	V4     wy[STREAM_CH][2];	// vertical weights per output row and channel, by tap position (position_weights)
 	int    last[2][STREAM_CH + 1];	// highest tap row of each output row (INT_MAX after the chunk's last row)
 	int    s_end[2];		// = last[c][nrows - 1]
 	int    simple[2];		// full chunk whose rows finish on CH consecutive source rows (the usual case)
 };
+typedef StreamMetaT<float4> StreamMeta;		// FP32 pipelines
+typedef StreamMetaT<dvec4> StreamMetaWide;	// WIDE: FP64 weights
 
 struct StreamHeader {
 	unsigned long long full[STREAM_MAX_NF];
@@ -190,8 +192,11 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *tm)
 // reference value| -- of a rounding boundary is queued per warp and recomputed with the reference's own FP64
 // arithmetic (interp_sample<ExactF64>, taps read from the window ring), 32 queued samples at a time so that the
 // FP64 work runs on full warps.  Everything else rounds to the same integer in both arithmetics.
-template <class S, int NCH, int INTERP, int P, int TW, bool ALT = false, bool REPAIR = false>
-__global__ void __launch_bounds__(2 * TW / P + 64, (2 * TW / P + 64) <= 192 ? 4 : 2)	// register budget: 4 (2) resident CTAs
+// WIDE (16-bit samples, Linear / Cubic): the bit-exact form on an FP64 pipeline.  The same separable sums in FP64 on
+// raw sample values (fixca_strip.cuh, WideCodec); a sample within WideCodec::kEps of a rounding boundary -- one in
+// half a million -- is recomputed in the reference's operation order by its own thread at the end of the chunk.
+template <class S, int NCH, int INTERP, int P, int TW, bool ALT = false, bool REPAIR = false, bool WIDE = false>
+__global__ void __launch_bounds__(2 * TW / P + 64, (2 * TW / P + 64) <= 192 && !WIDE ? 4 : 2)	// register budget: 4 (2) resident CTAs
 stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUtensorMap tm_win,
 	      const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ CUtensorMap tm_out,
 	      const __grid_constant__ StreamFanout fan)
@@ -212,8 +217,11 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	static_assert(ALT || HALF % 32 == 0, "a warp must not straddle the two channels");
 	static_assert(NTC % 32 == 0, "whole compute warps");
 	static_assert(2 * CH <= 32, "one producer lane per (channel, row) of a chunk");
+	static_assert(!(WIDE && (REPAIR || INTERP == 0)), "WIDE is its own exact form");
+	typedef typename std::conditional<WIDE, double, float>::type A;		// the pipeline's arithmetic type
+	typedef typename std::conditional<WIDE, StreamMetaWide, StreamMeta>::type Meta;
 	StreamHeader *hdr = reinterpret_cast<StreamHeader *>(smem);
-	StreamMeta *meta = reinterpret_cast<StreamMeta *>(smem + a.off_ytab);
+	Meta *meta = reinterpret_cast<Meta *>(smem + a.off_ytab);
 	unsigned char *win = smem + a.off_win;
 	unsigned char *stage = smem + a.off_out;
 
@@ -287,7 +295,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				mbar_wait_sleepy(&done[inf], (uint32_t)(ipar ^ 1), 2000u);
 			const int y_first = ya + i * CH;
 			const int nr = min(CH, yb - y_first);
-			StreamMeta &m = meta[inf];
+			Meta &m = meta[inf];
 			const int ch = (lane / CH) & 1, r = lane % CH;
 			const bool mine = lane < 2 * CH && r < nr;
 			int last = 0;
@@ -302,6 +310,8 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			if (mine) {
 				if constexpr (INTERP == 0)
 					last = nearest_index(a.g.y[ch], y_first + r);
+				else if constexpr (WIDE)
+					m.wy[r][ch] = position_weights_wide<INTERP>(a.g.y[ch], y_first + r, H, kWideScale, last);
 				else
 					m.wy[r][ch] = position_weights<INTERP, REPAIR>(a.g.y[ch], y_first + r, H, StripCodec<S>::kInvMax, last);
 				m.last[ch][r] = last;
@@ -415,7 +425,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		int jnf = 0, jstg = 0, jpar = 0;	// j % NF, j % NSTG, (j / NF) & 1
 		for (int j = 0; j < nchunks; ++j) {
 			mbar_wait(&full[jnf], (uint32_t)jpar);
-			const StreamMeta &m = meta[jnf];
+			const Meta &m = meta[jnf];
 			uint64_t *const done_bar = &done[jnf];
 			unsigned char *q = stage + jstg * STAGE_BYTES + qoff;
 			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
@@ -440,19 +450,20 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		}
 	} else {
 	typedef StripCodec<S> Codec;
+	typedef typename std::conditional<WIDE, WideCodec<S>, StripCodec<S>>::type LoadCodec;
 
 	// regular: the P columns share one window of NS consecutive samples; wt[k][jj] weighs sample k + jj.
 	// otherwise ("bent": tap windows squeezed against an image edge, fix-ca.c:1271-1298): column k reads its
 	// own T consecutive samples from byte offset cofs[k]; wt[k][jj < T] weighs sample jj, clamped taps merged.
 	// Both forms run the same row loop without index arithmetic, so a bent warp costs about as much as a
 	// regular one (a per-tap path with clamps in the loop made every CTA of an edge strip a 1.4x straggler).
-	float wt[P][NW];
+	A wt[P][NW];
 	int cofs[P];		// ... relative to colbase
 	int colbase;		// byte offset of shared sample 0 from the window row start
 	int cmax;		// bent form: offset of the image's last column (samples past it carry no weight)
 	bool regular;
 	{
-		float w[P][4];
+		A w[P][4];
 		int tap[P][T];	// clamp-to-edge tap columns minus k
 		int bmin = INT_MAX;
 #pragma unroll
@@ -461,25 +472,32 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			// clipped by the TMA store); past the image the coordinate clamps to W - 1 ...
 			double td;
 			const int i0 = base_index(a.g.x[c], x0 + lt * P + k, td);
-			if (REPAIR) {	// FP64 weights, rounded once (the error bound counts one rounding per weight)
-				double wd[4];
-				tap_weights_d<INTERP>(td, wd);
+			if constexpr (WIDE) {
+				tap_weights_d<INTERP>(td, w[k]);
 #pragma unroll
 				for (int j = 0; j < 4; ++j)
-					w[k][j] = (float)wd[j];
+					w[k][j] = w[k][j] * kWideScale + 0.0;
 			} else {
-				tap_weights<INTERP>((float)td, w[k]);
-			}
+				if (REPAIR) {	// FP64 weights, rounded once (the error bound counts one rounding per weight)
+					double wd[4];
+					tap_weights_d<INTERP>(td, wd);
 #pragma unroll
-			for (int j = 0; j < 4; ++j)
-				w[k][j] = w[k][j] * Codec::kHScale + 0.f;	// power of two (integer samples are read as subnormals); -0 -> +0: the sign of an all-zero sum must not depend on the fold
+					for (int j = 0; j < 4; ++j)
+						w[k][j] = (float)wd[j];
+				} else {
+					tap_weights<INTERP>((float)td, w[k]);
+				}
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+					w[k][j] = w[k][j] * Codec::kHScale + 0.f;	// power of two (integer samples are read as subnormals); -0 -> +0: the sign of an all-zero sum must not depend on the fold
+			}
 			// ... with zero weights, so that they do not bend a warp of the last strip
 			if (x0 + lt * P + k > xl)
-				w[k][0] = w[k][1] = w[k][2] = w[k][3] = 0.f;
+				w[k][0] = w[k][1] = w[k][2] = w[k][3] = 0;
 #pragma unroll
 			for (int j = 0; j < T; ++j) {
 				tap[k][j] = clampi(i0 - OFF + j, 0, W - 1) - k;
-				if (w[k][j] != 0.f)
+				if (w[k][j] != 0)
 					bmin = min(bmin, tap[k][j]);
 			}
 		}
@@ -498,7 +516,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		for (int k = 0; k < P; ++k)
 #pragma unroll
 			for (int j = 0; j < T; ++j)
-				regular = regular && (w[k][j] == 0.f || tap[k][j] - bmin <= NW - 1);
+				regular = regular && (w[k][j] == 0 || tap[k][j] - bmin <= NW - 1);
 		regular = __all_sync(0xffffffffu, regular);
 		// The usual thread: no tap clamped, every column's window starts 0 or 1 samples after the group's
 		// first sample -- its weights are the tap weights, shifted by that drift (20 selects instead of the
@@ -518,7 +536,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				const bool drift = tap[k][0] != bmin;
 #pragma unroll
 				for (int jj = 0; jj < NW; ++jj) {
-					const float w0 = jj < T ? w[k][jj] : 0.f, w1 = jj >= 1 ? w[k][jj - 1] : 0.f;
+					const A w0 = jj < T ? w[k][jj] : 0, w1 = jj >= 1 ? w[k][jj - 1] : 0;
 					wt[k][jj] = drift ? w1 : w0;
 				}
 			}
@@ -527,11 +545,11 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			for (int k = 0; k < P; ++k)
 #pragma unroll
 				for (int jj = 0; jj < NW; ++jj) {
-					float v = 0.f;
+					A v = 0;
 #pragma unroll
 					for (int j = 0; j < T; ++j) {
 						const int at = regular ? tap[k][j] - bmin : tap[k][j] - tap[k][0];
-						v += (w[k][j] != 0.f && at == jj) ? w[k][j] : 0.f;
+						v += (w[k][j] != 0 && at == jj) ? w[k][j] : 0;
 					}
 					wt[k][jj] = v;
 				}
@@ -551,12 +569,12 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	// Ring of the last four horizontal rows.  `ph` = slot the next source row goes to; the newest row
 	// sits in slot ph - 1, the row p below it in slot ph - 1 - p (mod 4).  The vertical weights come
 	// ordered by that distance p (position_weights), so the arithmetic is independent of ph.
-	float hr[4][P];
+	A hr[4][P];
 #pragma unroll
 	for (int u = 0; u < 4; ++u)
 #pragma unroll
 		for (int k = 0; k < P; ++k)
-			hr[u][k] = 0.f;
+			hr[u][k] = 0;
 	int ph = (5 - T) & 3;	// after the T - 1 priming rows of a segment the ring is back at slot 0
 	// the thread's view of the window ring: every row pointer already carries its column offset
 	// (32-bit shared-window addresses: one add / compare / select per row; with generic pointers the
@@ -599,7 +617,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				rq_n += __popc(m);
 			}
 		}
-		if (rq_n >= 32)
+		while (rq_n >= 32)	// (a row of an image full of exact ties queues up to 32 * P samples)
 			repair(32, y_first, stg);
 	};
 
@@ -614,16 +632,17 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		int jnf = 0, jstg = 0, jpar = 0;	// j % NF, j % NSTG, (j / NF) & 1
 		for (int j = 0; j < nchunks; ++j) {
 			mbar_wait(&full[jnf], (uint32_t)jpar);
-			const StreamMeta &m = meta[jnf];
+			const Meta &m = meta[jnf];
 			uint64_t *const done_bar = &done[jnf];
 			unsigned char *const stg = stage + jstg * STAGE_BYTES;	// this chunk's staging buffer
 			unsigned char *q = stg + qoff;
 			const int y_first = ya + j * CH;
-			int er = 0;		// REPAIR: chunk row the next emit writes
+			int er = 0;		// REPAIR / WIDE: chunk row the next emit writes
+			[[maybe_unused]] unsigned wflags = 0;	// WIDE: this thread's near-tie samples of the chunk, bit = chunk row * P + column
 			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
 			jstg = jstg + 1 == NSTG ? 0 : jstg + 1;
 			const int s_end = m.s_end[c];
-			const float4 *wy = &m.wy[0][c];		// [row][channel]: stride 2
+			const auto *wy = &m.wy[0][c];		// [row][channel]: stride 2
 			const int *lastp = m.last[c];
 			int next_last = lastp[0];
 
@@ -635,33 +654,44 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			}
 
 			// a source row's samples / the P horizontal results from them, in either form
-			auto load_row = [&](const uint32_t p, float (&smp)[NSL]) {
+			auto load_row = [&](const uint32_t p, A (&smp)[NSL]) {
 				if (REG) {
 #pragma unroll
 					for (int mm = 0; mm < NSL; ++mm)
-						smp[mm] = Codec::load_at(p + mm * BPP);
+						smp[mm] = LoadCodec::load_at(p + mm * BPP);
 				} else {
 #pragma unroll
 					for (int k = 0; k < P; ++k)
 #pragma unroll
 						for (int jj = 0; jj < T; ++jj)
-							smp[k * T + jj] = Codec::load_at(p + (uint32_t)min(cofs[k] + jj * BPP, cmax));
+							smp[k * T + jj] = LoadCodec::load_at(p + (uint32_t)min(cofs[k] + jj * BPP, cmax));
 				}
 			};
-			auto hfilter = [&](const float (&smp)[NSL], float (&out)[P]) {
+			auto hfilter = [&](const A (&smp)[NSL], A (&out)[P]) {
 #pragma unroll
 				for (int k = 0; k < P; ++k) {
-					float v = wt[k][0] * smp[REG ? k : k * T];
+					A v = wt[k][0] * smp[REG ? k : k * T];
 #pragma unroll
 					for (int jj = 1; jj < NWV; ++jj)
-						v = fmaf(wt[k][jj], smp[REG ? k + jj : k * T + jj], v);
+						v = fma(wt[k][jj], smp[REG ? k + jj : k * T + jj], v);
 					out[k] = v;
+				}
+			};
+			// one output row of the P columns from the ring (newest row in slot U) into chunk row `row` at q
+			auto vemit = [&](auto slot, const auto &wrow, unsigned char *const qrow, const int row) {
+				constexpr int U = decltype(slot)::value;
+				if constexpr (WIDE) {
+					wflags |= vertical_emit_wide<INTERP, U, P, BPP, WideCodec<S>>(hr, wrow, qrow) << (row * P);
+				} else {
+					const unsigned fl = vertical_emit<INTERP, U, P, BPP, Codec, REPAIR>(hr, wrow, qrow);
+					if (REPAIR)
+						enqueue(fl, row, y_first, stg);
 				}
 			};
 			// one source row through the horizontal filter into ring slot U
 			auto hrow = [&](auto slot) {
 				constexpr int U = decltype(slot)::value;
-				float smp[NSL];
+				A smp[NSL];
 				load_row(prow, smp);
 				hfilter(smp, hr[U]);
 				++s_done;
@@ -671,12 +701,9 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			};
 			// the output rows completed by the newest row (slot U)
 			auto emit = [&](auto slot) {
-				constexpr int U = decltype(slot)::value;
 #pragma unroll 1
 				while (next_last <= s_done) {
-					const unsigned fl = vertical_emit<INTERP, U, P, BPP, Codec, REPAIR>(hr, *wy, q);
-					if (REPAIR)
-						enqueue(fl, er++, y_first, stg);
+					vemit(slot, *wy, q, er++);
 					wy += 2;
 					q += OUT_PITCH;
 					next_last = *++lastp;
@@ -717,7 +744,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				if (ph != 0) {	// bring the ring to slot 0 (after a general chunk; rare)
 					auto rotate = [&](auto by) {
 						constexpr int N = decltype(by)::value;
-						float t[4][P];
+						A t[4][P];
 #pragma unroll
 						for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -743,7 +770,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				constexpr int UNR = P >= 4 ? 4 : CH;
 				static_assert(CH % UNR == 0 && UNR % 4 == 0, "unroll must divide the chunk and cover whole ring turns");
 				// (bent warps load and filter row by row: their P * T samples are not double-buffered)
-				float smp[REG ? 2 : 1][NSL];
+				A smp[REG ? 2 : 1][NSL];
 				if (REG)
 					load_row(prow, smp[0]);
 #pragma unroll 1
@@ -759,15 +786,12 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 						else
 							load_row(prow, smp[0]);
 						hfilter(smp[REG ? u & 1 : 0], hr[u & 3]);
-						unsigned fl;
-						switch (u & 3) {
-						case 0: fl = vertical_emit<INTERP, 0, P, BPP, Codec, REPAIR>(hr, wy[2 * u], q + u * OUT_PITCH); break;
-						case 1: fl = vertical_emit<INTERP, 1, P, BPP, Codec, REPAIR>(hr, wy[2 * u], q + u * OUT_PITCH); break;
-						case 2: fl = vertical_emit<INTERP, 2, P, BPP, Codec, REPAIR>(hr, wy[2 * u], q + u * OUT_PITCH); break;
-						default: fl = vertical_emit<INTERP, 3, P, BPP, Codec, REPAIR>(hr, wy[2 * u], q + u * OUT_PITCH); break;
+						switch (u & 3) {	// (static ring slots: u is a constant after unrolling)
+						case 0: vemit(std::integral_constant<int, 0>(), wy[2 * u], q + u * OUT_PITCH, er++); break;
+						case 1: vemit(std::integral_constant<int, 1>(), wy[2 * u], q + u * OUT_PITCH, er++); break;
+						case 2: vemit(std::integral_constant<int, 2>(), wy[2 * u], q + u * OUT_PITCH, er++); break;
+						default: vemit(std::integral_constant<int, 3>(), wy[2 * u], q + u * OUT_PITCH, er++); break;
 						}
-						if (REPAIR)
-							enqueue(fl, er++, y_first, stg);
 						prow = pnext;
 					}
 					wy += 2 * UNR;
@@ -789,6 +813,19 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			if (REPAIR)	// what is left of the queue (its rows and taps belong to this chunk)
 				while (rq_n > 0)
 					repair(min(rq_n, 32), y_first, stg);
+			if constexpr (WIDE) {
+				// near-tie samples (2e-6 of all): the reference's own arithmetic (fix-ca.c:1135-1186, :1204-1320),
+				// taps read from the window ring, whose rows stay valid until the chunk is handed over
+				while (wflags) {
+					const int b = __ffs((int)wflags) - 1;
+					wflags &= wflags - 1;
+					const int wr = b / P, wk = b - wr * P;
+					const S v = interp_sample<S, INTERP, ExactF64>(a.g, c, x0 + lt * P + wk, y_first + wr, [&](int row, int col) {
+						return *reinterpret_cast<const S *>(win + (row % NR) * wpitch + col * BPP + 2 * c * (int)sizeof(S) - wb0);
+					});
+					*reinterpret_cast<S *>(stg + wr * OUT_PITCH + (lt * P + wk) * BPP + 2 * c * (int)sizeof(S)) = v;
+				}
+			}
 			// staging writes -> visible to the TMA store the producer issues after this barrier
 			warp_arrive(done_bar);
 		}
@@ -799,7 +836,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	bool narrow = regular && HAS_NARROW && !STREAM_DEBUG_BIT(a, 2);	// debug bit 1: A/B runs without the narrow form
 #pragma unroll
 	for (int k = 0; k < P; ++k)
-		narrow = narrow && wt[k][NW - 1] == 0.f;
+		narrow = narrow && wt[k][NW - 1] == 0;
 	narrow = __all_sync(0xffffffffu, narrow);
 	if (HAS_NARROW && narrow)
 		run(std::integral_constant<int, HAS_NARROW ? 2 : 1>());

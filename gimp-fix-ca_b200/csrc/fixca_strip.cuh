@@ -259,6 +259,86 @@ __device__ __forceinline__ unsigned vertical_emit(const float (&hr)[4][P], const
 	return flags;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// WIDE: the FP64 primary arithmetic of the exact-repair stream kernels for 16-bit samples.
+// Bit-identical output needs the reference's operation order (64 FP64 operations per Cubic sample) only where
+// the result is in doubt: the same separable sum evaluated in FP64 on raw sample values -- 12 FP64 operations
+// per sample -- is within kEps LSB of the reference's own FP64 value, so every sample further than kEps from a
+// rounding boundary rounds to the reference's integer; the others (2 kEps of all samples) are recomputed with
+// interp_sample<ExactF64>.  Raw integer samples enter the DFMAs as subnormal doubles (low word = the sample,
+// high word 0: v * 2^-1074, exact; no conversion instruction); the horizontal and the vertical weights carry
+// 2^537 each, so the vertical sum lands in LSB units.
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(16) dvec4 { double x, y, z, w; };
+constexpr double kWideScale = 0x1p537;		// 537 + 537 = 1074
+template <class S> struct WideCodec;
+template <> struct WideCodec<uint16_t> {
+	// |separable FP64 value - reference FP64 value| <= 3.5e-8 LSB for raw samples <= 65535
+	static constexpr double kEps = 1e-6;
+	static constexpr int kMaxInt = 65535;
+	__device__ __forceinline__ static double load_at(uint32_t saddr)
+	{
+		unsigned v;
+		asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+		return __hiloint2double(0, (int)v);
+	}
+};
+template <> struct WideCodec<u15_t> {	// raw codes run to 65535 (out-of-range inputs): the bound of u16; clip at 1.0 = 32768
+	static constexpr double kEps = 1e-6;
+	static constexpr int kMaxInt = 32768;
+	__device__ __forceinline__ static double load_at(uint32_t saddr) { return WideCodec<uint16_t>::load_at(saddr); }
+};
+
+// position_weights in FP64 (no rounding to FP32), scaled by `scale`
+template <int INTERP>
+__device__ __forceinline__ dvec4 position_weights_wide(const Axis &ay, int y, int H, double scale, int &last)
+{
+	constexpr int T = INTERP == 1 ? 2 : 4;
+	constexpr int OFF = INTERP == 1 ? 0 : 1;
+	double td;
+	const int i0 = base_index(ay, y, td);
+	last = clampi(i0 - OFF + T - 1, 0, H - 1);
+	double wd[4], posd[4] = {0.0, 0.0, 0.0, 0.0};
+	tap_weights_d<INTERP>(td, wd);
+#pragma unroll
+	for (int j = 0; j < T; ++j) {
+		const int p = last - clampi(i0 - OFF + j, 0, H - 1);
+#pragma unroll
+		for (int m = 0; m < 4; ++m)
+			posd[m] += (p == m) ? wd[j] * scale : 0.0;
+	}
+	dvec4 r;
+	r.x = posd[3]; r.y = posd[2]; r.z = posd[1]; r.w = posd[0];
+	return r;
+}
+
+// vertical_emit in FP64: the sum in LSB units -> clip to [0, max] (clip_d) and round (set_pixel) through the
+// 1.5 * 2^52 addition; returns a mask of the columns whose value lies within kEps of a rounding boundary (those are
+// recomputed in the reference's own operation order by the caller; an exact tie always is)
+template <int INTERP, int U, int P, int BPP, class WC>
+__device__ __forceinline__ unsigned vertical_emit_wide(const double (&hr)[4][P], const dvec4 &w, unsigned char *q)
+{
+	constexpr double MAGIC = 6755399441055744.0;	// 2^52 + 2^51
+	unsigned flags = 0;
+#pragma unroll
+	for (int k = 0; k < P; ++k) {
+		double v;
+		if (INTERP == 1) {
+			v = w.z * hr[(U + 3) & 3][k];
+		} else {
+			v = w.x * hr[(U + 1) & 3][k];
+			v = fma(w.y, hr[(U + 2) & 3][k], v);
+			v = fma(w.z, hr[(U + 3) & 3][k], v);
+		}
+		v = fma(w.w, hr[U][k], v);
+		const double t = v + MAGIC;			// |v| <= 1.6 * 65535: the low word of t is round-to-nearest(v)
+		const int n = min(max(__double2loint(t), 0), WC::kMaxInt);
+		*reinterpret_cast<uint16_t *>(q + k * BPP) = (uint16_t)n;
+		flags |= (fabs(v - (t - MAGIC)) >= 0.5 - WC::kEps) ? 1u << k : 0u;
+	}
+	return flags;
+}
+
 // S      sample type (uint8_t, uint16_t, float)
 // NCH    3 or 4 samples per pixel
 // INTERP 1 Linear, 2 Cubic

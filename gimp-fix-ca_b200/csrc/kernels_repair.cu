@@ -7,26 +7,41 @@
 
 namespace fixca {
 
-// Only 8-bit samples: there the bound (|FP32 - reference| <= 2.7e-4 LSB) sends 0.05 % of the samples to the FP64
-// repair and EXACT runs 2.1x (Cubic) / 1.7x (Linear) faster than the FP64 tile kernel.  For 16-bit samples the same bound
-// is 0.07 LSB, 14 % of the samples need the repair, and the kernel measured 2.34 ms against 1.19 ms (100 MP RGB16
-// Cubic): they stay on tiled_kernel<ExactF64>.
+// 8-bit samples: the FP32 pipeline's bound (|FP32 - reference| <= 2.7e-4 LSB) sends 0.05 % of the samples to the FP64
+// repair and EXACT runs 2.1x (Cubic) / 1.7x (Linear) faster than the FP64 tile kernel.  For 16-bit samples the same
+// bound is 0.07 LSB, 14 % of the samples need the repair, and that kernel measured 2.34 ms against 1.19 ms (100 MP
+// RGB16 Cubic): they take the WIDE form instead -- the separable sums in FP64 (12 FP64 operations per sample against
+// the reference order's 64), bound 3.5e-8 LSB, two samples in a million recomputed.
 // layouts as in kernels_fast.cu (columns per thread, strip width)
 #define REPAIR_ENTRIES(S, TAG, P3, TW3, P4, TW4)                                                              \
 	{ (kernel_fn)stream_kernel<S, 3, 1, P3, TW3, false, true>, "stream/linear/f32+f64/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1, 1 }, \
 	{ (kernel_fn)stream_kernel<S, 4, 1, P4, TW4, false, true>, "stream/linear/f32+f64/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1, 1 }, \
 	{ (kernel_fn)stream_kernel<S, 3, 2, P3, TW3, false, true>, "stream/cubic/f32+f64/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1, 1 },  \
 	{ (kernel_fn)stream_kernel<S, 4, 2, P4, TW4, false, true>, "stream/cubic/f32+f64/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1, 1 }
+#define WIDE_ENTRIES(S, TAG, P3, TW3, P4, TW4, ALT4)                                                          \
+	{ (kernel_fn)stream_kernel<S, 3, 1, P3, TW3, false, false, true>, "stream/linear/f64+exact/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1, 2 }, \
+	{ (kernel_fn)stream_kernel<S, 4, 1, P4, TW4, ALT4, false, true>, "stream/linear/f64+exact/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1, 2 },  \
+	{ (kernel_fn)stream_kernel<S, 3, 2, P3, TW3, false, false, true>, "stream/cubic/f64+exact/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1, 2 },  \
+	{ (kernel_fn)stream_kernel<S, 4, 2, P4, TW4, ALT4, false, true>, "stream/cubic/f64+exact/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1, 2 }
 
 static const KernelEntry repair_table[] = {
 	REPAIR_ENTRIES(uint8_t, "u8", 4, 256, 3, 192),
+	WIDE_ENTRIES(uint16_t, "u16", 2, 256, 3, 192, true),
+	WIDE_ENTRIES(u15_t, "u15", 2, 256, 3, 192, true),
 };
 
 const KernelEntry *lookup_exact_stream(SampleKind kind, int nch, int interp)
 {
-	if (kind != SK_U8 || (nch != 3 && nch != 4) || (interp != 1 && interp != 2) || tuning().exact_tiled)
+	if ((nch != 3 && nch != 4) || (interp != 1 && interp != 2) || tuning().exact_tiled)
 		return nullptr;
-	return &repair_table[(interp - 1) * 2 + (nch - 3)];
+	int s;
+	switch (kind) {
+	case SK_U8:  s = 0; break;
+	case SK_U16: s = 1; break;
+	case SK_U15: s = 2; break;
+	default: return nullptr;
+	}
+	return &repair_table[s * 4 + (interp - 1) * 2 + (nch - 3)];
 }
 
 } // namespace fixca

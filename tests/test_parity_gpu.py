@@ -33,7 +33,7 @@ def _need_gpu(fx):
 @pytest.mark.parametrize("force", ["auto", "direct", "tiled"])
 def test_golden_suite_bit_exact(fx, force, tuning):
     """EXACT arithmetic through each of its kernel families: auto = the streaming kernel with exact repair of
-    near-tie samples for 8/16-bit integers (f32+f64) and tiled_kernel<ExactF64> for the rest; tiled = the FP64 tile
+    near-tie samples for 8-bit (f32+f64) and 16-bit (f64+exact) integers and tiled_kernel<ExactF64> for the rest; tiled = the FP64 tile
     kernel for every format (FIXCA_EXACT_KERNEL=tiled); direct = the per-pixel kernel."""
     if force == "tiled":
         tuning("FIXCA_EXACT_KERNEL", "tiled")
@@ -47,9 +47,9 @@ def test_golden_suite_bit_exact(fx, force, tuning):
             bad.append(c["name"])
     assert not bad, "%d of %d golden cases differ (%s), first: %s" % (len(bad), len(golden()["suite"]), force, bad[:8])
     if force == "auto":
-        assert {"stream/f32+f64", "tiled/f64"} <= kernels, kernels
+        assert {"stream/f32+f64", "stream/f64+exact", "tiled/f64"} <= kernels, kernels
     elif force == "tiled":
-        assert "tiled/f64" in kernels and "stream/f32+f64" not in kernels, kernels
+        assert "tiled/f64" in kernels and not {"stream/f32+f64", "stream/f64+exact"} & kernels, kernels
     else:
         assert {k.split("/")[0] for k in kernels} == {"direct"}, kernels
 
@@ -334,15 +334,15 @@ def test_multi_device_bands_and_frames(fx, checker):
 
 def test_fanout_stores_every_destination(fx, checker):
     """fixca_cuda_region_dev_fanout: one launch stores the band into several frames (the all-gather form; here all
-    frames live on this GPU).  Streaming kernels (FAST, None) fan out in ONE launch; EXACT goes launch by launch.
+    frames live on this GPU).  Streaming kernels (FAST, None, EXACT on 8-/16-bit samples) fan out in ONE launch; the FP64 tile kernel goes launch by launch.
     Every frame holds the single-destination result, and nothing outside the band's rows is written."""
     import torch
 
     h, w, ch = 403, 640, 3
     st = torch.cuda.current_stream().cuda_stream
     for dt, interp, flags, streaming in (("u2", 2, fx.PRECISION_FAST, True), ("u1", 0, fx.PRECISION_EXACT, True),
-                                         ("f4", 1, fx.PRECISION_FAST, True), ("u2", 2, fx.PRECISION_EXACT, False),
-                                         ("u1", 2, fx.PRECISION_EXACT, True)):
+                                         ("f4", 1, fx.PRECISION_FAST, True), ("u2", 2, fx.PRECISION_EXACT, True),
+                                         ("u1", 2, fx.PRECISION_EXACT, True), ("f4", 2, fx.PRECISION_EXACT, False)):
         img = orc.synth_image(h, w, ch, dt, 91)
         kw = dict(KW, lens_x=300, lens_y=128, interpolation=interp)
         p = fx.FixCaParams(**kw)
@@ -380,7 +380,7 @@ def test_device_resident_entry_with_torch_buffers(fx, checker):
     fx.fix_ca_region_dev(src.data_ptr(), w * 6, 0, h, dst.data_ptr(), w * 6, 0, w, h, 6, 2, fx.FixCaParams(**kw), 0, h,
                          fx.PRECISION_EXACT, stream)
     torch.cuda.synchronize()
-    assert fx.last_kernel().startswith("tiled")
+    assert fx.last_kernel().startswith("stream/cubic/f64+exact")
     assert dst.cpu().numpy().view(np.uint16).tobytes() == want.tobytes()
     # a band whose source rows are a sub-range of the image (what one rank of a multi-GPU run holds)
     lo, hi = fx.band_source_rows(w, h, fx.FixCaParams(**kw), 100, 180)
@@ -594,7 +594,7 @@ def test_u15_golden_suite_bit_exact(fx):
         if md5(got) != c["md5"]:
             bad.append(c["name"])
     assert not bad, "%d u15 cases differ, first: %s" % (len(bad), bad[:8])
-    assert {"stream/none/copy", "tiled/cubic/f64", "tiled/linear/f64"} <= kernels, kernels
+    assert {"stream/none/copy", "stream/cubic/f64+exact", "stream/linear/f64+exact"} <= kernels, kernels
 
 
 @pytest.mark.parametrize("variant", ["stream", "strip"])
@@ -618,6 +618,37 @@ def test_u15_fast_within_one_lsb(fx, variant, tuning):
     assert worst <= FAST_LSB_TOL, worst
     assert nbad / n < 5e-3, nbad / n
     assert kernels == {variant}, kernels
+
+
+def test_exact_repair_kernels_on_exact_ties(fx, checker, tuning):
+    """The exact-repair stream kernels (8-bit: FP32 + FP64 repair; 16-bit / u15: FP64 separable + reference-order
+    repair) decide every sample that is NOT near a rounding boundary in their fast arithmetic; here most samples ARE on
+    one: pure half- and quarter-pixel directional shifts make the Linear / Cubic weights dyadic (1/2, 9/16, 1/16 ...),
+    so a large share of the results are exact .5 ties, whose rounding depends on the reference's own operation order.
+    Identical bytes to the checker, and to the FP64 tile kernel."""
+    chk15 = orc.u15_checker()
+    n_ties = 0
+    for dtype, ch, interp, shifts in itertools.product(("u1", "u2", "u15"), (3, 4), (1, 2),
+                                                       ((0.5, -0.5, 0.5, 0.5), (0.25, 0.5, -0.75, 1.5), (0.5, 0.0, 0.0, -0.5))):
+        h, w = 203, 1031
+        kw = dict(blue=0.0, red=0.0, x_blue=shifts[0], x_red=shifts[1], y_blue=shifts[2], y_red=shifts[3],
+                  lens_x=w // 2, lens_y=h // 2, interpolation=interp)
+        if dtype == "u15":
+            img = orc.synth_u15(h, w, ch, seed=h + ch + interp, wide=False)
+            want = chk15.region(img, orc.Params(**kw), bpc=orc.BPC_U15)
+            bpc = dict(bpc=fx.BPC_U15)
+        else:
+            img = orc.synth_image(h, w, ch, dtype, seed=77 + ch + interp)
+            want = checker.region(img, orc.Params(**kw))
+            bpc = {}
+        got = fx.correct(img, fx.FixCaParams(**kw), flags=fx.PRECISION_EXACT, **bpc)
+        assert "f32+f64" in fx.last_kernel() or "f64+exact" in fx.last_kernel(), fx.last_kernel()
+        assert got.tobytes() == want.tobytes(), (dtype, ch, interp, shifts, fx.last_kernel())
+        # how many samples sat on an exact tie (Linear, half-pixel shift in x only: (a + b) / 2 with a + b odd)
+        if interp == 1 and shifts == (0.5, 0.0, 0.0, -0.5) and dtype != "u15":
+            a = img[:, :, 2].astype(np.int64)
+            n_ties += int(((a[:, :-1] + a[:, 1:]) & 1).sum())
+    assert n_ties > 100000, n_ties
 
 
 # ---------------------------------------------------------------------------------------------
@@ -653,7 +684,8 @@ def test_full_size_properties(fx, checker, name, h, w, ch, dtype, kw, tuning):
     tol = FLOAT_ABS_TOL if dtype == "f4" else FAST_LSB_TOL
     p = fx.FixCaParams(**kw)
     full = fx.correct(img, p)
-    assert fx.last_kernel().startswith("stream/%s/f32+f64" % ("linear" if kw["interpolation"] == 1 else "cubic") if dtype == "u1" else "tiled")
+    interp_name = "linear" if kw["interpolation"] == 1 else "cubic"
+    assert fx.last_kernel().startswith({"u1": "stream/%s/f32+f64" % interp_name, "u2": "stream/%s/f64+exact" % interp_name}.get(dtype, "tiled"))
     # green / alpha untouched everywhere
     assert (full[..., 1] == img[..., 1]).all() and (ch == 3 or (full[..., 3] == img[..., 3]).all())
     # oracle on sampled bands (top edge, an interior band straddling chunk borders, bottom edge)
@@ -667,8 +699,8 @@ def test_full_size_properties(fx, checker, name, h, w, ch, dtype, kw, tuning):
     fx.correct(img, p, y1=h // 3, y2=h, out=halves)
     assert md5(halves) == md5(full)
     del halves
-    # the FP64 tile kernel (the exact path of the float formats) computes the same bytes as the repair kernel
-    if dtype == "u1":
+    # the FP64 tile kernel (the exact path of the float formats) computes the same bytes as the repair kernels
+    if dtype in ("u1", "u2"):
         tuning("FIXCA_EXACT_KERNEL", "tiled")
         other = fx.correct(img, p)
         assert fx.last_kernel().startswith("tiled") and md5(other) == md5(full)
