@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -85,6 +86,7 @@ static void read_tuning_locked()
 	t.stream_depth = env_int("FIXCA_STREAM_DEPTH", 0);
 	t.stream_segs = env_int("FIXCA_STREAM_SEGS", 0);
 	t.stream_waves = env_int("FIXCA_STREAM_WAVES", 0);
+	t.stream_tlead = env_int("FIXCA_STREAM_TLEAD", 0);
 	t.stream_debug = env_int("FIXCA_STREAM_DEBUG", 0);
 	t.no_pdl = env_int("FIXCA_NO_PDL", 0);
 	t.verbose = env_int("FIXCA_VERBOSE", 0);
@@ -216,6 +218,9 @@ struct Plan {
 	StreamFanout fan;	// further destinations of a fan-out launch (fan.n = 0 otherwise)
 	void *fan_dst[STREAM_MAX_FAN];	// their base pointers (row dst_row0), as requested
 	int src_rows_avail = 0;	// rows of the source band present at args.src
+	// stream kernel: the per-chunk tables args.meta_tab / args.span_tab point into (device memory, shared by every
+	// plan of the same band, y axes and kernel family; freed with the last plan that holds them)
+	std::shared_ptr<void> tables;
 	// a batch of equal frames in one launch (stream kernels: grid.z = frame, 3-D tensor maps)
 	int nframes = 1;
 	size_t src_frame_stride = 0, dst_frame_stride = 0;
@@ -526,6 +531,86 @@ static int resident_ctas(const KernelEntry *k, int threads, size_t smem, int dev
 	return n;
 }
 
+// The per-chunk tables of a streaming plan (stream_meta_kernel): vertical weights / tap rows and source-row spans of
+// every 8-row chunk of [y1, y2).  They depend on the y axes, the band, the kernel family and (None) the ring geometry
+// only, so plans that differ in buffers, pitches, strips or frames share one table: a small per-thread cache keyed
+// by exactly those inputs.  Filled on a private stream and waited for here -- a plan is made once per distinct call
+// (the plan cache), a table once per distinct band.
+static bool stream_tables(const KernelEntry *k, const Format &f, int dev, Plan &pl)
+{
+	struct Key {
+		int interp, mode, kind, y1, y2, ring_rows, win_pitch, dev, height;
+		int center[2], size[2];
+		double scale[2], shift[2];
+	};
+	struct Slot { Key key; std::shared_ptr<void> mem; size_t span_off; bool used; };
+	constexpr int SLOTS = 64;
+	static thread_local Slot slots[SLOTS];
+	static thread_local int next = 0;
+	static thread_local cudaStream_t fill_stream[64];	// per device, created on first use (never destroyed: process lifetime)
+	KernelArgs &a = pl.args;
+	Key key;
+	memset(&key, 0, sizeof key);
+	key.interp = a.g.interp; key.mode = k->repair; key.kind = a.g.interp ? (int)f.kind : 0;
+	key.y1 = a.y1; key.y2 = a.y2; key.dev = dev; key.height = a.g.height;
+	if (a.g.interp == 0) { key.ring_rows = a.ring_rows; key.win_pitch = a.win_pitch; }
+	for (int c = 0; c < 2; ++c) {
+		key.center[c] = a.g.y[c].center; key.size[c] = a.g.y[c].size;
+		key.scale[c] = a.g.y[c].scale; key.shift[c] = a.g.y[c].shift;
+	}
+	const int nchunks = (a.y2 - a.y1 + STREAM_CH - 1) / STREAM_CH;
+	const size_t rec = stream_meta_record_bytes(k->repair);
+	for (Slot &s : slots)
+		if (s.used && !memcmp(&s.key, &key, sizeof key)) {
+			pl.tables = s.mem;
+			a.meta_tab = s.mem.get();
+			a.span_tab = (const unsigned char *)s.mem.get() + s.span_off;
+			return true;
+		}
+	if (dev < 0 || dev >= 64)
+		return false;
+	int cur = -1;
+	if (cudaGetDevice(&cur) != cudaSuccess)
+		return false;
+	if (cur != dev && cudaSetDevice(dev) != cudaSuccess)
+		return false;
+	bool ok = false;
+	void *mem = nullptr;
+	const size_t span_off = align_up((size_t)nchunks * rec, 256);
+	const size_t bytes = span_off + (size_t)nchunks * sizeof(StreamSpan);
+	do {
+		if (!fill_stream[dev] && cudaStreamCreateWithFlags(&fill_stream[dev], cudaStreamNonBlocking) != cudaSuccess)
+			break;
+		if (cudaMalloc(&mem, bytes) != cudaSuccess)
+			break;
+		if (cudaMemsetAsync(mem, 0, bytes, fill_stream[dev]) != cudaSuccess)
+			break;
+		if (launch_stream_meta(a.g.interp, k->repair, f.kind, a, mem, (unsigned char *)mem + span_off, nchunks, fill_stream[dev]) != cudaSuccess)
+			break;
+		if (cudaStreamSynchronize(fill_stream[dev]) != cudaSuccess)
+			break;
+		ok = true;
+	} while (0);
+	if (!ok) {
+		cudaGetLastError();
+		if (mem)
+			cudaFree(mem);
+	}
+	if (cur != dev)
+		cudaSetDevice(cur);
+	if (!ok)
+		return false;
+	// (cudaFree waits for the device: no launch of a plan that held the table can still be reading it)
+	std::shared_ptr<void> sp(mem, [](void *p) { if (cudaFree(p) != cudaSuccess) cudaGetLastError(); });
+	Slot &s = slots[next];
+	next = (next + 1) % SLOTS;
+	s.key = key; s.mem = sp; s.span_off = span_off; s.used = true;
+	pl.tables = sp;
+	a.meta_tab = mem;
+	a.span_tab = (const unsigned char *)mem + span_off;
+	return true;
+}
+
 static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g, int y1, int y2, int dev, int limit, Plan &pl)
 {
 	const int CH = STREAM_CH;
@@ -534,7 +619,7 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	wb = (int)align_up((size_t)wb, 32);	// the window box: 4 * wb must keep ring groups 128-byte aligned
 	if (wb > 2048 || k->tw * f.bpp > 2048)
 		return false;			// TMA boxes are at most 256 elements (of 8 bytes) wide
-	const int threads = 2 * k->tw / k->strip_p + 64;
+	const int threads = 2 * k->tw / k->strip_p + 32;	// compute warps + the TMA warp
 	// As many CTAs per SM as shared memory allows up to ~32 compute warps: the narrow pixel formats are
 	// instruction-bound and have small CTAs (measured: RGB8 0.086 -> 0.062 ms, RGBA16 0.155 -> 0.131 ms
 	// going from 2 to 4 CTAs per SM); the 3-channel 16-bit / float strips fit 2 per SM at depth 2.
@@ -629,6 +714,7 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 	a.ring_rows = (int)ring_rows;
 	a.seg_rows = seg_rows;
 	a.depth = depth;
+	a.tile_lead = (depth >= 2 && tuning().stream_tlead != 1) ? 2 : 1;
 	a.debug = tuning().stream_debug;	// honoured by -DFIXCA_TUNING builds only
 	a.off_ytab = (int)off_meta;
 	a.off_win = (int)off_win;
@@ -656,7 +742,7 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 		if (!make_tensor_map(pl.fan.tm[i], pl.fan_dst[i], (size_t)a.dst_pitch, row_bytes, dst_rows, nf, dfs, (unsigned)(k->tw * f.bpp), CH))
 			return false;
 	}
-	return true;
+	return stream_tables(k, f, dev, pl);
 }
 
 // Planning costs tens of microseconds (window scans in FP64, three tensor-map encodes), a third of

@@ -24,7 +24,7 @@ struct KernelEntry {
 	int         ycoef_bytes;// per-row table entry size (tiled)
 	int         sample_bytes;
 	int         strip_p;	// > 0: strip_kernel with this many columns per thread (blockDim = 2 * tw / strip_p)
-	int         stream;	// != 0: stream_kernel (blockDim = 2 * tw / strip_p + 64, grid = strips x segments)
+	int         stream;	// != 0: stream_kernel (blockDim = 2 * tw / strip_p + 32, grid = strips x segments)
 	int         repair;	// 1: the exact-repair form of stream_kernel (FP32 pipeline, per-warp queues in shared memory); 2: WIDE (FP64 pipeline)
 };
 
@@ -42,6 +42,7 @@ struct Tuning {
 	int stream_noalt = 0;	// FIXCA_STREAM_NOALT=1
 	int tile_h = 0, tile_ctas = 3;
 	int stream_ctas = 0, stream_depth = 0, stream_segs = 0, stream_waves = 0;
+	int stream_tlead = 0;	// FIXCA_STREAM_TLEAD=1|2: chunks the pass-through tile is requested ahead (default 2 at depth >= 2)
 	int stream_debug = 0;	// honoured by -DFIXCA_TUNING builds only
 	int no_pdl = 0, verbose = 0;
 	int chunk_mb = 0, copy_threads = 0;
@@ -61,6 +62,12 @@ const KernelEntry *lookup_exact_stream(SampleKind kind, int nch, int interp);
 const KernelEntry *lookup_fast(SampleKind kind, int nch, int interp, bool tiled);
 // variant: 0 direct, 2 strip, 3 stream, 4 narrower stream (may be nullptr)
 const KernelEntry *lookup_fast_variant(SampleKind kind, int nch, int interp, int variant);
+
+// kernels_meta.cu: fills the per-plan tables of a streaming launch (KernelArgs::meta_tab / span_tab), one record per
+// 8-row chunk of [a.y1, a.y2); mode = KernelEntry::repair (0 FP32 weights, 1 exact-repair, 2 WIDE)
+size_t stream_meta_record_bytes(int mode);
+cudaError_t launch_stream_meta(int interp, int mode, SampleKind kind, const KernelArgs &a, void *meta, void *span, int nchunks,
+			       cudaStream_t st);
 
 // kernels_preview.cu: saturate() + centerline() on destination rows [y1, y2) (fix-ca.c:1322-1327)
 cudaError_t launch_preview(int kind, int nch, unsigned char *dst, long long pitch, int dst_row0, int y1, int y2, int width,

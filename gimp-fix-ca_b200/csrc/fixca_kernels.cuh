@@ -62,8 +62,12 @@ struct KernelArgs {
 	int  seg_rows;			// output rows per CTA (multiple of the chunk height)
 	int  ring_rows;			// window ring capacity in rows (multiple of 4)
 	int  depth;			// chunks prefetched ahead (pipeline depth D)
+	int  tile_lead;			// chunks the pass-through tile + record are requested ahead: 2 (needs depth >= 2) or 1
 	int  debug;			// bit 0: skip the arithmetic (timing experiments only)
 	int  off_rq;			// exact-repair stream kernels: per-warp queues of near-tie samples (u16 entries)
+	// per-plan tables in global memory, one record per 8-row chunk of [y1, y2) (stream_meta_kernel fills them)
+	const void *meta_tab;		// StreamMeta / StreamMetaWide records: vertical weights and tap rows of the chunk's rows
+	const void *span_tab;		// StreamSpan records: first / last source row the chunk touches
 };
 
 // 15-bit unsigned samples in 16-bit storage (babl's "u15": 0 .. 32768 <-> [0.0, 1.0]).  The reference rejects

@@ -25,9 +25,11 @@
 //     zero-filled / clipped by the TMA unit.  (A first version issued one bulk copy per row --
 //     24 per chunk -- and the producer's own instruction stream, ~1.9 us per chunk, was the
 //     critical path of the whole kernel: profiles/r01_stream_pipe_sweep_i.md.)
-//   * a second helper warp computes the per-row vertical weights of the chunks ahead (FP64
-//     coordinates, fix-ca.c:813-820, weights ordered by tap position), so the compute
-//     warps never touch FP64 and the TMA warp never waits for arithmetic;
+//   * the per-row vertical weights (FP64 coordinates, fix-ca.c:813-820, weights ordered by tap position) and
+//     the source rows every chunk touches are the same for every strip and every frame: stream_meta_kernel
+//     fills a table of them once per launch plan (one StreamMeta + StreamSpan per 8-row chunk) and the TMA
+//     lane copies a chunk's record into shared memory with the chunk's pass-through tile.  (Until r02 a
+//     second helper warp recomputed them in every CTA: 12 % of the RGB8 kernel's instructions.)
 //   * the compute warps never meet at a CTA barrier: they wait on "full" mbarriers and arrive on
 //     "done" mbarriers.
 //
@@ -85,6 +87,9 @@ template <class V4> struct StreamMetaT {
 };
 typedef StreamMetaT<float4> StreamMeta;		// FP32 pipelines
 typedef StreamMetaT<dvec4> StreamMetaWide;	// WIDE: FP64 weights
+static_assert(sizeof(StreamMeta) % 16 == 0 && sizeof(StreamMetaWide) % 16 == 0, "records move as bulk copies");
+// first / last source row the chunk's output rows touch, over both channels (what the TMA lane has to have in the ring)
+struct alignas(8) StreamSpan { int lo, hi; };
 
 struct StreamHeader {
 	unsigned long long full[STREAM_MAX_NF];
@@ -177,9 +182,94 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *tm)
 	asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// stream_meta_kernel: the per-plan tables of a streaming launch, one warp per 8-row chunk of [y1, y2).
+//   meta[j]  vertical weights by tap position (position_weights: FP64 coordinates fix-ca.c:813-820, Linear
+//            :1141-1148, Cubic :1219-1256), newest tap row of every output row, the "simple" flags
+//   span[j]  first / last source row the chunk touches over both channels
+// The records depend on the y axes, the band [y1, y2) and, for None, the ring geometry -- not on the strip, the
+// frame or the buffers -- so every CTA of every launch of the plan reads the same table (L2-resident after the
+// first strip).  MODE 0: FP32 weights; 1: the exact-repair form (weights in FP64, rounded once); 2: WIDE (FP64).
+// ---------------------------------------------------------------------------------------------------------
+template <int INTERP, int MODE>
+__global__ void __launch_bounds__(128) stream_meta_kernel(const KernelArgs a, const float inv_max, void *const meta_out,
+							   StreamSpan *const span_out, const int nchunks)
+{
+	constexpr int CH = STREAM_CH;
+	constexpr int T = INTERP == 0 ? 1 : INTERP == 1 ? 2 : 4;
+	constexpr int OFF = INTERP == 2 ? 1 : 0;
+	static_assert(!(INTERP == 0 && MODE != 0), "None has one form");
+	typedef typename std::conditional<MODE == 2, StreamMetaWide, StreamMeta>::type Meta;
+	const int lane = threadIdx.x & 31;
+	const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (i >= nchunks)
+		return;
+	const int H = a.g.height;
+	const int y_first = a.y1 + i * CH;
+	const int nr = min(CH, a.y2 - y_first);
+	Meta &m = reinterpret_cast<Meta *>(meta_out)[i];
+	const int ch = (lane / CH) & 1, r = lane % CH;
+	const bool mine = lane < 2 * CH && r < nr;
+	int last = 0;
+	if constexpr (INTERP == 0) {
+		// None: the ring offset of the one source row each output row copies from (rows past
+		// the band's end repeat its last row: the copy loop is not predicated, the store clips)
+		if (lane < 2 * CH) {
+			const int src = nearest_index(a.g.y[ch], min(y_first + r, a.y2 - 1));
+			m.wy[r][ch] = make_float4(__int_as_float((src % a.ring_rows) * a.win_pitch), 0.f, 0.f, 0.f);
+		}
+	}
+	if (mine) {
+		if constexpr (INTERP == 0)
+			last = nearest_index(a.g.y[ch], y_first + r);
+		else if constexpr (MODE == 2)
+			m.wy[r][ch] = position_weights_wide<INTERP>(a.g.y[ch], y_first + r, H, kWideScale, last);
+		else
+			m.wy[r][ch] = position_weights<INTERP, MODE == 1>(a.g.y[ch], y_first + r, H, inv_max, last);
+		m.last[ch][r] = last;
+		if (r == nr - 1) {
+			m.last[ch][nr] = INT_MAX;
+			m.s_end[ch] = last;
+		}
+	}
+	// "simple": a full chunk in which every row completes exactly one source row after
+	// the previous one -- one horizontal row in, one output row out, CH times
+	const int prev = __shfl_up_sync(0xffffffffu, last, 1);
+	const bool ok = mine && (r == 0 || last == prev + 1);
+	const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+	if (lane < 2) {
+		const unsigned want = ((1u << CH) - 1u) << (lane * CH);
+		m.simple[lane] = (nr == CH) && ((okmask & want) == want);
+	}
+	// first source row of the chunk's first output row, last source row of its last one (the map is monotone);
+	// fix-ca.c:1105-1106 None, :1219-1256 Cubic
+	if (lane < 2) {
+		const int y = lane == 0 ? y_first : y_first + nr - 1;
+		int lo = INT_MAX, hi = 0;
+#pragma unroll
+		for (int c = 0; c < 2; ++c) {
+			int first, lastr;
+			if constexpr (INTERP == 0) {
+				first = lastr = nearest_index(a.g.y[c], y);
+			} else {
+				double td;
+				const int i0 = base_index(a.g.y[c], y, td);
+				first = max(i0 - OFF, 0);
+				lastr = min(i0 + T - 1 - OFF, H - 1);
+			}
+			lo = min(lo, first);
+			hi = max(hi, lastr);
+		}
+		if (lane == 0)
+			span_out[i].lo = lo;
+		else
+			span_out[i].hi = hi;
+	}
+}
+
 // Dynamic shared memory: [StreamHeader | StreamMeta[D + 1] | window ring (ring_rows x win_pitch) |
 //                         staging (3 x CH x TW x BPP)]
-// blockDim.x == 2 * TW / P compute threads + 64 (the TMA warp and the row-coefficient warp).
+// blockDim.x == 2 * TW / P compute threads + 32 (the TMA warp).
 //
 // tm_win   source image, box = win_pitch bytes x 4 rows     (window ring groups)
 // tm_tile  source image, box = TW * BPP bytes x CH rows      (pass-through pixels of a chunk)
@@ -196,7 +286,7 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *tm)
 // raw sample values (fixca_strip.cuh, WideCodec); a sample within WideCodec::kEps of a rounding boundary -- one in
 // half a million -- is recomputed in the reference's operation order by its own thread at the end of the chunk.
 template <class S, int NCH, int INTERP, int P, int TW, bool ALT = false, bool REPAIR = false, bool WIDE = false>
-__global__ void __launch_bounds__(2 * TW / P + 64, (2 * TW / P + 64) <= 192 && !WIDE ? 4 : 2)	// register budget: 4 (2) resident CTAs
+__global__ void __launch_bounds__(2 * TW / P + 32, (2 * TW / P) <= 128 && !WIDE ? 4 : 2)	// register budget: 4 (2) resident CTAs
 stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUtensorMap tm_win,
 	      const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ CUtensorMap tm_out,
 	      const __grid_constant__ StreamFanout fan)
@@ -226,7 +316,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	unsigned char *stage = smem + a.off_out;
 
 	const int tid = threadIdx.x;
-	const int W = a.g.width, H = a.g.height;
+	const int W = a.g.width;
 	const int x0 = blockIdx.x * TW;
 	const int xl = min(x0 + TW, W) - 1;
 	const int ya = a.y1 + blockIdx.y * a.seg_rows;
@@ -235,10 +325,17 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	const int NR = a.ring_rows;
 	const int wpitch = a.win_pitch;
 
+	// the TMA warp's first look at the plan's span table (used after the set-up below: the load's latency overlaps it)
+	const int cj0 = (ya - a.y1) / CH;		// the segment's first chunk in the plan's tables
+	const int2 *const span = reinterpret_cast<const int2 *>(a.span_tab) + cj0;	// StreamSpan {lo, hi} records
+	int2 sp_lane = make_int2(0, 0);
+	if (tid >= NTC)
+		sp_lane = __ldg(&span[min(tid - NTC, nchunks - 1)]);
+
 	// ---- one-time: barriers and the strip's column extent ----
 	if (tid == 0) {
 		for (int i = 0; i < NF; ++i) {
-			mbar_init(reinterpret_cast<uint64_t *>(&hdr->full[i]), 3);	// window rows, pass-through tile, row coefficients
+			mbar_init(reinterpret_cast<uint64_t *>(&hdr->full[i]), 2);	// window rows; pass-through tile + the chunk's record
 			mbar_init(reinterpret_cast<uint64_t *>(&hdr->done[i]), NTC / 32);	// one arrival per compute warp (warp_arrive)
 		}
 		fence_mbar_init();
@@ -261,105 +358,32 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	uint64_t *full = reinterpret_cast<uint64_t *>(hdr->full);
 	uint64_t *done = reinterpret_cast<uint64_t *>(hdr->done);
 
-	// first / last source row output row y of channel ch touches (fix-ca.c:1105-1106 None, :1219-1256 Cubic)
-	auto first_tap_row = [&](int ch, int y) {
-		if constexpr (INTERP == 0) {
-			return nearest_index(a.g.y[ch], y);
-		} else {
-			double td;
-			return max(base_index(a.g.y[ch], y, td) - OFF, 0);
-		}
-	};
-	auto last_tap_row = [&](int ch, int y) {
-		if constexpr (INTERP == 0) {
-			return nearest_index(a.g.y[ch], y);
-		} else {
-			double td;
-			return min(base_index(a.g.y[ch], y, td) + T - 1 - OFF, H - 1);
-		}
-	};
-
-	if (tid >= NTC + 32) {
-		// =====================================================================
-		// row-coefficient warp: vertical weights and bookkeeping of the chunks ahead
-		// =====================================================================
-		const int lane = tid - NTC - 32;
-		int inf = 0, ipar = 0;	// i % NF, (i / NF) & 1
-		for (int i = 0; i < nchunks; ++i) {
-			if (i >= NF)	// the slot's previous tenant (chunk i - NF) must be finished
-#ifdef FIXCA_TUNING
-				if (a.debug >> 8)
-					mbar_wait_naps(&done[inf], (uint32_t)(ipar ^ 1), (uint32_t)(a.debug >> 8));
-				else
-#endif
-				mbar_wait_sleepy(&done[inf], (uint32_t)(ipar ^ 1), 2000u);
-			const int y_first = ya + i * CH;
-			const int nr = min(CH, yb - y_first);
-			Meta &m = meta[inf];
-			const int ch = (lane / CH) & 1, r = lane % CH;
-			const bool mine = lane < 2 * CH && r < nr;
-			int last = 0;
-			if constexpr (INTERP == 0) {
-				// None: the ring offset of the one source row each output row copies from (rows past
-				// the band's end repeat its last row: the copy loop is not predicated, the store clips)
-				if (lane < 2 * CH) {
-					const int src = nearest_index(a.g.y[ch], min(y_first + r, yb - 1));
-					m.wy[r][ch] = make_float4(__int_as_float((src % NR) * wpitch), 0.f, 0.f, 0.f);
-				}
-			}
-			if (mine) {
-				if constexpr (INTERP == 0)
-					last = nearest_index(a.g.y[ch], y_first + r);
-				else if constexpr (WIDE)
-					m.wy[r][ch] = position_weights_wide<INTERP>(a.g.y[ch], y_first + r, H, kWideScale, last);
-				else
-					m.wy[r][ch] = position_weights<INTERP, REPAIR>(a.g.y[ch], y_first + r, H, StripCodec<S>::kInvMax, last);
-				m.last[ch][r] = last;
-				if (r == nr - 1) {
-					m.last[ch][nr] = INT_MAX;
-					m.s_end[ch] = last;
-				}
-			}
-			// "simple": a full chunk in which every row completes exactly one source row after
-			// the previous one -- one horizontal row in, one output row out, CH times
-			const int prev = __shfl_up_sync(0xffffffffu, last, 1);
-			const bool ok = mine && (r == 0 || last == prev + 1);
-			const unsigned okmask = __ballot_sync(0xffffffffu, ok);
-			if (lane < 2) {
-				const unsigned want = ((1u << CH) - 1u) << (lane * CH);
-				m.simple[lane] = (nr == CH) && ((okmask & want) == want);
-			}
-			__syncwarp();
-			if (lane == 0)
-				mbar_arrive(&full[inf]);	// release: the metadata above is visible to the waiters
-			if (++inf == NF) { inf = 0; ipar ^= 1; }
-		}
-		return;
-	}
 	if (tid >= NTC) {
 		// =====================================================================
 		// TMA warp (one elected lane): window groups and pass-through tiles in, finished chunks out
 		// =====================================================================
-		if (tid != NTC)
-			return;
-		griddep_launch_dependents();
-		griddep_wait();		// the only thread of the CTA that reads or writes global memory
-		prefetch_tensormap(&tm_win);
-		prefetch_tensormap(&tm_tile);
-		prefetch_tensormap(&tm_out);
-		for (int e = 0; e < fan.n; ++e)
-			prefetch_tensormap(&fan.tm[e]);
+		// Which source rows a chunk needs comes from the plan's span table (written long before this launch: no
+		// dependency on the previous grid).  The first D + 1 records are fetched by the warp's lanes at once;
+		// after that the lane reads one record per chunk, a whole chunk period before it is needed.
+		int hi_next = __shfl_sync(0xffffffffu, sp_lane.y, 0);	// last source row of the next chunk to request
+		if (tid == NTC) {
+			griddep_launch_dependents();
+			griddep_wait();		// the only thread of the CTA that reads or writes image memory
+			prefetch_tensormap(&tm_win);
+			prefetch_tensormap(&tm_tile);
+			prefetch_tensormap(&tm_out);
+			for (int e = 0; e < fan.n; ++e)
+				prefetch_tensormap(&fan.tm[e]);
+		}
 		const int NRG = NR >> 2;		// ring capacity in 4-row groups
 		const int group_bytes = 4 * wpitch;
 		const int c0_win = wb0 >> 3, c0_tile = (x0 * BPP) >> 3;
 		const int frame = blockIdx.z;		// a batch of equal frames: one grid layer per frame
-		int loaded_g;				// highest 4-row group already requested
-		loaded_g = (min(first_tap_row(0, ya), first_tap_row(1, ya)) >> 2) - 1;
+		int loaded_g = (sp_lane.x >> 2) - 1;	// highest 4-row group already requested (lane 0: before the segment's first row)
 		int gslot = (loaded_g + 1) % NRG;	// ring slot of group loaded_g + 1
 		int wnf = 0;				// window requests: i % NF
-		auto request_window = [&](int i) {	// the source rows chunk i adds to the ring
-			const int y_last = min(ya + i * CH + CH, yb) - 1;
-			const int hi_g = max(max(last_tap_row(0, y_last), last_tap_row(1, y_last)) >> 2, loaded_g);
+		auto request_window = [&](const int row_hi) {	// the source rows up to row_hi join the ring (the next chunk's)
+			const int hi_g = max(row_hi >> 2, loaded_g);
 			uint64_t *bar = &full[wnf];
 			mbar_arrive_expect_tx(bar, (uint32_t)((hi_g - loaded_g) * group_bytes));
 			for (int g = loaded_g + 1; g <= hi_g; ++g) {
@@ -369,25 +393,45 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			loaded_g = hi_g;
 			wnf = wnf + 1 == NF ? 0 : wnf + 1;
 		};
+		const unsigned char *const meta_src = reinterpret_cast<const unsigned char *>(a.meta_tab) + (size_t)cj0 * sizeof(Meta);
 		int tnf = 0, tstg = 0;			// tile requests: i % NF, i % NSTG
-		auto request_tile = [&](int i) {	// chunk i's own pixels -> its staging buffer
-			// the buffer's previous tenant (chunk i - NSTG) was stored two iterations ago
-			bulk_wait_read<1>();
+		// Chunk i's own pixels -> its staging buffer, its record -> its metadata slot; requested TLEAD chunks ahead.
+		// TLEAD = 2 (depth >= 2): the buffer's previous tenant is the chunk whose store was issued a moment ago, so
+		// the lane first waits until that store has read the buffer -- it would only be polling the next `done`
+		// barrier otherwise -- and the tile has two chunk periods to arrive instead of one (the compute warps spent 9 %
+		// of their time waiting for it: an L2 round trip under load is about one chunk period of a narrow strip).
+		// The metadata slot's previous tenant (chunk i - NF) was handed over before that store was issued.
+		const int TLEAD = a.tile_lead;
+		auto request_tile = [&](int i) {
+			if (TLEAD == 2)
+				bulk_wait_read<0>();
+			else
+				bulk_wait_read<1>();	// (tenant stored two iterations ago)
 			uint64_t *bar = &full[tnf];
-			mbar_arrive_expect_tx(bar, (uint32_t)STAGE_BYTES);
+			mbar_arrive_expect_tx(bar, (uint32_t)(STAGE_BYTES + sizeof(Meta)));
 			tma_load_3d(stage + tstg * STAGE_BYTES, &tm_tile, c0_tile, ya + i * CH - a.src_row0, frame, bar);
+			bulk_load(&meta[tnf], meta_src + (size_t)i * sizeof(Meta), (uint32_t)sizeof(Meta), bar);
 			tnf = tnf + 1 == NF ? 0 : tnf + 1;
 			tstg = tstg + 1 == NSTG ? 0 : tstg + 1;
 		};
-		for (int i = 0; i < D && i < nchunks; ++i)
-			request_window(i);
-		request_tile(0);
+		// (the whole warp walks the first D + 1 records so that lane 0 gets them by shuffle)
+		for (int i = 0; i < D && i < nchunks; ++i) {
+			if (tid == NTC)
+				request_window(hi_next);
+			hi_next = __shfl_sync(0xffffffffu, sp_lane.y, min(i + 1, 31));
+		}
+		if (tid != NTC)
+			return;
+		for (int i = 0; i < TLEAD && i < nchunks; ++i)
+			request_tile(i);
 		int jnf = 0, jstg = 0, jpar = 0;	// j % NF, j % NSTG, (j / NF) & 1
 		for (int j = 0; j < nchunks; ++j) {
-			if (j + D < nchunks)
-				request_window(j + D);
-			if (j + 1 < nchunks)
-				request_tile(j + 1);
+			if (j + D < nchunks) {
+				request_window(hi_next);
+				hi_next = __ldg(&span[min(j + D + 1, nchunks - 1)]).y;
+			}
+			if (j + TLEAD < nchunks)
+				request_tile(j + TLEAD);
 #ifdef FIXCA_TUNING
 			if (a.debug >> 8)
 				mbar_wait_naps(&done[jnf], (uint32_t)jpar, (uint32_t)(a.debug >> 8));

@@ -134,6 +134,19 @@ if __name__ == "__main__":
         run("8K rgba16 cubic fast", 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
         run("50MP rgb f32 cubic fast", 6144, 8192, 3, torch.float32, -4, 2, F)
         run("50MP rgba f32 cubic fast", 6144, 8192, 4, torch.float32, -4, 2, F)
+    if which == "tlead":    # pass-through tile requested 1 / 2 chunks ahead
+        for tl in ("1", "2"):
+            os.environ["FIXCA_STREAM_TLEAD"] = tl
+            run_batch("4K rgb8 cubic tlead" + tl, 64, 2160, 3840, 3, torch.uint8, 1, 2, F)
+            run("4K rgb8 cubic tlead" + tl, 2160, 3840, 3, torch.uint8, 1, 2, F)
+            run("24MP rgb8 cubic tlead" + tl, 4000, 6000, 3, torch.uint8, 1, 2, F)
+            run("24MP rgb8 linear tlead" + tl, 4000, 6000, 3, torch.uint8, 1, 1, F)
+            run("33MP rgba8 cubic tlead" + tl, 4320, 7680, 4, torch.uint8, 1, 2, F)
+            run("100MP rgb16 cubic tlead" + tl, 8192, 12288, 3, torch.int16, 2, 2, F)
+            run("8K rgba16 cubic tlead" + tl, 4320, 7680, 4, torch.int16, 2, 2, F, lens=(658, 1280))
+            run("50MP rgb f32 cubic tlead" + tl, 6144, 8192, 3, torch.float32, -4, 2, F)
+            run("50MP rgba f32 cubic tlead" + tl, 6144, 8192, 4, torch.float32, -4, 2, F)
+        os.environ.pop("FIXCA_STREAM_TLEAD")
     if which == "small":    # launches dominated by the fixed cost
         run("4K rgb8 cubic fast", 2160, 3840, 3, torch.uint8, 1, 2, F)
         run("4K rgb8 linear fast", 2160, 3840, 3, torch.uint8, 1, 1, F)
