@@ -52,7 +52,8 @@
 namespace fixca {
 
 // Timing experiments (FIXCA_STREAM_DEBUG: bit 0 skips the arithmetic -- wrong pixels --, bit 1 disables the narrow
-// form) exist in -DFIXCA_TUNING builds only (make TUNING=1); the release library ignores KernelArgs::debug.
+// form, bit 2 skips the window / tile loads, bit 3 the stores) exist in -DFIXCA_TUNING builds only (make TUNING=1); the
+// release library ignores KernelArgs::debug.
 #ifdef FIXCA_TUNING
 #define STREAM_DEBUG_BIT(a, bit) ((a).debug & (bit))
 #else
@@ -385,10 +386,14 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		auto request_window = [&](const int row_hi) {	// the source rows up to row_hi join the ring (the next chunk's)
 			const int hi_g = max(row_hi >> 2, loaded_g);
 			uint64_t *bar = &full[wnf];
-			mbar_arrive_expect_tx(bar, (uint32_t)((hi_g - loaded_g) * group_bytes));
-			for (int g = loaded_g + 1; g <= hi_g; ++g) {
-				tma_load_3d(win + gslot * group_bytes, &tm_win, c0_win, 4 * g - a.src_row0, frame, bar);
-				gslot = gslot + 1 == NRG ? 0 : gslot + 1;
+			if (STREAM_DEBUG_BIT(a, 4)) {	// timing experiment: no window loads (the compute warps filter stale shared memory)
+				mbar_arrive(bar);
+			} else {
+				mbar_arrive_expect_tx(bar, (uint32_t)((hi_g - loaded_g) * group_bytes));
+				for (int g = loaded_g + 1; g <= hi_g; ++g) {
+					tma_load_3d(win + gslot * group_bytes, &tm_win, c0_win, 4 * g - a.src_row0, frame, bar);
+					gslot = gslot + 1 == NRG ? 0 : gslot + 1;
+				}
 			}
 			loaded_g = hi_g;
 			wnf = wnf + 1 == NF ? 0 : wnf + 1;
@@ -408,8 +413,12 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			else
 				bulk_wait_read<1>();	// (tenant stored two iterations ago)
 			uint64_t *bar = &full[tnf];
-			mbar_arrive_expect_tx(bar, (uint32_t)(STAGE_BYTES + sizeof(Meta)));
-			tma_load_3d(stage + tstg * STAGE_BYTES, &tm_tile, c0_tile, ya + i * CH - a.src_row0, frame, bar);
+			if (STREAM_DEBUG_BIT(a, 4)) {	// timing experiment: the record only
+				mbar_arrive_expect_tx(bar, (uint32_t)sizeof(Meta));
+			} else {
+				mbar_arrive_expect_tx(bar, (uint32_t)(STAGE_BYTES + sizeof(Meta)));
+				tma_load_3d(stage + tstg * STAGE_BYTES, &tm_tile, c0_tile, ya + i * CH - a.src_row0, frame, bar);
+			}
 			bulk_load(&meta[tnf], meta_src + (size_t)i * sizeof(Meta), (uint32_t)sizeof(Meta), bar);
 			tnf = tnf + 1 == NF ? 0 : tnf + 1;
 			tstg = tstg + 1 == NSTG ? 0 : tstg + 1;
@@ -438,6 +447,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			else
 #endif
 			mbar_wait_sleepy(&done[jnf], (uint32_t)jpar, 500u);
+			if (!STREAM_DEBUG_BIT(a, 8))	// (timing experiment: no stores either)
 			tma_store_3d(&tm_out, c0_tile, ya + j * CH - a.dst_row0, frame, stage + jstg * STAGE_BYTES);
 			for (int e = 0; e < fan.n; ++e)		// the same chunk into the other frames (peer GPUs, over NVLink)
 				tma_store_3d(&fan.tm[e], c0_tile, ya + j * CH - a.dst_row0, frame, stage + jstg * STAGE_BYTES);
@@ -673,188 +683,150 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		constexpr bool REG = FORM != 0;
 		constexpr int NWV = FORM == 0 ? T : FORM == 1 ? NW : NW - 1;	// weights per column
 		constexpr int NSL = REG ? P + NWV - 1 : P * T;			// samples a thread loads per source row
+		// ---- state of the chunk in hand (set by begin_chunk) ----
+		int j = 0;				// chunk of the segment
 		int jnf = 0, jstg = 0, jpar = 0;	// j % NF, j % NSTG, (j / NF) & 1
-		for (int j = 0; j < nchunks; ++j) {
-			mbar_wait(&full[jnf], (uint32_t)jpar);
-			const Meta &m = meta[jnf];
-			uint64_t *const done_bar = &done[jnf];
-			unsigned char *const stg = stage + jstg * STAGE_BYTES;	// this chunk's staging buffer
-			unsigned char *q = stg + qoff;
-			const int y_first = ya + j * CH;
-			int er = 0;		// REPAIR / WIDE: chunk row the next emit writes
-			[[maybe_unused]] unsigned wflags = 0;	// WIDE: this thread's near-tie samples of the chunk, bit = chunk row * P + column
-			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
-			jstg = jstg + 1 == NSTG ? 0 : jstg + 1;
-			const int s_end = m.s_end[c];
-			const auto *wy = &m.wy[0][c];		// [row][channel]: stride 2
-			const int *lastp = m.last[c];
-			int next_last = lastp[0];
+		const Meta *m = nullptr;
+		uint64_t *done_bar = nullptr;
+		unsigned char *stg = nullptr;		// this chunk's staging buffer
+		unsigned char *q = nullptr;		// ... at the thread's first column, next row to emit
+		int y_first = 0;
+		int er = 0;				// REPAIR / WIDE: chunk row the next emit writes
+		[[maybe_unused]] unsigned wflags = 0;	// WIDE: this thread's near-tie samples of the chunk, bit = chunk row * P + column
+		int s_end = 0;
+		typedef typename std::remove_reference<decltype(meta[0].wy[0][0])>::type WY;
+		const WY *wy = nullptr;			// [row][channel]: stride 2
+		const int *lastp = nullptr;
+		int next_last = 0;
 
-			if (STREAM_DEBUG_BIT(a, 1)) {	// timing experiment: memory pipeline only (results are wrong)
-				s_done = s_end;
-				prow = win_c + (uint32_t)(((s_done + 1) % NR) * wpitch);
-				warp_arrive(done_bar);
-				continue;
+		// a source row's samples / the P horizontal results from them, in either form
+		auto load_row = [&](const uint32_t p, A (&smp)[NSL]) {
+			if (REG) {
+#pragma unroll
+				for (int mm = 0; mm < NSL; ++mm)
+					smp[mm] = LoadCodec::load_at(p + mm * BPP);
+			} else {
+#pragma unroll
+				for (int k = 0; k < P; ++k)
+#pragma unroll
+					for (int jj = 0; jj < T; ++jj)
+						smp[k * T + jj] = LoadCodec::load_at(p + (uint32_t)min(cofs[k] + jj * BPP, cmax));
 			}
-
-			// a source row's samples / the P horizontal results from them, in either form
-			auto load_row = [&](const uint32_t p, A (&smp)[NSL]) {
-				if (REG) {
+		};
+		auto hfilter = [&](const A (&smp)[NSL], A (&out)[P]) {
 #pragma unroll
-					for (int mm = 0; mm < NSL; ++mm)
-						smp[mm] = LoadCodec::load_at(p + mm * BPP);
-				} else {
+			for (int k = 0; k < P; ++k) {
+				A v = wt[k][0] * smp[REG ? k : k * T];
 #pragma unroll
-					for (int k = 0; k < P; ++k)
-#pragma unroll
-						for (int jj = 0; jj < T; ++jj)
-							smp[k * T + jj] = LoadCodec::load_at(p + (uint32_t)min(cofs[k] + jj * BPP, cmax));
-				}
-			};
-			auto hfilter = [&](const A (&smp)[NSL], A (&out)[P]) {
-#pragma unroll
-				for (int k = 0; k < P; ++k) {
-					A v = wt[k][0] * smp[REG ? k : k * T];
-#pragma unroll
-					for (int jj = 1; jj < NWV; ++jj)
-						v = fma(wt[k][jj], smp[REG ? k + jj : k * T + jj], v);
-					out[k] = v;
-				}
-			};
-			// one output row of the P columns from the ring (newest row in slot U) into chunk row `row` at q
-			auto vemit = [&](auto slot, const auto &wrow, unsigned char *const qrow, const int row) {
-				constexpr int U = decltype(slot)::value;
-				if constexpr (WIDE) {
-					wflags |= vertical_emit_wide<INTERP, U, P, BPP, WideCodec<S>>(hr, wrow, qrow) << (row * P);
-				} else {
-					const unsigned fl = vertical_emit<INTERP, U, P, BPP, Codec, REPAIR>(hr, wrow, qrow);
-					if (REPAIR)
-						enqueue(fl, row, y_first, stg);
-				}
-			};
-			// one source row through the horizontal filter into ring slot U
-			auto hrow = [&](auto slot) {
-				constexpr int U = decltype(slot)::value;
-				A smp[NSL];
-				load_row(prow, smp);
-				hfilter(smp, hr[U]);
-				++s_done;
-				prow += (uint32_t)wpitch;
-				if (prow == win_end)
-					prow = win_c;
-			};
-			// the output rows completed by the newest row (slot U)
-			auto emit = [&](auto slot) {
+				for (int jj = 1; jj < NWV; ++jj)
+					v = fma(wt[k][jj], smp[REG ? k + jj : k * T + jj], v);
+				out[k] = v;
+			}
+		};
+		// one output row of the P columns from the ring (newest row in slot U) into chunk row `row` at q
+		auto vemit = [&](auto slot, const auto &wrow, unsigned char *const qrow, const int row) {
+			constexpr int U = decltype(slot)::value;
+			if constexpr (WIDE) {
+				wflags |= vertical_emit_wide<INTERP, U, P, BPP, WideCodec<S>>(hr, wrow, qrow) << (row * P);
+			} else {
+				const unsigned fl = vertical_emit<INTERP, U, P, BPP, Codec, REPAIR>(hr, wrow, qrow);
+				if (REPAIR)
+					enqueue(fl, row, y_first, stg);
+			}
+		};
+		// one source row through the horizontal filter into ring slot U
+		auto hrow = [&](auto slot) {
+			constexpr int U = decltype(slot)::value;
+			A smp[NSL];
+			load_row(prow, smp);
+			hfilter(smp, hr[U]);
+			++s_done;
+			prow += (uint32_t)wpitch;
+			if (prow == win_end)
+				prow = win_c;
+		};
+		// the output rows completed by the newest row (slot U)
+		auto emit = [&](auto slot) {
 #pragma unroll 1
-				while (next_last <= s_done) {
-					vemit(slot, *wy, q, er++);
-					wy += 2;
-					q += OUT_PITCH;
-					next_last = *++lastp;
-				}
-			};
-			// general walk: source rows up to `upto`, emitting whatever they complete
-			auto walk = [&](const int upto) {
+			while (next_last <= s_done) {
+				vemit(slot, *wy, q, er++);
+				wy += 2;
+				q += OUT_PITCH;
+				next_last = *++lastp;
+			}
+		};
+		// general walk: source rows up to `upto`, emitting whatever they complete
+		auto walk = [&](const int upto) {
 #pragma unroll 1
-				while (s_done < upto) {
-					switch (ph) {
-					case 0:
-						hrow(std::integral_constant<int, 0>());
-						emit(std::integral_constant<int, 0>());
-						ph = 1;
-						if (s_done >= upto) break;
-					case 1:
-						hrow(std::integral_constant<int, 1>());
-						emit(std::integral_constant<int, 1>());
-						ph = 2;
-						if (s_done >= upto) break;
-					case 2:
-						hrow(std::integral_constant<int, 2>());
-						emit(std::integral_constant<int, 2>());
-						ph = 3;
-						if (s_done >= upto) break;
-					default:
-						hrow(std::integral_constant<int, 3>());
-						emit(std::integral_constant<int, 3>());
-						ph = 0;
-					}
-				}
-			};
-
-			if (m.simple[c] && next_last > s_done) {
-				// Steady state: CH consecutive source rows in, CH output rows out.  Rows below the
-				// first output's newest tap (a segment's first chunk: T - 1 of them) only prime the ring.
-				walk(next_last - 1);
-				if (ph != 0) {	// bring the ring to slot 0 (after a general chunk; rare)
-					auto rotate = [&](auto by) {
-						constexpr int N = decltype(by)::value;
-						A t[4][P];
-#pragma unroll
-						for (int u = 0; u < 4; ++u)
-#pragma unroll
-							for (int k = 0; k < P; ++k)
-								t[u][k] = hr[(u + N) & 3][k];
-#pragma unroll
-						for (int u = 0; u < 4; ++u)
-#pragma unroll
-							for (int k = 0; k < P; ++k)
-								hr[u][k] = t[u][k];
-					};
-					switch (ph) {
-					case 1: rotate(std::integral_constant<int, 1>()); break;
-					case 2: rotate(std::integral_constant<int, 2>()); break;
-					default: rotate(std::integral_constant<int, 3>()); break;
-					}
+			while (s_done < upto) {
+				switch (ph) {
+				case 0:
+					hrow(std::integral_constant<int, 0>());
+					emit(std::integral_constant<int, 0>());
+					ph = 1;
+					if (s_done >= upto) break;
+				case 1:
+					hrow(std::integral_constant<int, 1>());
+					emit(std::integral_constant<int, 1>());
+					ph = 2;
+					if (s_done >= upto) break;
+				case 2:
+					hrow(std::integral_constant<int, 2>());
+					emit(std::integral_constant<int, 2>());
+					ph = 3;
+					if (s_done >= upto) break;
+				default:
+					hrow(std::integral_constant<int, 3>());
+					emit(std::integral_constant<int, 3>());
 					ph = 0;
 				}
-				// UNR rows unrolled (whole ring turns, so slots stay static); the next row's samples are
-				// loaded before the current row's arithmetic (the loads never wait on the stores).
-				// Wide column groups unroll one ring turn only: 8 rows of P = 4 are 8 KB of code and
-				// "no instruction" became the top stall (profiles/r01_ncu_stream_narrow_A.md).
-				constexpr int UNR = P >= 4 ? 4 : CH;
-				static_assert(CH % UNR == 0 && UNR % 4 == 0, "unroll must divide the chunk and cover whole ring turns");
-				// (bent warps load and filter row by row: their P * T samples are not double-buffered)
-				A smp[REG ? 2 : 1][NSL];
-				if (REG)
-					load_row(prow, smp[0]);
-#pragma unroll 1
-				for (int it = 0; it < CH / UNR; ++it) {
-#pragma unroll
-					for (int u = 0; u < UNR; ++u) {
-						uint32_t pnext = prow + (uint32_t)wpitch;
-						if (pnext == win_end)
-							pnext = win_c;
-						// (after the chunk's last row the samples are simply dropped)
-						if (REG)
-							load_row(pnext, smp[REG ? (u + 1) & 1 : 0]);
-						else
-							load_row(prow, smp[0]);
-						hfilter(smp[REG ? u & 1 : 0], hr[u & 3]);
-						switch (u & 3) {	// (static ring slots: u is a constant after unrolling)
-						case 0: vemit(std::integral_constant<int, 0>(), wy[2 * u], q + u * OUT_PITCH, er++); break;
-						case 1: vemit(std::integral_constant<int, 1>(), wy[2 * u], q + u * OUT_PITCH, er++); break;
-						case 2: vemit(std::integral_constant<int, 2>(), wy[2 * u], q + u * OUT_PITCH, er++); break;
-						default: vemit(std::integral_constant<int, 3>(), wy[2 * u], q + u * OUT_PITCH, er++); break;
-						}
-						prow = pnext;
-					}
-					wy += 2 * UNR;
-					q += UNR * OUT_PITCH;
-				}
-				s_done += CH;
-			} else {
-				// rows of this chunk whose taps were all produced while walking the previous chunk
-				if (next_last <= s_done) {
-					switch (ph) {
-					case 1: emit(std::integral_constant<int, 0>()); break;
-					case 2: emit(std::integral_constant<int, 1>()); break;
-					case 3: emit(std::integral_constant<int, 2>()); break;
-					default: emit(std::integral_constant<int, 3>()); break;
-					}
-				}
-				walk(s_end);
 			}
-			if (REPAIR)	// what is left of the queue (its rows and taps belong to this chunk)
+		};
+		// bring the ring to slot 0 (the unrolled loop's slots are static)
+		auto rotate_to_slot0 = [&]() {
+			auto rotate = [&](auto by) {
+				constexpr int N = decltype(by)::value;
+				A t[4][P];
+#pragma unroll
+				for (int u = 0; u < 4; ++u)
+#pragma unroll
+					for (int k = 0; k < P; ++k)
+						t[u][k] = hr[(u + N) & 3][k];
+#pragma unroll
+				for (int u = 0; u < 4; ++u)
+#pragma unroll
+					for (int k = 0; k < P; ++k)
+						hr[u][k] = t[u][k];
+			};
+			switch (ph) {
+			case 0: break;
+			case 1: rotate(std::integral_constant<int, 1>()); break;
+			case 2: rotate(std::integral_constant<int, 2>()); break;
+			default: rotate(std::integral_constant<int, 3>()); break;
+			}
+			ph = 0;
+		};
+
+		// wait for chunk j's rows, pass-through tile and record; returns whether it can take the unrolled loop: a full
+		// chunk whose rows complete on the next CH source rows, ring at slot 0
+		auto begin_chunk = [&]() -> bool {
+			mbar_wait(&full[jnf], (uint32_t)jpar);
+			m = &meta[jnf];
+			done_bar = &done[jnf];
+			stg = stage + jstg * STAGE_BYTES;
+			q = stg + qoff;
+			y_first = ya + j * CH;
+			er = 0;
+			wflags = 0;
+			s_end = m->s_end[c];
+			wy = &m->wy[0][c];
+			lastp = m->last[c];
+			next_last = lastp[0];
+			return m->simple[c] && next_last == s_done + 1 && ph == 0;
+		};
+		// hand the chunk over: repairs first (their rows and taps belong to this chunk), then the barrier
+		auto end_chunk = [&]() {
+			if (REPAIR)	// what is left of the queue
 				while (rq_n > 0)
 					repair(min(rq_n, 32), y_first, stg);
 			if constexpr (WIDE) {
@@ -872,11 +844,108 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			}
 			// staging writes -> visible to the TMA store the producer issues after this barrier
 			warp_arrive(done_bar);
+			if (++jnf == NF) { jnf = 0; jpar ^= 1; }
+			jstg = jstg + 1 == NSTG ? 0 : jstg + 1;
+			++j;
+		};
+		// Steady state: CH consecutive source rows in, CH output rows out.  UNR rows unrolled (whole ring turns, so
+		// slots stay static); the next row's samples are loaded before the current row's arithmetic (the loads never
+		// wait on the stores).  Wide column groups unroll one ring turn only: 8 rows of P = 4 are 8 KB of code and
+		// "no instruction" became the top stall (profiles/r01_ncu_stream_narrow_A.md).
+		auto steady_chunk = [&]() {
+			constexpr int UNR = P >= 4 ? 4 : CH;
+			static_assert(CH % UNR == 0 && UNR % 4 == 0, "unroll must divide the chunk and cover whole ring turns");
+			// (bent warps load and filter row by row: their P * T samples are not double-buffered)
+			A smp[REG ? 2 : 1][NSL];
+			if (REG)
+				load_row(prow, smp[0]);
+#pragma unroll 1
+			for (int it = 0; it < CH / UNR; ++it) {
+#pragma unroll
+				for (int u = 0; u < UNR; ++u) {
+					uint32_t pnext = prow + (uint32_t)wpitch;
+					if (pnext == win_end)
+						pnext = win_c;
+					// (after the chunk's last row the samples are simply dropped)
+					if (REG)
+						load_row(pnext, smp[REG ? (u + 1) & 1 : 0]);
+					else
+						load_row(prow, smp[0]);
+					hfilter(smp[REG ? u & 1 : 0], hr[u & 3]);
+					switch (u & 3) {	// (static ring slots: u is a constant after unrolling)
+					case 0: vemit(std::integral_constant<int, 0>(), wy[2 * u], q + u * OUT_PITCH, er++); break;
+					case 1: vemit(std::integral_constant<int, 1>(), wy[2 * u], q + u * OUT_PITCH, er++); break;
+					case 2: vemit(std::integral_constant<int, 2>(), wy[2 * u], q + u * OUT_PITCH, er++); break;
+					default: vemit(std::integral_constant<int, 3>(), wy[2 * u], q + u * OUT_PITCH, er++); break;
+					}
+					prow = pnext;
+				}
+				wy += 2 * UNR;
+				q += UNR * OUT_PITCH;
+			}
+			s_done += CH;
+		};
+
+		// The chunk loop is a nest: the inner loop runs consecutive steady-state chunks and touches the ring of
+		// horizontal rows through static register slots only; everything else (a segment's first chunk, whose first
+		// T - 1 rows only prime the ring; chunks at a discontinuity of the row map; the band's last, partial chunk) takes
+		// the general walk outside it.  (As one loop with both paths in its body the compiler moved the 4 x P ring
+		// registers between the two paths' assignments around every chunk: 24 of ~90 hand-over instructions per thread.)
+		if (nchunks <= 0)
+			return;
+		bool steady = begin_chunk();
+		for (;;) {
+			if (STREAM_DEBUG_BIT(a, 1)) {	// timing experiment: memory pipeline only (results are wrong)
+				s_done = s_end;
+				prow = win_c + (uint32_t)(((s_done + 1) % NR) * wpitch);
+				end_chunk();
+				if (j == nchunks)
+					return;
+				begin_chunk();
+				continue;
+			}
+			if (steady) {
+#pragma unroll 1
+				do {
+					steady_chunk();
+					end_chunk();
+					if (j == nchunks)
+						return;
+					steady = begin_chunk();
+				} while (steady);
+			}
+			// general chunk.  A full chunk that only lacks its priming rows (a segment's first) is primed here and then
+			// takes the unrolled rows too.
+			if (m->simple[c] && next_last > s_done) {
+				walk(next_last - 1);
+				rotate_to_slot0();
+				steady_chunk();
+			} else {
+				// rows of this chunk whose taps were all produced while walking the previous chunk
+				if (next_last <= s_done) {
+					switch (ph) {
+					case 1: emit(std::integral_constant<int, 0>()); break;
+					case 2: emit(std::integral_constant<int, 1>()); break;
+					case 3: emit(std::integral_constant<int, 2>()); break;
+					default: emit(std::integral_constant<int, 3>()); break;
+					}
+				}
+				walk(s_end);
+				rotate_to_slot0();	// (the next chunk may take the unrolled rows again)
+			}
+			end_chunk();
+			if (j == nchunks)
+				return;
+			steady = begin_chunk();
 		}
 	};
 	// (measured: 100 MP RGB16 Cubic 0.212 -> 0.208 ms, RGBA8 0.068 -> 0.066 ms; four-column groups (RGB8)
 	// did not gain -- Linear lost 10 % -- so they keep the one regular form)
+#ifdef FIXCA_EXP_NARROW4
+	constexpr bool HAS_NARROW = P == 2 || P == 3 || P == 4;
+#else
 	constexpr bool HAS_NARROW = P == 2 || P == 3;
+#endif
 	bool narrow = regular && HAS_NARROW && !STREAM_DEBUG_BIT(a, 2);	// debug bit 1: A/B runs without the narrow form
 #pragma unroll
 	for (int k = 0; k < P; ++k)

@@ -147,6 +147,23 @@ if __name__ == "__main__":
             run("50MP rgb f32 cubic tlead" + tl, 6144, 8192, 3, torch.float32, -4, 2, F)
             run("50MP rgba f32 cubic tlead" + tl, 6144, 8192, 4, torch.float32, -4, 2, F)
         os.environ.pop("FIXCA_STREAM_TLEAD")
+    if which == "u8":       # the 8-bit layouts only (A/B runs of two builds: FIXCA_LIB)
+        run_batch("4K rgb8 cubic", 64, 2160, 3840, 3, torch.uint8, 1, 2, F)
+        run("4K rgb8 cubic fast", 2160, 3840, 3, torch.uint8, 1, 2, F)
+        run("24MP rgb8 cubic fast", 4000, 6000, 3, torch.uint8, 1, 2, F)
+        run("24MP rgb8 linear fast", 4000, 6000, 3, torch.uint8, 1, 1, F)
+        run("33MP rgba8 cubic fast", 4320, 7680, 4, torch.uint8, 1, 2, F)
+        run("24MP rgb8 cubic exact", 4000, 6000, 3, torch.uint8, 1, 2, E)
+    if which == "split":    # FIXCA_LIB = the TUNING build: memory pipeline only (1), compute only (4: no loads, 12: no loads, no stores)
+        for dbg in ("0", "1", "4", "12"):
+            os.environ["FIXCA_STREAM_DEBUG"] = dbg
+            run_batch("4K rgb8 cubic dbg" + dbg, 64, 2160, 3840, 3, torch.uint8, 1, 2, F)
+            run("24MP rgb8 cubic dbg" + dbg, 4000, 6000, 3, torch.uint8, 1, 2, F)
+            run("24MP rgb8 linear dbg" + dbg, 4000, 6000, 3, torch.uint8, 1, 1, F)
+            run("24MP rgb8 none dbg" + dbg, 4000, 6000, 3, torch.uint8, 1, 0, E)
+            run("33MP rgba8 cubic dbg" + dbg, 4320, 7680, 4, torch.uint8, 1, 2, F)
+            run("100MP rgb16 cubic dbg" + dbg, 8192, 12288, 3, torch.int16, 2, 2, F)
+        os.environ.pop("FIXCA_STREAM_DEBUG")
     if which == "small":    # launches dominated by the fixed cost
         run("4K rgb8 cubic fast", 2160, 3840, 3, torch.uint8, 1, 2, F)
         run("4K rgb8 linear fast", 2160, 3840, 3, torch.uint8, 1, 1, F)
