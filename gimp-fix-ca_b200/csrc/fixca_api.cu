@@ -220,7 +220,7 @@ struct Plan {
 	int src_rows_avail = 0;	// rows of the source band present at args.src
 	// stream kernel: the per-chunk tables args.meta_tab / args.span_tab point into (device memory, shared by every
 	// plan of the same band, y axes and kernel family; freed with the last plan that holds them)
-	std::shared_ptr<void> tables;
+	std::shared_ptr<void> tables, col_tables;
 	// a batch of equal frames in one launch (stream kernels: grid.z = frame, 3-D tensor maps)
 	int nframes = 1;
 	size_t src_frame_stride = 0, dst_frame_stride = 0;
@@ -531,53 +531,31 @@ static int resident_ctas(const KernelEntry *k, int threads, size_t smem, int dev
 	return n;
 }
 
-// The per-chunk tables of a streaming plan (stream_meta_kernel): vertical weights / tap rows and source-row spans of
-// every 8-row chunk of [y1, y2).  They depend on the y axes, the band, the kernel family and (None) the ring geometry
-// only, so plans that differ in buffers, pitches, strips or frames share one table: a small per-thread cache keyed
-// by exactly those inputs.  Filled on a private stream and waited for here -- a plan is made once per distinct call
-// (the plan cache), a table once per distinct band.
-static bool stream_tables(const KernelEntry *k, const Format &f, int dev, Plan &pl)
+// Per-plan tables of the streaming kernels live in device memory and are shared by every plan with the same inputs:
+// a small per-thread cache keyed by exactly what the fill kernel reads.  A table is filled on a private stream and
+// waited for here -- a plan is made once per distinct call (the plan cache), a table once per distinct band / image
+// width.  `fill(mem, stream)` launches the fill kernel(s).
+template <class Key, class Fill>
+static std::shared_ptr<void> cached_table(int tag, const Key &key, int dev, size_t bytes, Fill fill)
 {
-	struct Key {
-		int interp, mode, kind, y1, y2, ring_rows, win_pitch, dev, height;
-		int center[2], size[2];
-		double scale[2], shift[2];
-	};
-	struct Slot { Key key; std::shared_ptr<void> mem; size_t span_off; bool used; };
-	constexpr int SLOTS = 64;
+	static_assert(sizeof(Key) <= 192, "table key");
+	struct Slot { int tag; unsigned char key[192]; std::shared_ptr<void> mem; bool used; };
+	constexpr int SLOTS = 96;
 	static thread_local Slot slots[SLOTS];
 	static thread_local int next = 0;
 	static thread_local cudaStream_t fill_stream[64];	// per device, created on first use (never destroyed: process lifetime)
-	KernelArgs &a = pl.args;
-	Key key;
-	memset(&key, 0, sizeof key);
-	key.interp = a.g.interp; key.mode = k->repair; key.kind = a.g.interp ? (int)f.kind : 0;
-	key.y1 = a.y1; key.y2 = a.y2; key.dev = dev; key.height = a.g.height;
-	if (a.g.interp == 0) { key.ring_rows = a.ring_rows; key.win_pitch = a.win_pitch; }
-	for (int c = 0; c < 2; ++c) {
-		key.center[c] = a.g.y[c].center; key.size[c] = a.g.y[c].size;
-		key.scale[c] = a.g.y[c].scale; key.shift[c] = a.g.y[c].shift;
-	}
-	const int nchunks = (a.y2 - a.y1 + STREAM_CH - 1) / STREAM_CH;
-	const size_t rec = stream_meta_record_bytes(k->repair);
-	for (Slot &s : slots)
-		if (s.used && !memcmp(&s.key, &key, sizeof key)) {
-			pl.tables = s.mem;
-			a.meta_tab = s.mem.get();
-			a.span_tab = (const unsigned char *)s.mem.get() + s.span_off;
-			return true;
-		}
+	for (Slot &sl : slots)
+		if (sl.used && sl.tag == tag && !memcmp(sl.key, &key, sizeof key))
+			return sl.mem;
 	if (dev < 0 || dev >= 64)
-		return false;
+		return nullptr;
 	int cur = -1;
 	if (cudaGetDevice(&cur) != cudaSuccess)
-		return false;
+		return nullptr;
 	if (cur != dev && cudaSetDevice(dev) != cudaSuccess)
-		return false;
+		return nullptr;
 	bool ok = false;
 	void *mem = nullptr;
-	const size_t span_off = align_up((size_t)nchunks * rec, 256);
-	const size_t bytes = span_off + (size_t)nchunks * sizeof(StreamSpan);
 	do {
 		if (!fill_stream[dev] && cudaStreamCreateWithFlags(&fill_stream[dev], cudaStreamNonBlocking) != cudaSuccess)
 			break;
@@ -585,7 +563,7 @@ static bool stream_tables(const KernelEntry *k, const Format &f, int dev, Plan &
 			break;
 		if (cudaMemsetAsync(mem, 0, bytes, fill_stream[dev]) != cudaSuccess)
 			break;
-		if (launch_stream_meta(a.g.interp, k->repair, f.kind, a, mem, (unsigned char *)mem + span_off, nchunks, fill_stream[dev]) != cudaSuccess)
+		if (fill(mem, fill_stream[dev]) != cudaSuccess)
 			break;
 		if (cudaStreamSynchronize(fill_stream[dev]) != cudaSuccess)
 			break;
@@ -599,15 +577,74 @@ static bool stream_tables(const KernelEntry *k, const Format &f, int dev, Plan &
 	if (cur != dev)
 		cudaSetDevice(cur);
 	if (!ok)
-		return false;
+		return nullptr;
 	// (cudaFree waits for the device: no launch of a plan that held the table can still be reading it)
 	std::shared_ptr<void> sp(mem, [](void *p) { if (cudaFree(p) != cudaSuccess) cudaGetLastError(); });
-	Slot &s = slots[next];
+	Slot &sl = slots[next];
 	next = (next + 1) % SLOTS;
-	s.key = key; s.mem = sp; s.span_off = span_off; s.used = true;
-	pl.tables = sp;
-	a.meta_tab = mem;
-	a.span_tab = (const unsigned char *)mem + span_off;
+	sl.tag = tag;
+	memset(sl.key, 0, sizeof sl.key);
+	memcpy(sl.key, &key, sizeof key);
+	sl.mem = sp;
+	sl.used = true;
+	return sp;
+}
+
+// The tables of a streaming plan:
+//   chunk table (stream_meta_kernel): vertical weights / tap rows and source-row spans of every 8-row chunk of
+//     [y1, y2): depends on the y axes, the band, the kernel family and (None) the ring geometry;
+//   column table (stream_cols_kernel): base index and codec-scaled tap weights of every column of the strips:
+//     depends on the x axes, the width, the kernel family and the sample codec.
+static bool stream_tables(const KernelEntry *k, const Format &f, int dev, int strips, Plan &pl)
+{
+	KernelArgs &a = pl.args;
+	struct ChunkKey {
+		int interp, mode, kind, y1, y2, ring_rows, win_pitch, dev, height;
+		int center[2], size[2];
+		double scale[2], shift[2];
+	} ck;
+	memset(&ck, 0, sizeof ck);
+	ck.interp = a.g.interp; ck.mode = k->repair; ck.kind = a.g.interp ? (int)f.kind : 0;
+	ck.y1 = a.y1; ck.y2 = a.y2; ck.dev = dev; ck.height = a.g.height;
+	if (a.g.interp == 0) { ck.ring_rows = a.ring_rows; ck.win_pitch = a.win_pitch; }
+	for (int c = 0; c < 2; ++c) {
+		ck.center[c] = a.g.y[c].center; ck.size[c] = a.g.y[c].size;
+		ck.scale[c] = a.g.y[c].scale; ck.shift[c] = a.g.y[c].shift;
+	}
+	const int nchunks = (a.y2 - a.y1 + STREAM_CH - 1) / STREAM_CH;
+	const size_t span_off = align_up((size_t)nchunks * stream_meta_record_bytes(k->repair), 256);
+	const KernelArgs args = a;
+	const int interp = a.g.interp, mode = k->repair;
+	const SampleKind kind = f.kind;
+	pl.tables = cached_table(1, ck, dev, span_off + (size_t)nchunks * sizeof(StreamSpan), [&](void *mem, cudaStream_t st) {
+		return launch_stream_meta(interp, mode, kind, args, mem, (unsigned char *)mem + span_off, nchunks, st);
+	});
+	if (!pl.tables)
+		return false;
+	a.meta_tab = pl.tables.get();
+	a.span_tab = (const unsigned char *)pl.tables.get() + span_off;
+
+	struct ColKey {
+		int interp, mode, kind, ncols, dev, width;
+		int center[2], size[2];
+		double scale[2], shift[2];
+	} xk;
+	memset(&xk, 0, sizeof xk);
+	const int ncols = strips * k->tw;
+	xk.interp = interp; xk.mode = mode; xk.kind = interp ? (int)f.kind : 0; xk.ncols = ncols; xk.dev = dev; xk.width = a.g.width;
+	for (int c = 0; c < 2; ++c) {
+		xk.center[c] = a.g.x[c].center; xk.size[c] = a.g.x[c].size;
+		xk.scale[c] = a.g.x[c].scale; xk.shift[c] = a.g.x[c].shift;
+	}
+	const size_t w_off = align_up((size_t)2 * ncols * sizeof(int), 256);
+	pl.col_tables = cached_table(2, xk, dev, w_off + (size_t)2 * ncols * stream_cols_weight_bytes(interp, mode) + 256, [&](void *mem, cudaStream_t st) {
+		return launch_stream_cols(interp, mode, kind, args, ncols, mem, (unsigned char *)mem + w_off, st);
+	});
+	if (!pl.col_tables)
+		return false;
+	a.col_i0 = (const int *)pl.col_tables.get();
+	a.col_w = (const unsigned char *)pl.col_tables.get() + w_off;
+	a.col_n = ncols;
 	return true;
 }
 
@@ -742,7 +779,7 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 		if (!make_tensor_map(pl.fan.tm[i], pl.fan_dst[i], (size_t)a.dst_pitch, row_bytes, dst_rows, nf, dfs, (unsigned)(k->tw * f.bpp), CH))
 			return false;
 	}
-	return stream_tables(k, f, dev, pl);
+	return stream_tables(k, f, dev, strips, pl);
 }
 
 // Planning costs tens of microseconds (window scans in FP64, three tensor-map encodes), a third of

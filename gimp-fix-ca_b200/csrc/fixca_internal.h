@@ -69,6 +69,10 @@ size_t stream_meta_record_bytes(int mode);
 cudaError_t launch_stream_meta(int interp, int mode, SampleKind kind, const KernelArgs &a, void *meta, void *span, int nchunks,
 			       cudaStream_t st);
 
+// ... and the per-plan column table (KernelArgs::col_i0 / col_w): ncols columns per channel
+size_t stream_cols_weight_bytes(int interp, int mode);
+cudaError_t launch_stream_cols(int interp, int mode, SampleKind kind, const KernelArgs &a, int ncols, void *i0, void *w, cudaStream_t st);
+
 // kernels_preview.cu: saturate() + centerline() on destination rows [y1, y2) (fix-ca.c:1322-1327)
 cudaError_t launch_preview(int kind, int nch, unsigned char *dst, long long pitch, int dst_row0, int y1, int y2, int width,
 			   int xc, int yc, double saturation, cudaStream_t st);

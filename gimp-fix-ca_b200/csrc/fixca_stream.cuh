@@ -268,6 +268,50 @@ __global__ void __launch_bounds__(128) stream_meta_kernel(const KernelArgs a, co
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// stream_cols_kernel: the per-plan column table, one thread per (channel, column) of the strips' column range
+// [0, ncols).  i0[c][x] = base index of the column's tap window (None: the nearest column), w[c][x] = its tap
+// weights, scaled for the codec (fix-ca.c:801-808 coordinates, :891-892 / :905-907 weights) -- what every compute
+// thread of every segment and frame used to evaluate in FP64 for its own P columns at CTA start (550 instructions
+// per warp, most of the fixed cost of a small launch).  MODE as in stream_meta_kernel; the expressions are the ones
+// strip_kernel evaluates in place (same bytes).
+// ---------------------------------------------------------------------------------------------------------
+template <int INTERP, int MODE>
+__global__ void __launch_bounds__(256) stream_cols_kernel(const KernelArgs a, const float hscale, const int ncols, int *const i0_out,
+							   void *const w_out)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+	if (x >= ncols)
+		return;
+	if constexpr (INTERP == 0) {
+		i0_out[c * ncols + x] = nearest_index(a.g.x[c], x);
+	} else {
+		double td;
+		i0_out[c * ncols + x] = base_index(a.g.x[c], x, td);
+		if constexpr (MODE == 2) {
+			double w[4];
+			tap_weights_d<INTERP>(td, w);
+			dvec4 v;
+			v.x = w[0] * kWideScale + 0.0; v.y = w[1] * kWideScale + 0.0; v.z = w[2] * kWideScale + 0.0; v.w = w[3] * kWideScale + 0.0;
+			reinterpret_cast<dvec4 *>(w_out)[c * ncols + x] = v;
+		} else {
+			float w[4];
+			if (MODE == 1) {	// FP64 weights, rounded once (the exact-repair error bound counts one rounding per weight)
+				double wd[4];
+				tap_weights_d<INTERP>(td, wd);
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+					w[j] = (float)wd[j];
+			} else {
+				tap_weights<INTERP>((float)td, w);
+			}
+			// power of two (integer samples are read as subnormals); -0 -> +0: the sign of an all-zero sum must not depend on the fold
+			reinterpret_cast<float4 *>(w_out)[c * ncols + x] =
+				make_float4(w[0] * hscale + 0.f, w[1] * hscale + 0.f, w[2] * hscale + 0.f, w[3] * hscale + 0.f);
+		}
+	}
+}
+
 // Dynamic shared memory: [StreamHeader | StreamMeta[D + 1] | window ring (ring_rows x win_pitch) |
 //                         staging (3 x CH x TW x BPP)]
 // blockDim.x == 2 * TW / P compute threads + 32 (the TMA warp).
@@ -475,7 +519,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		int cofs[P];
 #pragma unroll
 		for (int k = 0; k < P; ++k)
-			cofs[k] = nearest_index(a.g.x[c], x0 + lt * P + k) * BPP + 2 * c * (int)sizeof(S) - wb0;
+			cofs[k] = __ldg(a.col_i0 + c * a.col_n + x0 + lt * P + k) * BPP + 2 * c * (int)sizeof(S) - wb0;
 		int jnf = 0, jstg = 0, jpar = 0;	// j % NF, j % NSTG, (j / NF) & 1
 		for (int j = 0; j < nchunks; ++j) {
 			mbar_wait(&full[jnf], (uint32_t)jpar);
@@ -524,26 +568,16 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		for (int k = 0; k < P; ++k) {
 			// columns past the tile's last one are computed like any other (their results are
 			// clipped by the TMA store); past the image the coordinate clamps to W - 1 ...
-			double td;
-			const int i0 = base_index(a.g.x[c], x0 + lt * P + k, td);
+			// (base index and codec-scaled tap weights: the plan's column table, stream_cols_kernel)
+			const int tcol = c * a.col_n + x0 + lt * P + k;
+			const int i0 = __ldg(a.col_i0 + tcol);
 			if constexpr (WIDE) {
-				tap_weights_d<INTERP>(td, w[k]);
-#pragma unroll
-				for (int j = 0; j < 4; ++j)
-					w[k][j] = w[k][j] * kWideScale + 0.0;
+				const double2 *const tw = reinterpret_cast<const double2 *>(a.col_w) + 2 * (size_t)tcol;
+				const double2 lo = __ldg(tw), hi = __ldg(tw + 1);
+				w[k][0] = lo.x; w[k][1] = lo.y; w[k][2] = hi.x; w[k][3] = hi.y;
 			} else {
-				if (REPAIR) {	// FP64 weights, rounded once (the error bound counts one rounding per weight)
-					double wd[4];
-					tap_weights_d<INTERP>(td, wd);
-#pragma unroll
-					for (int j = 0; j < 4; ++j)
-						w[k][j] = (float)wd[j];
-				} else {
-					tap_weights<INTERP>((float)td, w[k]);
-				}
-#pragma unroll
-				for (int j = 0; j < 4; ++j)
-					w[k][j] = w[k][j] * Codec::kHScale + 0.f;	// power of two (integer samples are read as subnormals); -0 -> +0: the sign of an all-zero sum must not depend on the fold
+				const float4 t4 = __ldg(reinterpret_cast<const float4 *>(a.col_w) + tcol);
+				w[k][0] = t4.x; w[k][1] = t4.y; w[k][2] = t4.z; w[k][3] = t4.w;
 			}
 			// ... with zero weights, so that they do not bend a warp of the last strip
 			if (x0 + lt * P + k > xl)
@@ -942,7 +976,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	// (measured: 100 MP RGB16 Cubic 0.212 -> 0.208 ms, RGBA8 0.068 -> 0.066 ms; four-column groups (RGB8)
 	// did not gain -- Linear lost 10 % -- so they keep the one regular form)
 #ifdef FIXCA_EXP_NARROW4
-	constexpr bool HAS_NARROW = P == 2 || P == 3 || P == 4;
+	constexpr bool HAS_NARROW = P == 2 || P == 3 || (P == 4 && !REPAIR);
 #else
 	constexpr bool HAS_NARROW = P == 2 || P == 3;
 #endif
