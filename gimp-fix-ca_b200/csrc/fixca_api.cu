@@ -679,7 +679,7 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 		int max_rows = 0;
 		for (int j = 0; j < nchunks_all; ++j)
 			max_rows = std::max(max_rows, c_hi[std::min(j + d, nchunks_all - 1)] - c_lo[j] + 1);
-		ring_rows = align_up((size_t)max_rows, 4) + 8;	// whole 4-row groups at both ends
+		ring_rows = ((size_t)max_rows + 6) / 4 * 4;	// whole 4-row groups: a run of R rows touches at most floor((R + 6) / 4) of them
 		off_meta = align_up(sizeof(StreamHeader), 16);
 		off_win = align_up(off_meta + (size_t)(d + 1) * (k->repair == 2 ? sizeof(StreamMetaWide) : sizeof(StreamMeta)), 128);
 		off_out = align_up(off_win + ring_rows * (size_t)wb, 128);
@@ -700,11 +700,13 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 		// 0.219 ms; 8K RGBA16 None 0.093 -> 0.089 ms, Linear 0.090 -> 0.087 ms: the strips of a row drift further
 		// apart and their requests lose the DRAM pages they share), a lone CTA per SM wants 4 (0.212 against
 		// 0.247 / 0.258 ms at depth 3 / 2).  The narrower strips (RGBA f32: 64 pixels = 1024 bytes, 8 compute
-		// warps per SM) keep the deepest pipeline that fits: capped at 2 they lose 8-10 %.
+		// warps per SM) keep the deepest pipeline that fits for None: capped at 2 the copies lose 8-10 % (r02, with the
+		// pass-through tile two chunks ahead: 50 MP RGBA f32 None 0.93 at depth 2, 1.00 at depth 3+; 33 MP RGBA8 None 0.80 /
+		// 0.87 at depth 4); Linear / Cubic are level or lose beyond depth 2 on every layout (RGBA8 Cubic 0.75 / 0.68 at 3).
 		const bool wide_strip = k->tw * f.bpp >= 1536;
 		for (int want = want_ctas; want >= 1 && !depth; --want) {
 			const size_t budget = std::min<size_t>(limit, (227 * 1024) / want - 1024);
-			for (int d = !wide_strip ? STREAM_MAX_D : want > 1 ? 2 : 4; d >= (want > 1 ? 2 : 1); --d) {
+			for (int d = (!wide_strip && g.interp == 0) ? STREAM_MAX_D : want > 1 ? 2 : 4; d >= (want > 1 ? 2 : 1); --d) {
 				layout(d);
 				if (total <= budget) {
 					depth = d;
@@ -730,10 +732,14 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 		waves = tuning().stream_waves;
 	segs *= waves;
 	if (pl.nframes > 1) {
-		// a batch fills the GPU with frames x strips x segments CTAs: long segments (>= 256 rows) so that
-		// a CTA's set-up and ring priming are spread over many chunks, as long as every SM slot gets a CTA
-		const int fill = (sm_count(dev) * per_sm + strips * pl.nframes - 1) / (strips * pl.nframes);
-		segs = std::max(fill, (rows + 255) / 256);
+		// a batch fills the GPU with frames x strips x segments CTAs: long segments (>= 512 rows) so that
+		// a CTA's set-up, ring priming and first chunk -- a fifth of the lifetime of a 240-row CTA -- are spread over
+		// many chunks, as long as there are CTAs for ~8 waves (128 x 4K RGB8 Cubic: 9 segments per frame 0.733, 2-4
+		// segments 0.748 of the HBM peak; 64 frames: 4-6 segments 0.727, 9 segments 0.711)
+		const int slots = sm_count(dev) * per_sm;
+		const int fill = (slots + strips * pl.nframes - 1) / (strips * pl.nframes);
+		const int waves8 = (8 * slots + strips * pl.nframes - 1) / (strips * pl.nframes);
+		segs = std::max(fill, std::min((rows + 255) / 256, std::max((rows + 511) / 512, waves8)));
 	}
 	const int forced = tuning().stream_segs;
 	if (forced > 0)

@@ -44,6 +44,9 @@
 #pragma once
 
 #include <type_traits>
+#ifdef FIXCA_EXP_TIMING
+#include <cstdio>
+#endif
 
 #include <cuda.h>	// CUtensorMap (the maps are encoded on the host, fixca_api.cu)
 
@@ -331,12 +334,19 @@ __global__ void __launch_bounds__(256) stream_cols_kernel(const KernelArgs a, co
 // raw sample values (fixca_strip.cuh, WideCodec); a sample within WideCodec::kEps of a rounding boundary -- one in
 // half a million -- is recomputed in the reference's operation order by its own thread at the end of the chunk.
 template <class S, int NCH, int INTERP, int P, int TW, bool ALT = false, bool REPAIR = false, bool WIDE = false>
+#ifdef FIXCA_EXP_LB5
+__global__ void __launch_bounds__(2 * TW / P + 32, (2 * TW / P) <= 128 && !WIDE ? 5 : 2)	// experiment: 5 resident CTAs (80 registers)
+#else
 __global__ void __launch_bounds__(2 * TW / P + 32, (2 * TW / P) <= 128 && !WIDE ? 4 : 2)	// register budget: 4 (2) resident CTAs
+#endif
 stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUtensorMap tm_win,
 	      const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ CUtensorMap tm_out,
 	      const __grid_constant__ StreamFanout fan)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
+#ifdef FIXCA_EXP_TIMING
+	const long long t_entry = clock64();
+#endif
 	constexpr int BPP = NCH * (int)sizeof(S);
 	constexpr int OUT_PITCH = TW * BPP;
 	constexpr int STAGE_BYTES = STREAM_CH * OUT_PITCH;
@@ -927,7 +937,14 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		// registers between the two paths' assignments around every chunk: 24 of ~90 hand-over instructions per thread.)
 		if (nchunks <= 0)
 			return;
+#ifdef FIXCA_EXP_TIMING
+		const long long t_setup = clock64();
+#endif
 		bool steady = begin_chunk();
+#ifdef FIXCA_EXP_TIMING
+		const long long t_data = clock64();
+		long long t_steady0 = 0;
+#endif
 		for (;;) {
 			if (STREAM_DEBUG_BIT(a, 1)) {	// timing experiment: memory pipeline only (results are wrong)
 				s_done = s_end;
@@ -939,6 +956,29 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				continue;
 			}
 			if (steady) {
+#ifdef FIXCA_EXP_TIMING
+				// experiment: where a compute warp's time goes in the steady state (one CTA reports)
+				long long t_rows = 0, t_end = 0, t_begin = 0;
+				int n_st = 0;
+				if (!t_steady0) t_steady0 = clock64();
+#pragma unroll 1
+				do {
+					const long long t0 = clock64();
+					steady_chunk();
+					const long long t1 = clock64();
+					end_chunk();
+					const long long t2 = clock64();
+					t_rows += t1 - t0; t_end += t2 - t1; ++n_st;
+					if (j == nchunks) {
+						if (blockIdx.x == 3 && blockIdx.y == 1 && blockIdx.z % 16 == 5 && (tid & 31) == 0)
+							printf("cta z%d warp %d: %d steady chunks, cycles per chunk: rows %lld, hand-over %lld, wait+entry %lld; CTA: set-up %lld, first data +%lld, first chunk +%lld, total %lld\n", (int)blockIdx.z, tid >> 5, n_st,
+							       t_rows / n_st, t_end / n_st, t_begin / max(n_st - 1, 1), t_setup - t_entry, t_data - t_setup, t_steady0 - t_data, clock64() - t_entry);
+						return;
+					}
+					steady = begin_chunk();
+					t_begin += clock64() - t2;
+				} while (steady);
+#else
 #pragma unroll 1
 				do {
 					steady_chunk();
@@ -947,6 +987,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 						return;
 					steady = begin_chunk();
 				} while (steady);
+#endif
 			}
 			// general chunk.  A full chunk that only lacks its priming rows (a segment's first) is primed here and then
 			// takes the unrolled rows too.
@@ -973,13 +1014,10 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			steady = begin_chunk();
 		}
 	};
-	// (measured: 100 MP RGB16 Cubic 0.212 -> 0.208 ms, RGBA8 0.068 -> 0.066 ms; four-column groups (RGB8)
-	// did not gain -- Linear lost 10 % -- so they keep the one regular form)
-#ifdef FIXCA_EXP_NARROW4
+	// (measured: 100 MP RGB16 Cubic 0.212 -> 0.208 ms, RGBA8 0.068 -> 0.066 ms.  Four-column groups (RGB8): one
+	// shared-memory wavefront and four FMAs less per row, 128 x 4K RGB8 Cubic 0.717 -> 0.732 of the HBM peak, Linear
+	// 0.670 -> 0.687; the exact-repair form keeps the one regular form -- with three row loops it spills.)
 	constexpr bool HAS_NARROW = P == 2 || P == 3 || (P == 4 && !REPAIR);
-#else
-	constexpr bool HAS_NARROW = P == 2 || P == 3;
-#endif
 	bool narrow = regular && HAS_NARROW && !STREAM_DEBUG_BIT(a, 2);	// debug bit 1: A/B runs without the narrow form
 #pragma unroll
 	for (int k = 0; k < P; ++k)

@@ -52,7 +52,7 @@ def run(name, h, w, ch, tdtype, bpc, interp, flags, reps=10, lens=None):
           % (name, fixca.last_kernel(), os.environ.get("FIXCA_TILE_H", "auto"), best, med, mp / (med * 1e-3), gbs, 100 * gbs / PEAK, PEAK), flush=True)
 
 
-def run_batch(name, nf, h, w, ch, tdtype, bpc, interp, flags, reps=5):
+def run_batch(name, nf, h, w, ch, tdtype, bpc, interp, flags, reps=5, only_batch=False):
     es = torch.empty((), dtype=tdtype).element_size()
     bpp = ch * es
     pitch = (w * bpp + 127) // 128 * 128
@@ -66,7 +66,7 @@ def run_batch(name, nf, h, w, ch, tdtype, bpc, interp, flags, reps=5):
     def loop():
         for k in range(nf):
             fixca.fix_ca_region_dev(src[k].data_ptr(), pitch, 0, h, dst[k].data_ptr(), pitch, 0, w, h, bpp, bpc, p, 0, h, flags, st)
-    for label, call in (("one launch", batch), ("per frame", loop)):
+    for label, call in (("one launch", batch), ("per frame", loop))[:1 if only_batch else 2]:
         for _ in range(2):
             call()
         torch.cuda.synchronize()
@@ -164,6 +164,37 @@ if __name__ == "__main__":
             run("33MP rgba8 cubic dbg" + dbg, 4320, 7680, 4, torch.uint8, 1, 2, F)
             run("100MP rgb16 cubic dbg" + dbg, 8192, 12288, 3, torch.int16, 2, 2, F)
         os.environ.pop("FIXCA_STREAM_DEBUG")
+    if which == "ctas5":    # FIXCA_LIB = a build with 5-CTA launch bounds: 5 CTAs per SM at depth 1 against the default
+        for env in ({}, {"FIXCA_STREAM_CTAS": "5", "FIXCA_STREAM_DEPTH": "1"}, {"FIXCA_STREAM_CTAS": "4", "FIXCA_STREAM_DEPTH": "1"}):
+            for k in ("FIXCA_STREAM_CTAS", "FIXCA_STREAM_DEPTH"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            os.environ["FIXCA_VERBOSE"] = "1"
+            tag = " ".join("%s=%s" % (k[13:], v) for k, v in env.items()) or "default"
+            run_batch("4K rgb8 cubic " + tag, 64, 2160, 3840, 3, torch.uint8, 1, 2, F)
+            os.environ["FIXCA_VERBOSE"] = "0"
+            run("24MP rgb8 cubic " + tag, 4000, 6000, 3, torch.uint8, 1, 2, F)
+            run("24MP rgb8 linear " + tag, 4000, 6000, 3, torch.uint8, 1, 1, F)
+            run("33MP rgba8 cubic " + tag, 4320, 7680, 4, torch.uint8, 1, 2, F)
+    if which == "segs":     # batch launches: rows per CTA (FIXCA_STREAM_SEGS segments per frame)
+        for nf in (128, 64):
+            for segs in ("0", "1", "2", "3", "4", "6", "9"):
+                os.environ["FIXCA_STREAM_SEGS"] = segs
+                run_batch("4K rgb8 cubic segs" + segs, nf, 2160, 3840, 3, torch.uint8, 1, 2, F, reps=5, only_batch=True)
+        os.environ.pop("FIXCA_STREAM_SEGS")
+    if which == "depth":    # pipeline depth sweep of the narrow-strip layouts
+        for d in ("0", "2", "3", "4", "6"):
+            os.environ["FIXCA_STREAM_DEPTH"] = d
+            os.environ["FIXCA_VERBOSE"] = "0"
+            for name, args in (("24MP rgb8 none", (4000, 6000, 3, torch.uint8, 1, 0, E)), ("24MP rgb8 linear", (4000, 6000, 3, torch.uint8, 1, 1, F)),
+                               ("24MP rgb8 cubic", (4000, 6000, 3, torch.uint8, 1, 2, F)), ("33MP rgba8 cubic", (4320, 7680, 4, torch.uint8, 1, 2, F)),
+                               ("33MP rgba8 none", (4320, 7680, 4, torch.uint8, 1, 0, E)),
+                               ("50MP rgba f32 cubic", (6144, 8192, 4, torch.float32, -4, 2, F)), ("50MP rgba f32 none", (6144, 8192, 4, torch.float32, -4, 0, E))):
+                try:
+                    run(name + " D" + d, *args)
+                except fixca.FixCaError as e:
+                    print(name, "D", d, str(e)[:80])
+        os.environ.pop("FIXCA_STREAM_DEPTH")
     if which == "small":    # launches dominated by the fixed cost
         run("4K rgb8 cubic fast", 2160, 3840, 3, torch.uint8, 1, 2, F)
         run("4K rgb8 linear fast", 2160, 3840, 3, torch.uint8, 1, 1, F)
