@@ -406,6 +406,67 @@ def test_device_resident_entry_with_torch_buffers(fx, checker):
     assert fx.last_kernel().startswith("direct") and d2.cpu().numpy().tobytes() == want2.tobytes()
 
 
+def test_plan_tables_survive_cache_churn_and_threads(fx, checker):
+    """The streaming kernels read per-plan chunk / column tables from device memory (stream_meta_kernel,
+    stream_cols_kernel); plans and tables sit in per-thread caches of 96 slots.  More distinct bands, widths and
+    modes than there are slots: evicted tables are freed only with the last plan that holds them, every result
+    stays identical to the reference's; then the same from four threads at once (per-thread caches, one device)."""
+    import threading
+
+    import torch
+
+    h, w = 301, 512
+    img = orc.synth_image(h, w, 3, "u1", 77)
+    kwc = dict(KW, lens_x=250, lens_y=140, interpolation=2)
+    want = {i: checker.region(img, orc.Params(**dict(kwc, interpolation=i))) for i in (0, 1, 2)}
+    src = torch.from_numpy(img).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def bands(seed, n):
+        rng = np.random.default_rng(seed)
+        out = torch.empty_like(src)
+        for k in range(n):
+            interp = int(rng.integers(0, 3))
+            y1 = int(rng.integers(0, h - 1))
+            y2 = int(rng.integers(y1 + 1, h + 1))
+            out.fill_(0x5A)
+            fx.fix_ca_region_dev(src.data_ptr(), w * 3, 0, h, out.data_ptr(), w * 3, 0, w, h, 3, 1,
+                                 fx.FixCaParams(**dict(kwc, interpolation=interp)), y1, y2, fx.PRECISION_EXACT, stream)
+            torch.cuda.synchronize()
+            got = out.cpu().numpy()
+            assert fx.last_kernel().startswith("stream"), fx.last_kernel()
+            assert (got[y1:y2] == want[interp][y1:y2]).all(), (seed, k, interp, y1, y2)
+            assert (got[:y1] == 0x5A).all() and (got[y2:] == 0x5A).all()
+
+    bands(1, 260)           # > 2 x 96 distinct plans: every slot of both caches is recycled
+    # widths: one column table each
+    for w2 in range(256, 256 + 16 * 110, 16):
+        img2 = orc.synth_image(9, w2, 3, "u1", w2)
+        s2 = torch.from_numpy(img2).cuda()
+        d2 = torch.empty_like(s2)
+        kw2 = dict(KW, lens_x=w2 // 2, lens_y=4, interpolation=1)
+        fx.fix_ca_region_dev(s2.data_ptr(), w2 * 3, 0, 9, d2.data_ptr(), w2 * 3, 0, w2, 9, 3, 1, fx.FixCaParams(**kw2), 0, 9,
+                             fx.PRECISION_EXACT, stream)
+        torch.cuda.synchronize()
+        if w2 % 256 == 0:
+            assert d2.cpu().numpy().tobytes() == checker.region(img2, orc.Params(**kw2)).tobytes(), w2
+    errors = []
+
+    def worker(seed):
+        try:
+            torch.cuda.set_device(0)
+            bands(seed, 40)
+        except BaseException as e:      # noqa: BLE001 -- reported on the main thread
+            errors.append((seed, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(100 + i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_rows_that_are_views_into_a_wider_buffer_are_not_overrun(fx, checker):
     """Device-resident destination rows that are a sub-rectangle of a wider buffer (pitch > row, width * bytes not a
     multiple of 16): by default nothing past width * bytes of a row is written (the per-pixel kernel takes the call);
