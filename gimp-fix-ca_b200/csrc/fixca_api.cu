@@ -915,10 +915,7 @@ static int check_flags(unsigned flags, int allow, const Format &f, const fixca_p
 		return fail(FIXCA_ERR_UNSUPPORTED, "%s: the preview overlay is a single-image call (fixca_cuda_region*, fixca_cuda_region_dev)", entry);
 	if ((flags & FIXCA_COLUMN_SELECTION) && !(allow & ALLOW_COLUMNS))
 		return fail(FIXCA_ERR_UNSUPPORTED, "%s: FIXCA_COLUMN_SELECTION is an option of fixca_cuda_region_ex only", entry);
-	if (f.kind == SK_U64 && p->interpolation != 0)
-		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples with Linear/Cubic need 80-bit long double arithmetic (fix-ca.c:728-733)");
-	if ((flags & FIXCA_PREVIEW_OVERLAY) && f.kind == SK_U64 && p->saturation != 0.0)
-		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples: the preview's saturation boost needs 80-bit long double arithmetic (fix-ca.c:728-733)");
+	(void)f; (void)p;	// (u64 samples were refused here until the x87 steps of get_pixel / set_pixel were restated: fixca_kernels.cuh)
 	return FIXCA_OK;
 }
 
@@ -1559,8 +1556,6 @@ extern "C" int fixca_cuda_preview(const unsigned char *src, unsigned char *prev,
 	int rc = host_prologue(src, prev, width, height, bytes, bpc, params, 0, width, y, y + ph, f, g, flags,
 			       ALLOW_PREVIEW, "fixca_cuda_preview");
 	if (rc) return rc;
-	if (f.kind == SK_U64)
-		return fail(FIXCA_ERR_UNSUPPORTED, "u64 samples: the 8-bit preview needs 80-bit long double arithmetic (fix-ca.c:728-733)");
 	int dev;
 	if ((rc = current_device_or(-1, dev))) return rc;
 	if (ph == 0)
@@ -1989,7 +1984,7 @@ extern "C" const char *fixca_strerror(int code)
 	case FIXCA_ERR_RANGE: return "parameter out of range";
 	case FIXCA_ERR_NO_DEVICE: return "no CUDA device";
 	case FIXCA_ERR_CUDA: return "CUDA error";
-	case FIXCA_ERR_UNSUPPORTED: return "u64 samples with Linear/Cubic are not supported";
+	case FIXCA_ERR_UNSUPPORTED: return "this entry point does not take that flag";
 	case FIXCA_ERR_NOMEM: return "out of device or pinned memory";
 	default: return "unknown error";
 	}

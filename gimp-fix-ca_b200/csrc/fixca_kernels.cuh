@@ -82,6 +82,41 @@ struct KernelArgs {
 struct u15_t { uint16_t v; };
 
 // ---------------------------------------------------------------------------
+// u64 samples: the reference decodes them through the x87's 80-bit long double (fix-ca.c:728-733) and encodes them
+// through `roundl(d * 18446744073709551615UL)` (:759-761).  Both are restated in integer / FP64 arithmetic:
+//   get_pixel  ret = RN53(RN64(v / (2^64 - 1))).  v / (2^64 - 1) = 0.VVVV... in base 2^64, so the 64 bits that
+//              follow the leading one are rotl(v, clz(v)) and what follows repeats them: the round bit is the
+//              top bit of that rotation -- always set -- and the sticky bits are never all zero, so the 64-bit
+//              mantissa is rotl(v, clz(v)) + 1 (v = 2^64 - 1 carries to exactly 1.0); then one rounding to 53
+//              bits, nearest-even.
+//   set_pixel  the constant 2^64 - 1 converts to the DOUBLE 2^64, the product is exact, roundl rounds half away,
+//              and the conversion of 2^64 itself (d = 1.0) to uint64_t is out of range: the compiled reference's
+//              x87 sequence (subtract 2^63, fistp, flip the top bit) yields 0 -- white wraps to black, and so it
+//              does here (checked against oracle/_ref, tests/golden/golden_u64.json).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double u64_get_pixel(uint64_t v)
+{
+	if (v == 0)
+		return 0.0;
+	const int lz = __clzll((long long)v);
+	const uint64_t r = lz ? (v << lz) | (v >> (64 - lz)) : v;
+	const double scale = __hiloint2double((1023 - 53 - lz) << 20, 0);	// 2^(11 - 64 - lz)
+	if (r == ~0ull)							// mantissa 2^64: v / (2^64 - 1) == 1 (lz == 0)
+		return 1.0;
+	const uint64_t n = r + 1;					// the x87 quotient's mantissa, top bit set
+	uint64_t m = n >> 11;
+	const uint64_t rem = n & 0x7FF;
+	if (rem > 0x400 || (rem == 0x400 && (m & 1)))
+		++m;							// <= 2^53: exact as a double
+	return __dmul_rn((double)m, scale);
+}
+__device__ __forceinline__ uint64_t u64_set_pixel(double d)	// d already through clip_d
+{
+	const double r = round(__dmul_rn(d, 18446744073709551616.0));
+	return r >= 18446744073709551616.0 ? 0ull : __double2ull_rz(r);
+}
+
+// ---------------------------------------------------------------------------
 // Arithmetic policies
 // ---------------------------------------------------------------------------
 template <class S> struct SampleMax;
@@ -118,6 +153,7 @@ struct ExactF64 {
 	__device__ __forceinline__ static double decode(uint8_t v)  { return div_by_max<255>(v); }
 	__device__ __forceinline__ static double decode(uint16_t v) { return div_by_max<65535>(v); }
 	__device__ __forceinline__ static double decode(uint32_t v) { return __ddiv_rn((double)v, 4294967295.0); }
+	__device__ __forceinline__ static double decode(uint64_t v) { return u64_get_pixel(v); }
 	__device__ __forceinline__ static double decode(u15_t v)    { return __dmul_rn((double)v.v, 0x1p-15); }	// v / 32768, exact
 	__device__ __forceinline__ static double decode(float v)    { return (double)v; }
 	__device__ __forceinline__ static double decode(double v)   { return v; }
@@ -133,6 +169,7 @@ struct ExactF64 {
 	__device__ __forceinline__ static void encode(uint8_t &o, double d)  { o = (uint8_t)__double2uint_rz(round(__dmul_rn(clip(d), 255.0))); }
 	__device__ __forceinline__ static void encode(uint16_t &o, double d) { o = (uint16_t)__double2uint_rz(round(__dmul_rn(clip(d), 65535.0))); }
 	__device__ __forceinline__ static void encode(uint32_t &o, double d) { o = __double2uint_rz(round(__dmul_rn(clip(d), 4294967295.0))); }
+	__device__ __forceinline__ static void encode(uint64_t &o, double d) { o = u64_set_pixel(clip(d)); }
 	__device__ __forceinline__ static void encode(u15_t &o, double d)    { o.v = (uint16_t)__double2uint_rz(round(__dmul_rn(clip(d), 32768.0))); }
 	__device__ __forceinline__ static void encode(float &o, double d)    { o = __double2float_rn(clip(d)); }
 	__device__ __forceinline__ static void encode(double &o, double d)   { o = clip(d); }

@@ -22,6 +22,7 @@ static const KernelEntry exact_table[] = {
 	EXACT_ENTRIES(double, "f64"),
 	EXACT_ENTRIES(__half, "f16"),
 	EXACT_ENTRIES(u15_t, "u15"),
+	EXACT_ENTRIES(uint64_t, "u64"),	// the x87 long double steps of get_pixel / set_pixel restated (fixca_kernels.cuh)
 };
 
 const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled)
@@ -35,6 +36,7 @@ const KernelEntry *lookup_exact(SampleKind kind, int nch, int interp, bool tiled
 	case SK_F64: s = 4; break;
 	case SK_F16: s = 5; break;
 	case SK_U15: s = 6; break;
+	case SK_U64: s = 7; break;
 	default: return nullptr;
 	}
 	if ((nch != 3 && nch != 4) || (interp != 1 && interp != 2))

@@ -39,9 +39,9 @@ template <> struct Norm<uint32_t> {
 	__device__ static double get(uint32_t v) { return (double)v / 4294967295.0; }
 	__device__ static uint32_t put(double d) { return (uint32_t)__double2ll_rz(round(d * 4294967295.0)); }
 };
-template <> struct Norm<uint64_t> {	// centre lines only: c is exactly 0 or 1 (the HSV path needs 80-bit long double)
-	__device__ static double get(uint64_t) { return 0.0; }
-	__device__ static uint64_t put(double d) { return d > 0.0 ? ~0ull : 0ull; }
+template <> struct Norm<uint64_t> {	// the x87 steps of get_pixel / set_pixel restated (fixca_kernels.cuh)
+	__device__ static double get(uint64_t v) { return u64_get_pixel(v); }
+	__device__ static uint64_t put(double d) { return u64_set_pixel(d); }
 };
 template <> struct Norm<float> {
 	__device__ static double get(float v) { return (double)v; }

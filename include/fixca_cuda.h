@@ -86,9 +86,11 @@ typedef struct fixca_params {
 #define FIXCA_ERR_RANGE       (-6)	/* fixca_check_params(): outside +-FIXCA_INPUT_MAX */
 #define FIXCA_ERR_NO_DEVICE   (-7)
 #define FIXCA_ERR_CUDA        (-8)	/* see fixca_cuda_last_error()                 */
-#define FIXCA_ERR_UNSUPPORTED (-9)	/* u64 samples with Linear/Cubic (the reference
-					   computes those in 80-bit long double,
-					   fix-ca.c:728-733,759-761)                     */
+#define FIXCA_ERR_UNSUPPORTED (-9)	/* a flag this entry point does not take
+					   (FIXCA_PREVIEW_OVERLAY on a batch call, ...);
+					   u64 Linear/Cubic is computed since r02: the
+					   x87 long double steps of fix-ca.c:728-733,
+					   759-761 restated in integer arithmetic        */
 #define FIXCA_ERR_NOMEM       (-10)
 
 /* ------------------------------------------------------------------------- */

@@ -335,6 +335,24 @@ def synth_u15(h: int, w: int, ch: int, seed: int, wide: bool = False) -> np.ndar
     return rng.integers(0, 65535 if wide else 32768, size=(h, w, ch), dtype=np.uint16, endpoint=True)
 
 
+U64_EXTREMES = np.array([0, 1, 2, (1 << 53) - 1, 1 << 53, (1 << 53) + 1, (1 << 63) - 1, 1 << 63, (1 << 63) + 1,
+                         (1 << 64) - (1 << 11) - 1, (1 << 64) - (1 << 11), (1 << 64) - (1 << 10) - 1, (1 << 64) - (1 << 10),
+                         (1 << 64) - (1 << 10) + 1, (1 << 64) - 2, (1 << 64) - 1, 0x8000000000000400, 0x80000000000003FF,
+                         0x8000000000000C00, 0x0000000100000000, 0x00000000FFFFFFFF], dtype=np.uint64)
+
+
+def synth_u64(h: int, w: int, ch: int, seed: int, extremes: bool = False) -> np.ndarray:
+    """Seeded full-range 64-bit samples; ``extremes``: half of them drawn from U64_EXTREMES -- the boundaries of the two
+    roundings in get_pixel's long double division (fix-ca.c:728-733) and the values that decode to 1.0, which
+    set_pixel (:759-761) wraps to 0 in the reference as compiled."""
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, np.iinfo(np.uint64).max, size=(h, w, ch), dtype=np.uint64, endpoint=True)
+    if extremes:
+        pick = rng.integers(0, len(U64_EXTREMES), size=(h, w, ch))
+        img = np.where(rng.random((h, w, ch)) < 0.5, U64_EXTREMES[pick], img)
+    return np.ascontiguousarray(img)
+
+
 def synth_image(h: int, w: int, ch: int, dtype: str, seed: int, wide: bool = False) -> np.ndarray:
     """Seeded synthetic image (PCG64), uniform noise: worst case for caches.
     ``wide`` draws floats from [-0.5, 1.5) to exercise clip_d (fix-ca.c:873-880)."""

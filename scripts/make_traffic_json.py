@@ -22,7 +22,14 @@ def kernel_name(md_kernel: str, exact: bool) -> str:
     fam, ty, ch, interp = m.group(1), m.group(2).strip(), int(m.group(3)), int(m.group(4))
     if fam == "tiled":   # tiled_kernel<Sample, CH, INTERP, Arith>
         return "tiled/%s/%s/%sx%d" % (["none", "linear", "cubic"][interp], "f64" if exact else "f32", KERNEL[ty], ch)
-    return "stream/%s/f32/%sx%d" % (["none", "linear", "cubic"][interp], KERNEL[ty], ch)
+    # stream_kernel<Sample, CH, INTERP, P, TW, ALT, REPAIR, WIDE>
+    flags = re.search(r"stream_kernel<[^>]*?, (\d+), (\d+), (\d+)>", md_kernel)
+    arith = "f32"
+    if flags and int(flags.group(3)):
+        arith = "f64+exact"
+    elif flags and int(flags.group(2)):
+        arith = "f32+f64"
+    return "stream/%s/%s/%sx%d" % (["none", "linear", "cubic"][interp], arith, KERNEL[ty], ch)
 
 
 def main(tag: str) -> None:

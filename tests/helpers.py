@@ -13,9 +13,20 @@ FIXTURE_RAW = os.path.join(ROOT, "oracle", "_ref", "full-branches.rgb")
 
 GOLDEN_HALF = os.path.join(ROOT, "tests", "golden", "golden_half.json")
 GOLDEN_U15 = os.path.join(ROOT, "tests", "golden", "golden_u15.json")
+GOLDEN_U64 = os.path.join(ROOT, "tests", "golden", "golden_u64.json")
 _golden = None
 _golden_half = None
 _golden_u15 = None
+_golden_u64 = None
+
+
+def golden_u64():
+    """Digests of Linear / Cubic on u64 samples (tests/golden/make_golden_u64.py)."""
+    global _golden_u64
+    if _golden_u64 is None:
+        with open(GOLDEN_U64) as f:
+            _golden_u64 = json.load(f)
+    return _golden_u64
 
 
 def golden_u15():
@@ -56,6 +67,8 @@ def fx_params(fx, c):
 
 
 def case_image(c) -> np.ndarray:
+    if c["dtype"] == "u64":     # full-range 64-bit samples, half of them at rounding boundaries when c["extremes"]
+        return orc.synth_u64(c["h"], c["w"], c["ch"], c["seed"], c.get("extremes", False))
     if c["dtype"] == "u15":     # 15-bit samples in uint16 storage (bpc = 15)
         return orc.synth_u15(c["h"], c["w"], c["ch"], c["seed"], c.get("wide", False))
     return orc.synth_image(c["h"], c["w"], c["ch"], c["dtype"], c["seed"], c.get("wide", False))

@@ -10,7 +10,7 @@ import pytest
 
 import oracle as orc
 from fixture_io import encode_gimp_bmp24
-from helpers import case_image, fixture_image, golden, golden_half, golden_u15, max_dim, md5, oracle_params
+from helpers import case_image, fixture_image, golden, golden_half, golden_u15, golden_u64, max_dim, md5, oracle_params
 
 
 def test_restatement_matches_golden_suite(restatement):
@@ -179,6 +179,33 @@ def test_half_reference_build_matches_golden_and_leaves_other_formats_alone(refe
     assert half.color_size("R'G'B' half", 6) == -2 and half.color_size("R'G'B'A half", 8) == -2
     assert reference.color_size("R'G'B' half", 6) == -99
     assert half.color_size("R'G'B' u16", 6) == 2 and half.color_size("R'G'B' float", 12) == -4
+
+
+# ---------------------------------------------------------------------------------------------
+# u64 Linear / Cubic: long double get_pixel, the out-of-range conversion in set_pixel (fix-ca.c:728-733, :759-761)
+# ---------------------------------------------------------------------------------------------
+def test_u64_restatement_matches_golden(restatement):
+    """The digests come from the compiled reference (oracle/_ref); the restatement takes the same x87 steps."""
+    g = golden_u64()
+    bad = [c["name"] for c in g["suite"] if md5(restatement.region(case_image(c), oracle_params(c))) != c["md5"]]
+    bad += [c["name"] for c in g["preview"]
+            if md5(restatement.region(case_image(c), oracle_params(c), preview=True)) != c["md5"]]
+    assert not bad, "%d u64 cases differ, first: %s" % (len(bad), bad[:5])
+    assert len(g["suite"]) >= 150 and sum(c["extremes"] for c in g["suite"]) >= 50
+
+
+def test_u64_white_wraps_to_black_in_the_compiled_reference(reference):
+    """set_pixel's `roundl(d * 18446744073709551615UL)` is 2^64 for d = 1.0 -- out of range for uint64_t, undefined in
+    C; the reference as compiled (gcc, x86-64) yields 0.  Pinned here because the CUDA path reproduces it."""
+    if not reference.available:
+        pytest.skip("oracle/_ref not built")
+    img = np.full((6, 8, 3), np.iinfo(np.uint64).max, dtype=np.uint64)
+    img[2, 3, 0] = 1 << 63
+    img[3, 3, 0] = (1 << 64) - (1 << 11)        # decodes to 1 - 2^-53: the largest value that survives
+    img[3, 4, 0] = (1 << 64) - (1 << 10) - 1    # rounds to 1.0 in get_pixel's second rounding
+    out = reference.region(img, orc.Params(interpolation=1, lens_x=4, lens_y=3))
+    assert out[0, 0, 0] == 0 and out[2, 3, 0] == 1 << 63 and out[3, 3, 0] == (1 << 64) - (1 << 11) and out[3, 4, 0] == 0
+    assert (out[..., 1] == img[..., 1]).all()   # green is copied
 
 
 # ---------------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@ import pytest
 
 import oracle as orc
 from fixture_io import encode_gimp_bmp24
-from helpers import golden_half, golden_u15, case_image, fixture_image, fx_params, golden, lsb_diff, max_dim, md5, oracle_params
+from helpers import golden_u64, golden_half, golden_u15, case_image, fixture_image, fx_params, golden, lsb_diff, max_dim, md5, oracle_params
 
 pytestmark = pytest.mark.gpu
 
@@ -105,7 +105,7 @@ SHAPES = [(1, 1), (2, 3), (7, 129), (129, 7), (64, 128), (65, 257), (301, 517), 
 
 
 @pytest.mark.parametrize("dtype,ch", [("u1", 3), ("u1", 4), ("u2", 3), ("u2", 4), ("u4", 3), ("u4", 4),
-                                      ("f4", 3), ("f4", 4), ("f8", 3), ("f8", 4)])
+                                      ("f4", 3), ("f4", 4), ("f8", 3), ("f8", 4), ("u8", 3), ("u8", 4)])
 def test_matrix_exact(fx, checker, dtype, ch):
     n = 0
     for (h, w), interp, lens in itertools.product(SHAPES, (0, 1, 2), ("c", (0, 0), (-1, -1))):
@@ -636,6 +636,29 @@ def test_float_pitch_padding_is_never_sampled(fx, checker):
         assert fx.last_kernel().startswith("stream")
         assert np.isfinite(got).all()
         assert np.abs(got.astype(np.float64) - want).max() <= FLOAT_ABS_TOL, (h, w, ch, interp)
+
+
+# ---------------------------------------------------------------------------------------------
+# u64 Linear / Cubic (fix-ca.c:728-733, :759-761): the x87 long double steps restated in integer arithmetic
+# ---------------------------------------------------------------------------------------------
+def test_u64_golden_suite_bit_exact(fx):
+    """EXACT Linear / Cubic and the preview overlay (saturation boost included) on u64 images, half of the samples at
+    the rounding boundaries of get_pixel's two roundings and at the values set_pixel wraps: identical bytes to the
+    compiled reference (198 digests + 36 preview digests), through the tiled and the direct kernel."""
+    g = golden_u64()
+    bad, kernels = [], set()
+    for c in g["suite"]:
+        for flags in (fx.PRECISION_EXACT, fx.PRECISION_EXACT | fx.FORCE_DIRECT, fx.PRECISION_FAST):    # FAST: u64 computes EXACT
+            got = fx.correct(case_image(c), fx_params(fx, c), flags=flags)
+            kernels.add(fx.last_kernel().rsplit("/", 1)[0])
+            if md5(got) != c["md5"]:
+                bad.append((c["name"], flags))
+    for c in g["preview"]:
+        got = fx.correct(case_image(c), fx_params(fx, c), flags=fx.PRECISION_EXACT | fx.PREVIEW_OVERLAY)
+        if md5(got) != c["md5"]:
+            bad.append((c["name"], "preview"))
+    assert not bad, "%d u64 cases differ, first: %s" % (len(bad), bad[:8])
+    assert {"tiled/cubic/f64", "tiled/linear/f64", "direct/cubic/f64", "direct/linear/f64"} <= kernels, kernels
 
 
 # ---------------------------------------------------------------------------------------------
