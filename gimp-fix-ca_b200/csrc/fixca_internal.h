@@ -46,6 +46,7 @@ struct Tuning {
 	int stream_debug = 0;	// honoured by -DFIXCA_TUNING builds only
 	int no_pdl = 0, verbose = 0;
 	int chunk_mb = 0, copy_threads = 0;
+	int no_chunk_ramp = 0;	// FIXCA_CHUNK_RAMP=0: uniform staging chunks for pinned callers (A/B)
 	int precision_fast = 0;	// FIXCA_PRECISION=fast: what the flag-less fixca_cuda_region() computes in
 };
 const Tuning &tuning();

@@ -406,6 +406,35 @@ def test_device_resident_entry_with_torch_buffers(fx, checker):
     assert fx.last_kernel().startswith("direct") and d2.cpu().numpy().tobytes() == want2.tobytes()
 
 
+def test_pinned_caller_chunk_ramp_changes_no_byte(fx, checker, tuning):
+    """Pinned callers (the patched plug-in's buffers, bench.py's e2e): the staging chunks ramp up at the start of a
+    band and down at its end (region_host_band_locked); the progress protocol and every byte are those of the
+    uniform chunking, and both are the reference's."""
+    h, w = 4000, 3000
+    src_p, dst_p = fx.PinnedBuffer(h * w * 6), fx.PinnedBuffer(h * w * 6)
+    try:
+        img = src_p.array(np.uint16, (h, w, 3))
+        img[...] = orc.synth_image(h, w, 3, "u2", 4242)
+        out = dst_p.array(np.uint16, (h, w, 3))
+        kw = dict(KW, lens_x=w // 2, lens_y=h // 2, interpolation=2)
+        digests = {}
+        for ramp in ("1", "0"):
+            tuning("FIXCA_CHUNK_MB", "8")
+            tuning("FIXCA_CHUNK_RAMP", ramp)
+            out[...] = 0
+            n0 = fx.launch_count()
+            fx.fix_ca_region(img, out, w, h, 6, 2, fx.FixCaParams(**kw), 0, w, 0, h, True, fx.PRECISION_EXACT)
+            digests[ramp] = (md5(out), fx.launch_count() - n0)
+        assert digests["1"][0] == digests["0"][0]
+        assert digests["1"][1] > digests["0"][1]            # more (smaller) chunks at the two ends
+        for y1, y2 in ((0, 40), (1990, 2030), (3960, 4000)):
+            want = checker.region(img, orc.Params(**kw), y1=y1, y2=y2)
+            assert (out[y1:y2] == want[y1:y2]).all(), (y1, y2)
+    finally:
+        src_p.free()
+        dst_p.free()
+
+
 def test_plan_tables_survive_cache_churn_and_threads(fx, checker):
     """The streaming kernels read per-plan chunk / column tables from device memory (stream_meta_kernel,
     stream_cols_kernel); plans and tables sit in per-thread caches of 96 slots.  More distinct bands, widths and
