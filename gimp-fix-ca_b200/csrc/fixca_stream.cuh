@@ -955,6 +955,14 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				begin_chunk();
 				continue;
 			}
+			// A full chunk that only lacks its priming rows (a segment's first: T - 1 of them) is primed by the general walk
+			// and then enters the one steady-state loop below (a second, inlined copy of the unrolled rows for this case cost
+			// the first chunk of every CTA a cold instruction cache: 4-6 k cycles against 2.4 k for a steady chunk).
+			if (!steady && m->simple[c] && next_last > s_done) {
+				walk(next_last - 1);
+				rotate_to_slot0();
+				steady = next_last == s_done + 1;
+			}
 			if (steady) {
 #ifdef FIXCA_EXP_TIMING
 				// experiment: where a compute warp's time goes in the steady state (one CTA reports)
@@ -970,7 +978,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 					const long long t2 = clock64();
 					t_rows += t1 - t0; t_end += t2 - t1; ++n_st;
 					if (j == nchunks) {
-						if (blockIdx.x == 3 && blockIdx.y == 1 && blockIdx.z % 16 == 5 && (tid & 31) == 0)
+						if (blockIdx.x == 3 && (blockIdx.y == 1 || blockIdx.y == 20) && (gridDim.z == 1 || blockIdx.z % 16 == 5) && (tid & 31) == 0)
 							printf("cta z%d warp %d: %d steady chunks, cycles per chunk: rows %lld, hand-over %lld, wait+entry %lld; CTA: set-up %lld, first data +%lld, first chunk +%lld, total %lld\n", (int)blockIdx.z, tid >> 5, n_st,
 							       t_rows / n_st, t_end / n_st, t_begin / max(n_st - 1, 1), t_setup - t_entry, t_data - t_setup, t_steady0 - t_data, clock64() - t_entry);
 						return;
@@ -988,26 +996,19 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 					steady = begin_chunk();
 				} while (steady);
 #endif
+				continue;	// (the chunk in hand is not steady: it may only lack priming rows)
 			}
-			// general chunk.  A full chunk that only lacks its priming rows (a segment's first) is primed here and then
-			// takes the unrolled rows too.
-			if (m->simple[c] && next_last > s_done) {
-				walk(next_last - 1);
-				rotate_to_slot0();
-				steady_chunk();
-			} else {
-				// rows of this chunk whose taps were all produced while walking the previous chunk
-				if (next_last <= s_done) {
-					switch (ph) {
-					case 1: emit(std::integral_constant<int, 0>()); break;
-					case 2: emit(std::integral_constant<int, 1>()); break;
-					case 3: emit(std::integral_constant<int, 2>()); break;
-					default: emit(std::integral_constant<int, 3>()); break;
-					}
+			// general chunk: rows of this chunk whose taps were all produced while walking the previous chunk, then the walk
+			if (next_last <= s_done) {
+				switch (ph) {
+				case 1: emit(std::integral_constant<int, 0>()); break;
+				case 2: emit(std::integral_constant<int, 1>()); break;
+				case 3: emit(std::integral_constant<int, 2>()); break;
+				default: emit(std::integral_constant<int, 3>()); break;
 				}
-				walk(s_end);
-				rotate_to_slot0();	// (the next chunk may take the unrolled rows again)
 			}
+			walk(s_end);
+			rotate_to_slot0();	// (the next chunk may take the unrolled rows again)
 			end_chunk();
 			if (j == nchunks)
 				return;
