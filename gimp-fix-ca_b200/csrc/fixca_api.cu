@@ -594,8 +594,9 @@ static std::shared_ptr<void> cached_table(int tag, const Key &key, int dev, size
 // The tables of a streaming plan:
 //   chunk table (stream_meta_kernel): vertical weights / tap rows and source-row spans of every 8-row chunk of
 //     [y1, y2): depends on the y axes, the band, the kernel family and (None) the ring geometry;
-//   column table (stream_cols_kernel): base index and codec-scaled tap weights of every column of the strips:
-//     depends on the x axes, the width, the kernel family and the sample codec.
+//   column tables: None -- the nearest source column of every column of the strips (stream_cols_kernel); Linear /
+//     Cubic -- every compute thread's column set-up, one record per strip and thread (stream_setup_kernel): depend on
+//     the x axes, the width and the kernel family.
 static bool stream_tables(const KernelEntry *k, const Format &f, int dev, int strips, Plan &pl)
 {
 	KernelArgs &a = pl.args;
@@ -626,26 +627,44 @@ static bool stream_tables(const KernelEntry *k, const Format &f, int dev, int st
 	a.span_tab = (const unsigned char *)pl.tables.get() + span_off;
 
 	struct ColKey {
-		int interp, mode, kind, ncols, dev, width;
+		const void *entry;	// the kernel family (sample type, layout, arithmetic)
+		int interp, ncols, dev, width;
 		int center[2], size[2];
 		double scale[2], shift[2];
 	} xk;
 	memset(&xk, 0, sizeof xk);
 	const int ncols = strips * k->tw;
-	xk.interp = interp; xk.mode = mode; xk.kind = interp ? (int)f.kind : 0; xk.ncols = ncols; xk.dev = dev; xk.width = a.g.width;
+	xk.entry = k; xk.interp = interp; xk.ncols = ncols; xk.dev = dev; xk.width = a.g.width;
 	for (int c = 0; c < 2; ++c) {
 		xk.center[c] = a.g.x[c].center; xk.size[c] = a.g.x[c].size;
 		xk.scale[c] = a.g.x[c].scale; xk.shift[c] = a.g.x[c].shift;
 	}
-	const size_t w_off = align_up((size_t)2 * ncols * sizeof(int), 256);
-	pl.col_tables = cached_table(2, xk, dev, w_off + (size_t)2 * ncols * stream_cols_weight_bytes(interp, mode) + 256, [&](void *mem, cudaStream_t st) {
-		return launch_stream_cols(interp, mode, kind, args, ncols, mem, (unsigned char *)mem + w_off, st);
+	if (interp == 0) {
+		// None: the nearest source column of every column (the entry does not matter: one table per width)
+		xk.entry = nullptr;
+		pl.col_tables = cached_table(2, xk, dev, (size_t)2 * ncols * sizeof(int) + 256, [&](void *mem, cudaStream_t st) {
+			return launch_stream_cols(args, ncols, mem, st);
+		});
+		if (!pl.col_tables)
+			return false;
+		a.col_i0 = (const int *)pl.col_tables.get();
+		a.col_n = ncols;
+		return true;
+	}
+	// Linear / Cubic: every compute thread's column set-up, one record per strip and thread
+	if (!k->setup || k->setup_rec_bytes <= 0)
+		return false;
+	const int nthreads = 2 * k->tw / k->strip_p;
+	void (*const setup)(const KernelArgs, void *) = k->setup;
+	pl.col_tables = cached_table(3, xk, dev, (size_t)strips * nthreads * k->setup_rec_bytes + 256, [&](void *mem, cudaStream_t st) {
+		KernelArgs aa = args;
+		void *out = mem;
+		void *params[] = {&aa, &out};
+		return cudaLaunchKernel((const void *)setup, dim3((unsigned)strips), dim3((unsigned)nthreads), params, 0, st);
 	});
 	if (!pl.col_tables)
 		return false;
-	a.col_i0 = (const int *)pl.col_tables.get();
-	a.col_w = (const unsigned char *)pl.col_tables.get() + w_off;
-	a.col_n = ncols;
+	a.setup_tab = pl.col_tables.get();
 	return true;
 }
 

@@ -26,7 +26,17 @@ struct KernelEntry {
 	int         strip_p;	// > 0: strip_kernel with this many columns per thread (blockDim = 2 * tw / strip_p)
 	int         stream;	// != 0: stream_kernel (blockDim = 2 * tw / strip_p + 32, grid = strips x segments)
 	int         repair;	// 1: the exact-repair form of stream_kernel (FP32 pipeline, per-warp queues in shared memory); 2: WIDE (FP64 pipeline)
+	// Linear / Cubic stream kernels: the kernel that fills the plan's column set-up table (grid = strips, block = the
+	// compute threads) and the size of one thread's record
+	void      (*setup)(const KernelArgs, void *);
+	int         setup_rec_bytes;
 };
+
+// table entry of stream_kernel<S, NCH, INTERP, P, TW, ALT, REPAIR, WIDE> (INTERP != 0) with its set-up kernel
+#define FIXCA_STREAM_ENTRY(NAME, S, NCH, INTERP, P, TW, ALT, REPAIR, WIDE)                                        \
+	{ (kernel_fn)stream_kernel<S, NCH, INTERP, P, TW, ALT, REPAIR, WIDE>, NAME, TW, 0, (int)sizeof(S), P, 1,  \
+	  (WIDE) ? 2 : (REPAIR) ? 1 : 0, stream_setup_kernel<S, NCH, INTERP, P, TW, ALT, REPAIR, WIDE>,            \
+	  (int)sizeof(StreamColumnState<typename std::conditional<WIDE, double, float>::type, P, (P) == 1 ? ((INTERP) == 1 ? 2 : 4) : ((INTERP) == 1 ? 3 : 5)>) }
 
 constexpr int TILE_W = 128;
 
@@ -70,9 +80,8 @@ size_t stream_meta_record_bytes(int mode);
 cudaError_t launch_stream_meta(int interp, int mode, SampleKind kind, const KernelArgs &a, void *meta, void *span, int nchunks,
 			       cudaStream_t st);
 
-// ... and the per-plan column table (KernelArgs::col_i0 / col_w): ncols columns per channel
-size_t stream_cols_weight_bytes(int interp, int mode);
-cudaError_t launch_stream_cols(int interp, int mode, SampleKind kind, const KernelArgs &a, int ncols, void *i0, void *w, cudaStream_t st);
+// ... and None's per-plan column table (KernelArgs::col_i0): ncols nearest source columns per channel
+cudaError_t launch_stream_cols(const KernelArgs &a, int ncols, void *i0, cudaStream_t st);
 
 // kernels_preview.cu: saturate() + centerline() on destination rows [y1, y2) (fix-ca.c:1322-1327)
 cudaError_t launch_preview(int kind, int nch, unsigned char *dst, long long pitch, int dst_row0, int y1, int y2, int width,

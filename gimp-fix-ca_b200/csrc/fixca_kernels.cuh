@@ -68,10 +68,11 @@ struct KernelArgs {
 	// per-plan tables in global memory, one record per 8-row chunk of [y1, y2) (stream_meta_kernel fills them)
 	const void *meta_tab;		// StreamMeta / StreamMetaWide records: vertical weights and tap rows of the chunk's rows
 	const void *span_tab;		// StreamSpan records: first / last source row the chunk touches
-	// per-plan column table (stream_cols_kernel): col_n columns per channel (the strips' whole column range)
-	const int  *col_i0;		// [2][col_n] base index of the tap window (None: nearest column)
-	const void *col_w;		// [2][col_n] codec-scaled tap weights, float4 (WIDE: 4 doubles); unused by None
+	// None: per-plan column table (stream_cols_kernel): [2][col_n] nearest source column, col_n = the strips' column range
+	const int  *col_i0;
 	int  col_n;
+	// Linear / Cubic: per-plan column set-up (stream_setup_kernel): one StreamColumnState per strip and compute thread
+	const void *setup_tab;
 };
 
 // 15-bit unsigned samples in 16-bit storage (babl's "u15": 0 .. 32768 <-> [0.0, 1.0]).  The reference rejects

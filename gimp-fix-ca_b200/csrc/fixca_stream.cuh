@@ -88,6 +88,7 @@ template <class V4> struct StreamMetaT {
 	int    last[2][STREAM_CH + 1];	// highest tap row of each output row (INT_MAX after the chunk's last row)
 	int    s_end[2];		// = last[c][nrows - 1]
 	int    simple[2];		// full chunk whose rows finish on CH consecutive source rows (the usual case)
+	int    first[2];		// lowest tap row of the chunk's first output row (where a segment that starts here begins to filter)
 };
 typedef StreamMetaT<float4> StreamMeta;		// FP32 pipelines
 typedef StreamMetaT<dvec4> StreamMetaWide;	// WIDE: FP64 weights
@@ -186,6 +187,31 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *tm)
 	asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
 
+// lowest / highest source row output row y touches, over both channels (None: the nearest row, fix-ca.c:1105-1106;
+// Linear :1141-1148; Cubic :1219-1256); the map is monotone, so a chunk's extremes sit at its first and last row
+template <int INTERP>
+__device__ __forceinline__ void stream_tap_rows(const Geometry &g, int y, int &lo, int &hi)
+{
+	constexpr int T = INTERP == 0 ? 1 : INTERP == 1 ? 2 : 4;
+	constexpr int OFF = INTERP == 2 ? 1 : 0;
+	lo = INT_MAX;
+	hi = 0;
+#pragma unroll
+	for (int c = 0; c < 2; ++c) {
+		int first, lastr;
+		if constexpr (INTERP == 0) {
+			first = lastr = nearest_index(g.y[c], y);
+		} else {
+			double td;
+			const int i0 = base_index(g.y[c], y, td);
+			first = max(i0 - OFF, 0);
+			lastr = min(i0 + T - 1 - OFF, g.height - 1);
+		}
+		lo = min(lo, first);
+		hi = max(hi, lastr);
+	}
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // stream_meta_kernel: the per-plan tables of a streaming launch, one warp per 8-row chunk of [y1, y2).
 //   meta[j]  vertical weights by tap position (position_weights: FP64 coordinates fix-ca.c:813-820, Linear
@@ -200,8 +226,7 @@ __global__ void __launch_bounds__(128) stream_meta_kernel(const KernelArgs a, co
 							   StreamSpan *const span_out, const int nchunks)
 {
 	constexpr int CH = STREAM_CH;
-	constexpr int T = INTERP == 0 ? 1 : INTERP == 1 ? 2 : 4;
-	constexpr int OFF = INTERP == 2 ? 1 : 0;
+	[[maybe_unused]] constexpr int OFF = INTERP == 2 ? 1 : 0;
 	static_assert(!(INTERP == 0 && MODE != 0), "None has one form");
 	typedef typename std::conditional<MODE == 2, StreamMetaWide, StreamMeta>::type Meta;
 	const int lane = threadIdx.x & 31;
@@ -235,6 +260,14 @@ __global__ void __launch_bounds__(128) stream_meta_kernel(const KernelArgs a, co
 			m.last[ch][nr] = INT_MAX;
 			m.s_end[ch] = last;
 		}
+		if (r == 0) {
+			if constexpr (INTERP == 0) {
+				m.first[ch] = last;
+			} else {
+				double td;
+				m.first[ch] = max(base_index(a.g.y[ch], y_first, td) - OFF, 0);
+			}
+		}
 	}
 	// "simple": a full chunk in which every row completes exactly one source row after
 	// the previous one -- one horizontal row in, one output row out, CH times
@@ -245,25 +278,10 @@ __global__ void __launch_bounds__(128) stream_meta_kernel(const KernelArgs a, co
 		const unsigned want = ((1u << CH) - 1u) << (lane * CH);
 		m.simple[lane] = (nr == CH) && ((okmask & want) == want);
 	}
-	// first source row of the chunk's first output row, last source row of its last one (the map is monotone);
-	// fix-ca.c:1105-1106 None, :1219-1256 Cubic
+	// first source row of the chunk's first output row, last source row of its last one
 	if (lane < 2) {
-		const int y = lane == 0 ? y_first : y_first + nr - 1;
-		int lo = INT_MAX, hi = 0;
-#pragma unroll
-		for (int c = 0; c < 2; ++c) {
-			int first, lastr;
-			if constexpr (INTERP == 0) {
-				first = lastr = nearest_index(a.g.y[c], y);
-			} else {
-				double td;
-				const int i0 = base_index(a.g.y[c], y, td);
-				first = max(i0 - OFF, 0);
-				lastr = min(i0 + T - 1 - OFF, H - 1);
-			}
-			lo = min(lo, first);
-			hi = max(hi, lastr);
-		}
+		int lo, hi;
+		stream_tap_rows<INTERP>(a.g, lane == 0 ? y_first : y_first + nr - 1, lo, hi);
 		if (lane == 0)
 			span_out[i].lo = lo;
 		else
@@ -272,47 +290,191 @@ __global__ void __launch_bounds__(128) stream_meta_kernel(const KernelArgs a, co
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// stream_cols_kernel: the per-plan column table, one thread per (channel, column) of the strips' column range
-// [0, ncols).  i0[c][x] = base index of the column's tap window (None: the nearest column), w[c][x] = its tap
-// weights, scaled for the codec (fix-ca.c:801-808 coordinates, :891-892 / :905-907 weights) -- what every compute
-// thread of every segment and frame used to evaluate in FP64 for its own P columns at CTA start (550 instructions
-// per warp, most of the fixed cost of a small launch).  MODE as in stream_meta_kernel; the expressions are the ones
-// strip_kernel evaluates in place (same bytes).
+// stream_cols_kernel (None): the nearest source column of every column of the strips' column range [0, ncols),
+// per channel (fix-ca.c:801-808, :1105-1106) -- what every copy thread used to evaluate in FP64 at CTA start.
 // ---------------------------------------------------------------------------------------------------------
-template <int INTERP, int MODE>
-__global__ void __launch_bounds__(256) stream_cols_kernel(const KernelArgs a, const float hscale, const int ncols, int *const i0_out,
-							   void *const w_out)
+template <int UNUSED = 0>	// (a template only so that the header can be included by several translation units)
+__global__ void __launch_bounds__(256) stream_cols_kernel(const KernelArgs a, const int ncols, int *const i0_out)
 {
 	const int x = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
-	if (x >= ncols)
-		return;
-	if constexpr (INTERP == 0) {
+	if (x < ncols)
 		i0_out[c * ncols + x] = nearest_index(a.g.x[c], x);
-	} else {
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Column set-up of the Linear / Cubic kernels.  What a compute thread needs for its P columns -- the folded
+// horizontal weights, the sample offsets, the form its warp runs -- depends on the strip and the thread, not on the
+// segment, the frame or the buffers: stream_setup_kernel evaluates it once per plan with the thread layout of the
+// main kernel (one CTA per strip, blockDim = the compute threads, so the warp votes are the same), and every CTA of
+// every launch loads its threads' records (7 x 16 bytes for RGB8) instead of re-deriving them: the set-up was
+// 4-6 k cycles of every CTA, a fifth of a one-wave launch (scripts/timing_probe.py).
+//
+// regular: the P columns share one window of NS consecutive samples; wt[k][jj] weighs sample k + jj.
+// otherwise ("bent": tap windows squeezed against an image edge, fix-ca.c:1271-1298): column k reads its
+// own T consecutive samples from byte offset cofs[k]; wt[k][jj < T] weighs sample jj, clamped taps merged.
+// Both forms run the same row loop without index arithmetic, so a bent warp costs about as much as a
+// regular one (a per-tap path with clamps in the loop made every CTA of an edge strip a 1.4x straggler).
+// ---------------------------------------------------------------------------------------------------------
+template <class A, int P, int NW> struct alignas(16) StreamColumnState {
+	A   wt[P][NW];
+	int cofs[P];		// ... relative to colbase
+	int colbase;		// byte offset of shared sample 0 from the window row start
+	int cmax;		// bent form: offset of the image's last column (samples past it carry no weight)
+	int form;		// of the thread's warp: 0 bent, 1 regular, 2 regular and narrow (the extra weight is 0 everywhere)
+};
+
+// the strip's column extent in the window: [col_lo, col_hi] with the slack of the P-column groups, and the byte
+// offset wb0 of the window's first column (16-byte aligned, may be negative); lo / hi = the tap ranges of the
+// strip's first / last column of both channels (tap_range)
+__device__ __forceinline__ void stream_strip_extent(int x0, int xl, int lo0, int lo1, int hi0, int hi1, int slack, int bpp,
+						    int &col_lo, int &col_hi, int &wb0)
+{
+	col_lo = min(x0, min(lo0, lo1));
+	col_hi = max(xl, max(hi0, hi1));
+	// Slack for the shared-sample windows of the P-column groups.  NOT clamped to the image: the TMA
+	// unit zero-fills columns outside it, and the clamp-to-edge rule is folded into the weights (a
+	// tap that would fall outside lands on the edge column; the zero-filled samples get weight 0).
+	col_lo -= slack;
+	col_hi += slack;
+	wb0 = (col_lo * bpp) & ~15;
+}
+
+template <class S, int NCH, int INTERP, int P, int TW, bool ALT, bool REPAIR, bool WIDE>
+__global__ void __launch_bounds__(2 * TW / P) stream_setup_kernel(const KernelArgs a, void *const out)
+{
+	constexpr int BPP = NCH * (int)sizeof(S);
+	constexpr int T = INTERP == 1 ? 2 : 4;
+	constexpr int OFF = INTERP == 2 ? 1 : 0;
+	constexpr int NW = P == 1 ? T : T + 1;
+	constexpr int NS = P + NW - 1;
+	constexpr int NTC = 2 * TW / P;
+	constexpr int HALF = TW / P;
+	constexpr bool HAS_NARROW = P == 2 || P == 3 || (P == 4 && !REPAIR);
+	static_assert(INTERP != 0, "None has no weights");
+	typedef typename std::conditional<WIDE, double, float>::type A;
+	typedef StripCodec<S> Codec;
+	__shared__ int s_lo[2], s_hi[2];
+	const int tid = threadIdx.x;
+	const int W = a.g.width;
+	const int x0 = blockIdx.x * TW;
+	const int xl = min(x0 + TW, W) - 1;
+	if (tid < 4) {
+		const int ch = tid & 1, last = tid >> 1;
+		int lo, hi;
+		tap_range(a.g.x[ch], INTERP, last ? xl : x0, lo, hi);
+		if (last) s_hi[ch] = hi; else s_lo[ch] = lo;
+	}
+	__syncthreads();
+	int col_lo, col_hi, wb0;
+	stream_strip_extent(x0, xl, s_lo[0], s_lo[1], s_hi[0], s_hi[1], STREAM_COL_SLACK(P), BPP, col_lo, col_hi, wb0);
+	const int c = ALT ? (tid & 1) : tid / HALF;	// 0 red, 1 blue (the main kernel's layout)
+	const int lt = ALT ? (tid >> 1) : tid - c * HALF;
+
+	StreamColumnState<A, P, NW> st;
+	A w[P][4];
+	int tap[P][T];	// clamp-to-edge tap columns minus k
+	int bmin = INT_MAX;
+#pragma unroll
+	for (int k = 0; k < P; ++k) {
+		// columns past the tile's last one are computed like any other (their results are
+		// clipped by the TMA store); past the image the coordinate clamps to W - 1 ...
 		double td;
-		i0_out[c * ncols + x] = base_index(a.g.x[c], x, td);
-		if constexpr (MODE == 2) {
-			double w[4];
-			tap_weights_d<INTERP>(td, w);
-			dvec4 v;
-			v.x = w[0] * kWideScale + 0.0; v.y = w[1] * kWideScale + 0.0; v.z = w[2] * kWideScale + 0.0; v.w = w[3] * kWideScale + 0.0;
-			reinterpret_cast<dvec4 *>(w_out)[c * ncols + x] = v;
+		const int i0 = base_index(a.g.x[c], x0 + lt * P + k, td);
+		if constexpr (WIDE) {
+			tap_weights_d<INTERP>(td, w[k]);
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				w[k][j] = w[k][j] * kWideScale + 0.0;
 		} else {
-			float w[4];
-			if (MODE == 1) {	// FP64 weights, rounded once (the exact-repair error bound counts one rounding per weight)
+			if (REPAIR) {	// FP64 weights, rounded once (the error bound counts one rounding per weight)
 				double wd[4];
 				tap_weights_d<INTERP>(td, wd);
 #pragma unroll
 				for (int j = 0; j < 4; ++j)
-					w[j] = (float)wd[j];
+					w[k][j] = (float)wd[j];
 			} else {
-				tap_weights<INTERP>((float)td, w);
+				tap_weights<INTERP>((float)td, w[k]);
 			}
-			// power of two (integer samples are read as subnormals); -0 -> +0: the sign of an all-zero sum must not depend on the fold
-			reinterpret_cast<float4 *>(w_out)[c * ncols + x] =
-				make_float4(w[0] * hscale + 0.f, w[1] * hscale + 0.f, w[2] * hscale + 0.f, w[3] * hscale + 0.f);
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				w[k][j] = w[k][j] * Codec::kHScale + 0.f;	// power of two (integer samples are read as subnormals); -0 -> +0: the sign of an all-zero sum must not depend on the fold
+		}
+		// ... with zero weights, so that they do not bend a warp of the last strip
+		if (x0 + lt * P + k > xl)
+			w[k][0] = w[k][1] = w[k][2] = w[k][3] = 0;
+#pragma unroll
+		for (int j = 0; j < T; ++j) {
+			tap[k][j] = clampi(i0 - OFF + j, 0, W - 1) - k;
+			if (w[k][j] != 0)
+				bmin = min(bmin, tap[k][j]);
 		}
 	}
+	if (bmin == INT_MAX)	// no column of this thread is inside the image
+		bmin = col_lo;
+	// regular: every tap that carries weight sits at shared sample k + j', 0 <= j' < NW, and the
+	// NS samples lie inside the window
+	bool regular = bmin >= col_lo && bmin + NS - 1 <= col_hi;
+	// Float samples: a zero weight does not silence a NaN.  Columns left of the image and right of
+	// its 16-byte-aligned row end are zero-filled by the TMA unit, but the bytes between width * BPP
+	// and that row end are whatever the caller's pitch padding holds: such windows go the bent way,
+	// which clamps its sample offsets to the last column.
+	if (is_float_sample<S>::value)
+		regular = regular && bmin + NS - 1 <= W - 1;
+#pragma unroll
+	for (int k = 0; k < P; ++k)
+#pragma unroll
+		for (int j = 0; j < T; ++j)
+			regular = regular && (w[k][j] == 0 || tap[k][j] - bmin <= NW - 1);
+	regular = __all_sync(0xffffffffu, regular);
+	// The usual thread: no tap clamped, every column's window starts 0 or 1 samples after the group's
+	// first sample -- its weights are the tap weights, shifted by that drift.
+	bool plain = regular;
+#pragma unroll
+	for (int k = 0; k < P; ++k) {
+		const int d = tap[k][0] - bmin;
+		plain = plain && (d == 0 || (NW > T && d == 1));
+#pragma unroll
+		for (int j = 1; j < T; ++j)
+			plain = plain && tap[k][j] == tap[k][0] + j;
+	}
+	if (plain) {
+#pragma unroll
+		for (int k = 0; k < P; ++k) {
+			const bool drift = tap[k][0] != bmin;
+#pragma unroll
+			for (int jj = 0; jj < NW; ++jj) {
+				const A w0 = jj < T ? w[k][jj] : 0, w1 = jj >= 1 ? w[k][jj - 1] : 0;
+				st.wt[k][jj] = drift ? w1 : w0;
+			}
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < P; ++k)
+#pragma unroll
+			for (int jj = 0; jj < NW; ++jj) {
+				A v = 0;
+#pragma unroll
+				for (int j = 0; j < T; ++j) {
+					const int at = regular ? tap[k][j] - bmin : tap[k][j] - tap[k][0];
+					v += (w[k][j] != 0 && at == jj) ? w[k][j] : 0;
+				}
+				st.wt[k][jj] = v;
+			}
+	}
+#pragma unroll
+	for (int k = 0; k < P; ++k)
+		st.cofs[k] = (tap[k][0] + k - bmin) * BPP;
+	st.colbase = bmin * BPP + 2 * c * (int)sizeof(S) - wb0;
+	st.cmax = (W - 1 - bmin) * BPP;
+	// narrow: regular, and no column group of the warp straddles a drift of the tap window (the usual case: the map
+	// drifts one sample every 1 / |scale - 1| columns), so the extra weight is 0 everywhere
+	bool narrow = regular && HAS_NARROW;
+#pragma unroll
+	for (int k = 0; k < P; ++k)
+		narrow = narrow && st.wt[k][NW - 1] == 0;
+	narrow = __all_sync(0xffffffffu, narrow);
+	st.form = narrow ? 2 : regular ? 1 : 0;
+	reinterpret_cast<StreamColumnState<A, P, NW> *>(out)[blockIdx.x * NTC + tid] = st;
 }
 
 // Dynamic shared memory: [StreamHeader | StreamMeta[D + 1] | window ring (ring_rows x win_pitch) |
@@ -351,9 +513,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	constexpr int OUT_PITCH = TW * BPP;
 	constexpr int STAGE_BYTES = STREAM_CH * OUT_PITCH;
 	constexpr int T = INTERP == 0 ? 1 : INTERP == 1 ? 2 : 4;	// taps per axis (None: the nearest sample)
-	constexpr int OFF = INTERP == 2 ? 1 : 0;
 	constexpr int NW = P == 1 ? T : T + 1;
-	constexpr int NS = P + NW - 1;
 	constexpr int NTC = 2 * TW / P;		// compute threads
 	constexpr int HALF = TW / P;
 	constexpr int CH = STREAM_CH;
@@ -380,12 +540,19 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	const int NR = a.ring_rows;
 	const int wpitch = a.win_pitch;
 
-	// the TMA warp's first look at the plan's span table (used after the set-up below: the load's latency overlaps it)
+	// the source rows the segment's first D + 1 chunks touch, one lane of the TMA warp each (later chunks: the plan's span table)
 	const int cj0 = (ya - a.y1) / CH;		// the segment's first chunk in the plan's tables
 	const int2 *const span = reinterpret_cast<const int2 *>(a.span_tab) + cj0;	// StreamSpan {lo, hi} records
 	int2 sp_lane = make_int2(0, 0);
-	if (tid >= NTC)
-		sp_lane = __ldg(&span[min(tid - NTC, nchunks - 1)]);
+	if (tid >= NTC && tid - NTC <= STREAM_MAX_D) {
+		// (evaluated, not loaded: at CTA start the table is a cold read -- 1-2 k cycles in front of the first TMA request
+		// of a one-wave launch; a lane per chunk takes a few hundred)
+		const int jc = min(tid - NTC, nchunks - 1);
+		int lo, hi, dummy;
+		stream_tap_rows<INTERP>(a.g, ya, lo, dummy);
+		stream_tap_rows<INTERP>(a.g, min(ya + jc * STREAM_CH + STREAM_CH, yb) - 1, dummy, hi);
+		sp_lane = make_int2(lo, hi);
+	}
 
 	// ---- one-time: barriers and the strip's column extent ----
 	if (tid == 0) {
@@ -402,14 +569,9 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		if (last) hdr->col_hi[ch] = hi; else hdr->col_lo[ch] = lo;
 	}
 	__syncthreads();
-	int col_lo = min(x0, min(hdr->col_lo[0], hdr->col_lo[1]));
-	int col_hi = max(xl, max(hdr->col_hi[0], hdr->col_hi[1]));
-	// Slack for the shared-sample windows of the P-column groups.  NOT clamped to the image: the TMA
-	// unit zero-fills columns outside it, and the clamp-to-edge rule is folded into the weights (a
-	// tap that would fall outside lands on the edge column; the zero-filled samples get weight 0).
-	col_lo -= STREAM_COL_SLACK(P);
-	col_hi += STREAM_COL_SLACK(P);
-	const int wb0 = (col_lo * BPP) & ~15;	// may be negative
+	int col_lo, col_hi, wb0;	// (wb0 may be negative)
+	stream_strip_extent(x0, xl, hdr->col_lo[0], hdr->col_lo[1], hdr->col_hi[0], hdr->col_hi[1], STREAM_COL_SLACK(P), BPP, col_lo, col_hi, wb0);
+	(void)col_lo; (void)col_hi;
 	uint64_t *full = reinterpret_cast<uint64_t *>(hdr->full);
 	uint64_t *done = reinterpret_cast<uint64_t *>(hdr->done);
 
@@ -481,7 +643,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		for (int i = 0; i < D && i < nchunks; ++i) {
 			if (tid == NTC)
 				request_window(hi_next);
-			hi_next = __shfl_sync(0xffffffffu, sp_lane.y, min(i + 1, 31));
+			hi_next = __shfl_sync(0xffffffffu, sp_lane.y, min(i + 1, STREAM_MAX_D));
 		}
 		if (tid != NTC)
 			return;
@@ -560,110 +722,26 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	typedef StripCodec<S> Codec;
 	typedef typename std::conditional<WIDE, WideCodec<S>, StripCodec<S>>::type LoadCodec;
 
-	// regular: the P columns share one window of NS consecutive samples; wt[k][jj] weighs sample k + jj.
-	// otherwise ("bent": tap windows squeezed against an image edge, fix-ca.c:1271-1298): column k reads its
-	// own T consecutive samples from byte offset cofs[k]; wt[k][jj < T] weighs sample jj, clamped taps merged.
-	// Both forms run the same row loop without index arithmetic, so a bent warp costs about as much as a
-	// regular one (a per-tap path with clamps in the loop made every CTA of an edge strip a 1.4x straggler).
-	A wt[P][NW];
-	int cofs[P];		// ... relative to colbase
-	int colbase;		// byte offset of shared sample 0 from the window row start
-	int cmax;		// bent form: offset of the image's last column (samples past it carry no weight)
-	bool regular;
+	// The thread's column set-up (folded horizontal weights, sample offsets, the form its warp runs): the plan's
+	// table, one record per strip and compute thread (stream_setup_kernel).
+	typedef StreamColumnState<A, P, NW> ColState;
+	static_assert(sizeof(ColState) % 16 == 0, "records are read as 16-byte vectors");
+	ColState cst;
 	{
-		A w[P][4];
-		int tap[P][T];	// clamp-to-edge tap columns minus k
-		int bmin = INT_MAX;
+		const uint4 *const src = reinterpret_cast<const uint4 *>(reinterpret_cast<const ColState *>(a.setup_tab) + (size_t)blockIdx.x * NTC + tid);
+		uint4 *const dstv = reinterpret_cast<uint4 *>(&cst);
 #pragma unroll
-		for (int k = 0; k < P; ++k) {
-			// columns past the tile's last one are computed like any other (their results are
-			// clipped by the TMA store); past the image the coordinate clamps to W - 1 ...
-			// (base index and codec-scaled tap weights: the plan's column table, stream_cols_kernel)
-			const int tcol = c * a.col_n + x0 + lt * P + k;
-			const int i0 = __ldg(a.col_i0 + tcol);
-			if constexpr (WIDE) {
-				const double2 *const tw = reinterpret_cast<const double2 *>(a.col_w) + 2 * (size_t)tcol;
-				const double2 lo = __ldg(tw), hi = __ldg(tw + 1);
-				w[k][0] = lo.x; w[k][1] = lo.y; w[k][2] = hi.x; w[k][3] = hi.y;
-			} else {
-				const float4 t4 = __ldg(reinterpret_cast<const float4 *>(a.col_w) + tcol);
-				w[k][0] = t4.x; w[k][1] = t4.y; w[k][2] = t4.z; w[k][3] = t4.w;
-			}
-			// ... with zero weights, so that they do not bend a warp of the last strip
-			if (x0 + lt * P + k > xl)
-				w[k][0] = w[k][1] = w[k][2] = w[k][3] = 0;
-#pragma unroll
-			for (int j = 0; j < T; ++j) {
-				tap[k][j] = clampi(i0 - OFF + j, 0, W - 1) - k;
-				if (w[k][j] != 0)
-					bmin = min(bmin, tap[k][j]);
-			}
-		}
-		if (bmin == INT_MAX)	// no column of this thread is inside the image
-			bmin = col_lo;
-		// regular: every tap that carries weight sits at shared sample k + j', 0 <= j' < NW, and the
-		// NS samples lie inside the window
-		regular = bmin >= col_lo && bmin + NS - 1 <= col_hi;
-		// Float samples: a zero weight does not silence a NaN.  Columns left of the image and right of
-		// its 16-byte-aligned row end are zero-filled by the TMA unit, but the bytes between width * BPP
-		// and that row end are whatever the caller's pitch padding holds: such windows go the bent way,
-		// which clamps its sample offsets to the last column.
-		if (is_float_sample<S>::value)
-			regular = regular && bmin + NS - 1 <= W - 1;
-#pragma unroll
-		for (int k = 0; k < P; ++k)
-#pragma unroll
-			for (int j = 0; j < T; ++j)
-				regular = regular && (w[k][j] == 0 || tap[k][j] - bmin <= NW - 1);
-		regular = __all_sync(0xffffffffu, regular);
-		// The usual thread: no tap clamped, every column's window starts 0 or 1 samples after the group's
-		// first sample -- its weights are the tap weights, shifted by that drift (20 selects instead of the
-		// P x NW x T compare-select-add fold below; the set-up is the launch ramp of every CTA).
-		bool plain = regular;
-#pragma unroll
-		for (int k = 0; k < P; ++k) {
-			const int d = tap[k][0] - bmin;
-			plain = plain && (d == 0 || (NW > T && d == 1));
-#pragma unroll
-			for (int j = 1; j < T; ++j)
-				plain = plain && tap[k][j] == tap[k][0] + j;
-		}
-		if (plain) {
-#pragma unroll
-			for (int k = 0; k < P; ++k) {
-				const bool drift = tap[k][0] != bmin;
-#pragma unroll
-				for (int jj = 0; jj < NW; ++jj) {
-					const A w0 = jj < T ? w[k][jj] : 0, w1 = jj >= 1 ? w[k][jj - 1] : 0;
-					wt[k][jj] = drift ? w1 : w0;
-				}
-			}
-		} else {
-#pragma unroll
-			for (int k = 0; k < P; ++k)
-#pragma unroll
-				for (int jj = 0; jj < NW; ++jj) {
-					A v = 0;
-#pragma unroll
-					for (int j = 0; j < T; ++j) {
-						const int at = regular ? tap[k][j] - bmin : tap[k][j] - tap[k][0];
-						v += (w[k][j] != 0 && at == jj) ? w[k][j] : 0;
-					}
-					wt[k][jj] = v;
-				}
-		}
-#pragma unroll
-		for (int k = 0; k < P; ++k)
-			cofs[k] = (tap[k][0] + k - bmin) * BPP;
-		colbase = bmin * BPP + 2 * c * (int)sizeof(S) - wb0;
-		cmax = (W - 1 - bmin) * BPP;
+		for (int i = 0; i < (int)(sizeof(ColState) / 16); ++i)
+			dstv[i] = __ldg(src + i);
 	}
+	A (&wt)[P][NW] = cst.wt;
+	int (&cofs)[P] = cst.cofs;	// ... relative to colbase
+	const int colbase = cst.colbase;	// byte offset of shared sample 0 from the window row start
+	const int cmax = cst.cmax;		// bent form: offset of the image's last column (samples past it carry no weight)
+	const bool regular = cst.form != 0;
 
-	int s_done;	// last source row this thread has filtered horizontally
-	{
-		double td;
-		s_done = max(base_index(a.g.y[c], ya, td) - OFF, 0) - 1;
-	}
+	// last source row this thread has filtered horizontally: the one below the first tap row of the segment's first output row
+	int s_done = __ldg(&reinterpret_cast<const Meta *>(a.meta_tab)[cj0].first[c]) - 1;
 	// Ring of the last four horizontal rows.  `ph` = slot the next source row goes to; the newest row
 	// sits in slot ph - 1, the row p below it in slot ph - 1 - p (mod 4).  The vertical weights come
 	// ordered by that distance p (position_weights), so the arithmetic is independent of ph.
@@ -1015,15 +1093,11 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			steady = begin_chunk();
 		}
 	};
-	// (measured: 100 MP RGB16 Cubic 0.212 -> 0.208 ms, RGBA8 0.068 -> 0.066 ms.  Four-column groups (RGB8): one
+	// form 2 (measured: 100 MP RGB16 Cubic 0.212 -> 0.208 ms, RGBA8 0.068 -> 0.066 ms.  Four-column groups (RGB8): one
 	// shared-memory wavefront and four FMAs less per row, 128 x 4K RGB8 Cubic 0.717 -> 0.732 of the HBM peak, Linear
 	// 0.670 -> 0.687; the exact-repair form keeps the one regular form -- with three row loops it spills.)
 	constexpr bool HAS_NARROW = P == 2 || P == 3 || (P == 4 && !REPAIR);
-	bool narrow = regular && HAS_NARROW && !STREAM_DEBUG_BIT(a, 2);	// debug bit 1: A/B runs without the narrow form
-#pragma unroll
-	for (int k = 0; k < P; ++k)
-		narrow = narrow && wt[k][NW - 1] == 0;
-	narrow = __all_sync(0xffffffffu, narrow);
+	const bool narrow = cst.form == 2 && !STREAM_DEBUG_BIT(a, 2);	// debug bit 1: A/B runs without the narrow form
 	if (HAS_NARROW && narrow)
 		run(std::integral_constant<int, HAS_NARROW ? 2 : 1>());
 	else if (regular)

@@ -43,10 +43,10 @@ static const KernelEntry strip_table[] = {
 // ALT4: 4-channel strips put red and blue of one pixel on neighbouring lanes (half the row span
 // per warp load: no 2-way / 4-way bank conflicts for 8- and 16-byte pixels).
 #define STREAM_ENTRIES(S, TAG, P3, TW3, P4, TW4, ALT4)                                                        \
-	{ (kernel_fn)stream_kernel<S, 3, 1, P3, TW3>, "stream/linear/f32/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1 }, \
-	{ (kernel_fn)stream_kernel<S, 4, 1, P4, TW4, ALT4>, "stream/linear/f32/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1 }, \
-	{ (kernel_fn)stream_kernel<S, 3, 2, P3, TW3>, "stream/cubic/f32/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1 },  \
-	{ (kernel_fn)stream_kernel<S, 4, 2, P4, TW4, ALT4>, "stream/cubic/f32/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1 }
+	FIXCA_STREAM_ENTRY("stream/linear/f32/" TAG "x3", S, 3, 1, P3, TW3, false, false, false),             \
+	FIXCA_STREAM_ENTRY("stream/linear/f32/" TAG "x4", S, 4, 1, P4, TW4, ALT4, false, false),              \
+	FIXCA_STREAM_ENTRY("stream/cubic/f32/" TAG "x3", S, 3, 2, P3, TW3, false, false, false),              \
+	FIXCA_STREAM_ENTRY("stream/cubic/f32/" TAG "x4", S, 4, 2, P4, TW4, ALT4, false, false)
 
 static const KernelEntry stream_table[] = {
 	STREAM_ENTRIES(uint8_t, "u8", 4, 256, 3, 192, false),	// 4-byte pixels: 3 columns = 12 bytes per lane, 7 loads per 3 outputs
@@ -59,23 +59,23 @@ static const KernelEntry stream_table[] = {
 // Narrower 16-bit RGBA strips for the calls whose window (strip + shift + slack columns) would not fit one
 // 2 KB TMA box at 192 columns (variant 4).
 static const KernelEntry stream_u16x4_tw128[] = {
-	{ (kernel_fn)stream_kernel<uint16_t, 4, 1, 1, 128, true>, "stream/linear/f32/u16x4/tw128", 128, 0, 2, 1, 1 },
-	{ (kernel_fn)stream_kernel<uint16_t, 4, 2, 1, 128, true>, "stream/cubic/f32/u16x4/tw128", 128, 0, 2, 1, 1 },
-	{ (kernel_fn)stream_kernel<__half, 4, 1, 1, 128, true>, "stream/linear/f32/f16x4/tw128", 128, 0, 2, 1, 1 },
-	{ (kernel_fn)stream_kernel<__half, 4, 2, 1, 128, true>, "stream/cubic/f32/f16x4/tw128", 128, 0, 2, 1, 1 },
+	FIXCA_STREAM_ENTRY("stream/linear/f32/u16x4/tw128", uint16_t, 4, 1, 1, 128, true, false, false),
+	FIXCA_STREAM_ENTRY("stream/cubic/f32/u16x4/tw128", uint16_t, 4, 2, 1, 128, true, false, false),
+	FIXCA_STREAM_ENTRY("stream/linear/f32/f16x4/tw128", __half, 4, 1, 1, 128, true, false, false),
+	FIXCA_STREAM_ENTRY("stream/cubic/f32/f16x4/tw128", __half, 4, 2, 1, 128, true, false, false),
 };
 
 // channel-per-warp variants of the 4-channel strips, for A/B runs (FIXCA_STREAM_NOALT=1)
 static const KernelEntry stream_x4_noalt[] = {
-	{ (kernel_fn)stream_kernel<uint16_t, 4, 1, 1, 128>, "stream/linear/f32/u16x4/noalt", 128, 0, 2, 1, 1 },
-	{ (kernel_fn)stream_kernel<uint16_t, 4, 2, 1, 128>, "stream/cubic/f32/u16x4/noalt", 128, 0, 2, 1, 1 },
-	{ (kernel_fn)stream_kernel<float, 4, 1, 1, 128>, "stream/linear/f32/f32x4/noalt", 128, 0, 4, 1, 1 },
-	{ (kernel_fn)stream_kernel<float, 4, 2, 1, 128>, "stream/cubic/f32/f32x4/noalt", 128, 0, 4, 1, 1 },
+	FIXCA_STREAM_ENTRY("stream/linear/f32/u16x4/noalt", uint16_t, 4, 1, 1, 128, false, false, false),
+	FIXCA_STREAM_ENTRY("stream/cubic/f32/u16x4/noalt", uint16_t, 4, 2, 1, 128, false, false, false),
+	FIXCA_STREAM_ENTRY("stream/linear/f32/f32x4/noalt", float, 4, 1, 1, 128, false, false, false),
+	FIXCA_STREAM_ENTRY("stream/cubic/f32/f32x4/noalt", float, 4, 2, 1, 128, false, false, false),
 };
 
 static const KernelEntry stream_u16x3_tw128[] = {
-	{ (kernel_fn)stream_kernel<uint16_t, 3, 1, 2, 128>, "stream/linear/f32/u16x3/tw128", 128, 0, 2, 2, 1 },
-	{ (kernel_fn)stream_kernel<uint16_t, 3, 2, 2, 128>, "stream/cubic/f32/u16x3/tw128", 128, 0, 2, 2, 1 },
+	FIXCA_STREAM_ENTRY("stream/linear/f32/u16x3/tw128", uint16_t, 3, 1, 2, 128, false, false, false),
+	FIXCA_STREAM_ENTRY("stream/cubic/f32/u16x3/tw128", uint16_t, 3, 2, 2, 128, false, false, false),
 };
 
 // narrower-tile variants of the headline format, for tuning (FIXCA_STRIP_TW=128)

@@ -44,40 +44,10 @@ cudaError_t launch_stream_meta(int interp, int mode, SampleKind kind, const Kern
 	return cudaGetLastError();
 }
 
-// the power of two the horizontal weights carry for this sample type (StripCodec<S>::kHScale)
-static float hscale_of(SampleKind kind)
-{
-	switch (kind) {
-	case SK_U8:  return StripCodec<uint8_t>::kHScale;
-	case SK_U16: return StripCodec<uint16_t>::kHScale;
-	case SK_U15: return StripCodec<u15_t>::kHScale;
-	default:     return 1.0f;
-	}
-}
-
-size_t stream_cols_weight_bytes(int interp, int mode) { return interp == 0 ? 0 : mode == 2 ? sizeof(dvec4) : sizeof(float4); }
-
-cudaError_t launch_stream_cols(int interp, int mode, SampleKind kind, const KernelArgs &a, int ncols, void *i0, void *w, cudaStream_t st)
+cudaError_t launch_stream_cols(const KernelArgs &a, int ncols, void *i0, cudaStream_t st)
 {
 	const dim3 block(256), grid((unsigned)((ncols + 255) / 256), 2);
-	const float hs = hscale_of(kind);
-	int *ip = reinterpret_cast<int *>(i0);
-	if (interp == 0)
-		stream_cols_kernel<0, 0><<<grid, block, 0, st>>>(a, hs, ncols, ip, w);
-	else if (interp == 1 && mode == 0)
-		stream_cols_kernel<1, 0><<<grid, block, 0, st>>>(a, hs, ncols, ip, w);
-	else if (interp == 1 && mode == 1)
-		stream_cols_kernel<1, 1><<<grid, block, 0, st>>>(a, hs, ncols, ip, w);
-	else if (interp == 1 && mode == 2)
-		stream_cols_kernel<1, 2><<<grid, block, 0, st>>>(a, hs, ncols, ip, w);
-	else if (interp == 2 && mode == 0)
-		stream_cols_kernel<2, 0><<<grid, block, 0, st>>>(a, hs, ncols, ip, w);
-	else if (interp == 2 && mode == 1)
-		stream_cols_kernel<2, 1><<<grid, block, 0, st>>>(a, hs, ncols, ip, w);
-	else if (interp == 2 && mode == 2)
-		stream_cols_kernel<2, 2><<<grid, block, 0, st>>>(a, hs, ncols, ip, w);
-	else
-		return cudaErrorInvalidValue;
+	stream_cols_kernel<0><<<grid, block, 0, st>>>(a, ncols, reinterpret_cast<int *>(i0));
 	return cudaGetLastError();
 }
 

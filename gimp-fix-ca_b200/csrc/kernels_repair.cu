@@ -14,15 +14,15 @@ namespace fixca {
 // the reference order's 64), bound 3.5e-8 LSB, two samples in a million recomputed.
 // layouts as in kernels_fast.cu (columns per thread, strip width)
 #define REPAIR_ENTRIES(S, TAG, P3, TW3, P4, TW4)                                                              \
-	{ (kernel_fn)stream_kernel<S, 3, 1, P3, TW3, false, true>, "stream/linear/f32+f64/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1, 1 }, \
-	{ (kernel_fn)stream_kernel<S, 4, 1, P4, TW4, false, true>, "stream/linear/f32+f64/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1, 1 }, \
-	{ (kernel_fn)stream_kernel<S, 3, 2, P3, TW3, false, true>, "stream/cubic/f32+f64/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1, 1 },  \
-	{ (kernel_fn)stream_kernel<S, 4, 2, P4, TW4, false, true>, "stream/cubic/f32+f64/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1, 1 }
+	FIXCA_STREAM_ENTRY("stream/linear/f32+f64/" TAG "x3", S, 3, 1, P3, TW3, false, true, false),          \
+	FIXCA_STREAM_ENTRY("stream/linear/f32+f64/" TAG "x4", S, 4, 1, P4, TW4, false, true, false),          \
+	FIXCA_STREAM_ENTRY("stream/cubic/f32+f64/" TAG "x3", S, 3, 2, P3, TW3, false, true, false),           \
+	FIXCA_STREAM_ENTRY("stream/cubic/f32+f64/" TAG "x4", S, 4, 2, P4, TW4, false, true, false)
 #define WIDE_ENTRIES(S, TAG, P3, TW3, P4, TW4, ALT4)                                                          \
-	{ (kernel_fn)stream_kernel<S, 3, 1, P3, TW3, false, false, true>, "stream/linear/f64+exact/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1, 2 }, \
-	{ (kernel_fn)stream_kernel<S, 4, 1, P4, TW4, ALT4, false, true>, "stream/linear/f64+exact/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1, 2 },  \
-	{ (kernel_fn)stream_kernel<S, 3, 2, P3, TW3, false, false, true>, "stream/cubic/f64+exact/" TAG "x3", TW3, 0, (int)sizeof(S), P3, 1, 2 },  \
-	{ (kernel_fn)stream_kernel<S, 4, 2, P4, TW4, ALT4, false, true>, "stream/cubic/f64+exact/" TAG "x4", TW4, 0, (int)sizeof(S), P4, 1, 2 }
+	FIXCA_STREAM_ENTRY("stream/linear/f64+exact/" TAG "x3", S, 3, 1, P3, TW3, false, false, true),        \
+	FIXCA_STREAM_ENTRY("stream/linear/f64+exact/" TAG "x4", S, 4, 1, P4, TW4, ALT4, false, true),         \
+	FIXCA_STREAM_ENTRY("stream/cubic/f64+exact/" TAG "x3", S, 3, 2, P3, TW3, false, false, true),         \
+	FIXCA_STREAM_ENTRY("stream/cubic/f64+exact/" TAG "x4", S, 4, 2, P4, TW4, ALT4, false, true)
 
 static const KernelEntry repair_table[] = {
 	REPAIR_ENTRIES(uint8_t, "u8", 4, 256, 3, 192),
