@@ -197,6 +197,11 @@ FIXCA_API int fixca_cuda_region_multi(const unsigned char *src, unsigned char *d
  * kernels need both pitches to be multiples of 16 bytes, both pointers 16-byte
  * aligned, and rows that are whole 16-byte units (or FIXCA_PADDING_SCRATCH);
  * otherwise the direct kernel is used.
+ * The first call with a new combination of geometry, band and buffers makes a
+ * launch plan: it allocates and fills small per-plan tables in device memory
+ * on a private stream and waits for them (tens of microseconds); repeated
+ * calls take the plan from a per-thread cache and only launch.  Make that
+ * first call outside a CUDA stream capture.
  */
 FIXCA_API int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int src_row0, int src_rows,
 				    void *d_dst, size_t dst_pitch, int dst_row0,
