@@ -6,6 +6,7 @@ FLOAT_ABS_TOL for float32 images (tolerances written here)."""
 import ctypes
 import hashlib
 import itertools
+import os
 
 import numpy as np
 import pytest
@@ -558,7 +559,16 @@ def test_device_batch_of_frames_matches_single_frames(fx, checker):
         assert (gap == 0x5A).all()
 
 
-@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+# FIXCA_FUZZ_SEEDS="100-160" runs more seeds than the four of the regular suite (a soak run on a GPU box)
+def _fuzz_seeds():
+    spec = os.environ.get("FIXCA_FUZZ_SEEDS", "")
+    if "-" in spec:
+        lo, hi = spec.split("-")
+        return list(range(int(lo), int(hi)))
+    return [11, 12, 13, 14]
+
+
+@pytest.mark.parametrize("seed", _fuzz_seeds())
 def test_fuzz_small_images_all_modes(fx, checker, seed):
     """Seeded random shapes (1..700 px, strips and chunks cut anywhere), formats, lens positions (inside, on the
     border, outside, the -1 reset value), lateral amounts and directional shifts over the plug-in's full +-30
@@ -570,7 +580,7 @@ def test_fuzz_small_images_all_modes(fx, checker, seed):
     for it in range(70):
         h = int(rng.choice([1, 2, 3, 5, 9, 17, 40, 97, 130, 260, 517]))
         w = int(rng.choice([1, 2, 4, 7, 31, 64, 129, 255, 256, 257, 400, 700]))
-        dt = str(rng.choice(["u1", "u2", "f4", "f2"]))
+        dt = str(rng.choice(["u1", "u2", "f4", "f2", "u1", "u2", "f4", "f2", "u4", "u8", "f8"]))       # (u32 / u64 / double: FAST computes EXACT)
         ch = int(rng.choice([3, 4]))
         interp = int(rng.integers(0, 3))
         lens = [(w // 2, h // 2), (0, 0), (-1, -1), (w - 1, h - 1), (w + 13, -7), (3, h + 40)][int(rng.integers(0, 6))]
@@ -594,7 +604,7 @@ def test_fuzz_small_images_all_modes(fx, checker, seed):
                 assert out[y1:y2].tobytes() == want[y1:y2].tobytes(), ctx
             else:
                 d, _ = lsb_diff(out[y1:y2], want[y1:y2])
-                assert d <= (FLOAT_ABS_TOL if dt == "f4" else HALF_ABS_TOL if dt == "f2" else FAST_LSB_TOL), ctx + (d,)
+                assert d <= (FLOAT_ABS_TOL if dt in ("f4", "f8") else HALF_ABS_TOL if dt == "f2" else FAST_LSB_TOL), ctx + (d,)
                 assert np.array_equal(out[y1:y2, :, 1], img[y1:y2, :, 1]), ctx
             fill = 7.0 if dt[0] == "f" else 0x5A
             assert (out[:y1] == fill).all() and (out[y2:] == fill).all(), ctx
