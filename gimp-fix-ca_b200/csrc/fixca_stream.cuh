@@ -477,6 +477,35 @@ __global__ void __launch_bounds__(2 * TW / P) stream_setup_kernel(const KernelAr
 	reinterpret_cast<StreamColumnState<A, P, NW> *>(out)[blockIdx.x * NTC + tid] = st;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The exact-repair kernels' slow path, OUT OF LINE: n <= 32 queued samples of a warp, one per lane, through the
+// reference's own arithmetic (fix-ca.c:1135-1186, :1204-1320): coordinates, clamp-to-edge taps read from the window
+// ring, FP64 in the reference's operation order.  One in ~2000 samples comes here; inlined at the four emit sites
+// of the unrolled rows (r02 (B)) its 180 FP64 instructions made the row loop 2300 instructions long -- four times
+// the instruction cache -- and the bit-identical 8-bit kernels ran at a third of the FAST ones' speed.
+// entry = chunk row << 8 | column in group << 5 | lane.
+// ---------------------------------------------------------------------------------------------------------
+template <class S, int NCH, int INTERP, int P, int TW>
+__device__ __noinline__ void stream_repair_samples(const Geometry *const g, const uint16_t *const entries, const int n, const int c,
+							const int x0, const int y_first, const unsigned char *const win, const int ring_rows,
+							const int wpitch, const int wb0, unsigned char *const stg)
+{
+	constexpr int BPP = NCH * (int)sizeof(S);
+	constexpr int OUT_PITCH = TW * BPP;
+	constexpr int HALF = TW / P;
+	const int tid = threadIdx.x, lane = tid & 31;
+	__syncwarp();
+	if (lane < n) {
+		const unsigned e = entries[lane];
+		const int elt = (tid & ~31) + (int)(e & 31u) - c * HALF, ek = (int)(e >> 5) & 7, er = (int)(e >> 8);
+		const S v = interp_sample<S, INTERP, ExactF64>(*g, c, x0 + elt * P + ek, y_first + er, [&](int row, int col) {
+			return *reinterpret_cast<const S *>(win + (row % ring_rows) * wpitch + col * BPP + 2 * c * (int)sizeof(S) - wb0);
+		});
+		*reinterpret_cast<S *>(stg + er * OUT_PITCH + (elt * P + ek) * BPP + 2 * c * (int)sizeof(S)) = v;
+	}
+	__syncwarp();
+}
+
 // Dynamic shared memory: [StreamHeader | StreamMeta[D + 1] | window ring (ring_rows x win_pitch) |
 //                         staging (3 x CH x TW x BPP)]
 // blockDim.x == 2 * TW / P compute threads + 32 (the TMA warp).
@@ -499,7 +528,10 @@ template <class S, int NCH, int INTERP, int P, int TW, bool ALT = false, bool RE
 #ifdef FIXCA_EXP_LB5
 __global__ void __launch_bounds__(2 * TW / P + 32, (2 * TW / P) <= 128 && !WIDE ? 5 : 2)	// experiment: 5 resident CTAs (80 registers)
 #else
-__global__ void __launch_bounds__(2 * TW / P + 32, (2 * TW / P) <= 128 && !WIDE ? 4 : 2)	// register budget: 4 (2) resident CTAs
+// register budget: 4 resident CTAs for the narrow-pixel FP32 kernels, 3 for their exact-repair forms (at 96 registers they
+// spilled 100-150 bytes per thread into the row loop: local-memory traffic on the shared-memory data pipe that bounds these
+// kernels, 24 MP RGB8 Cubic EXACT 0.117 ms), 2 for the wide strips and the FP64 pipelines
+__global__ void __launch_bounds__(2 * TW / P + 32, (2 * TW / P) <= 128 && !WIDE ? (REPAIR ? 3 : 4) : 2)
 #endif
 stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUtensorMap tm_win,
 	      const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ CUtensorMap tm_out,
@@ -766,20 +798,11 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	const int lane = tid & 31;
 	uint16_t *const rq = reinterpret_cast<uint16_t *>(smem + a.off_rq) + (REPAIR ? (tid >> 5) * RQ_CAP : 0);
 	int rq_n = 0;				// warp-uniform
-	// n <= 32 queued samples, one per lane, through the reference's own arithmetic (fix-ca.c:1135-1186, :1204-1320):
-	// coordinates, clamp-to-edge taps read from the window ring, FP64 in the reference's operation order
+	// n <= 32 queued samples, one per lane, recomputed out of line (stream_repair_samples)
 	auto repair = [&](const int n, const int y_first, unsigned char *const stg) {
-		__syncwarp();
-		if (lane < n) {
-			const unsigned e = rq[rq_n - n + lane];
-			const int elt = (tid & ~31) + (int)(e & 31u) - c * HALF, ek = (int)(e >> 5) & 7, er = (int)(e >> 8);
-			const S v = interp_sample<S, INTERP, ExactF64>(a.g, c, x0 + elt * P + ek, y_first + er, [&](int row, int col) {
-				return *reinterpret_cast<const S *>(win + (row % NR) * wpitch + col * BPP + 2 * c * (int)sizeof(S) - wb0);
-			});
-			*reinterpret_cast<S *>(stg + er * OUT_PITCH + (elt * P + ek) * BPP + 2 * c * (int)sizeof(S)) = v;
-		}
+		if constexpr (REPAIR)
+			stream_repair_samples<S, NCH, INTERP, P, TW>(&a.g, rq + (rq_n - n), n, c, x0, y_first, win, NR, wpitch, wb0, stg);
 		rq_n -= n;
-		__syncwarp();
 	};
 	// the columns `flags` marks in chunk row r join the queue; a full warp's worth is repaired at once
 	auto enqueue = [&](const unsigned flags, const int r, const int y_first, unsigned char *const stg) {

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Run one workload a few times (for ncu):
-    python scripts/profile_one.py <fast|exact|linear|none|rgb8|rgb8lin|rgba16|rgb8_4k> [reps]
+    python scripts/profile_one.py <fast|exact|linear|none|rgb8|rgb8lin|rgb8exact|rgb8linexact|rgba16|rgb8_4k> [reps]
     python scripts/profile_one.py wl:<bench.py workload name>[:exact] [reps]      (bench.py's own shapes and parameters)
 A 512 MB buffer is rewritten between launches, so every launch starts with an L2 that holds none of its input
 (what bench.py's rotating buffer sets arrange): the captured DRAM traffic is the kernel's own."""
@@ -36,6 +36,8 @@ else:
         "none":   (8192, 12288, 3, 2, 2, 0, fixca.PRECISION_EXACT),
         "rgb8":   (4000, 6000, 3, 1, 1, 2, fixca.PRECISION_FAST),
         "rgb8lin": (4000, 6000, 3, 1, 1, 1, fixca.PRECISION_FAST),
+        "rgb8exact": (4000, 6000, 3, 1, 1, 2, fixca.PRECISION_EXACT),
+        "rgb8linexact": (4000, 6000, 3, 1, 1, 1, fixca.PRECISION_EXACT),
         "rgba16": (4320, 7680, 4, 2, 2, 2, fixca.PRECISION_FAST),
         "rgb8_4k": (2160, 3840, 3, 1, 1, 2, fixca.PRECISION_FAST),
     }[which]
