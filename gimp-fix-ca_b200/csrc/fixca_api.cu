@@ -78,6 +78,7 @@ static void read_tuning_locked()
 	t.none_tiled = e && !strcmp(e, "tiled");
 	e = getenv("FIXCA_EXACT_KERNEL");
 	t.exact_tiled = e && !strcmp(e, "tiled");
+	t.exact_inline = e && !strcmp(e, "inline");
 	t.strip_tw128 = env_int("FIXCA_STRIP_TW", 0) == 128;
 	t.stream_noalt = env_int("FIXCA_STREAM_NOALT", 0) != 0;
 	t.tile_h = env_int("FIXCA_TILE_H", 0);
@@ -222,6 +223,9 @@ struct Plan {
 	// stream kernel: the per-chunk tables args.meta_tab / args.span_tab point into (device memory, shared by every
 	// plan of the same band, y axes and kernel family; freed with the last plan that holds them)
 	std::shared_ptr<void> tables, col_tables;
+	// deferred exact-repair form: the launch's queue of near-tie samples (args.rq_ctl / rq_entries), owned by the plan --
+	// two launches of one plan must not run concurrently (they would be writing the same destination anyway)
+	std::shared_ptr<void> repair_queue;
 	// a batch of equal frames in one launch (stream kernels: grid.z = frame, 3-D tensor maps)
 	int nframes = 1;
 	size_t src_frame_stride = 0, dst_frame_stride = 0;
@@ -591,6 +595,29 @@ static std::shared_ptr<void> cached_table(int tag, const Key &key, int dev, size
 	return sp;
 }
 
+// device memory owned by a plan (freed with its last holder; cudaFree waits for the device); the first `zero` bytes cleared
+static std::shared_ptr<void> device_scratch(int dev, size_t bytes, size_t zero)
+{
+	int cur = -1;
+	if (cudaGetDevice(&cur) != cudaSuccess)
+		return nullptr;
+	if (cur != dev && cudaSetDevice(dev) != cudaSuccess)
+		return nullptr;
+	void *mem = nullptr;
+	bool ok = cudaMalloc(&mem, bytes) == cudaSuccess;
+	ok = ok && (!zero || cudaMemset(mem, 0, zero) == cudaSuccess);	// (synchronous: ordered before every later launch)
+	if (!ok) {
+		cudaGetLastError();
+		if (mem)
+			cudaFree(mem);
+	}
+	if (cur != dev)
+		cudaSetDevice(cur);
+	if (!ok)
+		return nullptr;
+	return std::shared_ptr<void>(mem, [](void *p) { if (cudaFree(p) != cudaSuccess) cudaGetLastError(); });
+}
+
 // The tables of a streaming plan:
 //   chunk table (stream_meta_kernel): vertical weights / tap rows and source-row spans of every 8-row chunk of
 //     [y1, y2): depends on the y axes, the band, the kernel family and (None) the ring geometry;
@@ -805,7 +832,26 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 		if (!make_tensor_map(pl.fan.tm[i], pl.fan_dst[i], (size_t)a.dst_pitch, row_bytes, dst_rows, nf, dfs, (unsigned)(k->tw * f.bpp), CH))
 			return false;
 	}
-	return stream_tables(k, f, dev, strips, pl);
+	if (!stream_tables(k, f, dev, strips, pl))
+		return false;
+	if (k->patch) {
+		// Queue of the deferred exact-repair form: 6.2e-4 of the samples are within the FP32 bound of a rounding boundary
+		// (DESIGN.md 4.6); every compute warp of the grid has its own region with room for 2.5 times what it expects plus
+		// 48 (the patch kernel recomputes a region that overflows), and a count
+		const int warps = 2 * k->tw / k->strip_p / 32;
+		const unsigned long long nregions = (unsigned long long)strips * segs * pl.nframes * warps;
+		const unsigned cap = (unsigned)align_up((size_t)((double)seg_rows * 32 * k->strip_p * 6.2e-4 * 2.5) + 48, 16);
+		const size_t counts = align_up((size_t)nregions * sizeof(unsigned), 256);
+		if (nregions > 0xffffffffull)
+			return false;
+		pl.repair_queue = device_scratch(dev, counts + (size_t)nregions * cap * sizeof(unsigned long long), 0);
+		if (!pl.repair_queue)
+			return false;
+		a.rq_ctl = (unsigned *)pl.repair_queue.get();
+		a.rq_entries = (unsigned long long *)((unsigned char *)pl.repair_queue.get() + counts);
+		a.rq_cap = cap;
+	}
+	return true;
 }
 
 // Planning costs tens of microseconds (window scans in FP64, three tensor-map encodes), a third of
@@ -918,6 +964,38 @@ static int launch_plan(const Plan &pl, cudaStream_t stream)
 	}
 	g_launches.fetch_add(1);
 	snprintf(tl_kernel, sizeof tl_kernel, "%s", pl.k->name);
+	if (pl.k->patch) {
+		// deferred exact repair: the queued near-tie samples are recomputed behind the streaming grid (the patch kernel
+		// waits for its completion: griddepcontrol.wait, or plain stream order)
+		PatchArgs pa;
+		memset(&pa, 0, sizeof pa);
+		pa.src_frame_stride = pl.nframes > 1 ? pl.src_frame_stride : 0;
+		pa.dst_frame_stride = pl.nframes > 1 ? pl.dst_frame_stride : 0;
+		pa.grid_x = (int)pl.grid.x;
+		pa.grid_y = (int)pl.grid.y;
+		pa.warps = (int)pl.block.x / 32 - 1;
+		pa.nregions = pl.grid.x * pl.grid.y * pl.grid.z * (unsigned)pa.warps;
+		pa.tw = pl.k->tw;
+		pa.p = pl.k->strip_p;
+		pa.nfan = pl.fan.n;
+		for (int i = 0; i < pl.fan.n; ++i)
+			pa.fan[i] = (unsigned char *)pl.fan_dst[i];
+		int dev = 0;
+		cudaGetDevice(&dev);
+		void *pparams[] = {&a, &pa};
+		cudaLaunchConfig_t cfg = {};
+		// a warp per region, eight regions per CTA, at most eight CTAs per SM (a queued sample is ~450 dependent FP64 instructions: latency, not throughput)
+		cfg.gridDim = dim3(std::min((pa.nregions + 7) / 8, (unsigned)(8 * sm_count(dev))));
+		cfg.blockDim = dim3(256);
+		cfg.stream = stream;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr;
+		cfg.numAttrs = tuning().no_pdl ? 0 : 1;
+		CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)pl.k->patch, pparams));
+		g_launches.fetch_add(1);
+	}
 	return FIXCA_OK;
 }
 

@@ -30,6 +30,9 @@ struct KernelEntry {
 	// compute threads) and the size of one thread's record
 	void      (*setup)(const KernelArgs, void *);
 	int         setup_rec_bytes;
+	// deferred exact-repair form (stream_kernel<..., REPAIR = 2>): the kernel launched behind it, which recomputes the
+	// queued near-tie samples (repair_patch_kernel)
+	void      (*patch)(const KernelArgs, const PatchArgs);
 };
 
 // table entry of stream_kernel<S, NCH, INTERP, P, TW, ALT, REPAIR, WIDE> (INTERP != 0) with its set-up kernel
@@ -48,6 +51,7 @@ struct Tuning {
 	int fast_kernel = 3;	// lookup_fast_variant(): 2 strip, 3 stream (FIXCA_FAST_KERNEL=strip|stream)
 	int none_tiled = 0;	// FIXCA_NONE_KERNEL=tiled
 	int exact_tiled = 0;	// FIXCA_EXACT_KERNEL=tiled: EXACT Linear / Cubic on tiled_kernel<ExactF64> for every format
+	int exact_inline = 0;	// FIXCA_EXACT_KERNEL=inline: 8-bit EXACT on the in-kernel repair form (A/B against the deferred form)
 	int strip_tw128 = 0;	// FIXCA_STRIP_TW=128
 	int stream_noalt = 0;	// FIXCA_STREAM_NOALT=1
 	int tile_h = 0, tile_ctas = 3;

@@ -73,6 +73,11 @@ struct KernelArgs {
 	int  col_n;
 	// Linear / Cubic: per-plan column set-up (stream_setup_kernel): one StreamColumnState per strip and compute thread
 	const void *setup_tab;
+	// exact-repair stream kernels, deferred form: every compute warp appends its near-tie samples to its own
+	// region of a queue in global memory (no atomics); repair_patch_kernel, launched behind the stream kernel, recomputes them
+	unsigned long long *rq_entries;	// [regions][rq_cap] linear sample indices ((frame * rows + y - y1) * width + x) * 2 + channel
+	unsigned *rq_ctl;		// [regions] samples the warp flagged (> rq_cap: the patch kernel recomputes the warp's whole region)
+	unsigned  rq_cap;		// region = (CTA of the grid, x fastest) * compute warps + warp
 };
 
 // 15-bit unsigned samples in 16-bit storage (babl's "u15": 0 .. 32768 <-> [0.0, 1.0]).  The reference rejects

@@ -339,7 +339,7 @@ __device__ __forceinline__ void stream_strip_extent(int x0, int xl, int lo0, int
 	wb0 = (col_lo * bpp) & ~15;
 }
 
-template <class S, int NCH, int INTERP, int P, int TW, bool ALT, bool REPAIR, bool WIDE>
+template <class S, int NCH, int INTERP, int P, int TW, bool ALT, int REPAIR, bool WIDE>
 __global__ void __launch_bounds__(2 * TW / P) stream_setup_kernel(const KernelArgs a, void *const out)
 {
 	constexpr int BPP = NCH * (int)sizeof(S);
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(2 * TW / P) stream_setup_kernel(const KernelAr
 	constexpr int NS = P + NW - 1;
 	constexpr int NTC = 2 * TW / P;
 	constexpr int HALF = TW / P;
-	constexpr bool HAS_NARROW = P == 2 || P == 3 || (P == 4 && !REPAIR);
+	constexpr bool HAS_NARROW = P == 2 || P == 3 || (P == 4 && REPAIR != 1);
 	static_assert(INTERP != 0, "None has no weights");
 	typedef typename std::conditional<WIDE, double, float>::type A;
 	typedef StripCodec<S> Codec;
@@ -506,6 +506,67 @@ __device__ __noinline__ void stream_repair_samples(const Geometry *const g, cons
 	__syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// repair_patch_kernel: the second half of the deferred exact-repair form.  Launched behind stream_kernel<..., REPAIR = 2>
+// (programmatic dependent launch: it waits for that grid's completion), it recomputes the queued near-tie samples with
+// the reference's own arithmetic (interp_sample<ExactF64>: fix-ca.c:1135-1186, :1204-1320; taps gathered from the source
+// image through L2) and overwrites them in the destination frame(s).  One warp per region (= compute warp of the
+// streaming grid), a lane per queued sample.  A region whose warp flagged more samples than its slots hold (an image
+// made of exact ties) is recomputed as a whole: slow, and still the reference's bytes.
+// ---------------------------------------------------------------------------------------------------------
+struct PatchArgs {
+	unsigned long long src_frame_stride, dst_frame_stride;	// bytes between the frames of a batch
+	unsigned nregions;			// CTAs of the streaming grid x compute warps
+	int grid_x, grid_y;			// the streaming grid (strips, segments; z = frames)
+	int warps, tw, p;			// compute warps per CTA, strip width, columns per thread
+	int nfan;				// further destination frames (fan-out / all-gather form)
+	unsigned char *fan[STREAM_MAX_FAN];
+};
+template <class S, int NCH, int INTERP>
+__global__ void __launch_bounds__(256) repair_patch_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ PatchArgs pa)
+{
+	griddep_launch_dependents();
+	griddep_wait();		// the streaming grid has completed: its queue, counts and destination bytes are visible
+	const unsigned W = (unsigned)a.g.width, rows = (unsigned)(a.y2 - a.y1);
+	const int lane = threadIdx.x & 31;
+	auto fix = [&](const unsigned long long frame, const int x, const int y, const int c) {
+		const unsigned char *const src = a.src + frame * pa.src_frame_stride;
+		const S v = interp_sample<S, INTERP, ExactF64>(a.g, c, x, y, [&](int row, int col) {
+			return reinterpret_cast<const S *>(src + (long long)(row - a.src_row0) * a.src_pitch)[(size_t)col * NCH + 2 * c];
+		});
+		const size_t at = frame * pa.dst_frame_stride + (size_t)((long long)(y - a.dst_row0) * a.dst_pitch) + ((size_t)x * NCH + 2 * c) * sizeof(S);
+		*reinterpret_cast<S *>(a.dst + at) = v;
+		for (int f = 0; f < pa.nfan; ++f)
+			*reinterpret_cast<S *>(pa.fan[f] + at) = v;
+	};
+	const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+	for (unsigned r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < pa.nregions; r += nwarps) {
+		const unsigned n = __ldcg(a.rq_ctl + r);
+		if (n <= a.rq_cap) {
+			const unsigned long long *const q = a.rq_entries + (size_t)r * a.rq_cap;
+			for (unsigned i = lane; i < n; i += 32) {
+				const unsigned long long e = __ldcg(q + i);
+				const unsigned long long px = e >> 1, fr = px / W;
+				fix(fr / rows, (int)(px % W), a.y1 + (int)(fr % rows), (int)(e & 1ull));
+			}
+		} else {
+			// the warp's whole region: rows of its CTA's segment x the 32 * P columns of its lanes, its channel
+			const unsigned cta = r / (unsigned)pa.warps, w = r % (unsigned)pa.warps;
+			const int bx = (int)(cta % (unsigned)pa.grid_x), by = (int)((cta / (unsigned)pa.grid_x) % (unsigned)pa.grid_y);
+			const unsigned long long frame = cta / ((unsigned)pa.grid_x * (unsigned)pa.grid_y);
+			const int half = pa.tw / pa.p, tid0 = (int)w * 32;
+			const int c = tid0 / half;
+			const int xa = bx * pa.tw + (tid0 - c * half) * pa.p, ncol = 32 * pa.p;
+			const int ya = a.y1 + by * a.seg_rows, yb = min(ya + a.seg_rows, a.y2);
+			for (int i = lane; i < (yb - ya) * ncol; i += 32) {
+				const int x = xa + i % ncol;
+				if (x < (int)W)
+					fix(frame, x, ya + i / ncol, c);
+			}
+		}
+	}
+}
+
 // Dynamic shared memory: [StreamHeader | StreamMeta[D + 1] | window ring (ring_rows x win_pitch) |
 //                         staging (3 x CH x TW x BPP)]
 // blockDim.x == 2 * TW / P compute threads + 32 (the TMA warp).
@@ -521,17 +582,20 @@ __device__ __noinline__ void stream_repair_samples(const Geometry *const g, cons
 // reference value| -- of a rounding boundary is queued per warp and recomputed with the reference's own FP64
 // arithmetic (interp_sample<ExactF64>, taps read from the window ring), 32 queued samples at a time so that the
 // FP64 work runs on full warps.  Everything else rounds to the same integer in both arithmetics.
+// REPAIR = 2, the deferred form (the default): the same test, but the near-tie samples are only appended to a queue in
+// global memory (KernelArgs::rq_*) and repair_patch_kernel (below), launched behind this grid, recomputes them from the
+// source image -- the FP64 function, its registers and the queue drains leave the streaming kernel (4 CTAs per SM again).
 // WIDE (16-bit samples, Linear / Cubic): the bit-exact form on an FP64 pipeline.  The same separable sums in FP64 on
 // raw sample values (fixca_strip.cuh, WideCodec); a sample within WideCodec::kEps of a rounding boundary -- one in
 // half a million -- is recomputed in the reference's operation order by its own thread at the end of the chunk.
-template <class S, int NCH, int INTERP, int P, int TW, bool ALT = false, bool REPAIR = false, bool WIDE = false>
+template <class S, int NCH, int INTERP, int P, int TW, bool ALT = false, int REPAIR = 0, bool WIDE = false>
 #ifdef FIXCA_EXP_LB5
 __global__ void __launch_bounds__(2 * TW / P + 32, (2 * TW / P) <= 128 && !WIDE ? 5 : 2)	// experiment: 5 resident CTAs (80 registers)
 #else
 // register budget: 4 resident CTAs for the narrow-pixel FP32 kernels, 3 for their exact-repair forms (at 96 registers they
 // spilled 100-150 bytes per thread into the row loop: local-memory traffic on the shared-memory data pipe that bounds these
 // kernels, 24 MP RGB8 Cubic EXACT 0.117 ms), 2 for the wide strips and the FP64 pipelines
-__global__ void __launch_bounds__(2 * TW / P + 32, (2 * TW / P) <= 128 && !WIDE ? (REPAIR ? 3 : 4) : 2)
+__global__ void __launch_bounds__(2 * TW / P + 32, (2 * TW / P) <= 128 && !WIDE ? (REPAIR == 1 ? 3 : 4) : 2)
 #endif
 stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUtensorMap tm_win,
 	      const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ CUtensorMap tm_out,
@@ -796,11 +860,15 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	static_assert(!(REPAIR && ALT), "the exact-repair form needs warp-uniform control flow");
 	constexpr int RQ_CAP = 32 + 32 * P;		// < 32 pending + what one output row can add
 	const int lane = tid & 31;
-	uint16_t *const rq = reinterpret_cast<uint16_t *>(smem + a.off_rq) + (REPAIR ? (tid >> 5) * RQ_CAP : 0);
+	uint16_t *const rq = reinterpret_cast<uint16_t *>(smem + a.off_rq) + (REPAIR == 1 ? (tid >> 5) * RQ_CAP : 0);
 	int rq_n = 0;				// warp-uniform
+	// ---- deferred form: this warp's region of the queue in global memory ----
+	[[maybe_unused]] const unsigned rq_region_id = ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (unsigned)(NTC / 32) + (unsigned)(tid >> 5);
+	[[maybe_unused]] unsigned long long *const rq_region = REPAIR == 2 ? a.rq_entries + (size_t)rq_region_id * a.rq_cap : nullptr;
+	[[maybe_unused]] unsigned rq_cnt = 0;	// warp-uniform
 	// n <= 32 queued samples, one per lane, recomputed out of line (stream_repair_samples)
 	auto repair = [&](const int n, const int y_first, unsigned char *const stg) {
-		if constexpr (REPAIR)
+		if constexpr (REPAIR == 1)
 			stream_repair_samples<S, NCH, INTERP, P, TW>(&a.g, rq + (rq_n - n), n, c, x0, y_first, win, NR, wpitch, wb0, stg);
 		rq_n -= n;
 	};
@@ -837,7 +905,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		unsigned char *q = nullptr;		// ... at the thread's first column, next row to emit
 		int y_first = 0;
 		int er = 0;				// REPAIR / WIDE: chunk row the next emit writes
-		[[maybe_unused]] unsigned wflags = 0;	// WIDE: this thread's near-tie samples of the chunk, bit = chunk row * P + column
+		[[maybe_unused]] unsigned wflags = 0;	// WIDE / deferred repair: this thread's near-tie samples of the chunk, bit = chunk row * P + column
 		int s_end = 0;
 		typedef typename std::remove_reference<decltype(meta[0].wy[0][0])>::type WY;
 		const WY *wy = nullptr;			// [row][channel]: stride 2
@@ -874,9 +942,11 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			if constexpr (WIDE) {
 				wflags |= vertical_emit_wide<INTERP, U, P, BPP, WideCodec<S>>(hr, wrow, qrow) << (row * P);
 			} else {
-				const unsigned fl = vertical_emit<INTERP, U, P, BPP, Codec, REPAIR>(hr, wrow, qrow);
-				if (REPAIR)
+				const unsigned fl = vertical_emit<INTERP, U, P, BPP, Codec, REPAIR != 0>(hr, wrow, qrow);
+				if constexpr (REPAIR == 1)
 					enqueue(fl, row, y_first, stg);
+				else if constexpr (REPAIR == 2)
+					wflags |= fl << (row * P);	// (CH * P <= 32 bits)
 			}
 		};
 		// one source row through the horizontal filter into ring slot U
@@ -971,9 +1041,32 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		};
 		// hand the chunk over: repairs first (their rows and taps belong to this chunk), then the barrier
 		auto end_chunk = [&]() {
-			if (REPAIR)	// what is left of the queue
+			if (REPAIR == 1)	// what is left of the queue
 				while (rq_n > 0)
 					repair(min(rq_n, 32), y_first, stg);
+			if constexpr (REPAIR == 2) {
+				// deferred form: the chunk's near-tie samples (6e-4 of all) join this warp's region of the launch's queue in
+				// global memory -- plain stores, slots counted per warp (an atomic counter cost every chunk an L2 round trip:
+				// with eight warps per CTA some warp flags a sample in nearly every chunk); repair_patch_kernel, launched
+				// behind this grid, recomputes them from the source image.  Samples beyond the region's capacity are only
+				// counted: the patch kernel then recomputes the warp's whole region.
+				static_assert(STREAM_CH * P <= 32, "one flag bit per sample of a thread's chunk");
+				unsigned pending = __ballot_sync(0xffffffffu, wflags != 0);
+				while (pending) {	// (one turn per flagged sample of the busiest lane: one, as a rule)
+					if (wflags) {
+						const int b = __ffs((int)wflags) - 1;
+						wflags &= wflags - 1;
+						const int wr = b / P, wk = b - wr * P;
+						const unsigned slot = rq_cnt + __popc(pending & ((1u << lane) - 1u));
+						if (slot < a.rq_cap) {
+							const unsigned long long row = (unsigned long long)blockIdx.z * (unsigned)(a.y2 - a.y1) + (unsigned)(y_first + wr - a.y1);
+							rq_region[slot] = ((row * (unsigned)W + (unsigned)(x0 + lt * P + wk)) << 1) | (unsigned)c;
+						}
+					}
+					rq_cnt += __popc(pending);
+					pending = __ballot_sync(0xffffffffu, wflags != 0);
+				}
+			}
 			if constexpr (WIDE) {
 				// near-tie samples (2e-6 of all): the reference's own arithmetic (fix-ca.c:1135-1186, :1204-1320),
 				// taps read from the window ring, whose rows stay valid until the chunk is handed over
@@ -1119,7 +1212,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 	// form 2 (measured: 100 MP RGB16 Cubic 0.212 -> 0.208 ms, RGBA8 0.068 -> 0.066 ms.  Four-column groups (RGB8): one
 	// shared-memory wavefront and four FMAs less per row, 128 x 4K RGB8 Cubic 0.717 -> 0.732 of the HBM peak, Linear
 	// 0.670 -> 0.687; the exact-repair form keeps the one regular form -- with three row loops it spills.)
-	constexpr bool HAS_NARROW = P == 2 || P == 3 || (P == 4 && !REPAIR);
+	constexpr bool HAS_NARROW = P == 2 || P == 3 || (P == 4 && REPAIR != 1);
 	const bool narrow = cst.form == 2 && !STREAM_DEBUG_BIT(a, 2);	// debug bit 1: A/B runs without the narrow form
 	if (HAS_NARROW && narrow)
 		run(std::integral_constant<int, HAS_NARROW ? 2 : 1>());
@@ -1127,6 +1220,9 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		run(std::integral_constant<int, 1>());
 	else
 		run(std::integral_constant<int, 0>());
+	if constexpr (REPAIR == 2)
+		if (lane == 0)
+			a.rq_ctl[rq_region_id] = rq_cnt;	// (every launch writes every region's count: nothing to reset)
 	}	// INTERP != 0
 }
 

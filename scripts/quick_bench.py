@@ -195,6 +195,19 @@ if __name__ == "__main__":
                 except fixca.FixCaError as e:
                     print(name, "D", d, str(e)[:80])
         os.environ.pop("FIXCA_STREAM_DEPTH")
+    if which == "exact8":   # bit-identical 8-bit: the deferred form (repair_patch_kernel behind the streaming kernel) against the in-kernel queues
+        for form in ("", "inline"):
+            os.environ["FIXCA_EXACT_KERNEL"] = form
+            tag = " exact " + (form or "deferred")
+            run("24MP rgb8 cubic" + tag, 4000, 6000, 3, torch.uint8, 1, 2, E)
+            run("24MP rgb8 linear" + tag, 4000, 6000, 3, torch.uint8, 1, 1, E)
+            run("4K rgb8 cubic" + tag, 2160, 3840, 3, torch.uint8, 1, 2, E)
+            run("33MP rgba8 cubic" + tag, 4320, 7680, 4, torch.uint8, 1, 2, E)
+            run_batch("4K rgb8 cubic" + tag, 32, 2160, 3840, 3, torch.uint8, 1, 2, E, only_batch=True)
+        os.environ.pop("FIXCA_EXACT_KERNEL")
+        run("24MP rgb8 cubic fast", 4000, 6000, 3, torch.uint8, 1, 2, F)
+        run("24MP rgb8 linear fast", 4000, 6000, 3, torch.uint8, 1, 1, F)
+        run("4K rgb8 cubic fast", 2160, 3840, 3, torch.uint8, 1, 2, F)
     if which == "small":    # launches dominated by the fixed cost
         run("4K rgb8 cubic fast", 2160, 3840, 3, torch.uint8, 1, 2, F)
         run("4K rgb8 linear fast", 2160, 3840, 3, torch.uint8, 1, 1, F)

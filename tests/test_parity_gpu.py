@@ -31,13 +31,14 @@ def _need_gpu(fx):
 # ---------------------------------------------------------------------------------------------
 # golden digests (produced by the reference's own code, tests/golden/make_golden.py)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("force", ["auto", "direct", "tiled"])
+@pytest.mark.parametrize("force", ["auto", "direct", "tiled", "inline"])
 def test_golden_suite_bit_exact(fx, force, tuning):
     """EXACT arithmetic through each of its kernel families: auto = the streaming kernel with exact repair of
     near-tie samples for 8-bit (f32+f64) and 16-bit (f64+exact) integers and tiled_kernel<ExactF64> for the rest; tiled = the FP64 tile
-    kernel for every format (FIXCA_EXACT_KERNEL=tiled); direct = the per-pixel kernel."""
-    if force == "tiled":
-        tuning("FIXCA_EXACT_KERNEL", "tiled")
+    kernel for every format (FIXCA_EXACT_KERNEL=tiled); direct = the per-pixel kernel; inline = 8-bit samples repaired
+    inside the streaming kernel (FIXCA_EXACT_KERNEL=inline) instead of by repair_patch_kernel behind it."""
+    if force in ("tiled", "inline"):
+        tuning("FIXCA_EXACT_KERNEL", force)
     flags = fx.PRECISION_EXACT | (fx.FORCE_DIRECT if force == "direct" else 0)
     bad, kernels = [], set()
     for c in golden()["suite"]:
@@ -49,6 +50,8 @@ def test_golden_suite_bit_exact(fx, force, tuning):
     assert not bad, "%d of %d golden cases differ (%s), first: %s" % (len(bad), len(golden()["suite"]), force, bad[:8])
     if force == "auto":
         assert {"stream/f32+f64", "stream/f64+exact", "tiled/f64"} <= kernels, kernels
+    elif force == "inline":
+        assert {"stream/f32+f64inline", "stream/f64+exact", "tiled/f64"} <= kernels and "stream/f32+f64" not in kernels, kernels
     elif force == "tiled":
         assert "tiled/f64" in kernels and not {"stream/f32+f64", "stream/f64+exact"} & kernels, kernels
     else:
@@ -359,7 +362,9 @@ def test_fanout_stores_every_destination(fx, checker):
             fx.fix_ca_region_dev_fanout(src.data_ptr(), pitch, 0, h, [f.data_ptr() for f in frames], pitch, 0, w, h, bpp,
                                         fx.bpc_of(img.dtype), p, y1, y2, flags, st)
             torch.cuda.synchronize()
-            assert fx.launch_count() - n0 == (1 if streaming else ndst), (dt, interp, ndst, fx.last_kernel())
+            # (8-bit EXACT: the streaming kernel + repair_patch_kernel behind it, which patches every destination)
+            per_call = 2 if fx.last_kernel().split("/")[2] == "f32+f64" else 1
+            assert fx.launch_count() - n0 == (per_call if streaming else ndst), (dt, interp, ndst, fx.last_kernel())
             for f in frames:
                 got = f[:, :w * bpp].cpu().numpy()
                 assert got[y1:y2].tobytes() == want[y1:y2].tobytes(), (dt, interp, ndst)
@@ -531,7 +536,8 @@ def test_device_batch_of_frames_matches_single_frames(fx, checker):
     launches = fx.load().fixca_cuda_launch_count
     for (h, w, ch, dt, interp, flags, nf) in ((270, 517, 3, "u1", 2, fx.PRECISION_FAST, 5), (64, 300, 4, "u2", 1, fx.PRECISION_FAST, 3),
                                               (130, 259, 3, "u2", 0, fx.PRECISION_EXACT, 4), (33, 100, 3, "f4", 2, fx.PRECISION_FAST, 2),
-                                              (40, 64, 3, "u2", 2, fx.PRECISION_EXACT, 3)):
+                                              (40, 64, 3, "u2", 2, fx.PRECISION_EXACT, 3), (270, 517, 3, "u1", 2, fx.PRECISION_EXACT, 5),
+                                              (97, 640, 4, "u1", 1, fx.PRECISION_EXACT, 3)):
         kw = dict(KW, lens_x=w // 2 - 3, lens_y=h // 2 + 5, interpolation=interp)
         p = fx.FixCaParams(**kw)
         frames = [orc.synth_image(h, w, ch, dt, seed=300 + k) for k in range(nf)]
@@ -549,7 +555,8 @@ def test_device_batch_of_frames_matches_single_frames(fx, checker):
                              flags | fx.PADDING_SCRATCH, stream)     # rows are pitched: their padding is scratch
         torch.cuda.synchronize()
         streaming = fx.last_kernel().startswith("stream")
-        assert launches() - n0 == (1 if streaming else nf), (fx.last_kernel(), launches() - n0)
+        per_call = 2 if fx.last_kernel().split("/")[2] == "f32+f64" else 1     # (+ repair_patch_kernel)
+        assert launches() - n0 == (per_call if streaming else nf), (fx.last_kernel(), launches() - n0)
         for k, fr in enumerate(frames):
             got = dst[k * fstride:k * fstride + pitch * h].view(h, pitch)[:, :w * bpp].cpu().numpy().view(fr.dtype).reshape(h, w, ch)
             single = fx.correct(fr, p, flags=flags)
@@ -743,15 +750,20 @@ def test_u15_fast_within_one_lsb(fx, variant, tuning):
     assert kernels == {variant}, kernels
 
 
-def test_exact_repair_kernels_on_exact_ties(fx, checker, tuning):
+@pytest.mark.parametrize("form", ["default", "inline"])
+def test_exact_repair_kernels_on_exact_ties(fx, checker, tuning, form):
     """The exact-repair stream kernels (8-bit: FP32 + FP64 repair; 16-bit / u15: FP64 separable + reference-order
     repair) decide every sample that is NOT near a rounding boundary in their fast arithmetic; here most samples ARE on
     one: pure half- and quarter-pixel directional shifts make the Linear / Cubic weights dyadic (1/2, 9/16, 1/16 ...),
     so a large share of the results are exact .5 ties, whose rounding depends on the reference's own operation order.
-    Identical bytes to the checker, and to the FP64 tile kernel."""
+    Identical bytes to the checker, and to the FP64 tile kernel.  8-bit samples, default form: far more samples are
+    flagged than the launch's queue holds, so repair_patch_kernel takes its whole-launch path; form = inline: the
+    per-warp queues inside the streaming kernel (FIXCA_EXACT_KERNEL=inline)."""
     chk15 = orc.u15_checker()
     n_ties = 0
-    for dtype, ch, interp, shifts in itertools.product(("u1", "u2", "u15"), (3, 4), (1, 2),
+    if form == "inline":
+        tuning("FIXCA_EXACT_KERNEL", "inline")
+    for dtype, ch, interp, shifts in itertools.product(("u1", "u2", "u15") if form == "default" else ("u1",), (3, 4), (1, 2),
                                                        ((0.5, -0.5, 0.5, 0.5), (0.25, 0.5, -0.75, 1.5), (0.5, 0.0, 0.0, -0.5))):
         h, w = 203, 1031
         kw = dict(blue=0.0, red=0.0, x_blue=shifts[0], x_red=shifts[1], y_blue=shifts[2], y_red=shifts[3],
@@ -766,6 +778,7 @@ def test_exact_repair_kernels_on_exact_ties(fx, checker, tuning):
             bpc = {}
         got = fx.correct(img, fx.FixCaParams(**kw), flags=fx.PRECISION_EXACT, **bpc)
         assert "f32+f64" in fx.last_kernel() or "f64+exact" in fx.last_kernel(), fx.last_kernel()
+        assert ("inline" in fx.last_kernel()) == (form == "inline"), fx.last_kernel()
         assert got.tobytes() == want.tobytes(), (dtype, ch, interp, shifts, fx.last_kernel())
         # how many samples sat on an exact tie (Linear, half-pixel shift in x only: (a + b) / 2 with a + b odd)
         if interp == 1 and shifts == (0.5, 0.0, 0.0, -0.5) and dtype != "u15":
