@@ -941,7 +941,9 @@ def run_cuda(args):
         workloads = []
         for name, ex, st in (("cfg2_24mp_rgb8_linear", False, 100), ("cfg3_8k_rgba16_cubic", False, 60),
                              ("cfg4_50mp_rgbf32_cubic", False, 40), ("cfg5_4k_rgb8_cubic", False, 200),
-                             ("cfg5_batch_4k_rgb8_cubic", False, 10), ("target_100mp_rgb16_cubic", True, 10)):
+                             ("cfg5_batch_4k_rgb8_cubic", False, 10), ("target_100mp_rgb16_cubic", True, 10),
+                             # the plug-in's default arithmetic (bit-identical) on GIMP's default precision (8 bit)
+                             ("cfg2_24mp_rgb8_linear", True, 50), ("cfg5_4k_rgb8_cubic", True, 100)):
             try:
                 workloads.append(device_workload(name, torch, fixca, dev, exact=ex, steps=st, check=not args.no_check))
             except Exception as e:

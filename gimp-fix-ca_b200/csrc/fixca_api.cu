@@ -984,8 +984,12 @@ static int launch_plan(const Plan &pl, cudaStream_t stream)
 		cudaGetDevice(&dev);
 		void *pparams[] = {&a, &pa};
 		cudaLaunchConfig_t cfg = {};
-		// a warp per region, eight regions per CTA, at most eight CTAs per SM (a queued sample is ~450 dependent FP64 instructions: latency, not throughput)
-		cfg.gridDim = dim3(std::min((pa.nregions + 7) / 8, (unsigned)(8 * sm_count(dev))));
+		// threads per region: what a region expects (6.2e-4 of its samples) plus four standard deviations, as a power of two
+		const double expect = (double)pl.args.seg_rows * 32 * pl.k->strip_p * 6.2e-4;
+		pa.lanes = 8;
+		while (pa.lanes < 256 && pa.lanes < expect + 4 * sqrt(expect) + 4)
+			pa.lanes *= 2;
+		cfg.gridDim = dim3((unsigned)std::min<unsigned long long>(((unsigned long long)pa.nregions * pa.lanes + 255) / 256, 1u << 30));
 		cfg.blockDim = dim3(256);
 		cfg.stream = stream;
 		cudaLaunchAttribute attr[1];

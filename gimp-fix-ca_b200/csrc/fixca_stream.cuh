@@ -510,8 +510,8 @@ __device__ __noinline__ void stream_repair_samples(const Geometry *const g, cons
 // repair_patch_kernel: the second half of the deferred exact-repair form.  Launched behind stream_kernel<..., REPAIR = 2>
 // (programmatic dependent launch: it waits for that grid's completion), it recomputes the queued near-tie samples with
 // the reference's own arithmetic (interp_sample<ExactF64>: fix-ca.c:1135-1186, :1204-1320; taps gathered from the source
-// image through L2) and overwrites them in the destination frame(s).  One warp per region (= compute warp of the
-// streaming grid), a lane per queued sample.  A region whose warp flagged more samples than its slots hold (an image
+// image through L2) and overwrites them in the destination frame(s).  A group of threads per region (= compute warp of
+// the streaming grid), a thread per queued sample.  A region whose warp flagged more samples than its slots hold (an image
 // made of exact ties) is recomputed as a whole: slow, and still the reference's bytes.
 // ---------------------------------------------------------------------------------------------------------
 struct PatchArgs {
@@ -519,6 +519,7 @@ struct PatchArgs {
 	unsigned nregions;			// CTAs of the streaming grid x compute warps
 	int grid_x, grid_y;			// the streaming grid (strips, segments; z = frames)
 	int warps, tw, p;			// compute warps per CTA, strip width, columns per thread
+	unsigned lanes;				// threads per region: a power of two, 8 .. 256
 	int nfan;				// further destination frames (fan-out / all-gather form)
 	unsigned char *fan[STREAM_MAX_FAN];
 };
@@ -528,7 +529,6 @@ __global__ void __launch_bounds__(256) repair_patch_kernel(const __grid_constant
 	griddep_launch_dependents();
 	griddep_wait();		// the streaming grid has completed: its queue, counts and destination bytes are visible
 	const unsigned W = (unsigned)a.g.width, rows = (unsigned)(a.y2 - a.y1);
-	const int lane = threadIdx.x & 31;
 	auto fix = [&](const unsigned long long frame, const int x, const int y, const int c) {
 		const unsigned char *const src = a.src + frame * pa.src_frame_stride;
 		const S v = interp_sample<S, INTERP, ExactF64>(a.g, c, x, y, [&](int row, int col) {
@@ -539,12 +539,16 @@ __global__ void __launch_bounds__(256) repair_patch_kernel(const __grid_constant
 		for (int f = 0; f < pa.nfan; ++f)
 			*reinterpret_cast<S *>(pa.fan[f] + at) = v;
 	};
-	const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
-	for (unsigned r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < pa.nregions; r += nwarps) {
+	// pa.lanes threads per region, a queued sample each: a sample is ~450 dependent FP64 instructions behind 16 gathered taps
+	// (~5 us of latency, hardly any throughput), so the host sizes the groups for ONE turn of this loop (with 8 lanes for
+	// the ~13 samples of a 24 MP image's regions the kernel took 40 us instead of 8)
+	const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned sl = t % pa.lanes;
+	for (unsigned r = t / pa.lanes; r < pa.nregions; r += gridDim.x * (blockDim.x / pa.lanes)) {
 		const unsigned n = __ldcg(a.rq_ctl + r);
 		if (n <= a.rq_cap) {
 			const unsigned long long *const q = a.rq_entries + (size_t)r * a.rq_cap;
-			for (unsigned i = lane; i < n; i += 32) {
+			for (unsigned i = sl; i < n; i += pa.lanes) {
 				const unsigned long long e = __ldcg(q + i);
 				const unsigned long long px = e >> 1, fr = px / W;
 				fix(fr / rows, (int)(px % W), a.y1 + (int)(fr % rows), (int)(e & 1ull));
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(256) repair_patch_kernel(const __grid_constant
 			const int c = tid0 / half;
 			const int xa = bx * pa.tw + (tid0 - c * half) * pa.p, ncol = 32 * pa.p;
 			const int ya = a.y1 + by * a.seg_rows, yb = min(ya + a.seg_rows, a.y2);
-			for (int i = lane; i < (yb - ya) * ncol; i += 32) {
+			for (int i = (int)sl; i < (yb - ya) * ncol; i += (int)pa.lanes) {
 				const int x = xa + i % ncol;
 				if (x < (int)W)
 					fix(frame, x, ya + i / ncol, c);
@@ -942,7 +946,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			if constexpr (WIDE) {
 				wflags |= vertical_emit_wide<INTERP, U, P, BPP, WideCodec<S>>(hr, wrow, qrow) << (row * P);
 			} else {
-				const unsigned fl = vertical_emit<INTERP, U, P, BPP, Codec, REPAIR != 0>(hr, wrow, qrow);
+				const unsigned fl = vertical_emit<INTERP, U, P, BPP, Codec, REPAIR>(hr, wrow, qrow);
 				if constexpr (REPAIR == 1)
 					enqueue(fl, row, y_first, stg);
 				else if constexpr (REPAIR == 2)

@@ -115,6 +115,13 @@ template <> struct StripCodec<uint8_t> {
 		*p = (unsigned char)__float_as_uint(r);
 		return fabsf(fmaf(sat01, kMax, 12582912.0f - r)) >= 0.5f - kEps;
 	}
+	// ... store, and return the distance of the FP32 value from the integer it rounds to (|.| >= 0.5 - kEps: near a boundary)
+	__device__ __forceinline__ static float store_resid(unsigned char *p, float sat01)
+	{
+		const float r = fmaf(sat01, kMax, 12582912.0f);
+		*p = (unsigned char)__float_as_uint(r);
+		return fmaf(sat01, kMax, 12582912.0f - r);
+	}
 };
 template <> struct StripCodec<uint16_t> {
 	static constexpr float kHScale = kIntHScale;
@@ -142,6 +149,12 @@ template <> struct StripCodec<uint16_t> {
 		*reinterpret_cast<uint16_t *>(p) = (uint16_t)__float_as_uint(r);
 		return fabsf(fmaf(sat01, kMax, 12582912.0f - r)) >= 0.5f - kEps;
 	}
+	__device__ __forceinline__ static float store_resid(unsigned char *p, float sat01)
+	{
+		const float r = fmaf(sat01, kMax, 12582912.0f);
+		*reinterpret_cast<uint16_t *>(p) = (uint16_t)__float_as_uint(r);
+		return fmaf(sat01, kMax, 12582912.0f - r);
+	}
 };
 template <> struct StripCodec<u15_t> {	// bpc = 15: the loads of u16, max = 32768
 	static constexpr float kHScale = kIntHScale;
@@ -159,6 +172,12 @@ template <> struct StripCodec<u15_t> {	// bpc = 15: the loads of u16, max = 3276
 		*reinterpret_cast<uint16_t *>(p) = (uint16_t)__float_as_uint(r);
 		return fabsf(fmaf(sat01, kMax, 12582912.0f - r)) >= 0.5f - kEps;
 	}
+	__device__ __forceinline__ static float store_resid(unsigned char *p, float sat01)
+	{
+		const float r = fmaf(sat01, kMax, 12582912.0f);
+		*reinterpret_cast<uint16_t *>(p) = (uint16_t)__float_as_uint(r);
+		return fmaf(sat01, kMax, 12582912.0f - r);
+	}
 };
 template <> struct StripCodec<float> {
 	static constexpr float kHScale = 1.0f;
@@ -172,6 +191,8 @@ template <> struct StripCodec<float> {
 	}
 	__device__ __forceinline__ static void store(unsigned char *p, float sat01) { *reinterpret_cast<float *>(p) = sat01; }
 	__device__ __forceinline__ static bool store_flag(unsigned char *p, float sat01) { store(p, sat01); return false; }
+	static constexpr float kEps = 0.f;
+	__device__ __forceinline__ static float store_resid(unsigned char *p, float sat01) { store(p, sat01); return 0.f; }
 };
 
 template <> struct StripCodec<__half> {	// bpc = -2: computed like float images, stored with one rounding to half
@@ -186,6 +207,8 @@ template <> struct StripCodec<__half> {	// bpc = -2: computed like float images,
 	}
 	__device__ __forceinline__ static void store(unsigned char *p, float sat01) { *reinterpret_cast<__half *>(p) = __float2half_rn(sat01); }
 	__device__ __forceinline__ static bool store_flag(unsigned char *p, float sat01) { store(p, sat01); return false; }
+	static constexpr float kEps = 0.f;
+	__device__ __forceinline__ static float store_resid(unsigned char *p, float sat01) { store(p, sat01); return 0.f; }
 };
 
 // Samples whose bit patterns include NaN / Inf (a zero weight does not silence them)
@@ -236,10 +259,13 @@ __device__ __forceinline__ float4 position_weights(const Axis &ay, int y, int H,
 // Chain order oldest -> newest; the last FMA saturates (clip_d, fix-ca.c:873-880).  Linear has taps
 // at the two newest positions only.
 // REPAIR: returns a mask of the columns whose FP32 value lies within Codec::kEps of a rounding boundary.
-template <int INTERP, int U, int P, int BPP, class Codec, bool REPAIR = false>
+// REPAIR = 2: the same mask, through one test per row: the largest residual of the P columns against the bound, and the
+// per-column tests only behind it (one thread-row in 400 has a near-tie sample: 5 instead of 3 * P test instructions).
+template <int INTERP, int U, int P, int BPP, class Codec, int REPAIR = 0>
 __device__ __forceinline__ unsigned vertical_emit(const float (&hr)[4][P], const float4 w, unsigned char *q)
 {
 	unsigned flags = 0;
+	[[maybe_unused]] float resid[P];
 #pragma unroll
 	for (int k = 0; k < P; ++k) {
 		float v;
@@ -251,10 +277,23 @@ __device__ __forceinline__ unsigned vertical_emit(const float (&hr)[4][P], const
 			v = fmaf(w.z, hr[(U + 3) & 3][k], v);
 		}
 		v = __saturatef(fmaf(w.w, hr[U][k], v));
-		if (REPAIR)
+		if (REPAIR == 2)
+			resid[k] = fabsf(Codec::store_resid(q + k * BPP, v));
+		else if (REPAIR)
 			flags |= Codec::store_flag(q + k * BPP, v) ? 1u << k : 0u;
 		else
 			Codec::store(q + k * BPP, v);
+	}
+	if constexpr (REPAIR == 2) {
+		float worst = resid[0];
+#pragma unroll
+		for (int k = 1; k < P; ++k)
+			worst = fmaxf(worst, resid[k]);
+		if (__builtin_expect(worst >= 0.5f - Codec::kEps, 0)) {
+#pragma unroll
+			for (int k = 0; k < P; ++k)
+				flags |= resid[k] >= 0.5f - Codec::kEps ? 1u << k : 0u;
+		}
 	}
 	return flags;
 }
