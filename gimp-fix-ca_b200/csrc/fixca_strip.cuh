@@ -357,7 +357,17 @@ __device__ __forceinline__ dvec4 position_weights_wide(const Axis &ay, int y, in
 template <int INTERP, int U, int P, int BPP, class WC>
 __device__ __forceinline__ unsigned vertical_emit_wide(const double (&hr)[4][P], const dvec4 &w, unsigned char *q)
 {
-	constexpr double MAGIC = 6755399441055744.0;	// 2^52 + 2^51
+	// Rounding and the boundary test in ONE FP64 addition: t = v + 0.5 + 1.5 * 2^22 lies in [2^22, 2^23) for every
+	// |v| < 2^21, so its mantissa is the fixed-point number (v + 0.5 + 2^21) * 2^30, rounded once (<= half a unit = 2^-31 LSB):
+	// bits 30+ are floor(v + 0.5) + 2^21 -- taken with one funnel shift, the exponent's bits that come along are a constant
+	// that goes into the clamp's bounds, and neither it nor 2^21 reaches the 16 bits stored -- and the low 30 bits are the
+	// fraction of v + 0.5, which is near 0 or 1 exactly when v is near a rounding boundary.  (r02 (C): v + 1.5 * 2^52, back
+	// again, the difference, a DSETP -- three FP64 additions and a compare per sample on the pipe that bounds the kernel.)
+	constexpr double MAGIC = 6291456.5;			// 1.5 * 2^22 + 0.5
+	constexpr int EXPO = (int)((0x415u << 22) & 0xffffffffu);	// (biased exponent of 2^22) << 22, what is left of it in 32 bits
+	constexpr int BASE = EXPO + (1 << 21);			// the funnel-shifted word of v + 0.5 = 0
+	constexpr unsigned EPS = (unsigned)(WC::kEps * 1073741824.0) + 26;	// kEps in units of 2^-30, + the addition's own half unit, + margin
+	static_assert(WC::kMaxInt <= 65536 && (BASE & 0xffff) == 0, "the stored 16 bits are the integer's own");
 	unsigned flags = 0;
 #pragma unroll
 	for (int k = 0; k < P; ++k) {
@@ -370,10 +380,13 @@ __device__ __forceinline__ unsigned vertical_emit_wide(const double (&hr)[4][P],
 			v = fma(w.z, hr[(U + 3) & 3][k], v);
 		}
 		v = fma(w.w, hr[U][k], v);
-		const double t = v + MAGIC;			// |v| <= 1.6 * 65535: the low word of t is round-to-nearest(v)
-		const int n = min(max(__double2loint(t), 0), WC::kMaxInt);
+		const double t = v + MAGIC;			// |v| <= 1.6 * 65535
+		const unsigned lo = (unsigned)__double2loint(t);
+		const int word = (int)__funnelshift_l(lo, (unsigned)__double2hiint(t), 2);	// EXPO + 2^21 + floor(v + 0.5)
+		const int n = min(max(word, BASE), BASE + WC::kMaxInt);
 		*reinterpret_cast<uint16_t *>(q + k * BPP) = (uint16_t)n;
-		flags |= (fabs(v - (t - MAGIC)) >= 0.5 - WC::kEps) ? 1u << k : 0u;
+		// fraction of v + 0.5 within EPS of 0 or 1 (the shift drops the two integer bits of the low word)
+		flags |= ((lo + EPS) << 2) <= ((2 * EPS) << 2) ? 1u << k : 0u;
 	}
 	return flags;
 }
