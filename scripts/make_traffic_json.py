@@ -27,8 +27,8 @@ def kernel_name(md_kernel: str, exact: bool) -> str:
     arith = "f32"
     if flags and int(flags.group(3)):
         arith = "f64+exact"
-    elif flags and int(flags.group(2)):
-        arith = "f32+f64"
+    elif flags and int(flags.group(2)):     # REPAIR: 1 in-kernel queues, 2 deferred (repair_patch_kernel behind it)
+        arith = "f32+f64" if int(flags.group(2)) == 2 else "f32+f64inline"
     return "stream/%s/%s/%sx%d" % (["none", "linear", "cubic"][interp], arith, KERNEL[ty], ch)
 
 
