@@ -12,8 +12,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "gimp-fix-ca_b200", "lib", "libfixca_cuda.so")
 MNEMONICS = ["UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "UTMAPF", "FFMA", "FMUL", "DFMA", "DMUL", "DADD", "LDS", "STS", "LDG", "PRMT",
              "ACQBULK", "UTMACMDFLUSH", "ELECT"]
-KERNELS = {"stream_kernel<unsigned short,3,2,2,256> (headline)": "_ZN5fixca13stream_kernelItLi3ELi2ELi2ELi256ELb0ELb0ELb0EEEvNS_10KernelArgsE14CUtensorMap_stS2_S2_NS_12StreamFanoutE",
-           "stream_kernel<unsigned char,3,2,4,256> (cfg5)": "_ZN5fixca13stream_kernelIhLi3ELi2ELi4ELi256ELb0ELb0ELb0EEEvNS_10KernelArgsE14CUtensorMap_stS2_S2_NS_12StreamFanoutE"}
+KERNELS = {"stream_kernel<unsigned short,3,2,2,256> (headline)": "_ZN5fixca13stream_kernelItLi3ELi2ELi2ELi256ELb0ELi0ELb0EEEvNS_10KernelArgsE14CUtensorMap_stS2_S2_NS_12StreamFanoutE",
+           "stream_kernel<unsigned char,3,2,4,256> (cfg5)": "_ZN5fixca13stream_kernelIhLi3ELi2ELi4ELi256ELb0ELi0ELb0EEEvNS_10KernelArgsE14CUtensorMap_stS2_S2_NS_12StreamFanoutE",
+           "stream_kernel<unsigned char,3,2,4,256,REPAIR=2> (8-bit EXACT)": "_ZN5fixca13stream_kernelIhLi3ELi2ELi4ELi256ELb0ELi2ELb0EEEvNS_10KernelArgsE14CUtensorMap_stS2_S2_NS_12StreamFanoutE",
+           "stream_kernel<unsigned short,3,2,2,256,WIDE> (16-bit EXACT)": "_ZN5fixca13stream_kernelItLi3ELi2ELi2ELi256ELb0ELi0ELb1EEEvNS_10KernelArgsE14CUtensorMap_stS2_S2_NS_12StreamFanoutE"}
 
 
 def census(text):
