@@ -975,13 +975,12 @@ static int launch_plan(const Plan &pl, cudaStream_t stream)
 		pa.grid_y = (int)pl.grid.y;
 		pa.warps = (int)pl.block.x / 32 - 1;
 		pa.nregions = pl.grid.x * pl.grid.y * pl.grid.z * (unsigned)pa.warps;
+		pa.nframes = (unsigned)pl.nframes;
 		pa.tw = pl.k->tw;
 		pa.p = pl.k->strip_p;
 		pa.nfan = pl.fan.n;
 		for (int i = 0; i < pl.fan.n; ++i)
 			pa.fan[i] = (unsigned char *)pl.fan_dst[i];
-		int dev = 0;
-		cudaGetDevice(&dev);
 		void *pparams[] = {&a, &pa};
 		cudaLaunchConfig_t cfg = {};
 		// threads per region: what a region expects (6.2e-4 of its samples) plus four standard deviations, as a power of two

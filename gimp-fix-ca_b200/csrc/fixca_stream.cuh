@@ -520,6 +520,7 @@ struct PatchArgs {
 	int grid_x, grid_y;			// the streaming grid (strips, segments; z = frames)
 	int warps, tw, p;			// compute warps per CTA, strip width, columns per thread
 	unsigned lanes;				// threads per region: a power of two, 8 .. 256
+	unsigned nframes;			// frames of the batch (grid z of the streaming launch)
 	int nfan;				// further destination frames (fan-out / all-gather form)
 	unsigned char *fan[STREAM_MAX_FAN];
 };
@@ -551,7 +552,8 @@ __global__ void __launch_bounds__(256) repair_patch_kernel(const __grid_constant
 			for (unsigned i = sl; i < n; i += pa.lanes) {
 				const unsigned long long e = __ldcg(q + i);
 				const unsigned long long px = e >> 1, fr = px / W;
-				fix(fr / rows, (int)(px % W), a.y1 + (int)(fr % rows), (int)(e & 1ull));
+				if (fr / rows < pa.nframes)	// (x < width and y1 <= y < y2 by construction)
+					fix(fr / rows, (int)(px % W), a.y1 + (int)(fr % rows), (int)(e & 1ull));
 			}
 		} else {
 			// the warp's whole region: rows of its CTA's segment x the 32 * P columns of its lanes, its channel
