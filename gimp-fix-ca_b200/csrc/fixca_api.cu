@@ -223,9 +223,9 @@ struct Plan {
 	// stream kernel: the per-chunk tables args.meta_tab / args.span_tab point into (device memory, shared by every
 	// plan of the same band, y axes and kernel family; freed with the last plan that holds them)
 	std::shared_ptr<void> tables, col_tables;
-	// deferred exact-repair form: the launch's queue of near-tie samples (args.rq_ctl / rq_entries), owned by the plan --
-	// two launches of one plan must not run concurrently (they would be writing the same destination anyway)
-	std::shared_ptr<void> repair_queue;
+	// deferred exact-repair form: size of the launch's queue of near-tie samples (counts, then args.rq_cap entries per
+	// region); the memory belongs to the launching thread's (device, stream) pair and is bound at launch (repair_queue())
+	size_t rq_counts_bytes = 0, rq_bytes = 0;
 	// a batch of equal frames in one launch (stream kernels: grid.z = frame, 3-D tensor maps)
 	int nframes = 1;
 	size_t src_frame_stride = 0, dst_frame_stride = 0;
@@ -595,27 +595,66 @@ static std::shared_ptr<void> cached_table(int tag, const Key &key, int dev, size
 	return sp;
 }
 
-// device memory owned by a plan (freed with its last holder; cudaFree waits for the device); the first `zero` bytes cleared
-static std::shared_ptr<void> device_scratch(int dev, size_t bytes, size_t zero)
+// Queue memory of the deferred exact-repair form (stream kernel -> repair_patch_kernel): one allocation per calling
+// thread, device and stream, grown to the largest launch seen.  Launches in one stream are ordered, so they can share it
+// (every launch writes every region's count before its patch kernel reads it: nothing carries over); launches in
+// different streams, or from different threads, never share one.  Growing frees the old block (cudaFree waits for the
+// device: no launch can still be using it).
+struct RepairQueueSlot { int dev; cudaStream_t stream; size_t bytes; void *mem; };
+static thread_local RepairQueueSlot tl_repair_queues[16];
+static void repair_queue_release()	// (the calling thread's; fixca_cuda_release())
 {
+	int cur = -1;
+	cudaGetDevice(&cur);
+	for (RepairQueueSlot &c : tl_repair_queues) {
+		if (c.mem && cudaSetDevice(c.dev) == cudaSuccess && cudaFree(c.mem) != cudaSuccess)
+			cudaGetLastError();
+		c.mem = nullptr;
+	}
+	if (cur >= 0)
+		cudaSetDevice(cur);
+}
+static void *repair_queue(int dev, cudaStream_t stream, size_t bytes)
+{
+	typedef RepairQueueSlot Slot;
+	constexpr int SLOTS = 16;
+	Slot (&slots)[SLOTS] = tl_repair_queues;
+	static thread_local int next = 0;
+	Slot *sl = nullptr;
+	for (Slot &c : slots)
+		if (c.mem && c.dev == dev && c.stream == stream)
+			sl = &c;
+	if (sl && sl->bytes >= bytes)
+		return sl->mem;
+	size_t had = sl ? sl->bytes : 0;	// (this stream's block is too small: grow geometrically)
+	if (!sl) {
+		sl = &slots[next];
+		next = (next + 1) % SLOTS;
+	}
 	int cur = -1;
 	if (cudaGetDevice(&cur) != cudaSuccess)
 		return nullptr;
-	if (cur != dev && cudaSetDevice(dev) != cudaSuccess)
+	if (sl->mem) {	// an older stream's block, or one that is too small
+		if (sl->dev != cur)
+			cudaSetDevice(sl->dev);
+		if (cudaFree(sl->mem) != cudaSuccess)
+			cudaGetLastError();
+		sl->mem = nullptr;
+	}
+	if (cudaSetDevice(dev) != cudaSuccess)
 		return nullptr;
+	const size_t want = std::max(bytes + bytes / 4, 2 * had);	// (the host driver's chunks ramp up: few regrowths)
 	void *mem = nullptr;
-	bool ok = cudaMalloc(&mem, bytes) == cudaSuccess;
-	ok = ok && (!zero || cudaMemset(mem, 0, zero) == cudaSuccess);	// (synchronous: ordered before every later launch)
-	if (!ok) {
+	if (cudaMalloc(&mem, want) != cudaSuccess) {
 		cudaGetLastError();
-		if (mem)
-			cudaFree(mem);
+		mem = nullptr;
 	}
 	if (cur != dev)
 		cudaSetDevice(cur);
-	if (!ok)
+	if (!mem)
 		return nullptr;
-	return std::shared_ptr<void>(mem, [](void *p) { if (cudaFree(p) != cudaSuccess) cudaGetLastError(); });
+	*sl = Slot{dev, stream, want, mem};
+	return mem;
 }
 
 // The tables of a streaming plan:
@@ -844,11 +883,8 @@ static bool plan_stream(const KernelEntry *k, const Format &f, const Geometry &g
 		const size_t counts = align_up((size_t)nregions * sizeof(unsigned), 256);
 		if (nregions > 0xffffffffull)
 			return false;
-		pl.repair_queue = device_scratch(dev, counts + (size_t)nregions * cap * sizeof(unsigned long long), 0);
-		if (!pl.repair_queue)
-			return false;
-		a.rq_ctl = (unsigned *)pl.repair_queue.get();
-		a.rq_entries = (unsigned long long *)((unsigned char *)pl.repair_queue.get() + counts);
+		pl.rq_counts_bytes = counts;
+		pl.rq_bytes = counts + (size_t)nregions * cap * sizeof(unsigned long long);
 		a.rq_cap = cap;
 	}
 	return true;
@@ -942,6 +978,15 @@ static int launch_plan(const Plan &pl, cudaStream_t stream)
 		}
 	}
 	KernelArgs a = pl.args;
+	if (pl.k->patch) {
+		int dev = 0;
+		CUDA_TRY(cudaGetDevice(&dev));
+		unsigned char *q = (unsigned char *)repair_queue(dev, stream, pl.rq_bytes);
+		if (!q)
+			return fail(FIXCA_ERR_NOMEM, "no device memory for the exact-repair queue (%zu bytes)", pl.rq_bytes);
+		a.rq_ctl = (unsigned *)q;
+		a.rq_entries = (unsigned long long *)(q + pl.rq_counts_bytes);
+	}
 	CUtensorMap tm[3] = {pl.tm_win, pl.tm_tile, pl.tm_out};
 	StreamFanout fan = pl.fan;
 	void *params[] = {&a, &tm[0], &tm[1], &tm[2], &fan};	// the tensor maps are only declared by stream kernels
@@ -2129,6 +2174,7 @@ extern "C" int fixca_cuda_device_count(void)
 extern "C" void fixca_cuda_release(void)
 {
 	pinned_pool_release();
+	repair_queue_release();
 	for (DeviceCtx &c : g_ctx) {
 		std::lock_guard<std::mutex> lock(c.mu);
 		c.release();

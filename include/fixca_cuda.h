@@ -204,8 +204,8 @@ FIXCA_API int fixca_cuda_region_multi(const unsigned char *src, unsigned char *d
  * first call outside a CUDA stream capture.
  * EXACT Linear / Cubic on 8-bit samples is two launches on `stream` (the streaming kernel, then
  * repair_patch_kernel, which recomputes the near-tie samples the first one queued); the queue
- * belongs to the plan, so do not run two calls with IDENTICAL arguments concurrently on
- * different streams (they would be writing the same destination bytes anyway).
+ * between them is device memory kept per calling thread, device and stream (grown to the
+ * largest launch seen; fixca_cuda_release() frees the calling thread's).
  */
 FIXCA_API int fixca_cuda_region_dev(const void *d_src, size_t src_pitch, int src_row0, int src_rows,
 				    void *d_dst, size_t dst_pitch, int dst_row0,

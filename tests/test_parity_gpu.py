@@ -373,6 +373,37 @@ def test_fanout_stores_every_destination(fx, checker):
         fx.fix_ca_region_dev_fanout(src.data_ptr(), pitch, 0, h, [src.data_ptr()] * 9, pitch, 0, w, h, bpp, -4, p, 0, h, flags, st)
 
 
+def test_exact8_concurrent_streams_and_many_buffers(fx, checker):
+    """8-bit EXACT is two launches joined by a queue in device memory (stream kernel -> repair_patch_kernel).  The queue is
+    kept per calling thread, device and stream: launches of the same geometry on two streams at once, launches that
+    alternate between a large and a small image on one stream (the queue grows), and one geometry over many buffer pairs
+    all return the reference's bytes."""
+    import torch
+
+    kw = dict(KW, lens_x=300, lens_y=128, interpolation=2)
+    p = fx.FixCaParams(**kw)
+    sizes = ((257, 640, 3), (97, 320, 4))
+    imgs = {sz: [orc.synth_image(sz[0], sz[1], sz[2], "u1", 500 + 10 * i + k) for k in range(6)] for i, sz in enumerate(sizes)}
+    want = {sz: [checker.region(im, orc.Params(**kw)) for im in imgs[sz]] for sz in sizes}
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    jobs = []
+    for rnd in range(3):
+        for k in range(6):
+            for si, sz in enumerate(sizes):      # the two sizes alternate on both streams
+                h, w, ch = sz
+                st = streams[(k + si + rnd) % 2]
+                with torch.cuda.stream(st):
+                    src = torch.from_numpy(imgs[sz][k]).cuda()
+                    dst = torch.full_like(src, 0x5A)
+                    fx.fix_ca_region_dev(src.data_ptr(), w * ch, 0, h, dst.data_ptr(), w * ch, 0, w, h, ch, 1, p, 0, h,
+                                         fx.PRECISION_EXACT, st.cuda_stream)
+                assert fx.last_kernel().split("/")[2] == "f32+f64", fx.last_kernel()
+                jobs.append((sz, k, src, dst))
+    torch.cuda.synchronize()
+    for sz, k, _src, dst in jobs:
+        assert dst.cpu().numpy().tobytes() == want[sz][k].tobytes(), (sz, k)
+
+
 def test_device_resident_entry_with_torch_buffers(fx, checker):
     import torch
 
