@@ -252,3 +252,37 @@ def test_color_size_half_extension(fx):
     assert fx.color_size_half("R'G'B'A half", 8) == -2
     for name, bpp in (("R'G'B' u8", 3), ("R'G'B'A u16", 8), ("RGB float", 12), ("RGBA double", 32), ("R'G'B' u15", 6), ("Y u8", 1)):
         assert fx.color_size_half(name, bpp) == fx.color_size(name, bpp)
+
+
+def test_wide_emit_fixed_point_rounding_and_boundary_test():
+    """vertical_emit_wide (fixca_strip.cuh) rounds a 16-bit result and tests its distance from a rounding
+    boundary with ONE FP64 addition: t = v + 0.5 + 1.5 * 2^22, the integer from a funnel shift of t's words, the test from
+    the low 30 bits.  Restated here bit for bit on 8 M values (uniform, and planted within a few 1e-6 of boundaries, on
+    them, and on integers): every value within kEps = 1e-6 LSB of a boundary is flagged, every value that is not flagged
+    gets round-to-nearest, and the flag rate stays at ~2 kEps."""
+    rng = np.random.default_rng(1)
+    magic = np.float64(6291456.5)
+    expo = (0x415 << 22) & 0xFFFFFFFF
+    base = expo + (1 << 21)
+    eps = int(1e-6 * 1073741824.0) + 26
+
+    def emit(v, kmax):
+        bits = (v + magic).view(np.uint64)
+        lo, hi = bits & np.uint64(0xFFFFFFFF), bits >> np.uint64(32)
+        word = (((hi << np.uint64(2)) | (lo >> np.uint64(30))) & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        n = np.clip(word, base, base + kmax) - base
+        assert ((np.clip(word, base, base + kmax) & 0xFFFF) == (n & 0xFFFF)).all()     # what the 16-bit store keeps
+        flag = (((lo + np.uint64(eps)) << np.uint64(2)) & np.uint64(0xFFFFFFFF)) <= np.uint64((2 * eps) << 2)
+        return n, flag
+
+    v = rng.uniform(-40000, 105000, 4_000_000)
+    k = rng.integers(-39000, 104000, 1_000_000).astype(np.float64)
+    d = rng.uniform(-3e-6, 3e-6, 1_000_000)
+    v = np.concatenate([v, k + 0.5 + d, k + 0.5, k, k + 0.5 + np.sign(d) * 1.05e-6])
+    dist = np.abs((v - np.floor(v)) - 0.5)
+    for kmax in (65535, 32768):
+        n, flag = emit(v, kmax)
+        want = np.clip(np.floor(v + 0.5), 0, kmax).astype(np.int64)
+        assert not ((dist <= 1e-6) & ~flag).any()
+        assert not (~flag & (n != want)).any()
+        assert flag[:4_000_000].mean() < 4e-6 and dist[flag].max() < 1.1e-6
