@@ -1030,8 +1030,17 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 
 		// wait for chunk j's rows, pass-through tile and record; returns whether it can take the unrolled loop: a full
 		// chunk whose rows complete on the next CH source rows, ring at slot 0
+#ifdef FIXCA_EXP_TIMING
+		long long t_waitacc = 0;	// cycles inside the `full` barrier waits of begin_chunk
+#endif
 		auto begin_chunk = [&]() -> bool {
+#ifdef FIXCA_EXP_TIMING
+			const long long tw0 = clock64();
 			mbar_wait(&full[jnf], (uint32_t)jpar);
+			t_waitacc += clock64() - tw0;
+#else
+			mbar_wait(&full[jnf], (uint32_t)jpar);
+#endif
 			m = &meta[jnf];
 			done_bar = &done[jnf];
 			stg = stage + jstg * STAGE_BYTES;
@@ -1179,8 +1188,8 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 					t_rows += t1 - t0; t_end += t2 - t1; ++n_st;
 					if (j == nchunks) {
 						if (blockIdx.x == 3 && (blockIdx.y == 1 || blockIdx.y == 20) && (gridDim.z == 1 || blockIdx.z % 16 == 5) && (tid & 31) == 0)
-							printf("cta z%d warp %d: %d steady chunks, cycles per chunk: rows %lld, hand-over %lld, wait+entry %lld; CTA: set-up %lld, first data +%lld, first chunk +%lld, total %lld\n", (int)blockIdx.z, tid >> 5, n_st,
-							       t_rows / n_st, t_end / n_st, t_begin / max(n_st - 1, 1), t_setup - t_entry, t_data - t_setup, t_steady0 - t_data, clock64() - t_entry);
+							printf("cta z%d warp %d: %d steady chunks, cycles per chunk: rows %lld, hand-over %lld, wait+entry %lld (of it inside the barrier wait %lld); CTA: set-up %lld, first data +%lld, first chunk +%lld, total %lld\n", (int)blockIdx.z, tid >> 5, n_st,
+							       t_rows / n_st, t_end / n_st, t_begin / max(n_st - 1, 1), t_waitacc / max(n_st, 1), t_setup - t_entry, t_data - t_setup, t_steady0 - t_data, clock64() - t_entry);
 						return;
 					}
 					steady = begin_chunk();
