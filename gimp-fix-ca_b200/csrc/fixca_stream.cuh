@@ -844,16 +844,18 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 
 	// last source row this thread has filtered horizontally: the one below the first tap row of the segment's first output row
 	int s_done = __ldg(&reinterpret_cast<const Meta *>(a.meta_tab)[cj0].first[c]) - 1;
-	// Ring of the last four horizontal rows.  `ph` = slot the next source row goes to; the newest row
-	// sits in slot ph - 1, the row p below it in slot ph - 1 - p (mod 4).  The vertical weights come
-	// ordered by that distance p (position_weights), so the arithmetic is independent of ph.
+	// Ring of the last four horizontal rows.  Between chunks the newest row sits in slot 3 and the row p below it in
+	// slot 3 - p: the unrolled steady-state rows write slots 0, 1, 2, 3, 0 ... (whole ring turns, so they leave that
+	// order behind), the general walk shifts the ring down a slot per source row (12 register moves for four
+	// columns: rows off the steady path are few, and ONE copy of their code instead of one per ring phase is a
+	// quarter of the instruction-cache footprint -- they ran at ~800 cycles per row, mostly instruction fetch).  The
+	// vertical weights come ordered by the distance p (position_weights), so the arithmetic is independent of the slot.
 	A hr[4][P];
 #pragma unroll
 	for (int u = 0; u < 4; ++u)
 #pragma unroll
 		for (int k = 0; k < P; ++k)
 			hr[u][k] = 0;
-	int ph = (5 - T) & 3;	// after the T - 1 priming rows of a segment the ring is back at slot 0
 	// the thread's view of the window ring: every row pointer already carries its column offset
 	// (32-bit shared-window addresses: one add / compare / select per row; with generic pointers the
 	// compiler kept a second, converted copy of the chain for the ld.shared operands)
@@ -955,81 +957,42 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 					wflags |= fl << (row * P);	// (CH * P <= 32 bits)
 			}
 		};
-		// one source row through the horizontal filter into ring slot U
-		auto hrow = [&](auto slot) {
-			constexpr int U = decltype(slot)::value;
+		// general walk -- one source row through the horizontal filter: the ring shifts down a slot, the new row goes to slot 3
+		auto hrow = [&]() {
 			A smp[NSL];
 			load_row(prow, smp);
-			hfilter(smp, hr[U]);
+#pragma unroll
+			for (int u = 0; u < 3; ++u)
+#pragma unroll
+				for (int k = 0; k < P; ++k)
+					hr[u][k] = hr[u + 1][k];
+			hfilter(smp, hr[3]);
 			++s_done;
 			prow += (uint32_t)wpitch;
 			if (prow == win_end)
 				prow = win_c;
 		};
-		// the output rows completed by the newest row (slot U)
-		auto emit = [&](auto slot) {
+		// ... and the output rows the newest row (slot 3) completes
+		auto emit = [&]() {
 #pragma unroll 1
 			while (next_last <= s_done) {
-				vemit(slot, *wy, q, er++);
+				vemit(std::integral_constant<int, 3>(), *wy, q, er++);
 				wy += 2;
 				q += OUT_PITCH;
 				next_last = *++lastp;
 			}
 		};
-		// general walk: source rows up to `upto`, emitting whatever they complete
+		// source rows up to `upto`, emitting whatever they complete
 		auto walk = [&](const int upto) {
 #pragma unroll 1
 			while (s_done < upto) {
-				switch (ph) {
-				case 0:
-					hrow(std::integral_constant<int, 0>());
-					emit(std::integral_constant<int, 0>());
-					ph = 1;
-					if (s_done >= upto) break;
-				case 1:
-					hrow(std::integral_constant<int, 1>());
-					emit(std::integral_constant<int, 1>());
-					ph = 2;
-					if (s_done >= upto) break;
-				case 2:
-					hrow(std::integral_constant<int, 2>());
-					emit(std::integral_constant<int, 2>());
-					ph = 3;
-					if (s_done >= upto) break;
-				default:
-					hrow(std::integral_constant<int, 3>());
-					emit(std::integral_constant<int, 3>());
-					ph = 0;
-				}
+				hrow();
+				emit();
 			}
-		};
-		// bring the ring to slot 0 (the unrolled loop's slots are static)
-		auto rotate_to_slot0 = [&]() {
-			auto rotate = [&](auto by) {
-				constexpr int N = decltype(by)::value;
-				A t[4][P];
-#pragma unroll
-				for (int u = 0; u < 4; ++u)
-#pragma unroll
-					for (int k = 0; k < P; ++k)
-						t[u][k] = hr[(u + N) & 3][k];
-#pragma unroll
-				for (int u = 0; u < 4; ++u)
-#pragma unroll
-					for (int k = 0; k < P; ++k)
-						hr[u][k] = t[u][k];
-			};
-			switch (ph) {
-			case 0: break;
-			case 1: rotate(std::integral_constant<int, 1>()); break;
-			case 2: rotate(std::integral_constant<int, 2>()); break;
-			default: rotate(std::integral_constant<int, 3>()); break;
-			}
-			ph = 0;
 		};
 
 		// wait for chunk j's rows, pass-through tile and record; returns whether it can take the unrolled loop: a full
-		// chunk whose rows complete on the next CH source rows, ring at slot 0
+		// chunk whose rows complete on the next CH source rows
 #ifdef FIXCA_EXP_TIMING
 		long long t_waitacc = 0;	// cycles inside the `full` barrier waits of begin_chunk
 #endif
@@ -1052,7 +1015,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			wy = &m->wy[0][c];
 			lastp = m->last[c];
 			next_last = lastp[0];
-			return m->simple[c] && next_last == s_done + 1 && ph == 0;
+			return m->simple[c] && next_last == s_done + 1;
 		};
 		// hand the chunk over: repairs first (their rows and taps belong to this chunk), then the barrier
 		auto end_chunk = [&]() {
@@ -1169,7 +1132,6 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 			// the first chunk of every CTA a cold instruction cache: 4-6 k cycles against 2.4 k for a steady chunk).
 			if (!steady && m->simple[c] && next_last > s_done) {
 				walk(next_last - 1);
-				rotate_to_slot0();
 				steady = next_last == s_done + 1;
 			}
 			if (steady) {
@@ -1208,16 +1170,8 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				continue;	// (the chunk in hand is not steady: it may only lack priming rows)
 			}
 			// general chunk: rows of this chunk whose taps were all produced while walking the previous chunk, then the walk
-			if (next_last <= s_done) {
-				switch (ph) {
-				case 1: emit(std::integral_constant<int, 0>()); break;
-				case 2: emit(std::integral_constant<int, 1>()); break;
-				case 3: emit(std::integral_constant<int, 2>()); break;
-				default: emit(std::integral_constant<int, 3>()); break;
-				}
-			}
+			emit();
 			walk(s_end);
-			rotate_to_slot0();	// (the next chunk may take the unrolled rows again)
 			end_chunk();
 			if (j == nchunks)
 				return;
