@@ -1115,7 +1115,8 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 		bool steady = begin_chunk();
 #ifdef FIXCA_EXP_TIMING
 		const long long t_data = clock64();
-		long long t_steady0 = 0;
+		long long t_steady0 = 0, t_wait0 = 0;
+		int n_general = 0, simple0 = m->simple[c], prime0 = next_last - s_done;
 #endif
 		for (;;) {
 			if (STREAM_DEBUG_BIT(a, 1)) {	// timing experiment: memory pipeline only (results are wrong)
@@ -1139,7 +1140,7 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				// experiment: where a compute warp's time goes in the steady state (one CTA reports)
 				long long t_rows = 0, t_end = 0, t_begin = 0;
 				int n_st = 0;
-				if (!t_steady0) t_steady0 = clock64();
+				if (!t_steady0) { t_steady0 = clock64(); t_wait0 = t_waitacc; }
 #pragma unroll 1
 				do {
 					const long long t0 = clock64();
@@ -1150,8 +1151,8 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 					t_rows += t1 - t0; t_end += t2 - t1; ++n_st;
 					if (j == nchunks) {
 						if (blockIdx.x == 3 && (blockIdx.y == 1 || blockIdx.y == 20) && (gridDim.z == 1 || blockIdx.z % 16 == 5) && (tid & 31) == 0)
-							printf("cta z%d warp %d: %d steady chunks, cycles per chunk: rows %lld, hand-over %lld, wait+entry %lld (of it inside the barrier wait %lld); CTA: set-up %lld, first data +%lld, first chunk +%lld, total %lld\n", (int)blockIdx.z, tid >> 5, n_st,
-							       t_rows / n_st, t_end / n_st, t_begin / max(n_st - 1, 1), t_waitacc / max(n_st, 1), t_setup - t_entry, t_data - t_setup, t_steady0 - t_data, clock64() - t_entry);
+							printf("cta z%d warp %d form %d: %d steady chunks, cycles per chunk: rows %lld, hand-over %lld, wait+entry %lld (of it inside the barrier wait %lld); CTA: set-up %lld, first data +%lld, first chunk +%lld (chunk 0 simple %d, rows to prime %d, general chunks first %d, barrier wait in it %lld), total %lld\n", (int)blockIdx.z, tid >> 5, FORM, n_st,
+							       t_rows / n_st, t_end / n_st, t_begin / max(n_st - 1, 1), t_waitacc / max(n_st, 1), t_setup - t_entry, t_data - t_setup, t_steady0 - t_data, simple0, prime0, n_general, t_wait0, clock64() - t_entry);
 						return;
 					}
 					steady = begin_chunk();
@@ -1170,6 +1171,9 @@ stream_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CUte
 				continue;	// (the chunk in hand is not steady: it may only lack priming rows)
 			}
 			// general chunk: rows of this chunk whose taps were all produced while walking the previous chunk, then the walk
+#ifdef FIXCA_EXP_TIMING
+			if (!t_steady0) ++n_general;
+#endif
 			emit();
 			walk(s_end);
 			end_chunk();
